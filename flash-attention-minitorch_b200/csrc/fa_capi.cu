@@ -1,0 +1,317 @@
+// fa_capi.cu -- the C ABI of libfa_b200.so (see include/fa_b200.h).
+//
+// Device-resident entry points dispatch to the tcgen05 kernels (bf16 / tf32) or the fp32 CUDA-core
+// kernels.  Host-pointer entry points reproduce the reference launchers
+// (src/flash_attn2_fw.cu:312-372, src/flash_attn2_bw.cu:279-369, src/flash_attn_fw.cu:302-359,
+// src/flash_attn_bw.cu:277-365): stage in, run, stage out, synchronise -- but through a persistent
+// grow-only device arena instead of 6-10 cudaMalloc/cudaFree pairs per call.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/fa_b200.h"
+#include "fa_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define FA_CUDA(expr, nlaunch)                                                                  \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) return fail(FA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    g_launches += (nlaunch);                                                                    \
+  } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- persistent device arena for the host-pointer API ---------------------------------------
+struct Arena {
+  void* base = nullptr;
+  size_t cap = 0;
+  int device = -1;
+  size_t used = 0;
+};
+Arena g_arena;
+std::mutex g_arena_mu;
+
+int arena_reset(size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(FA_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  if (g_arena.base && (g_arena.device != dev || g_arena.cap < bytes)) {
+    cudaFree(g_arena.base);
+    g_arena = Arena();
+  }
+  if (!g_arena.base) {
+    size_t cap = align_up(bytes + (bytes >> 3), (size_t)2 << 20);
+    e = cudaMalloc(&g_arena.base, cap);
+    if (e != cudaSuccess) {
+      g_arena = Arena();
+      return fail(FA_ERR_CUDA, "cudaMalloc(%zu) for the staging arena: %s", cap, cudaGetErrorString(e));
+    }
+    g_arena.cap = cap;
+    g_arena.device = dev;
+  }
+  g_arena.used = 0;
+  return FA_OK;
+}
+template <typename T>
+T* arena_take(size_t count) {
+  size_t off = align_up(g_arena.used, 256);
+  g_arena.used = off + count * sizeof(T);
+  return reinterpret_cast<T*>(static_cast<char*>(g_arena.base) + off);
+}
+
+int g_host_precision = -1;  // -1: not yet initialised from the environment
+int host_precision() {
+  if (g_host_precision < 0) {
+    const char* s = getenv("FA_B200_HOST_PRECISION");
+    int v = FA_PREC_AUTO;
+    if (s) {
+      if (!strcmp(s, "fp32") || !strcmp(s, "simt")) v = FA_PREC_FP32_SIMT;
+      else if (!strcmp(s, "tf32")) v = FA_PREC_TF32_TC;
+      else if (!strcmp(s, "bf16")) v = FA_PREC_BF16_TC;
+    }
+    g_host_precision = v;
+  }
+  return g_host_precision;
+}
+
+bool valid_shape(int bh, int T, int d) { return bh > 0 && T > 0 && d > 0 && d <= 128; }
+
+// Which arithmetic actually runs for (dtype, requested precision, d).  Returns <0 if unsupported.
+int resolve_precision(int dtype, int precision, int d, bool backward) {
+  const bool tc_ok = backward ? fa::tc_bwd_supported(d) : fa::tc_fwd_supported(d);
+  if (dtype == FA_DTYPE_BF16) {
+    if (precision == FA_PREC_AUTO || precision == FA_PREC_BF16_TC) return tc_ok ? FA_PREC_BF16_TC : FA_PREC_FP32_SIMT;
+    if (precision == FA_PREC_FP32_SIMT) return FA_PREC_FP32_SIMT;
+    return -1;
+  }
+  if (dtype == FA_DTYPE_F32) {
+    if (precision == FA_PREC_AUTO || precision == FA_PREC_FP32_SIMT) return FA_PREC_FP32_SIMT;
+    if (precision == FA_PREC_BF16_TC) return tc_ok ? FA_PREC_BF16_TC : FA_PREC_FP32_SIMT;
+    if (precision == FA_PREC_TF32_TC) return FA_PREC_FP32_SIMT;  // tf32 kernels not built yet: exact fp32 instead
+  }
+  return -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fa_b200_version(void) { return 100; }
+const char* fa_b200_last_error(void) { return g_err; }
+unsigned long long fa_b200_launch_count(void) { return g_launches.load(); }
+
+int fa_b200_fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* m_out, float* l_out,
+                int dtype, int precision, int batch_heads, int T, int d, int causal, void* stream) {
+  if (!q || !k || !v || !o) return fail(FA_ERR_BAD_ARG, "fa_b200_fwd: null tensor pointer");
+  if (!valid_shape(batch_heads, T, d)) return fail(FA_ERR_BAD_ARG, "fa_b200_fwd: bad shape BH=%d T=%d d=%d", batch_heads, T, d);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int prec = resolve_precision(dtype, precision, d, false);
+  if (prec < 0) return fail(FA_ERR_BAD_ARG, "fa_b200_fwd: dtype %d / precision %d not supported", dtype, precision);
+  if (dtype == FA_DTYPE_BF16) {
+    if (prec != FA_PREC_BF16_TC)
+      return fail(FA_ERR_UNSUPPORTED, "fa_b200_fwd: bf16 storage needs d in {64,128} (got %d)", d);
+    FA_CUDA(fa::tc_fwd((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, o, false, lse, m_out,
+                       l_out, batch_heads, T, d, causal != 0, st), 1);
+    return FA_OK;
+  }
+  if (prec != FA_PREC_FP32_SIMT)
+    return fail(FA_ERR_UNSUPPORTED, "fa_b200_fwd: fp32 storage with tensor-core precision needs the host API");
+  FA_CUDA(fa::simt_fwd((const float*)q, (const float*)k, (const float*)v, (float*)o, lse, m_out, l_out, batch_heads, T,
+                       d, causal != 0, st), 1);
+  return FA_OK;
+}
+
+size_t fa_b200_bwd_workspace_bytes(int dtype, int precision, int batch_heads, int T, int d) {
+  if (!valid_shape(batch_heads, T, d)) return 0;
+  const int prec = resolve_precision(dtype, precision, d, true);
+  const size_t rows = (size_t)batch_heads * T, n = rows * d;
+  if (prec == FA_PREC_BF16_TC && dtype == FA_DTYPE_BF16) return fa::tc_bwd_workspace_bytes(batch_heads, T, d);
+  size_t bytes = align_up(rows * sizeof(float), 256);            // delta
+  if (dtype == FA_DTYPE_BF16) bytes += 8 * align_up(n * sizeof(float), 256);  // fp32 images of 5 inputs + 3 grads
+  return bytes;
+}
+
+int fa_b200_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_out, const float* lse,
+                void* dq, void* dk, void* dv, int dtype, int precision, int batch_heads, int T, int d, int causal,
+                int accumulate_dq, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!q || !k || !v || !o || !d_out || !lse || !dq || !dk || !dv)
+    return fail(FA_ERR_BAD_ARG, "fa_b200_bwd: null tensor pointer");
+  if (!valid_shape(batch_heads, T, d)) return fail(FA_ERR_BAD_ARG, "fa_b200_bwd: bad shape BH=%d T=%d d=%d", batch_heads, T, d);
+  const int prec = resolve_precision(dtype, precision, d, true);
+  if (prec < 0) return fail(FA_ERR_BAD_ARG, "fa_b200_bwd: dtype %d / precision %d not supported", dtype, precision);
+  const size_t need = fa_b200_bwd_workspace_bytes(dtype, precision, batch_heads, T, d);
+  if (need && (!workspace || workspace_bytes < need))
+    return fail(FA_ERR_WORKSPACE, "fa_b200_bwd: workspace %zu bytes < required %zu", workspace_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t rows = (size_t)batch_heads * T, n = rows * d;
+  char* ws = static_cast<char*>(workspace);
+
+  if (dtype == FA_DTYPE_BF16 && prec == FA_PREC_BF16_TC) {
+    FA_CUDA(fa::tc_bwd((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+                       (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_out, lse, dq, dk, dv, false, accumulate_dq != 0,
+                       workspace, batch_heads, T, d, causal != 0, st), 3);
+    return FA_OK;
+  }
+  float* delta = reinterpret_cast<float*>(ws);
+  ws += align_up(rows * sizeof(float), 256);
+  if (dtype == FA_DTYPE_F32) {
+    FA_CUDA(fa::simt_bwd_prep((const float*)o, (const float*)d_out, delta, nullptr, nullptr, nullptr, rows, d, st), 1);
+    FA_CUDA(fa::simt_bwd((const float*)q, (const float*)k, (const float*)v, (const float*)d_out, lse, delta, (float*)dq,
+                         (float*)dk, (float*)dv, batch_heads, T, d, causal != 0, accumulate_dq != 0, st), 2);
+    return FA_OK;
+  }
+  // bf16 storage, head dim outside the tensor-core set: widen to fp32, run the CUDA-core kernels, narrow back
+  float* f[8];
+  for (int i = 0; i < 8; ++i) {
+    f[i] = reinterpret_cast<float*>(ws);
+    ws += align_up(n * sizeof(float), 256);
+  }
+  const void* src[5] = {q, k, v, o, d_out};
+  for (int i = 0; i < 5; ++i) FA_CUDA(fa::cvt_bf16_to_f32((const __nv_bfloat16*)src[i], f[i], n, st), 1);
+  if (accumulate_dq) FA_CUDA(fa::cvt_bf16_to_f32((const __nv_bfloat16*)dq, f[5], n, st), 1);
+  FA_CUDA(fa::simt_bwd_prep(f[3], f[4], delta, nullptr, nullptr, nullptr, rows, d, st), 1);
+  FA_CUDA(fa::simt_bwd(f[0], f[1], f[2], f[4], lse, delta, f[5], f[6], f[7], batch_heads, T, d, causal != 0,
+                       accumulate_dq != 0, st), 2);
+  void* dst[3] = {dq, dk, dv};
+  for (int i = 0; i < 3; ++i) FA_CUDA(fa::cvt_f32_to_bf16(f[5 + i], (__nv_bfloat16*)dst[i], n, st), 1);
+  return FA_OK;
+}
+
+void fa_b200_set_host_precision(int precision) { g_host_precision = precision; }
+int fa_b200_get_host_precision(void) { return host_precision(); }
+void fa_b200_release_arena(void) {
+  std::lock_guard<std::mutex> lk(g_arena_mu);
+  if (g_arena.base) cudaFree(g_arena.base);
+  g_arena = Arena();
+}
+
+int fa_b200_host_fwd(const float* q, const float* k, const float* v, float* out, float* l, float* m, int batch,
+                     int N, int d, int causal, int convention, void* stream) {
+  if (!q || !k || !v || !out || !l || !m) return fail(FA_ERR_BAD_ARG, "fa_b200_host_fwd: null pointer");
+  if (!valid_shape(batch, N, d)) return fail(FA_ERR_BAD_ARG, "fa_b200_host_fwd: bad shape batch=%d N=%d d=%d", batch, N, d);
+  if (convention != FA_CONV_FA1 && convention != FA_CONV_FA2)
+    return fail(FA_ERR_BAD_ARG, "fa_b200_host_fwd: unknown convention %d", convention);
+  std::lock_guard<std::mutex> lk(g_arena_mu);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t rows = (size_t)batch * N, n = rows * d;
+  const int prec = resolve_precision(FA_DTYPE_F32, host_precision(), d, false);
+  if (prec < 0) return fail(FA_ERR_BAD_ARG, "fa_b200_host_fwd: bad precision setting %d", host_precision());
+  const bool tc = prec == FA_PREC_BF16_TC;
+  size_t bytes = 4 * align_up(n * 4, 256) + 3 * align_up(rows * 4, 256) + (tc ? 3 * align_up(n * 2, 256) : 0) + 4096;
+  if (int rc = arena_reset(bytes)) return rc;
+  float* dq = arena_take<float>(n);
+  float* dk = arena_take<float>(n);
+  float* dv = arena_take<float>(n);
+  float* dout = arena_take<float>(n);
+  float* dlse = arena_take<float>(rows);
+  float* dm = arena_take<float>(rows);
+  float* dl = arena_take<float>(rows);
+  FA_CUDA(cudaMemcpyAsync(dq, q, n * 4, cudaMemcpyHostToDevice, st), 0);
+  FA_CUDA(cudaMemcpyAsync(dk, k, n * 4, cudaMemcpyHostToDevice, st), 0);
+  FA_CUDA(cudaMemcpyAsync(dv, v, n * 4, cudaMemcpyHostToDevice, st), 0);
+  const bool fa1 = convention == FA_CONV_FA1;
+  if (tc) {
+    __nv_bfloat16* bq = arena_take<__nv_bfloat16>(n);
+    __nv_bfloat16* bk = arena_take<__nv_bfloat16>(n);
+    __nv_bfloat16* bv = arena_take<__nv_bfloat16>(n);
+    FA_CUDA(fa::cvt_f32_to_bf16(dq, bq, n, st), 1);
+    FA_CUDA(fa::cvt_f32_to_bf16(dk, bk, n, st), 1);
+    FA_CUDA(fa::cvt_f32_to_bf16(dv, bv, n, st), 1);
+    FA_CUDA(fa::tc_fwd(bq, bk, bv, dout, true, dlse, fa1 ? dm : nullptr, fa1 ? dl : nullptr, batch, N, d, causal != 0, st), 1);
+  } else {
+    FA_CUDA(fa::simt_fwd(dq, dk, dv, dout, dlse, fa1 ? dm : nullptr, fa1 ? dl : nullptr, batch, N, d, causal != 0, st), 1);
+  }
+  FA_CUDA(cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, st), 0);
+  if (fa1) {
+    FA_CUDA(cudaMemcpyAsync(l, dl, rows * 4, cudaMemcpyDeviceToHost, st), 0);
+    FA_CUDA(cudaMemcpyAsync(m, dm, rows * 4, cudaMemcpyDeviceToHost, st), 0);
+  } else {
+    // FA-2 libraries return the logsumexp in `l` and never write `m` (src/flash_attn2_fw.cu:283-289)
+    FA_CUDA(cudaMemcpyAsync(l, dlse, rows * 4, cudaMemcpyDeviceToHost, st), 0);
+  }
+  FA_CUDA(cudaStreamSynchronize(st), 0);
+  return FA_OK;
+}
+
+int fa_b200_host_bwd(const float* q, const float* k, const float* v, const float* out, const float* out_grad,
+                     float* q_grad, float* k_grad, float* v_grad, const float* l, const float* m, int batch, int N,
+                     int d, int causal, int convention, void* stream) {
+  if (!q || !k || !v || !out || !out_grad || !q_grad || !k_grad || !v_grad || !l || !m)
+    return fail(FA_ERR_BAD_ARG, "fa_b200_host_bwd: null pointer");
+  if (!valid_shape(batch, N, d)) return fail(FA_ERR_BAD_ARG, "fa_b200_host_bwd: bad shape batch=%d N=%d d=%d", batch, N, d);
+  if (convention != FA_CONV_FA1 && convention != FA_CONV_FA2)
+    return fail(FA_ERR_BAD_ARG, "fa_b200_host_bwd: unknown convention %d", convention);
+  std::lock_guard<std::mutex> lk(g_arena_mu);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t rows = (size_t)batch * N, n = rows * d;
+  const int prec = resolve_precision(FA_DTYPE_F32, host_precision(), d, true);
+  if (prec < 0) return fail(FA_ERR_BAD_ARG, "fa_b200_host_bwd: bad precision setting %d", host_precision());
+  const bool tc = prec == FA_PREC_BF16_TC;
+  const size_t ws_bytes = tc ? fa::tc_bwd_workspace_bytes(batch, N, d) : 0;
+  size_t bytes = 8 * align_up(n * 4, 256) + 4 * align_up(rows * 4, 256) + (tc ? 5 * align_up(n * 2, 256) : 0) +
+                 align_up(ws_bytes, 256) + 4096;
+  if (int rc = arena_reset(bytes)) return rc;
+  float* dq = arena_take<float>(n);
+  float* dk = arena_take<float>(n);
+  float* dv = arena_take<float>(n);
+  float* dout = arena_take<float>(n);
+  float* ddo = arena_take<float>(n);
+  float* gq = arena_take<float>(n);
+  float* gk = arena_take<float>(n);
+  float* gv = arena_take<float>(n);
+  float* dl = arena_take<float>(rows);
+  float* dm = arena_take<float>(rows);
+  float* dlse = arena_take<float>(rows);
+  float* ddelta = arena_take<float>(rows);
+  FA_CUDA(cudaMemcpyAsync(dq, q, n * 4, cudaMemcpyHostToDevice, st), 0);
+  FA_CUDA(cudaMemcpyAsync(dk, k, n * 4, cudaMemcpyHostToDevice, st), 0);
+  FA_CUDA(cudaMemcpyAsync(dv, v, n * 4, cudaMemcpyHostToDevice, st), 0);
+  FA_CUDA(cudaMemcpyAsync(dout, out, n * 4, cudaMemcpyHostToDevice, st), 0);
+  FA_CUDA(cudaMemcpyAsync(ddo, out_grad, n * 4, cudaMemcpyHostToDevice, st), 0);
+  // the reference accumulates into whatever the caller put in q_grad (src/flash_attn2_bw.cu:228)
+  FA_CUDA(cudaMemcpyAsync(gq, q_grad, n * 4, cudaMemcpyHostToDevice, st), 0);
+  FA_CUDA(cudaMemcpyAsync(dl, l, rows * 4, cudaMemcpyHostToDevice, st), 0);
+  const bool fa1 = convention == FA_CONV_FA1;
+  const float* lse = dl;
+  if (fa1) {
+    FA_CUDA(cudaMemcpyAsync(dm, m, rows * 4, cudaMemcpyHostToDevice, st), 0);
+    FA_CUDA(fa::lse_from_lm(dl, dm, dlse, rows, st), 1);
+    lse = dlse;
+  }
+  if (tc) {
+    __nv_bfloat16* b[5];
+    const float* src[5] = {dq, dk, dv, dout, ddo};
+    for (int i = 0; i < 5; ++i) {
+      b[i] = arena_take<__nv_bfloat16>(n);
+      FA_CUDA(fa::cvt_f32_to_bf16(src[i], b[i], n, st), 1);
+    }
+    void* ws = ws_bytes ? arena_take<char>(ws_bytes) : nullptr;
+    FA_CUDA(fa::tc_bwd(b[0], b[1], b[2], b[3], b[4], lse, gq, gk, gv, true, true, ws, batch, N, d, causal != 0, st), 3);
+  } else {
+    FA_CUDA(fa::simt_bwd_prep(dout, ddo, ddelta, nullptr, nullptr, nullptr, rows, d, st), 1);
+    FA_CUDA(fa::simt_bwd(dq, dk, dv, ddo, lse, ddelta, gq, gk, gv, batch, N, d, causal != 0, true, st), 2);
+  }
+  FA_CUDA(cudaMemcpyAsync(q_grad, gq, n * 4, cudaMemcpyDeviceToHost, st), 0);
+  FA_CUDA(cudaMemcpyAsync(k_grad, gk, n * 4, cudaMemcpyDeviceToHost, st), 0);
+  FA_CUDA(cudaMemcpyAsync(v_grad, gv, n * 4, cudaMemcpyDeviceToHost, st), 0);
+  FA_CUDA(cudaStreamSynchronize(st), 0);
+  return FA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,385 @@
+// fa_fwd_sm100.cu -- flash-attention forward for sm_100a: tcgen05.mma + TMEM + TMA.
+//
+// Replaces the reference kernels src/flash_attn2_fw.cu:23-297 (FA-2 forward) and
+// src/flash_attn_fw.cu:22-287 (FA-1 forward; same O, different saved statistics).
+//
+// One CTA owns 256 consecutive query rows of one (batch, head): two 128-row Q tiles that share
+// every K/V tile streamed through shared memory.  Warp roles:
+//   warps 0-3   softmax group for Q tile 0   (thread r owns row r: TMEM lane r)
+//   warps 4-7   softmax group for Q tile 1
+//   warp  8     TMA producer (one lane): Q once, then the K/V ring
+//   warp  9     MMA issuer   (one lane): S_t = Q_t K_j^T and O_t += P_t V_j
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [384,384+D).  P_t (bf16) overwrites the
+// first 64 columns of S_t and is consumed as the TMEM A operand of the PV MMA, so probabilities
+// never touch shared memory.  The MMA order  PV0(j) QK0(j+1) PV1(j) QK1(j+1)  keeps the tensor
+// pipe busy with one tile while the other tile's softmax runs.
+//
+// Online softmax: running reference max m_ref per row; O is only rescaled in TMEM when the new
+// row max exceeds m_ref by more than 2^8 in the exp2 domain (exact: the final 1/l normalisation
+// and the saved logsumexp use the same m_ref), so the usual per-step O correction disappears
+// after the first tiles.
+#include <cuda.h>
+#include <math.h>
+
+#include "fa_internal.h"
+#include "fa_ptx.cuh"
+#include "fa_tma_host.h"
+
+namespace fa {
+
+namespace {
+
+constexpr int kBlockM = 128;  // rows per Q tile (= TMEM lanes)
+constexpr int kBlockN = 128;  // keys per K/V tile
+constexpr int kFwdThreads = 320;
+
+struct FwdParams {
+  int T, BH, causal;
+  float tau;         // 1/sqrt(d)
+  float scale_log2;  // tau * log2(e)
+  void* o;
+  float* lse;
+  float* m_out;
+  float* l_out;
+};
+
+template <int D>
+struct FwdCfg {
+  static constexpr int kStages = D >= 128 ? 2 : 4;
+  static constexpr int kBoxes = D / 64;                   // 64-column (128-byte) TMA boxes per tile row
+  static constexpr int kBoxBytes = 128 * 128;             // 128 rows x 128 B
+  static constexpr int kTileBytes = kBoxes * kBoxBytes;   // one 128 x D bf16 tile
+  static constexpr int kSmemBytes = (2 + 2 * kStages) * kTileBytes + 1024;
+};
+
+struct FwdBarriers {
+  uint64_t q_full;
+  uint64_t k_full[4], k_empty[4], v_full[4], v_empty[4];
+  uint64_t s_full[2], p_full[2], o_full[2];
+};
+
+template <typename OutT>
+__device__ __forceinline__ void store_row_chunk32(OutT* dst, const float* x);
+
+template <>
+__device__ __forceinline__ void store_row_chunk32<float>(float* dst, const float* x) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+}
+template <>
+__device__ __forceinline__ void store_row_chunk32<__nv_bfloat16>(__nv_bfloat16* dst, const float* x) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    uint4 v;
+    v.x = pack_bf16x2(x[i], x[i + 1]);
+    v.y = pack_bf16x2(x[i + 2], x[i + 3]);
+    v.z = pack_bf16x2(x[i + 4], x[i + 5]);
+    v.w = pack_bf16x2(x[i + 6], x[i + 7]);
+    *reinterpret_cast<uint4*>(dst + i) = v;
+  }
+}
+
+template <int D, typename OutT>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+              const __grid_constant__ CUtensorMap map_v, const FwdParams p) {
+  using Cfg = FwdCfg<D>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 2 * Cfg::kTileBytes;
+  uint8_t* sV = sK + S * Cfg::kTileBytes;
+  __shared__ FwdBarriers bars;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int T = p.T;
+  const int bh = blockIdx.y;
+  const int blk = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;  // heavy causal blocks first
+  const int nkv = (T + kBlockN - 1) / kBlockN;
+  const int n0 = p.causal ? min(2 * blk + 1, nkv) : nkv;
+  const int n1 = p.causal ? min(2 * blk + 2, nkv) : nkv;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars.q_full, 1);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&bars.k_full[i], 1);
+      mbar_init(&bars.k_empty[i], 1);
+      mbar_init(&bars.v_full[i], 1);
+      mbar_init(&bars.v_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bars.s_full[t], 1);
+      mbar_init(&bars.p_full[t], 4);  // one arrival per softmax warp
+      mbar_init(&bars.o_full[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(&tmem_base_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&map_q);
+      tma_prefetch_desc(&map_k);
+      tma_prefetch_desc(&map_v);
+      mbar_arrive_expect_tx(&bars.q_full, 2 * Cfg::kTileBytes);
+      for (int t = 0; t < 2; ++t)
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_3d(sQ + t * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_q, &bars.q_full, b * 64,
+                      (2 * blk + t) * kBlockM, bh, kEvictFirst);
+      for (int j = 0; j < n1; ++j) {
+        const int st = j % S;
+        const uint32_t ph = (j / S) & 1;
+        mbar_wait(&bars.k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&bars.k_full[st], Cfg::kTileBytes);
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_3d(sK + st * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_k, &bars.k_full[st], b * 64, j * kBlockN,
+                      bh, kEvictLast);
+        mbar_wait(&bars.v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&bars.v_full[st], Cfg::kTileBytes);
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_3d(sV + st * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_v, &bars.v_full[st], b * 64, j * kBlockN,
+                      bh, kEvictLast);
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kBlockM, kBlockN, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kBlockM, D, 0, 1);
+      const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV);
+      auto issue_qk = [&](int t, int st) {
+        const uint32_t qa = sQa + t * Cfg::kTileBytes, ka = sKa + st * Cfg::kTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * Cfg::kBoxBytes + (kk & 3) * 32;
+          umma_ss(tmem + t * 128, make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk,
+                  kk > 0);
+        }
+      };
+      auto issue_pv = [&](int t, int st, bool acc) {
+        const uint32_t va = sVa + st * Cfg::kTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < kBlockN / 16; ++kk) {
+          umma_ts(tmem + 256 + t * 128, tmem + t * 128 + kk * 8,
+                  make_smem_desc(va + kk * 2048, Cfg::kBoxBytes, 1024), idesc_pv, (acc || kk > 0) ? 1u : 0u);
+        }
+      };
+      mbar_wait(&bars.q_full, 0);
+      mbar_wait(&bars.k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      umma_commit(&bars.s_full[0]);
+      issue_qk(1, 0);
+      umma_commit(&bars.s_full[1]);
+      umma_commit(&bars.k_empty[0]);
+      for (int j = 0; j < n1; ++j) {
+        const int st = j % S;
+        const uint32_t ph = (j / S) & 1;
+        const int jn = j + 1, stn = jn % S;
+        const uint32_t phn = (jn / S) & 1;
+        mbar_wait(&bars.v_full[st], ph);
+        if (j < n0) {
+          mbar_wait(&bars.p_full[0], j & 1);
+          tc_fence_after();
+          issue_pv(0, st, j > 0);
+          umma_commit(&bars.o_full[0]);
+        }
+        if (jn < n0) {
+          mbar_wait(&bars.k_full[stn], phn);
+          tc_fence_after();
+          issue_qk(0, stn);
+          umma_commit(&bars.s_full[0]);
+        }
+        mbar_wait(&bars.p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, st, j > 0);
+        umma_commit(&bars.o_full[1]);
+        umma_commit(&bars.v_empty[st]);
+        if (jn < n1) {
+          mbar_wait(&bars.k_full[stn], phn);
+          tc_fence_after();
+          issue_qk(1, stn);
+          umma_commit(&bars.s_full[1]);
+          umma_commit(&bars.k_empty[stn]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax groups
+    const int t = warp >> 2;
+    const int r = threadIdx.x & 127;
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + t * 128 + lane_base;
+    const uint32_t tO = tmem + 256 + t * 128 + lane_base;
+    const int qt = 2 * blk + t;
+    const int nt = t == 0 ? n0 : n1;
+    const int row_g = qt * kBlockM + r;
+    const float c2 = p.scale_log2;
+    float m_ref = -INFINITY;   // reference max (raw S units) used in the exponent
+    float m_true = -INFINITY;  // true running row max (only needed for the FA-1 statistics)
+    float l = 0.f;
+
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&bars.s_full[t], j & 1);
+      tc_fence_after();
+      float s[128];
+      {
+        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+        tmem_ld_x32(tS + 0, sr + 0);
+        tmem_ld_x32(tS + 32, sr + 32);
+        tmem_ld_x32(tS + 64, sr + 64);
+        tmem_ld_x32(tS + 96, sr + 96);
+        tmem_wait_ld();
+      }
+      const bool diag = p.causal && (j == qt);
+      const bool tail = (j == nkv - 1) && (T - j * kBlockN < kBlockN);
+      if (diag || tail) {
+        int limit = 127;
+        if (diag) limit = r;
+        if (tail) limit = min(limit, T - 1 - j * kBlockN);
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (c > limit) s[c] = -INFINITY;
+      }
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int c = 4; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, s[c]);
+        mx1 = fmaxf(mx1, s[c + 1]);
+        mx2 = fmaxf(mx2, s[c + 2]);
+        mx3 = fmaxf(mx3, s[c + 3]);
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      m_true = fmaxf(m_true, mx);
+      if (j == 0) {
+        m_ref = mx;
+      } else {
+        const bool need = (mx - m_ref) * c2 > 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          // O_t must be quiescent: PV(t, j-1) retired, PV(t, j) not yet issued (it waits for our P).
+          mbar_wait(&bars.o_full[t], (j - 1) & 1);
+          tc_fence_after();
+          const float m_new = fmaxf(m_ref, mx);
+          const float f = ex2_approx((m_ref - m_new) * c2);
+          l *= f;
+          m_ref = m_new;
+#pragma unroll
+          for (int c0 = 0; c0 < D; c0 += 32) {
+            uint32_t orr[32];
+            tmem_ld_x32(tO + c0, orr);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
+            tmem_st_x32(tO + c0, orr);
+          }
+        }
+      }
+      const float nm = -m_ref * c2;
+      float l0 = 0.f, l1 = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 128; c += 2) {
+        const float p0 = ex2_approx(fmaf(s[c], c2, nm));
+        const float p1 = ex2_approx(fmaf(s[c + 1], c2, nm));
+        l0 += p0;
+        l1 += p1;
+        pk[c >> 1] = pack_bf16x2(p0, p1);
+      }
+      l += l0 + l1;
+      tmem_st_x32(tS + 0, pk);
+      tmem_st_x32(tS + 32, pk + 32);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.p_full[t]);
+    }
+
+    // epilogue: O_t / l -> global, statistics
+    mbar_wait(&bars.o_full[t], (nt - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const bool row_ok = row_g < T;
+    OutT* orow = reinterpret_cast<OutT*>(p.o) + ((size_t)bh * T + (row_ok ? row_g : 0)) * D;
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t orr[32];
+      tmem_ld_x32(tO + c0, orr);
+      tmem_wait_ld();
+      float x[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(orr[i]) * inv_l;
+      if (row_ok) store_row_chunk32<OutT>(orow + c0, x);
+    }
+    if (row_ok) {
+      const size_t idx = (size_t)bh * T + row_g;
+      if (p.lse) p.lse[idx] = m_ref * p.tau + logf(l);
+      if (p.m_out) p.m_out[idx] = m_true * p.tau;
+      if (p.l_out) p.l_out[idx] = l * expf((m_ref - m_true) * p.tau);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+template <int D, typename OutT>
+cudaError_t launch_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, float* lse,
+                       float* m_out, float* l_out, int BH, int T, bool causal, cudaStream_t st) {
+  using Cfg = FwdCfg<D>;
+  CUtensorMap mq, mk, mv;
+  if (make_tmap_3d(&mq, q, 2, D, T, BH, 64, kBlockM)) return cudaErrorInvalidValue;
+  if (make_tmap_3d(&mk, k, 2, D, T, BH, 64, kBlockN)) return cudaErrorInvalidValue;
+  if (make_tmap_3d(&mv, v, 2, D, T, BH, 64, kBlockN)) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd_kernel<D, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  FwdParams p;
+  p.T = T;
+  p.BH = BH;
+  p.causal = causal ? 1 : 0;
+  p.tau = sqrtf(1.0f / (float)D);
+  p.scale_log2 = p.tau * 1.4426950408889634f;
+  p.o = o;
+  p.lse = lse;
+  p.m_out = m_out;
+  p.l_out = l_out;
+  dim3 grid((T + 2 * kBlockM - 1) / (2 * kBlockM), BH);
+  fa_fwd_kernel<D, OutT><<<grid, kFwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool tc_fwd_supported(int d) { return d == 64 || d == 128; }
+
+cudaError_t tc_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, bool o_is_f32,
+                   float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st) {
+  if (BH > 65535) return cudaErrorInvalidValue;
+  if (d == 128) {
+    return o_is_f32 ? launch_fwd<128, float>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st)
+                    : launch_fwd<128, __nv_bfloat16>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
+  }
+  if (d == 64) {
+    return o_is_f32 ? launch_fwd<64, float>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st)
+                    : launch_fwd<64, __nv_bfloat16>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace fa

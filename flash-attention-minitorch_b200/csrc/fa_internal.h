@@ -1,0 +1,41 @@
+// fa_internal.h -- declarations shared between the translation units of libfa_b200.so.
+// Nothing here is part of the C ABI (see include/fa_b200.h for that).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace fa {
+
+// ---- fp32 CUDA-core path (fa_simt.cu) -------------------------------------------------------
+cudaError_t simt_fwd(const float* q, const float* k, const float* v, float* o, float* lse, float* m_out,
+                     float* l_out, int BH, int T, int d, bool causal, cudaStream_t st);
+cudaError_t simt_bwd_prep(const float* o, const float* dO, float* delta, const float* l_in, const float* m_in,
+                          float* lse_out, size_t rows, int d, cudaStream_t st);
+cudaError_t simt_bwd(const float* q, const float* k, const float* v, const float* dO, const float* lse,
+                     const float* delta, float* dq, float* dk, float* dv, int BH, int T, int d, bool causal,
+                     bool accumulate_dq, cudaStream_t st);
+
+// ---- tcgen05 path (fa_fwd_sm100.cu / fa_bwd_sm100.cu) ---------------------------------------
+// bf16 Q/K/V laid out (BH, T, d) contiguous.  `o` is bf16 or fp32 depending on o_is_f32.
+// lse = natural-log logsumexp of tau*QK^T per row (the FA-2 "L"); m_out/l_out (optional) give the
+// FA-1 pair (row max of tau*S, sum exp(tau*S - m)).
+bool tc_fwd_supported(int d);
+cudaError_t tc_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, bool o_is_f32,
+                   float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st);
+
+bool tc_bwd_supported(int d);
+size_t tc_bwd_workspace_bytes(int BH, int T, int d);
+// dq/dk/dv are bf16 or fp32 (grads_f32).  workspace: tc_bwd_workspace_bytes() bytes of device memory.
+cudaError_t tc_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* o,
+                   const __nv_bfloat16* dO, const float* lse, void* dq, void* dk, void* dv, bool grads_f32,
+                   bool accumulate_dq, void* workspace, int BH, int T, int d, bool causal, cudaStream_t st);
+
+// ---- elementwise helpers (fa_util.cu) -------------------------------------------------------
+cudaError_t cvt_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st);
+cudaError_t cvt_bf16_to_f32(const __nv_bfloat16* src, float* dst, size_t n, cudaStream_t st);
+// lse = m + log(l)   (FA-1 convention -> FA-2 convention)
+cudaError_t lse_from_lm(const float* l, const float* m, float* lse, size_t n, cudaStream_t st);
+
+}  // namespace fa

@@ -1,0 +1,120 @@
+/* fa_b200.h -- C ABI of libfa_b200.so: B200 (sm_100a) flash-attention forward + backward.
+ *
+ * This is the drop-in boundary for the flash-attention path of pdrebello/flash-attention-minitorch.
+ * Two surfaces:
+ *
+ *  1. The reference's own host-pointer entry points, bit-for-bit the same signatures its ctypes
+ *     loader binds (reference minitorch/cuda_kernel_ops.py:549-576 and :613-647):
+ *         launch_flash_attn_fw   replaces  src/flash_attn_fw.cu:302-359  (FA-1: l = sum exp, m = row max)
+ *                                and       src/flash_attn2_fw.cu:312-372 (FA-2: l = logsumexp, m untouched)
+ *         launch_flash_attn_bw   replaces  src/flash_attn_bw.cu:277-365  and src/flash_attn2_bw.cu:279-369
+ *     They are exported -- under exactly those names -- by the six shim libraries that
+ *     compile_cuda.sh writes to minitorch/cuda_kernels/ (flash_attn_fw.so, flash_attn_bw.so,
+ *     flash_attn_causal_fw.so, flash_attn_causal_bw.so, flash_attn2_fw.so, flash_attn2_bw.so; reference
+ *     loader: minitorch/cuda_kernel_ops.py:27-35).  Each shim forwards to fa_b200_host_fwd /
+ *     fa_b200_host_bwd below with the (l, m) convention of the library it replaces.
+ *
+ *  2. A device-resident API (fa_b200_fwd / fa_b200_bwd) that takes device pointers, supports bf16
+ *     storage, and returns error codes.  The reference has no equivalent: every one of its calls
+ *     stages through host memory.  This is the surface the throughput numbers are measured on.
+ *
+ * All tensors are dense row-major (batch_heads, T, d); batch_heads = B*H flattened exactly as the
+ * reference does (cuda_kernel_ops.py:542-547).  Plain pointers and sizes only; no framework types.
+ */
+#ifndef FA_B200_H_
+#define FA_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ---- */
+#define FA_OK 0
+#define FA_ERR_BAD_ARG 1      /* null pointer, non-positive size, unsupported d/dtype/precision */
+#define FA_ERR_CUDA 2         /* a CUDA runtime call or kernel launch failed; see fa_b200_last_error() */
+#define FA_ERR_WORKSPACE 3    /* workspace pointer null or too small */
+#define FA_ERR_UNSUPPORTED 4  /* shape not covered by the requested precision */
+
+/* ---- storage dtypes of q/k/v/o/dO/dq/dk/dv in the device API ---- */
+#define FA_DTYPE_F32 0
+#define FA_DTYPE_BF16 1
+
+/* ---- arithmetic used for the two contractions ----
+ * AUTO      : bf16 storage -> BF16_TC; fp32 storage -> TF32_TC when the shape is covered, else FP32_SIMT
+ * FP32_SIMT : fp32 FMA on CUDA cores (any d <= 128 -- the reference's own limit, src/flash_attn_fw.cu:43 -- and any T); exact-fp32 cross-check path
+ * TF32_TC   : tcgen05.mma kind::tf32, fp32 storage
+ * BF16_TC   : tcgen05.mma kind::f16 (bf16 inputs, fp32 accumulate); fp32 storage is converted on device */
+#define FA_PREC_AUTO 0
+#define FA_PREC_FP32_SIMT 1
+#define FA_PREC_TF32_TC 2
+#define FA_PREC_BF16_TC 3
+
+/* ---- (l, m) conventions of the reference's two kernel families ---- */
+#define FA_CONV_FA1 1 /* l = sum_j exp(s_j - m), m = max_j s_j           (src/flash_attn_fw.cu:262-284) */
+#define FA_CONV_FA2 2 /* l = m + log(sum_j exp(s_j - m)), m left as is   (src/flash_attn2_fw.cu:279-294) */
+
+int fa_b200_version(void);
+/* Thread-local, NUL-terminated description of the last failure on this thread ("" if none). */
+const char* fa_b200_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (all entry points). */
+unsigned long long fa_b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-resident API.  All pointers are device pointers valid on the current device; `stream`
+ * is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous w.r.t. the host.
+ *
+ * fa_b200_fwd:  O = softmax(tau * Q K^T [+ causal mask]) V,  tau = 1/sqrt(d)
+ *   q,k,v : [batch_heads, T, d] of `dtype`            o : same shape/dtype (output)
+ *   lse   : [batch_heads, T] fp32 logsumexp (natural log) of the scaled scores -- the FA-2 "L" (may be NULL)
+ *   m_out, l_out : optional FA-1 statistics (row max, sum exp); NULL to skip
+ * ------------------------------------------------------------------------------------------ */
+int fa_b200_fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* m_out, float* l_out,
+                int dtype, int precision, int batch_heads, int T, int d, int causal, void* stream);
+
+/* Scratch bytes fa_b200_bwd needs for this problem (0 is a valid answer). */
+size_t fa_b200_bwd_workspace_bytes(int dtype, int precision, int batch_heads, int T, int d);
+
+/* fa_b200_bwd: dQ, dK, dV of the above given dO, recomputing P from `lse`.
+ *   accumulate_dq != 0 : dq += result (reference semantics, src/flash_attn2_bw.cu:228); else dq = result.
+ *   dk, dv are always overwritten. */
+int fa_b200_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_out, const float* lse,
+                void* dq, void* dk, void* dv, int dtype, int precision, int batch_heads, int T, int d, int causal,
+                int accumulate_dq, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-pointer API: the reference ABI with an explicit convention and an error code.
+ * All pointers are HOST fp32 buffers (pageable or pinned).  The call stages through a process-global
+ * device arena, runs on `stream`, and returns after the outputs have landed in host memory.
+ * ------------------------------------------------------------------------------------------ */
+int fa_b200_host_fwd(const float* q, const float* k, const float* v, float* out, float* l, float* m, int batch,
+                     int N, int d, int causal, int convention, void* stream);
+int fa_b200_host_bwd(const float* q, const float* k, const float* v, const float* out, const float* out_grad,
+                     float* q_grad, float* k_grad, float* v_grad, const float* l, const float* m, int batch, int N,
+                     int d, int causal, int convention, void* stream);
+/* Arithmetic used by the host-pointer API (FA_PREC_*).  Default FA_PREC_AUTO; also settable with the
+ * environment variable FA_B200_HOST_PRECISION = auto | fp32 | tf32 | bf16 read at first use. */
+void fa_b200_set_host_precision(int precision);
+int fa_b200_get_host_precision(void);
+/* Release the device arena held by the host-pointer API. */
+void fa_b200_release_arena(void);
+
+/* ------------------------------------------------------------------------------------------
+ * The reference entry points themselves.  Exported by the six shim libraries (not by libfa_b200.so,
+ * where the two conventions would collide on one symbol name).  `stream` is a cudaStream_t.
+ * On failure they print to stderr and exit(EXIT_FAILURE), as the reference does
+ * (src/flash_attn2_fw.cu:356-362).
+ * ------------------------------------------------------------------------------------------ */
+#ifdef FA_B200_DECLARE_REFERENCE_ABI
+void launch_flash_attn_fw(float* q, float* k, float* v, float* out, float* l, float* m, int batch, int N, int d,
+                          bool causal_mask, void* stream);
+void launch_flash_attn_bw(float* q, float* k, float* v, float* out, float* out_grad, float* q_grad, float* k_grad,
+                          float* v_grad, float* l, float* m, int batch, int N, int d, bool causal_mask,
+                          void* stream);
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_B200_H_ */

@@ -1,0 +1,344 @@
+// fa_check.cu -- standalone (no Python) GPU check + timing driver for libfa_b200.so.
+//
+//   fa_check simt            CUDA-core kernels vs an in-file CPU fp64 attention, small shapes
+//   fa_check fwd             tcgen05 forward (bf16) vs the CUDA-core fp32 kernels on the same bf16-rounded inputs
+//   fa_check bwd             tcgen05 backward (bf16) vs the CUDA-core fp32 backward
+//   fa_check time [BH T d causal iters]   CUDA-event timing of forward (+ backward when available)
+//
+// This is developer tooling for quick iteration on a GPU box; the judged parity tests live in tests/.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../include/fa_b200.h"
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);  \
+      exit(2);                                                                         \
+    }                                                                                  \
+  } while (0)
+#define FA(x)                                                        \
+  do {                                                               \
+    int rc_ = (x);                                                   \
+    if (rc_ != FA_OK) {                                              \
+      printf("fa error %d: %s (%s)\n", rc_, fa_b200_last_error(), #x); \
+      return 1;                                                      \
+    }                                                                \
+  } while (0)
+
+static uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+static float urand() {  // U(-1, 1)
+  rng_state ^= rng_state << 13;
+  rng_state ^= rng_state >> 7;
+  rng_state ^= rng_state << 17;
+  return (float)((rng_state >> 11) * (1.0 / 9007199254740992.0)) * 2.f - 1.f;
+}
+static float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+struct Dev {
+  std::vector<void*> ptrs;
+  template <typename T>
+  T* alloc(size_t n) {
+    void* p;
+    CK(cudaMalloc(&p, n * sizeof(T) + 256));
+    ptrs.push_back(p);
+    return (T*)p;
+  }
+  ~Dev() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+};
+
+static void cpu_attention(const std::vector<float>& q, const std::vector<float>& k, const std::vector<float>& v,
+                          const std::vector<float>& dO, int BH, int T, int d, bool causal, std::vector<double>& o,
+                          std::vector<double>& lse, std::vector<double>& dq, std::vector<double>& dk,
+                          std::vector<double>& dv) {
+  const double tau = 1.0 / sqrt((double)d);
+  o.assign((size_t)BH * T * d, 0);
+  lse.assign((size_t)BH * T, 0);
+  dq.assign(o.size(), 0);
+  dk.assign(o.size(), 0);
+  dv.assign(o.size(), 0);
+  std::vector<double> p(T), dp(T);
+  for (int b = 0; b < BH; ++b) {
+    const float* Q = &q[(size_t)b * T * d];
+    const float* K = &k[(size_t)b * T * d];
+    const float* V = &v[(size_t)b * T * d];
+    const float* G = &dO[(size_t)b * T * d];
+    for (int i = 0; i < T; ++i) {
+      int jend = causal ? i + 1 : T;
+      double m = -1e300;
+      for (int j = 0; j < jend; ++j) {
+        double s = 0;
+        for (int c = 0; c < d; ++c) s += (double)Q[i * d + c] * K[j * d + c];
+        p[j] = s * tau;
+        m = fmax(m, p[j]);
+      }
+      double l = 0;
+      for (int j = 0; j < jend; ++j) {
+        p[j] = exp(p[j] - m);
+        l += p[j];
+      }
+      lse[(size_t)b * T + i] = m + log(l);
+      double* O = &o[((size_t)b * T + i) * d];
+      for (int j = 0; j < jend; ++j) {
+        p[j] /= l;
+        for (int c = 0; c < d; ++c) O[c] += p[j] * V[j * d + c];
+      }
+      double D = 0;
+      for (int c = 0; c < d; ++c) D += O[c] * G[i * d + c];
+      for (int j = 0; j < jend; ++j) {
+        double x = 0;
+        for (int c = 0; c < d; ++c) x += (double)G[i * d + c] * V[j * d + c];
+        double ds = p[j] * (x - D);
+        for (int c = 0; c < d; ++c) {
+          dv[((size_t)b * T + j) * d + c] += p[j] * G[i * d + c];
+          dq[((size_t)b * T + i) * d + c] += tau * ds * K[j * d + c];
+          dk[((size_t)b * T + j) * d + c] += tau * ds * Q[i * d + c];
+        }
+      }
+    }
+  }
+}
+
+template <typename A, typename B>
+static void err_stats(const std::vector<A>& got, const std::vector<B>& ref, double& max_abs, double& rel_inf) {
+  double ma = 0, mr = 0;
+  for (size_t i = 0; i < got.size(); ++i) {
+    double e = fabs((double)got[i] - (double)ref[i]);
+    if (!(e <= ma)) ma = e;
+    mr = fmax(mr, fabs((double)ref[i]));
+  }
+  max_abs = ma;
+  rel_inf = ma / (mr > 0 ? mr : 1);
+}
+
+static int check_simt() {
+  int bad = 0;
+  const int shapes[][3] = {{3, 1, 32}, {2, 40, 32}, {2, 127, 64}, {2, 128, 64}, {1, 327, 34}, {2, 200, 128}, {1, 65, 100}};
+  for (auto& sh : shapes)
+    for (int causal = 0; causal < 2; ++causal) {
+      const int BH = sh[0], T = sh[1], d = sh[2];
+      const size_t n = (size_t)BH * T * d, rows = (size_t)BH * T;
+      std::vector<float> q(n), k(n), v(n), g(n);
+      for (auto& x : q) x = urand();
+      for (auto& x : k) x = urand();
+      for (auto& x : v) x = urand();
+      for (auto& x : g) x = urand();
+      std::vector<double> ro, rl, rdq, rdk, rdv;
+      cpu_attention(q, k, v, g, BH, T, d, causal, ro, rl, rdq, rdk, rdv);
+      Dev dev;
+      float *dq_ = dev.alloc<float>(n), *dk_ = dev.alloc<float>(n), *dv_ = dev.alloc<float>(n), *do_ = dev.alloc<float>(n),
+            *dg = dev.alloc<float>(n), *gq = dev.alloc<float>(n), *gk = dev.alloc<float>(n), *gv = dev.alloc<float>(n),
+            *dl = dev.alloc<float>(rows);
+      CK(cudaMemcpy(dq_, q.data(), n * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dk_, k.data(), n * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dv_, v.data(), n * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dg, g.data(), n * 4, cudaMemcpyHostToDevice));
+      FA(fa_b200_fwd(dq_, dk_, dv_, do_, dl, nullptr, nullptr, FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, nullptr));
+      size_t wsb = fa_b200_bwd_workspace_bytes(FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d);
+      char* ws = dev.alloc<char>(wsb);
+      FA(fa_b200_bwd(dq_, dk_, dv_, do_, dg, dl, gq, gk, gv, FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, 0, ws, wsb,
+                     nullptr));
+      CK(cudaDeviceSynchronize());
+      std::vector<float> ho(n), hl(rows), hq(n), hk(n), hv(n);
+      CK(cudaMemcpy(ho.data(), do_, n * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(hl.data(), dl, rows * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(hq.data(), gq, n * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(hk.data(), gk, n * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(hv.data(), gv, n * 4, cudaMemcpyDeviceToHost));
+      double e[5], r;
+      err_stats(ho, ro, e[0], r);
+      err_stats(hl, rl, e[1], r);
+      err_stats(hq, rdq, e[2], r);
+      err_stats(hk, rdk, e[3], r);
+      err_stats(hv, rdv, e[4], r);
+      bool ok = e[0] < 1e-5 && e[1] < 1e-5 && e[2] < 5e-5 && e[3] < 5e-5 && e[4] < 5e-5;
+      printf("simt BH=%d T=%4d d=%3d causal=%d  maxabs O %.2e L %.2e dQ %.2e dK %.2e dV %.2e  %s\n", BH, T, d, causal,
+             e[0], e[1], e[2], e[3], e[4], ok ? "OK" : "FAIL");
+      bad += !ok;
+    }
+  return bad;
+}
+
+struct Problem {
+  int BH, T, d, causal;
+  size_t n, rows;
+  std::vector<float> q, k, v, g;            // bf16-rounded values held as fp32
+  std::vector<__nv_bfloat16> qb, kb, vb, gb;
+  void init(int BH_, int T_, int d_, int causal_, float scale = 1.f) {
+    BH = BH_; T = T_; d = d_; causal = causal_;
+    n = (size_t)BH * T * d; rows = (size_t)BH * T;
+    q.resize(n); k.resize(n); v.resize(n); g.resize(n);
+    qb.resize(n); kb.resize(n); vb.resize(n); gb.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      q[i] = bf16r(urand() * scale); k[i] = bf16r(urand() * scale); v[i] = bf16r(urand()); g[i] = bf16r(urand());
+      qb[i] = __float2bfloat16(q[i]); kb[i] = __float2bfloat16(k[i]); vb[i] = __float2bfloat16(v[i]); gb[i] = __float2bfloat16(g[i]);
+    }
+  }
+};
+
+static std::vector<float> d2h_bf16(const __nv_bfloat16* p, size_t n) {
+  std::vector<__nv_bfloat16> t(n);
+  cudaMemcpy(t.data(), p, n * 2, cudaMemcpyDeviceToHost);
+  std::vector<float> r(n);
+  for (size_t i = 0; i < n; ++i) r[i] = __bfloat162float(t[i]);
+  return r;
+}
+static std::vector<float> d2h_f32(const float* p, size_t n) {
+  std::vector<float> r(n);
+  cudaMemcpy(r.data(), p, n * 4, cudaMemcpyDeviceToHost);
+  return r;
+}
+
+// tcgen05 (bf16) vs CUDA-core fp32 on identical bf16-rounded inputs
+static int check_tc(bool do_bwd, int BH, int T, int d, int causal, float scale) {
+  Problem pr;
+  pr.init(BH, T, d, causal, scale);
+  const size_t n = pr.n, rows = pr.rows;
+  Dev dev;
+  float *fq = dev.alloc<float>(n), *fk = dev.alloc<float>(n), *fv = dev.alloc<float>(n), *fo = dev.alloc<float>(n),
+        *fg = dev.alloc<float>(n), *fgq = dev.alloc<float>(n), *fgk = dev.alloc<float>(n), *fgv = dev.alloc<float>(n),
+        *fl = dev.alloc<float>(rows), *fm = dev.alloc<float>(rows), *fs = dev.alloc<float>(rows);
+  __nv_bfloat16 *bq = dev.alloc<__nv_bfloat16>(n), *bk = dev.alloc<__nv_bfloat16>(n), *bv = dev.alloc<__nv_bfloat16>(n),
+                *bo = dev.alloc<__nv_bfloat16>(n), *bg = dev.alloc<__nv_bfloat16>(n), *bgq = dev.alloc<__nv_bfloat16>(n),
+                *bgk = dev.alloc<__nv_bfloat16>(n), *bgv = dev.alloc<__nv_bfloat16>(n);
+  float *bl = dev.alloc<float>(rows), *bm = dev.alloc<float>(rows), *bs = dev.alloc<float>(rows);
+  CK(cudaMemcpy(fq, pr.q.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(fk, pr.k.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(fv, pr.v.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(fg, pr.g.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(bq, pr.qb.data(), n * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(bk, pr.kb.data(), n * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(bv, pr.vb.data(), n * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(bg, pr.gb.data(), n * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(bo, 0xff, n * 2));
+  FA(fa_b200_fwd(fq, fk, fv, fo, fl, fm, fs, FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, nullptr));
+  FA(fa_b200_fwd(bq, bk, bv, bo, bl, bm, bs, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, nullptr));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("tc fwd BH=%d T=%d d=%d causal=%d: CUDA ERROR %s\n", BH, T, d, causal, cudaGetErrorString(e));
+    exit(3);
+  }
+  double ea, er, la, lr, ma, mr, sa, sr;
+  {
+    auto ref = d2h_f32(fo, n);
+    auto got = d2h_bf16(bo, n);
+    err_stats(got, ref, ea, er);
+    auto rl = d2h_f32(fl, rows), gl = d2h_f32(bl, rows);
+    err_stats(gl, rl, la, lr);
+    auto rm = d2h_f32(fm, rows), gm = d2h_f32(bm, rows);
+    err_stats(gm, rm, ma, mr);
+    auto rs = d2h_f32(fs, rows), gs = d2h_f32(bs, rows);
+    err_stats(gs, rs, sa, sr);
+  }
+  bool ok = er < 2e-2 && la < 2e-2 && ma < 2e-2 && sr < 2e-2;
+  printf("tc fwd BH=%d T=%5d d=%3d causal=%d scale=%.0f  O rel %.2e (abs %.2e)  LSE abs %.2e  m abs %.2e  l rel %.2e  %s\n",
+         BH, T, d, causal, scale, er, ea, la, ma, sr, ok ? "OK" : "FAIL");
+  int bad = !ok;
+  if (do_bwd) {
+    size_t wf = fa_b200_bwd_workspace_bytes(FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d);
+    size_t wb = fa_b200_bwd_workspace_bytes(FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d);
+    char* wsf = dev.alloc<char>(wf);
+    char* wsb = dev.alloc<char>(wb);
+    FA(fa_b200_bwd(fq, fk, fv, fo, fg, fl, fgq, fgk, fgv, FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, 0, wsf, wf, nullptr));
+    FA(fa_b200_bwd(bq, bk, bv, bo, bg, bl, bgq, bgk, bgv, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, wsb, wb, nullptr));
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("tc bwd BH=%d T=%d d=%d causal=%d: CUDA ERROR %s\n", BH, T, d, causal, cudaGetErrorString(e));
+      exit(3);
+    }
+    double a[3], r[3];
+    err_stats(d2h_bf16(bgq, n), d2h_f32(fgq, n), a[0], r[0]);
+    err_stats(d2h_bf16(bgk, n), d2h_f32(fgk, n), a[1], r[1]);
+    err_stats(d2h_bf16(bgv, n), d2h_f32(fgv, n), a[2], r[2]);
+    bool okb = r[0] < 2e-2 && r[1] < 2e-2 && r[2] < 2e-2;
+    printf("tc bwd BH=%d T=%5d d=%3d causal=%d  dQ rel %.2e  dK rel %.2e  dV rel %.2e  %s\n", BH, T, d, causal, r[0], r[1],
+           r[2], okb ? "OK" : "FAIL");
+    bad += !okb;
+  }
+  return bad;
+}
+
+static int time_tc(int BH, int T, int d, int causal, int iters, bool do_bwd) {
+  const size_t n = (size_t)BH * T * d, rows = (size_t)BH * T;
+  Dev dev;
+  __nv_bfloat16* t[9];
+  for (auto& p : t) p = dev.alloc<__nv_bfloat16>(n);
+  float* lse = dev.alloc<float>(rows);
+  {  // random fill through a small host buffer repeated
+    std::vector<__nv_bfloat16> h(1 << 20);
+    for (auto& x : h) x = __float2bfloat16(urand());
+    for (int i = 0; i < 5; ++i)
+      for (size_t off = 0; off < n; off += h.size())
+        CK(cudaMemcpy(t[i] + off, h.data(), std::min(h.size(), n - off) * 2, cudaMemcpyHostToDevice));
+  }
+  size_t wb = do_bwd ? fa_b200_bwd_workspace_bytes(FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d) : 0;
+  char* ws = dev.alloc<char>(wb);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const double ffwd = 4.0 * BH * (double)T * T * d * (causal ? 0.5 : 1.0);
+  for (int i = 0; i < 3; ++i) FA(fa_b200_fwd(t[0], t[1], t[2], t[3], lse, nullptr, nullptr, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, nullptr));
+  CK(cudaDeviceSynchronize());
+  cudaEventRecord(e0);
+  for (int i = 0; i < iters; ++i) FA(fa_b200_fwd(t[0], t[1], t[2], t[3], lse, nullptr, nullptr, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, nullptr));
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms /= iters;
+  printf("time fwd BH=%d T=%d d=%d causal=%d: %.3f ms  %.1f TFLOP/s\n", BH, T, d, causal, ms, ffwd / ms * 1e-9);
+  if (do_bwd) {
+    for (int i = 0; i < 2; ++i)
+      FA(fa_b200_bwd(t[0], t[1], t[2], t[3], t[4], lse, t[5], t[6], t[7], FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, ws, wb, nullptr));
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i)
+      FA(fa_b200_bwd(t[0], t[1], t[2], t[3], t[4], lse, t[5], t[6], t[7], FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, ws, wb, nullptr));
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    printf("time bwd BH=%d T=%d d=%d causal=%d: %.3f ms  %.1f TFLOP/s\n", BH, T, d, causal, ms, 2.5 * ffwd / ms * 1e-9);
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  std::string mode = argc > 1 ? argv[1] : "simt";
+  int bad = 0;
+  if (mode == "simt") {
+    bad = check_simt();
+  } else if (mode == "fwd" || mode == "bwd") {
+    const bool b = mode == "bwd";
+    if (argc >= 6) {
+      bad = check_tc(b, atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argc > 6 ? atof(argv[6]) : 1.f);
+    } else {
+      for (int d : {128, 64})
+        for (int causal : {0, 1})
+          for (int T : {128, 256, 384, 1000, 1024, 2048 + 77}) bad += check_tc(b, 3, T, d, causal, 1.f);
+      // large-magnitude scores: exercises the lazy rescale of O
+      bad += check_tc(b, 2, 1024, 128, 1, 6.f);
+      bad += check_tc(b, 2, 1024, 64, 0, 8.f);
+    }
+  } else if (mode == "time") {
+    int BH = argc > 2 ? atoi(argv[2]) : 512, T = argc > 3 ? atoi(argv[3]) : 4096, d = argc > 4 ? atoi(argv[4]) : 128;
+    int causal = argc > 5 ? atoi(argv[5]) : 1, iters = argc > 6 ? atoi(argv[6]) : 10;
+    bool b = argc > 7 ? atoi(argv[7]) != 0 : false;
+    return time_tc(BH, T, d, causal, iters, b);
+  }
+  printf("fa_check %s: %d failing cases\n", mode.c_str(), bad);
+  return bad ? 1 : 0;
+}
