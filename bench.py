@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the flash-attention path (BASELINE.json / SURVEY.md §8d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[2] -- FA-2 forward+backward, causal, B=32 H=16 T=4096 d=128,
+bf16 -- per GPU.  A "step" is one forward + one backward over one such batch.  With N GPUs every rank owns its
+own B*H = 512 independent heads (weak scaling; heads are sharded, the attention path has no collective).
+`value` is the whole-job TFLOP/s with inputs resident in HBM (algorithmic FLOPs 14*BH*T^2*d*0.5 per step, per
+GPU, summed over ranks / max-over-ranks CUDA-event time).  `e2e` is the same metric through the reference's
+host-pointer ABI (fa_b200_host_fwd / fa_b200_host_bwd behind launch_flash_attn_fw / _bw): fp32 HOST buffers
+(pinned), host<->device copies inside the timed region.  `cpu_baseline` / `--impl reference` time the CPU
+restatement of the reference's own attention path (oracle/attention_oracle.c, all host cores) on a bounded
+sample of the same workload.  torch is used for device memory, streams and torch.distributed only.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "flash-attention-minitorch_b200"))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="cfg3: FA-2 fw+bw causal B=32 H=16 T=4096 d=128 bf16 (BASELINE.json configs[2])",
+                B=32, H=16, T=4096, d=128, causal=True)
+METRIC = "attention fw+bw TFLOP/s (whole job)"
+
+
+def flops_fwd(BH, T, d, causal):
+    return 4.0 * BH * T * T * d * (0.5 if causal else 1.0)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                p = json.load(f)
+            return dict(tflops=float(p["bf16_tflops_sustained"]), burst=float(p["bf16_tflops"]), hbm=float(p["hbm_gbs"]),
+                        source="MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)")
+        except Exception:
+            pass
+    return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, source="fallback of B200_PROFILING.md (sustained ~1.4 PFLOP/s)")
+
+
+class ClockSampler:
+    """nvidia-smi in the background during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        clocks, maxc, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.tmp.name) as f:
+            for line in f:
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    clocks.append(float(parts[1]))
+                    maxc.append(float(parts[2]))
+                    power.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for n, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(n)
+        os.unlink(self.tmp.name)
+        if not clocks:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [c for c, p in zip(clocks, power) if p >= 0.5 * max(power)] or clocks
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(maxc), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(clocks)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs (the only places that touch oracle/)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_sample(heads: int, T: int, d: int, causal: bool, repeats: int = 1):
+    """Reference CPU attention path (C restatement, all host cores) on `heads` heads of the workload."""
+    import numpy as np
+    from oracle import c_oracle
+    rng = np.random.default_rng(3001)
+    q, k, v, g = (rng.uniform(-1, 1, (heads, T, d)).astype(np.float32) for _ in range(4))
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        c_oracle.attention(q, k, v, g, causal)
+        best = min(best, time.perf_counter() - t0)
+    fl = 3.5 * flops_fwd(heads, T, d, causal)
+    return dict(seconds=best, tflops=fl / best * 1e-12, cores=c_oracle.num_threads())
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w = WORKLOAD
+    heads = 4  # four (b, h) problems of the workload per step: ~seconds of CPU work with all cores
+    for _ in range(args.warmup):
+        cpu_reference_sample(heads, w["T"], w["d"], w["causal"])
+    times, cores = [], 1
+    for _ in range(args.steps):
+        r = cpu_reference_sample(heads, w["T"], w["d"], w["causal"])
+        times.append(r["seconds"])
+        cores = r["cores"]
+    total = sum(times)
+    value = 3.5 * flops_fwd(heads, w["T"], w["d"], w["causal"]) * args.steps / total * 1e-12
+    sample = f"{heads} of {w['B'] * w['H']} (b,h) problems per step (T={w['T']}, d={w['d']}, causal), fp32, fw+bw"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from fa_b200 import _lib, device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load_library()
+
+    w = WORKLOAD
+    BH, T, d, causal = w["B"] * w["H"], w["T"], w["d"], w["causal"]
+    torch.manual_seed(3001 + rank)
+    mk = lambda: (torch.rand(BH, T, d, device=dev) * 2 - 1).to(torch.bfloat16)  # noqa: E731
+    q, k, v, g = mk(), mk(), mk(), mk()
+    grads = (torch.empty_like(q), torch.empty_like(q), torch.empty_like(q))
+    ws = device.bwd_workspace(q)
+
+    def step():
+        o, lse = device.flash_attn_fwd(q, k, v, causal)
+        device.flash_attn_bwd(q, k, v, o, g, lse, causal, workspace=ws, out=grads)
+        return o, lse
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+
+    # per-kernel durations for the roofline object (same stream, same inputs, events around each call)
+    fw_ms, bw_ms = [], []
+    o, lse = device.flash_attn_fwd(q, k, v, causal)
+    for _ in range(min(args.steps, 5)):
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        o, lse = device.flash_attn_fwd(q, k, v, causal)
+        b.record()
+        device.flash_attn_bwd(q, k, v, o, g, lse, causal, workspace=ws, out=grads)
+        c.record()
+        torch.cuda.synchronize()
+        fw_ms.append(a.elapsed_time(b))
+        bw_ms.append(b.elapsed_time(c))
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    f_step = 3.5 * flops_fwd(BH, T, d, causal)
+    value = f_step * world / (ms_step * 1e-3) * 1e-12
+
+    # ---- e2e: reference-facing host-pointer ABI, pinned fp32 host buffers, copies inside the timed region
+    e2e = run_e2e(lib, dev, BH, T, d, causal, steps=min(args.steps, 2), world=world)
+
+    line = None
+    if rank == 0:
+        peaks = measured_peaks()
+        fw, bw = statistics.mean(fw_ms), statistics.mean(bw_ms)
+        dom_is_bw = bw >= fw
+        dom_ms = bw if dom_is_bw else fw
+        dom_fl = (2.5 if dom_is_bw else 1.0) * flops_fwd(BH, T, d, causal)
+        achieved = dom_fl / (dom_ms * 1e-3) * 1e-12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("bwd" if dom_is_bw else "fwd")
+            except Exception:
+                traffic = None
+        cpu = cpu_reference_sample(16, T, d, causal)
+        line = {"metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": w["name"], "batch_heads_per_gpu": BH, "global_batch_heads": BH * world, "seq_len": T,
+                           "head_dim": d, "causal": causal, "parallelism": f"batch*heads sharded x{world}, no collective",
+                           "l2": "inputs (8 x 537 MB per GPU) exceed the 126 MB L2; no flush between iterations",
+                           "flops_per_step_per_gpu": f_step},
+                "per_gpu_tflops": value / world,
+                "frac_of_spec_bf16_2250": value / world / 2250.0,
+                "kernel_ms": {"forward": fw, "backward": bw},
+                "roofline": {"bound": "tensor", "kernel": "backward" if dom_is_bw else "forward", "achieved": achieved,
+                             "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
+                             "peak_source": peaks["source"],
+                             "forward": {"achieved": flops_fwd(BH, T, d, causal) / (fw * 1e-3) * 1e-12,
+                                         "frac": flops_fwd(BH, T, d, causal) / (fw * 1e-3) * 1e-12 / peaks["tflops"]}},
+                "cpu_baseline": {"value": cpu["tflops"], "unit": "TFLOP/s", "cores": cpu["cores"], "kind": "port",
+                                 "sample": f"16 of {BH} (b,h) problems, fw+bw, fp32, {cpu['seconds']:.2f} s"},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(lib, dev, BH, T, d, causal, steps, world):
+    """Same workload through fa_b200_host_fwd/bwd (what launch_flash_attn_fw/_bw forward to): pinned fp32 host
+    buffers in, fp32 host buffers out, bf16 tensor-core arithmetic on the device.  Returns the e2e object."""
+    import torch
+    import torch.distributed as dist
+    from fa_b200 import _lib
+    n, rows = BH * T * d, BH * T
+    pin = lambda *shape: torch.empty(*shape, dtype=torch.float32, pin_memory=True)  # noqa: E731
+    hq, hk, hv, hg = pin(n), pin(n), pin(n), pin(n)
+    for h in (hq, hk, hv, hg):  # fill on the device (fast), land in pinned host memory
+        h.copy_((torch.rand(n, device=dev) * 2 - 1).to(torch.bfloat16).float())
+    ho, hgq, hgk, hgv = pin(n), pin(n), pin(n), pin(n)
+    hl, hm = pin(rows), pin(rows)
+    hgq.zero_()
+    hm.fill_(-3.4028234663852886e38)
+    torch.cuda.synchronize()
+    prev = lib.fa_b200_get_host_precision()
+    lib.fa_b200_set_host_precision(_lib.FA_PREC_BF16_TC)
+    stream = torch.cuda.current_stream().cuda_stream
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+
+    def step():
+        _lib.check(lib.fa_b200_host_fwd(P(hq), P(hk), P(hv), P(ho), P(hl), P(hm), BH, T, d, int(causal), _lib.FA_CONV_FA2, stream))
+        _lib.check(lib.fa_b200_host_bwd(P(hq), P(hk), P(hv), P(ho), P(hg), P(hgq), P(hgk), P(hgv), P(hl), P(hm), BH, T, d,
+                                        int(causal), _lib.FA_CONV_FA2, stream))
+    try:
+        step()  # warm-up: arena allocation, first-touch
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        lib.fa_b200_set_host_precision(prev)
+        lib.fa_b200_release_arena()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    f_step = 3.5 * flops_fwd(BH, T, d, causal)
+    h2d = (3 * n + 6 * n + rows) * 4   # fwd: q,k,v ; bwd: q,k,v,out,out_grad,q_grad + L
+    d2h = (n + rows + 3 * n) * 4       # fwd: out, L ; bwd: q_grad,k_grad,v_grad
+    return {"value": f_step * world / (ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": ms, "steps": steps,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "api": "fa_b200_host_fwd + fa_b200_host_bwd (reference ABI launch_flash_attn_fw/_bw), pinned fp32 host buffers, bf16 tensor-core arithmetic"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,80 @@
+"""ctypes binding of libfa_b200.so -- one function per declaration in include/fa_b200.h."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # flash-attention-minitorch_b200/
+LIB_DIR = os.path.join(PKG_ROOT, "lib")
+SHIM_DIR = os.path.join(PKG_ROOT, "minitorch", "cuda_kernels")
+
+# status codes / enums of include/fa_b200.h
+FA_OK, FA_ERR_BAD_ARG, FA_ERR_CUDA, FA_ERR_WORKSPACE, FA_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
+FA_DTYPE_F32, FA_DTYPE_BF16 = 0, 1
+FA_PREC_AUTO, FA_PREC_FP32_SIMT, FA_PREC_TF32_TC, FA_PREC_BF16_TC = 0, 1, 2, 3
+FA_CONV_FA1, FA_CONV_FA2 = 1, 2
+
+SHIM_NAMES = ("flash_attn_fw", "flash_attn_bw", "flash_attn_causal_fw", "flash_attn_causal_bw",
+              "flash_attn2_fw", "flash_attn2_bw")
+
+
+class LibraryMissingError(RuntimeError):
+    """Raised when the CUDA library is not built.  The product has no CPU fallback by design."""
+
+
+class FaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"fa_b200 error {code}: {msg}")
+        self.code = code
+
+
+def library_path() -> str:
+    return os.path.join(LIB_DIR, "libfa_b200.so")
+
+
+def shim_path(name: str) -> str:
+    return os.path.join(SHIM_DIR, name + ".so")
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise LibraryMissingError(
+            f"{path} not found: build it with flash-attention-minitorch_b200/compile_cuda.sh "
+            "(or __graft_entry__.build()); this package has no CPU fallback")
+    lib = ctypes.CDLL(path)
+    vp, f32p, ci, sz = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    lib.fa_b200_version.restype = ci
+    lib.fa_b200_last_error.restype = ctypes.c_char_p
+    lib.fa_b200_launch_count.restype = ctypes.c_ulonglong
+    lib.fa_b200_fwd.argtypes = [vp, vp, vp, vp, f32p, f32p, f32p, ci, ci, ci, ci, ci, ci, vp]
+    lib.fa_b200_fwd.restype = ci
+    lib.fa_b200_bwd_workspace_bytes.argtypes = [ci, ci, ci, ci, ci]
+    lib.fa_b200_bwd_workspace_bytes.restype = sz
+    lib.fa_b200_bwd.argtypes = [vp, vp, vp, vp, vp, f32p, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, sz, vp]
+    lib.fa_b200_bwd.restype = ci
+    lib.fa_b200_host_fwd.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    lib.fa_b200_host_fwd.restype = ci
+    lib.fa_b200_host_bwd.argtypes = [vp] * 10 + [ci, ci, ci, ci, ci, vp]
+    lib.fa_b200_host_bwd.restype = ci
+    lib.fa_b200_set_host_precision.argtypes = [ci]
+    lib.fa_b200_set_host_precision.restype = None
+    lib.fa_b200_get_host_precision.restype = ci
+    lib.fa_b200_release_arena.restype = None
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != FA_OK:
+        raise FaError(rc, load_library().fa_b200_last_error().decode())
+
+
+def launch_count() -> int:
+    return int(load_library().fa_b200_launch_count())

@@ -1,0 +1,273 @@
+"""Parity tests proper (B200, `-m gpu`): every call goes through the C ABI of libfa_b200.so.
+
+Bars (BASELINE.md §5 / north_star):
+  * fp32 path  : max-abs <= 1e-3 on O, dQ, dK, dV against the reference's vanilla attention (golden fixtures
+                 produced by the reference itself + the pinned oracle)
+  * bf16 path  : ||x - ref||_inf / ||ref||_inf <= 2e-2 per tensor against the fp64 oracle evaluated on the
+                 same bf16-rounded inputs
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_files
+from fa_b200 import _lib, device
+from fa_b200 import minitorch_compat as mt
+from oracle import attention_oracle as ao
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+FP32_ATOL = 1e-3   # north_star: max-abs 1e-3 on the fp32/TF32 path
+BF16_REL = 2e-2    # north_star: relative 2e-2 on the bf16 path
+
+
+def rel_inf(x, ref):
+    return float(np.abs(np.asarray(x, np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def _mt4(a, be, requires_grad=False):
+    return mt.tensor_from_numpy(np.ascontiguousarray(a[None]), backend=be, requires_grad=requires_grad)
+
+
+# ----------------------------------------------------------------------------------------------
+# 1. the reference operator surface, on fixtures computed by the reference itself
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", ["flash_attn", "flash_attn_causal", "flash_attn2"])
+@pytest.mark.parametrize("name", golden_files("mt_"))
+def test_tensor_flash_attn_matches_reference_vanilla(cuda_device, name, method):
+    """Reads like kernel_tests/test_flashattn_{fw,bw}.py: custom = q.flash_attn*(k, v, causal); baseline =
+    vanilla minitorch attention (here: its recorded output)."""
+    g = np.load(os.path.join(GOLDEN, name))
+    causal = bool(g["causal"])
+    be = mt.TensorBackend(mt.CudaKernelOps)
+    q, k, v = (_mt4(g[x], be, True) for x in ("q", "k", "v"))
+    out = getattr(q, method)(k, v, causal_mask=causal)
+    assert out.shape == (1,) + g["q"].shape
+    assert np.abs(out.to_numpy()[0] - g["o"]).max() <= FP32_ATOL
+    out.backward(_mt4(g["d_out"], be))
+    for t, key in ((q, "dq"), (k, "dk"), (v, "dv")):
+        assert np.abs(t.grad.to_numpy()[0] - g[key]).max() <= FP32_ATOL, key
+
+
+@pytest.mark.parametrize("name", golden_files("fap_"))
+def test_saved_statistics_follow_each_family_convention(cuda_device, name):
+    """FA-1 libraries return l = sum exp(s - m), m = rowmax; FA-2 returns L in `l` and leaves `m` as passed
+    (-FLT_MAX) -- pinned by the authors' flash_attn_python.py outputs."""
+    g = np.load(os.path.join(GOLDEN, name))
+    be = mt.TensorBackend(mt.CudaKernelOps)
+    q, k, v = (_mt4(g[x].astype(np.float32), be) for x in ("q", "k", "v"))
+    o1, l1, m1 = mt.CudaKernelOps.flash_attn_fw(q, k, v, mt.tensor(False))
+    assert np.abs(o1.to_numpy()[0] - g["o_fa1"]).max() <= FP32_ATOL
+    assert np.abs(m1.to_numpy()[0] - g["m_fa1"]).max() <= 1e-5
+    assert rel_inf(l1.to_numpy()[0], g["l_fa1"]) <= 1e-5
+    o2, l2, m2 = mt.CudaKernelOps.flash_attn2_fw(q, k, v, mt.tensor(False))
+    assert np.abs(l2.to_numpy()[0] - g["L_fa2"]).max() <= 1e-4
+    assert np.all(m2.to_numpy() == -np.finfo(np.float32).max)
+    # each backward consumes its own convention
+    dO = _mt4(g["d_out"].astype(np.float32), be)
+    for fam, (o, l, m) in (("fa1", (o1, l1, m1)), ("fa2", (o2, l2, m2))):
+        bw = mt.CudaKernelOps.flash_attn_bw if fam == "fa1" else mt.CudaKernelOps.flash_attn2_bw
+        dq, dk, dv, _ = bw(q, k, v, o, dO, l, m, mt.tensor(False))
+        for got, key in ((dq, "dq_"), (dk, "dk_"), (dv, "dv_")):
+            assert np.abs(got.to_numpy()[0] - g[key + fam]).max() <= FP32_ATOL
+
+
+def test_backward_accumulates_into_q_grad_like_reference(cuda_device):
+    """src/flash_attn2_bw.cu:228 atomically adds into the q_grad the caller passed; k_grad / v_grad are overwritten."""
+    lib = _lib.load_library()
+    BH, T, d = 2, 48, 32
+    q, k, v, g = ao.make_inputs(BH, T, d, seed=5)
+    dq_ref, dk_ref, dv_ref, o_ref, L = ao.attention_backward(q, k, v, g, True, np.float64)
+    o = o_ref.astype(np.float32)
+    l = L.astype(np.float32)
+    m = np.full((BH, T), -np.finfo(np.float32).max, np.float32)
+    qg = np.full_like(q, 0.25)
+    kg = np.full_like(q, 7.0)
+    vg = np.full_like(q, 7.0)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    _lib.check(lib.fa_b200_host_bwd(p(q), p(k), p(v), p(o), p(g), p(qg), p(kg), p(vg), p(l), p(m), BH, T, d, 1,
+                                    _lib.FA_CONV_FA2, None))
+    assert np.abs(qg - (dq_ref + 0.25)).max() <= FP32_ATOL
+    assert np.abs(kg - dk_ref).max() <= FP32_ATOL and np.abs(vg - dv_ref).max() <= FP32_ATOL
+
+
+# ----------------------------------------------------------------------------------------------
+# 2. device-resident API, bf16 tensor-core path vs the oracle on the same bf16-rounded inputs
+# ----------------------------------------------------------------------------------------------
+def _bf16_problem(BH, T, d, seed, scale=1.0):
+    q, k, v, g = ao.make_inputs(BH, T, d, seed)
+    return tuple(ao.bf16_round(x * s) for x, s in ((q, scale), (k, scale), (v, 1.0), (g, 1.0)))
+
+
+def _to_dev(a, dev, bf16=True):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return t.to(torch.bfloat16) if bf16 else t
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("BH,T,d", [(3, 128, 128), (2, 256, 64), (2, 1000, 128), (1, 777, 64), (2, 1, 64), (2, 129, 128),
+                                    (1, 2048, 128)])
+def test_device_bf16_forward_backward_vs_oracle(cuda_device, BH, T, d, causal):
+    import torch
+    q, k, v, g = _bf16_problem(BH, T, d, seed=100 + T + d)
+    dq_r, dk_r, dv_r, o_r, L_r = ao.attention_backward(q, k, v, g, causal, np.float64)
+    tq, tk, tv, tg = (_to_dev(x, cuda_device) for x in (q, k, v, g))
+    o, lse, m, l = device.flash_attn_fwd(tq, tk, tv, causal, want_lm=True)
+    assert o.dtype == torch.bfloat16
+    assert rel_inf(o.float().cpu().numpy(), o_r) <= BF16_REL
+    assert np.abs(lse.cpu().numpy() - L_r).max() <= 2e-3
+    assert np.abs((m + torch.log(l)).cpu().numpy() - L_r).max() <= 2e-3
+    dq, dk, dv = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, causal)
+    for got, ref, name in ((dq, dq_r, "dq"), (dk, dk_r, "dk"), (dv, dv_r, "dv")):
+        assert rel_inf(got.float().cpu().numpy(), ref) <= BF16_REL, name
+
+
+def test_device_bf16_large_scores_exercise_lazy_rescale(cuda_device):
+    """|s| up to ~40: the running max moves by far more than the 2^8 slack, so O must be rescaled in TMEM."""
+    q, k, v, g = _bf16_problem(2, 1024, 128, seed=77, scale=6.0)
+    for causal in (False, True):
+        o_r, p, m_r, l_r, L_r = ao.attention_forward(q, k, v, causal, np.float64)
+        o, lse = device.flash_attn_fwd(*(_to_dev(x, cuda_device) for x in (q, k, v)), causal)
+        assert rel_inf(o.float().cpu().numpy(), o_r) <= BF16_REL
+        assert np.abs(lse.cpu().numpy() - L_r).max() <= 1e-2
+
+
+@pytest.mark.parametrize("d", [32, 34, 100])
+def test_device_fp32_any_head_dim(cuda_device, d):
+    """Head dims outside the tensor-core set (the MT model's d=32, the reference test's d=34) on the exact fp32 path."""
+    q, k, v, g = ao.make_inputs(2, 77, d, seed=d)
+    dq_r, dk_r, dv_r, o_r, L_r = ao.attention_backward(q, k, v, g, True, np.float64)
+    tq, tk, tv, tg = (_to_dev(x, cuda_device, bf16=False) for x in (q, k, v, g))
+    o, lse = device.flash_attn_fwd(tq, tk, tv, True)
+    assert np.abs(o.cpu().numpy() - o_r).max() <= 1e-5
+    dq, dk, dv = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, True)
+    for got, ref in ((dq, dq_r), (dk, dk_r), (dv, dv_r)):
+        assert np.abs(got.cpu().numpy() - ref).max() <= 1e-4
+
+
+def test_host_api_bf16_precision(cuda_device):
+    """The reference ABI (host fp32 buffers) computing in bf16 on the tensor cores."""
+    lib = _lib.load_library()
+    BH, T, d = 4, 512, 128
+    q, k, v, g = _bf16_problem(BH, T, d, seed=9)
+    dq_r, dk_r, dv_r, o_r, L_r = ao.attention_backward(q, k, v, g, True, np.float64)
+    out = np.zeros_like(q)
+    l = np.zeros((BH, T), np.float32)
+    m = np.full((BH, T), -np.finfo(np.float32).max, np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    prev = lib.fa_b200_get_host_precision()
+    lib.fa_b200_set_host_precision(_lib.FA_PREC_BF16_TC)
+    try:
+        _lib.check(lib.fa_b200_host_fwd(p(q), p(k), p(v), p(out), p(l), p(m), BH, T, d, 1, _lib.FA_CONV_FA2, None))
+        assert rel_inf(out, o_r) <= BF16_REL and np.abs(l - L_r).max() <= 2e-3
+        qg, kg, vg = np.zeros_like(q), np.zeros_like(q), np.zeros_like(q)
+        _lib.check(lib.fa_b200_host_bwd(p(q), p(k), p(v), p(out), p(g), p(qg), p(kg), p(vg), p(l), p(m), BH, T, d, 1,
+                                        _lib.FA_CONV_FA2, None))
+        for got, ref in ((qg, dq_r), (kg, dk_r), (vg, dv_r)):
+            assert rel_inf(got, ref) <= BF16_REL
+    finally:
+        lib.fa_b200_set_host_precision(prev)
+
+
+# ----------------------------------------------------------------------------------------------
+# 3. BASELINE.json full sizes: size-independent properties + sampled heads against the C oracle
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cfg3(cuda_device):
+    """configs[2]: B=32 H=16 T=4096 d=128 bf16 causal (a quarter of the heads: 128 of 512, to bound test time)."""
+    import torch
+    torch.manual_seed(3001)
+    BH, T, d = 128, 4096, 128
+    mk = lambda: (torch.rand(BH, T, d, device=cuda_device) * 2 - 1).to(torch.bfloat16)  # noqa: E731
+    return dict(BH=BH, T=T, d=d, q=mk(), k=mk(), v=mk(), g=mk())
+
+
+def test_full_size_rows_of_p_sum_to_one(cuda_device, cfg3):
+    import torch
+    ones = torch.ones_like(cfg3["v"])
+    o, lse = device.flash_attn_fwd(cfg3["q"], cfg3["k"], ones, True)
+    assert float((o.float() - 1).abs().max()) <= 1e-2  # V = 1  =>  O = rowsum(P) = 1
+
+
+def test_full_size_causality_and_determinism(cuda_device, cfg3):
+    import torch
+    q, k, v, T = cfg3["q"], cfg3["k"], cfg3["v"], cfg3["T"]
+    o1, l1 = device.flash_attn_fwd(q, k, v, True)
+    o2, l2 = device.flash_attn_fwd(q, k, v, True)
+    assert torch.equal(o1, o2) and torch.equal(l1, l2)  # forward is deterministic
+    k2, v2 = k.clone(), v.clone()
+    k2[:, T // 2:] = 3.0  # the future may not leak into the first half
+    v2[:, T // 2:] = -5.0
+    o3, l3 = device.flash_attn_fwd(q, k2, v2, True)
+    assert torch.equal(o1[:, :T // 2], o3[:, :T // 2]) and torch.equal(l1[:, :T // 2], l3[:, :T // 2])
+
+
+def test_full_size_sampled_heads_vs_c_oracle(cuda_device, cfg3):
+    """Two (b, h) slices of the full-size problem against the CPU oracle on identical bf16-rounded inputs."""
+    q, k, v, g = cfg3["q"], cfg3["k"], cfg3["v"], cfg3["g"]
+    o, lse = device.flash_attn_fwd(q, k, v, True)
+    dq, dk, dv = device.flash_attn_bwd(q, k, v, o, g, lse, True)
+    for h in (0, 97):
+        f = lambda t: t[h:h + 1].float().cpu().numpy()  # noqa: E731
+        r = c_oracle.attention(f(q), f(k), f(v), f(g), causal=True)
+        assert rel_inf(f(o), r["o"].astype(np.float64)) <= BF16_REL
+        assert np.abs(f(lse) - r["lse"]).max() <= 5e-3
+        for got, key in ((dq, "dq"), (dk, "dk"), (dv, "dv")):
+            assert rel_inf(f(got), r[key].astype(np.float64)) <= BF16_REL, key
+
+
+def test_full_size_backward_identities(cuda_device, cfg3):
+    """sum_j dV_j = sum_i dO_i (rows of P sum to one) and <dQ, Q> = <dK, K> (S is bilinear), per head; and
+    backward is linear in dO."""
+    import torch
+    q, k, v, g = cfg3["q"], cfg3["k"], cfg3["v"], cfg3["g"]
+    o, lse = device.flash_attn_fwd(q, k, v, True)
+    dq, dk, dv = device.flash_attn_bwd(q, k, v, o, g, lse, True)
+    lhs, rhs = dv.float().sum(1), g.float().sum(1)
+    assert float((lhs - rhs).abs().max() / rhs.abs().max()) <= BF16_REL
+    a = (dq.float() * q.float()).sum((1, 2))
+    b = (dk.float() * k.float()).sum((1, 2))
+    assert float((a - b).abs().max() / a.abs().max()) <= 5e-2
+    dq2, dk2, dv2 = device.flash_attn_bwd(q, k, v, o, (g.float() * 2).to(torch.bfloat16), lse, True)
+    assert float((dv2.float() - 2 * dv.float()).abs().max() / dv.float().abs().max()) <= BF16_REL
+    assert float((dq2.float() - 2 * dq.float()).abs().max() / dq.float().abs().max()) <= BF16_REL
+
+
+def test_cfg2_shape_fp32_forward_sampled(cuda_device):
+    """configs[1]: non-causal forward, T=1024, d=64, fp32 storage through the reference ABI (a slice of B*H)."""
+    BH, T, d = 16, 1024, 64
+    q, k, v, g = ao.make_inputs(BH, T, d, seed=2001)
+    r = c_oracle.attention(q, k, v, None, causal=False)
+    be = mt.TensorBackend(mt.CudaKernelOps)
+    out = _mt4(q, be).flash_attn2(_mt4(k, be), _mt4(v, be), causal_mask=False)
+    assert np.abs(out.to_numpy()[0] - r["o"]).max() <= FP32_ATOL
+
+
+# ----------------------------------------------------------------------------------------------
+# 4. error behaviour and launch accounting
+# ----------------------------------------------------------------------------------------------
+def test_errors_are_reported_not_swallowed(cuda_device):
+    import torch
+    x = torch.zeros(2, 16, 96, device=cuda_device, dtype=torch.bfloat16)
+    with pytest.raises(_lib.FaError):
+        device.flash_attn_fwd(x, x, x, False)  # bf16 storage needs d in {64, 128}
+    y = torch.zeros(2, 16, 64, device=cuda_device, dtype=torch.float32)
+    lse = torch.zeros(2, 16, device=cuda_device)
+    lib = _lib.load_library()
+    rc = lib.fa_b200_bwd(y.data_ptr(), y.data_ptr(), y.data_ptr(), y.data_ptr(), y.data_ptr(), lse.data_ptr(),
+                         y.data_ptr(), y.data_ptr(), y.data_ptr(), _lib.FA_DTYPE_F32, _lib.FA_PREC_AUTO, 2, 16, 64, 0, 0,
+                         None, 0, None)
+    assert rc == _lib.FA_ERR_WORKSPACE
+
+
+def test_launch_counter_counts_kernels(cuda_device):
+    import torch
+    before = _lib.launch_count()
+    x = (torch.rand(2, 256, 64, device=cuda_device) - 0.5).to(torch.bfloat16)
+    o, lse = device.flash_attn_fwd(x, x, x, True)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == before + 1
