@@ -172,10 +172,11 @@ def run_ours(args):
     mk = lambda: (torch.rand(BH, T, d, device=dev) * 2 - 1).to(torch.bfloat16)  # noqa: E731
     q, k, v, g = mk(), mk(), mk(), mk()
     grads = (torch.empty_like(q), torch.empty_like(q), torch.empty_like(q))
+    outs = (torch.empty_like(q), torch.empty(BH, T, dtype=torch.float32, device=dev))
     ws = device.bwd_workspace(q)
 
     def step():
-        o, lse = device.flash_attn_fwd(q, k, v, causal)
+        o, lse = device.flash_attn_fwd(q, k, v, causal, out=outs)
         device.flash_attn_bwd(q, k, v, o, g, lse, causal, workspace=ws, out=grads)
         return o, lse
 
@@ -201,18 +202,20 @@ def run_ours(args):
     launches = _lib.launch_count() - launches0
 
     # per-kernel durations for the roofline object (same stream, same inputs, events around each call)
-    fw_ms, bw_ms = [], []
-    o, lse = device.flash_attn_fwd(q, k, v, causal)
-    for _ in range(min(args.steps, 5)):
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record()
-        o, lse = device.flash_attn_fwd(q, k, v, causal)
-        b.record()
+    # (back-to-back launches between events so that host launch latency is not on the timed path)
+    reps = max(3, min(args.steps, 10))
+    o, lse = outs
+    a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        device.flash_attn_fwd(q, k, v, causal, out=outs)
+    b.record()
+    for _ in range(reps):
         device.flash_attn_bwd(q, k, v, o, g, lse, causal, workspace=ws, out=grads)
-        c.record()
-        torch.cuda.synchronize()
-        fw_ms.append(a.elapsed_time(b))
-        bw_ms.append(b.elapsed_time(c))
+    c.record()
+    torch.cuda.synchronize()
+    fw_ms, bw_ms = [a.elapsed_time(b) / reps], [b.elapsed_time(c) / reps]
     clocks = sampler.stop()
 
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)

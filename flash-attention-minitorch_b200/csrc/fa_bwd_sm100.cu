@@ -1,14 +1,555 @@
-// fa_bwd_sm100.cu -- flash-attention backward for sm_100a (tcgen05 + TMEM + TMA).  [placeholder: round-1 WIP]
+// fa_bwd_sm100.cu -- flash-attention backward for sm_100a: tcgen05.mma + TMEM + TMA.
+//
+// Replaces the reference kernels src/flash_attn2_bw.cu:21-263 (FA-2 backward: P = exp(S - L), atomicAdd
+// into dQ) and src/flash_attn_bw.cu:21-261 (FA-1 backward; its (l, m) pair is folded into L up front).
+//
+// One CTA owns one 128-row K/V tile j of one (batch, head) and streams the Q/dO tiles i that attend
+// to it (i >= j when causal).  All five contractions of a tile pair run on the tensor pipe, with the
+// score matrices held TRANSPOSED (lanes = key rows) so that P^T is directly the TMEM A operand of dV:
+//     S^T  = K_j  Q_i^T          (smem x smem  -> TMEM)        P^T = exp2(c S^T - L_i)        [registers]
+//     dP^T = V_j  dO_i^T         (smem x smem  -> TMEM)        dS^T = tau P^T o (dP^T - D_i)   [registers]
+//     dV_j += P^T  dO_i          (TMEM x smem  -> TMEM, accumulates over i)
+//     dK_j += dS^T Q_i           (smem x smem  -> TMEM, accumulates over i)
+//     dQ_i  = dS   K_j           (smem(MN-major view of dS^T) x smem -> TMEM) -> fp32 TMA reduce-add to HBM
+// The same shared-memory tile serves two roles through the descriptor's major-ness bit: Q_i / dO_i are
+// K-major B operands of S^T / dP^T and MN-major B operands of dK / dV; dS^T is the K-major A of dK and the
+// MN-major A of dQ; K_j is the K-major A of S^T and the MN-major B of dQ.  Nothing is transposed in memory.
+//
+// Warp roles (512 threads): warps 0-7 compute (thread = one key row x 64 query columns), warps 8-11 drain
+// dQ (TMEM -> swizzled smem -> cp.reduce.async.bulk), warp 12 TMA producer, warp 13 MMA issuer.
+// MMA issue order per step  dQ(i) dK(i) dP(i+1) dV(i+1) S(i+2)  keeps the pipe busy while the compute warps
+// turn S(i+1) into P and dP(i+1) into dS.  TMEM (512 columns): S | dP | dV | dK, with dQ aliasing dP when
+// d = 128 (dP(i+1) is only issued after dQ(i) has been drained) and a separate region when d = 64.
+#include <cuda.h>
+#include <math.h>
+
 #include "fa_internal.h"
+#include "fa_ptx.cuh"
+#include "fa_tma_host.h"
 
 namespace fa {
 
-bool tc_bwd_supported(int) { return false; }
-size_t tc_bwd_workspace_bytes(int, int, int) { return 0; }
-cudaError_t tc_bwd(const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*,
-                   const __nv_bfloat16*, const float*, void*, void*, void*, bool, bool, void*, int, int, int, bool,
-                   cudaStream_t) {
-  return cudaErrorNotSupported;
+namespace {
+
+constexpr int kTile = 128;
+constexpr int kBwdThreads = 512;
+constexpr int kBoxBytes = 128 * 128;  // 128 rows x 128 B
+
+struct BwdParams {
+  int T, Tpad, causal;
+  float tau, scale_log2;
+  const float* lse_pad;    // [BH][Tpad]  lse * log2(e); +inf on padding rows (=> P = 0 there)
+  const float* delta_pad;  // [BH][Tpad]  rowsum(dO o O); 0 on padding rows
+  void* dk;
+  void* dv;
+};
+
+template <int D>
+struct BwdCfg {
+  static constexpr int kBoxes = D / 64;
+  static constexpr int kTileBytes = kBoxes * kBoxBytes;
+  static constexpr int kQStages = 2;
+  static constexpr int kDoStages = D >= 128 ? 1 : 2;
+  static constexpr bool kAliasDq = D >= 128;
+  // shared-memory map (bytes)
+  static constexpr int kOffK = 0;
+  static constexpr int kOffV = kOffK + kTileBytes;
+  static constexpr int kOffQ = kOffV + kTileBytes;
+  static constexpr int kOffDO = kOffQ + kQStages * kTileBytes;
+  static constexpr int kOffDS = kOffDO + kDoStages * kTileBytes;  // dS^T: 128 x 128 bf16 = two boxes
+  static constexpr int kOffStage = kOffDS + 2 * kBoxBytes;        // dQ staging: 2 x (128 rows x 32 fp32)
+  static constexpr int kOffStats = kOffStage + 2 * kBoxBytes;     // [2 stages][L, delta][128] fp32
+  static constexpr int kOffBars = kOffStats + 2 * 2 * 128 * 4;
+  static constexpr int kSmemBytes = kOffBars + 256;
+  // TMEM columns
+  static constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 256 + D;
+  static constexpr uint32_t kColDQ = kAliasDq ? kColDP : 256 + 2 * D;
+};
+
+struct BwdBarriers {
+  uint64_t kv_full;
+  uint64_t q_full[2], q_empty[2], do_full[2], do_empty[2];
+  uint64_t s_full, p_full, dp_full, ds_full, ds_empty, dq_full, dq_drained, dkv_full;
+};
+
+template <typename OutT>
+__device__ __forceinline__ void store_chunk32(OutT* dst, const uint32_t* r);
+template <>
+__device__ __forceinline__ void store_chunk32<float>(float* dst, const uint32_t* r) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4)
+    *reinterpret_cast<uint4*>(dst + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+}
+template <>
+__device__ __forceinline__ void store_chunk32<__nv_bfloat16>(__nv_bfloat16* dst, const uint32_t* r) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    uint4 v;
+    v.x = pack_bf16x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+    v.y = pack_bf16x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+    v.z = pack_bf16x2(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+    v.w = pack_bf16x2(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+    *reinterpret_cast<uint4*>(dst + i) = v;
+  }
+}
+
+template <int D, typename OutT>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+              const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
+              const __grid_constant__ CUtensorMap map_dq, const BwdParams p) {
+  using Cfg = BwdCfg<D>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need 1024-B alignment
+  uint8_t* sK = smem + Cfg::kOffK;
+  uint8_t* sV = smem + Cfg::kOffV;
+  uint8_t* sQ = smem + Cfg::kOffQ;
+  uint8_t* sDO = smem + Cfg::kOffDO;
+  uint8_t* sDS = smem + Cfg::kOffDS;
+  uint8_t* sStage = smem + Cfg::kOffStage;
+  float* sStats = reinterpret_cast<float*>(smem + Cfg::kOffStats);
+  BwdBarriers& bars = *reinterpret_cast<BwdBarriers*>(smem + Cfg::kOffBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffBars + 192);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int T = p.T;
+  const int bh = blockIdx.y;
+  const int j = blockIdx.x;  // K/V tile
+  const int nq = (T + kTile - 1) / kTile;
+  const int i0 = p.causal ? j : 0;
+  const int n = nq - i0;  // number of Q tiles this CTA visits (>= 1)
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars.kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.q_full[s], 1);
+      mbar_init(&bars.q_empty[s], 1);
+      mbar_init(&bars.do_full[s], 1);
+      mbar_init(&bars.do_empty[s], 1);
+    }
+    mbar_init(&bars.s_full, 1);
+    mbar_init(&bars.p_full, 8);
+    mbar_init(&bars.dp_full, 1);
+    mbar_init(&bars.ds_full, 8);
+    mbar_init(&bars.ds_empty, 1);
+    mbar_init(&bars.dq_full, 1);
+    mbar_init(&bars.dq_drained, 4);
+    mbar_init(&bars.dkv_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= 12) {
+    reg_dealloc<88>();
+  }
+  if (warp == 12) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&map_q);
+      tma_prefetch_desc(&map_k);
+      tma_prefetch_desc(&map_v);
+      tma_prefetch_desc(&map_do);
+      mbar_arrive_expect_tx(&bars.kv_full, 2 * Cfg::kTileBytes);
+      for (int b = 0; b < Cfg::kBoxes; ++b) {
+        tma_load_3d(sK + b * kBoxBytes, &map_k, &bars.kv_full, b * 64, j * kTile, bh, kEvictFirst);
+        tma_load_3d(sV + b * kBoxBytes, &map_v, &bars.kv_full, b * 64, j * kTile, bh, kEvictFirst);
+      }
+      for (int il = 0; il < n; ++il) {
+        const int i = i0 + il;
+        const int s = il & 1;
+        mbar_wait(&bars.q_empty[s], ((il >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars.q_full[s], Cfg::kTileBytes + 1024);
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_3d(sQ + s * Cfg::kTileBytes + b * kBoxBytes, &map_q, &bars.q_full[s], b * 64, i * kTile, bh,
+                      kEvictLast);
+        const size_t soff = (size_t)bh * p.Tpad + (size_t)i * kTile;
+        bulk_load_1d(sStats + s * 256, p.lse_pad + soff, 512, &bars.q_full[s]);
+        bulk_load_1d(sStats + s * 256 + 128, p.delta_pad + soff, 512, &bars.q_full[s]);
+        const int sd = il % Cfg::kDoStages;
+        mbar_wait(&bars.do_empty[sd], ((il / Cfg::kDoStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars.do_full[sd], Cfg::kTileBytes);
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_3d(sDO + sd * Cfg::kTileBytes + b * kBoxBytes, &map_do, &bars.do_full[sd], b * 64, i * kTile, bh,
+                      kEvictLast);
+      }
+    }
+  } else if (warp == 13) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_sT = make_idesc(kFmtBF16, 128, 128, 0, 0);  // K-major x K-major
+      constexpr uint32_t idesc_acc = make_idesc(kFmtBF16, 128, D, 0, 1);   // (TMEM | K-major) x MN-major
+      constexpr uint32_t idesc_dq = make_idesc(kFmtBF16, 128, D, 1, 1);    // MN-major x MN-major
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sDO), aDS = smem_u32(sDS);
+      // [128 x D] tile, K-major operand, k-step kk of 16 elements
+      auto kmaj = [](uint32_t base, int kk) { return make_smem_desc(base + (kk >> 2) * kBoxBytes + (kk & 3) * 32, 16, 1024); };
+      // tile viewed MN-major: 16 "K" rows per step, MN atoms (64 elements) one box apart
+      auto mnmaj = [](uint32_t base, int kk) { return make_smem_desc(base + kk * 2048, kBoxBytes, 1024); };
+      auto issue_sT = [&](uint32_t a_tile, uint32_t b_tile, uint32_t col) {  // S^T or dP^T
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) umma_ss(tmem + col, kmaj(a_tile, kk), kmaj(b_tile, kk), idesc_sT, kk > 0);
+      };
+      auto issue_dv = [&](uint32_t do_tile, bool acc) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tmem + Cfg::kColDV, tmem + Cfg::kColS + (kk >> 2) * 64 + (kk & 3) * 8, mnmaj(do_tile, kk), idesc_acc,
+                  (acc || kk > 0) ? 1u : 0u);
+      };
+      auto issue_dk = [&](uint32_t q_tile, bool acc) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tmem + Cfg::kColDK, kmaj(aDS, kk), mnmaj(q_tile, kk), idesc_acc, (acc || kk > 0) ? 1u : 0u);
+      };
+      auto issue_dq = [&]() {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + Cfg::kColDQ, mnmaj(aDS, kk), mnmaj(aK, kk), idesc_dq, kk > 0);
+      };
+      auto q_tile = [&](int il) { return aQ + (il & 1) * Cfg::kTileBytes; };
+      auto do_tile = [&](int il) { return aDO + (il % Cfg::kDoStages) * Cfg::kTileBytes; };
+
+      mbar_wait(&bars.kv_full, 0);
+      mbar_wait(&bars.q_full[0], 0);
+      tc_fence_after();
+      issue_sT(aK, q_tile(0), Cfg::kColS);
+      umma_commit(&bars.s_full);
+      mbar_wait(&bars.do_full[0], 0);
+      tc_fence_after();
+      issue_sT(aV, do_tile(0), Cfg::kColDP);
+      umma_commit(&bars.dp_full);
+      mbar_wait(&bars.p_full, 0);
+      tc_fence_after();
+      issue_dv(do_tile(0), false);
+      umma_commit(&bars.do_empty[0]);
+      if (n > 1) {
+        mbar_wait(&bars.q_full[1], 0);
+        tc_fence_after();
+        issue_sT(aK, q_tile(1), Cfg::kColS);
+        umma_commit(&bars.s_full);
+      }
+      for (int il = 0; il < n; ++il) {
+        mbar_wait(&bars.ds_full, il & 1);
+        if (!Cfg::kAliasDq && il > 0) mbar_wait(&bars.dq_drained, (il - 1) & 1);
+        tc_fence_after();
+        issue_dq();
+        umma_commit(&bars.dq_full);
+        issue_dk(q_tile(il), il > 0);
+        umma_commit(&bars.ds_empty);
+        umma_commit(&bars.q_empty[il & 1]);
+        if (il + 1 < n) {
+          const int nx = il + 1;
+          if (Cfg::kAliasDq) mbar_wait(&bars.dq_drained, il & 1);
+          mbar_wait(&bars.do_full[nx % Cfg::kDoStages], (nx / Cfg::kDoStages) & 1);
+          tc_fence_after();
+          issue_sT(aV, do_tile(nx), Cfg::kColDP);
+          umma_commit(&bars.dp_full);
+          mbar_wait(&bars.p_full, nx & 1);
+          tc_fence_after();
+          issue_dv(do_tile(nx), true);
+          umma_commit(&bars.do_empty[nx % Cfg::kDoStages]);
+          if (il + 2 < n) {
+            const int n2 = il + 2;
+            mbar_wait(&bars.q_full[n2 & 1], (n2 >> 1) & 1);
+            tc_fence_after();
+            issue_sT(aK, q_tile(n2), Cfg::kColS);
+            umma_commit(&bars.s_full);
+          }
+        }
+      }
+      umma_commit(&bars.dkv_full);
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ compute warps
+    reg_alloc<168>();
+    const int g = warp >> 2;                 // which half of the 128 query columns
+    const int r = (warp & 3) * 32 + lane;    // key row within the tile == TMEM lane
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + Cfg::kColS + lane_base;
+    const uint32_t tDP = tmem + Cfg::kColDP + lane_base;
+    const float c2 = p.scale_log2;
+    uint8_t* ds_row = sDS + g * kBoxBytes + r * 128;
+    for (int il = 0; il < n; ++il) {
+      const int i = i0 + il;
+      const float* sL = sStats + (il & 1) * 256 + g * 64;
+      const float* sD = sL + 128;
+      // ---- P^T = exp2(c * S^T - L)
+      mbar_wait(&bars.q_full[il & 1], (il >> 1) & 1);  // L / delta of this Q tile have landed
+      mbar_wait(&bars.s_full, il & 1);
+      tc_fence_after();
+      float pr[64];
+      {
+        uint32_t* u = reinterpret_cast<uint32_t*>(pr);
+        tmem_ld_x32(tS + g * 64, u);
+        tmem_ld_x32(tS + g * 64 + 32, u + 32);
+        tmem_wait_ld();
+      }
+      const bool diag = p.causal && (i == j);
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        const float4 L4 = *reinterpret_cast<const float4*>(sL + c);
+        pr[c + 0] = ex2_approx(fmaf(pr[c + 0], c2, -L4.x));
+        pr[c + 1] = ex2_approx(fmaf(pr[c + 1], c2, -L4.y));
+        pr[c + 2] = ex2_approx(fmaf(pr[c + 2], c2, -L4.z));
+        pr[c + 3] = ex2_approx(fmaf(pr[c + 3], c2, -L4.w));
+      }
+      if (diag) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (g * 64 + c < r) pr[c] = 0.f;  // key index > query index
+      }
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) pk[c >> 1] = pack_bf16x2(pr[c], pr[c + 1]);
+        // P^T of query columns [64g, 64g+64) goes to TMEM columns [64g, 64g+32): inside the S columns this
+        // thread group has already consumed, so the two groups never touch each other's unread scores
+        tmem_st_x32(tS + g * 64, pk);
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.p_full);
+      // ---- dS^T = tau * P^T o (dP^T - delta)
+      mbar_wait(&bars.dp_full, il & 1);
+      tc_fence_after();
+      float dp[64];
+      {
+        uint32_t* u = reinterpret_cast<uint32_t*>(dp);
+        tmem_ld_x32(tDP + g * 64, u);
+        tmem_ld_x32(tDP + g * 64 + 32, u + 32);
+        tmem_wait_ld();
+      }
+      if (il > 0) mbar_wait(&bars.ds_empty, (il - 1) & 1);  // dK(i-1) / dQ(i-1) have finished reading dS
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        float ds[8];
+#pragma unroll
+        for (int e = 0; e < 8; e += 4) {
+          const float4 D4 = *reinterpret_cast<const float4*>(sD + ch * 8 + e);
+          ds[e + 0] = pr[ch * 8 + e + 0] * (dp[ch * 8 + e + 0] - D4.x) * p.tau;
+          ds[e + 1] = pr[ch * 8 + e + 1] * (dp[ch * 8 + e + 1] - D4.y) * p.tau;
+          ds[e + 2] = pr[ch * 8 + e + 2] * (dp[ch * 8 + e + 2] - D4.z) * p.tau;
+          ds[e + 3] = pr[ch * 8 + e + 3] * (dp[ch * 8 + e + 3] - D4.w) * p.tau;
+        }
+        uint4 v;
+        v.x = pack_bf16x2(ds[0], ds[1]);
+        v.y = pack_bf16x2(ds[2], ds[3]);
+        v.z = pack_bf16x2(ds[4], ds[5]);
+        v.w = pack_bf16x2(ds[6], ds[7]);
+        *reinterpret_cast<uint4*>(ds_row + ((ch ^ (r & 7)) << 4)) = v;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.ds_full);
+    }
+    // ---- epilogue: group 0 stores dV_j, group 1 stores dK_j
+    mbar_wait(&bars.dkv_full, 0);
+    tc_fence_after();
+    const int kv_row = j * kTile + r;
+    const bool row_ok = kv_row < T;
+    OutT* out = reinterpret_cast<OutT*>(g == 0 ? p.dv : p.dk) + ((size_t)bh * T + (row_ok ? kv_row : 0)) * D;
+    const uint32_t tAcc = tmem + (g == 0 ? Cfg::kColDV : Cfg::kColDK) + lane_base;
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t rr[32];
+      tmem_ld_x32(tAcc + c0, rr);
+      tmem_wait_ld();
+      if (row_ok) store_chunk32<OutT>(out + c0, rr);
+    }
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ dQ drain warps
+    reg_dealloc<88>();
+    const int w = warp - 8;
+    const int r = w * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t tDQ = tmem + Cfg::kColDQ + (uint32_t(w * 32) << 16);
+    const bool leader = (warp == 8 && lane == 0);
+    uint32_t chunk_no = 0;
+    for (int il = 0; il < n; ++il) {
+      const int i = i0 + il;
+      mbar_wait(&bars.dq_full, il & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c, ++chunk_no) {
+        uint8_t* buf = sStage + (chunk_no & 1) * kBoxBytes;
+        uint32_t rr[32];
+        tmem_ld_x32(tDQ + c * 32, rr);
+        tmem_wait_ld();
+        if (c == D / 32 - 1) {  // all of dQ(i) is in registers: the TMEM region may be overwritten
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.dq_drained);
+        }
+        if (leader && chunk_no >= 2) tma_store_wait_read<1>();  // staging buffer no longer being read
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<uint4*>(buf + r * 128 + ((ch ^ (r & 7)) << 4)) =
+              make_uint4(rr[ch * 4], rr[ch * 4 + 1], rr[ch * 4 + 2], rr[ch * 4 + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (leader) {
+          tma_reduce_add_3d(&map_dq, buf, c * 32, i * kTile, bh);
+          tma_store_commit();
+        }
+      }
+    }
+    if (leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) tmem_dealloc(tmem, 512);
+}
+
+// delta = rowsum(dO o O), lse -> log2 domain, both padded to a multiple of 128 rows per head
+template <int D>
+__global__ void fa_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO,
+                                   const float* __restrict__ lse, float* __restrict__ lse_pad,
+                                   float* __restrict__ delta_pad, int T, int Tpad, size_t total_rows_pad) {
+  const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= total_rows_pad) return;
+  const size_t bh = row / Tpad;
+  const int t = (int)(row - bh * Tpad);
+  if (t >= T) {
+    if (lane == 0) {
+      lse_pad[row] = INFINITY;
+      delta_pad[row] = 0.f;
+    }
+    return;
+  }
+  const size_t base = (bh * T + t) * D;
+  float acc = 0.f;
+  if constexpr (D == 128) {
+    const uint2 a = *reinterpret_cast<const uint2*>(o + base + lane * 4);
+    const uint2 b = *reinterpret_cast<const uint2*>(dO + base + lane * 4);
+    const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* bh2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float2 x = __bfloat1622float2(ah[i]), y = __bfloat1622float2(bh2[i]);
+      acc = fmaf(x.x, y.x, acc);
+      acc = fmaf(x.y, y.y, acc);
+    }
+  } else {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + base + lane * 2);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(dO + base + lane * 2);
+    const float2 x = __bfloat1622float2(a), y = __bfloat1622float2(b);
+    acc = fmaf(x.x, y.x, fmaf(x.y, y.y, 0.f));
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    delta_pad[row] = acc;
+    lse_pad[row] = lse[bh * T + t] * 1.4426950408889634f;
+  }
+}
+
+// dq (bf16) = [dq +] acc
+__global__ void fa_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, size_t n,
+                                         int accumulate) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += stride) {
+    float4 a = reinterpret_cast<const float4*>(acc)[i];
+    uint2* dst = reinterpret_cast<uint2*>(dq) + i;
+    if (accumulate) {
+      const uint2 old = *dst;
+      const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old);
+      const float2 x = __bfloat1622float2(oh[0]), y = __bfloat1622float2(oh[1]);
+      a.x += x.x; a.y += x.y; a.z += y.x; a.w += y.y;
+    }
+    *dst = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+  }
+}
+
+size_t pad_rows(int T) { return (size_t)((T + kTile - 1) / kTile) * kTile; }
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+template <int D, typename OutT>
+cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* o,
+                       const __nv_bfloat16* dO, const float* lse, void* dq, void* dk, void* dv, bool accumulate_dq,
+                       void* workspace, int BH, int T, bool causal, cudaStream_t st) {
+  using Cfg = BwdCfg<D>;
+  constexpr bool kF32 = sizeof(OutT) == 4;
+  const size_t Tpad = pad_rows(T);
+  const size_t n = (size_t)BH * T * D;
+  char* ws = static_cast<char*>(workspace);
+  float* lse_pad = reinterpret_cast<float*>(ws);
+  ws += align256((size_t)BH * Tpad * 4);
+  float* delta_pad = reinterpret_cast<float*>(ws);
+  ws += align256((size_t)BH * Tpad * 4);
+  float* dq_acc = kF32 ? static_cast<float*>(dq) : reinterpret_cast<float*>(ws);
+  cudaError_t e;
+  if (!kF32 || !accumulate_dq) {
+    e = cudaMemsetAsync(dq_acc, 0, n * 4, st);
+    if (e != cudaSuccess) return e;
+  }
+  {
+    const size_t rows = (size_t)BH * Tpad;
+    const int warps = 8;
+    fa_bwd_prep_kernel<D><<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, st>>>(o, dO, lse, lse_pad, delta_pad, T,
+                                                                                          (int)Tpad, rows);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  CUtensorMap mq, mk, mv, mdo, mdq;
+  if (make_tmap_3d(&mq, q, 2, D, T, BH, 64, kTile)) return cudaErrorInvalidValue;
+  if (make_tmap_3d(&mk, k, 2, D, T, BH, 64, kTile)) return cudaErrorInvalidValue;
+  if (make_tmap_3d(&mv, v, 2, D, T, BH, 64, kTile)) return cudaErrorInvalidValue;
+  if (make_tmap_3d(&mdo, dO, 2, D, T, BH, 64, kTile)) return cudaErrorInvalidValue;
+  if (make_tmap_3d(&mdq, dq_acc, 4, D, T, BH, 32, kTile)) return cudaErrorInvalidValue;
+  e = cudaFuncSetAttribute(fa_bwd_kernel<D, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  BwdParams p;
+  p.T = T;
+  p.Tpad = (int)Tpad;
+  p.causal = causal ? 1 : 0;
+  p.tau = sqrtf(1.0f / (float)D);
+  p.scale_log2 = p.tau * 1.4426950408889634f;
+  p.lse_pad = lse_pad;
+  p.delta_pad = delta_pad;
+  p.dk = dk;
+  p.dv = dv;
+  dim3 grid((unsigned)(Tpad / kTile), BH);
+  fa_bwd_kernel<D, OutT><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (!kF32) {
+    fa_bwd_dq_convert_kernel<<<148 * 8, 256, 0, st>>>(dq_acc, static_cast<__nv_bfloat16*>(dq), n, accumulate_dq ? 1 : 0);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace
+
+bool tc_bwd_supported(int d) { return d == 64 || d == 128; }
+
+size_t tc_bwd_workspace_bytes(int BH, int T, int d) {
+  // lse_pad + delta_pad + fp32 dQ accumulator (the latter only used for bf16 gradients)
+  return 2 * align256((size_t)BH * pad_rows(T) * 4) + align256((size_t)BH * T * d * 4);
+}
+
+cudaError_t tc_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* o,
+                   const __nv_bfloat16* dO, const float* lse, void* dq, void* dk, void* dv, bool grads_f32,
+                   bool accumulate_dq, void* workspace, int BH, int T, int d, bool causal, cudaStream_t st) {
+  if (BH > 65535 || !workspace) return cudaErrorInvalidValue;
+  if (d == 128) {
+    return grads_f32 ? launch_bwd<128, float>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, st)
+                     : launch_bwd<128, __nv_bfloat16>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, st);
+  }
+  if (d == 64) {
+    return grads_f32 ? launch_bwd<64, float>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, st)
+                     : launch_bwd<64, __nv_bfloat16>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, st);
+  }
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace fa

@@ -302,7 +302,7 @@ int fa_b200_host_bwd(const float* q, const float* k, const float* v, const float
       FA_CUDA(fa::cvt_f32_to_bf16(src[i], b[i], n, st), 1);
     }
     void* ws = ws_bytes ? arena_take<char>(ws_bytes) : nullptr;
-    FA_CUDA(fa::tc_bwd(b[0], b[1], b[2], b[3], b[4], lse, gq, gk, gv, true, true, ws, batch, N, d, causal != 0, st), 3);
+    FA_CUDA(fa::tc_bwd(b[0], b[1], b[2], b[3], b[4], lse, gq, gk, gv, true, true, ws, batch, N, d, causal != 0, st), 2);
   } else {
     FA_CUDA(fa::simt_bwd_prep(dout, ddo, ddelta, nullptr, nullptr, nullptr, rows, d, st), 1);
     FA_CUDA(fa::simt_bwd(dq, dk, dv, ddo, lse, ddelta, gq, gk, gv, batch, N, d, causal != 0, true, st), 2);

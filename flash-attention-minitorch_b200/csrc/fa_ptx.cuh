@@ -104,6 +104,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, uin
         "r"(c2), "l"(hint)
       : "memory");
 }
+// 1-D bulk copy global -> shared (size multiple of 16 B, both addresses 16-B aligned)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const void* map, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                :

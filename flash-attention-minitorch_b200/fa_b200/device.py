@@ -32,15 +32,19 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def flash_attn_fwd(q, k, v, causal: bool, precision: int = _lib.FA_PREC_AUTO, want_lm: bool = False):
-    """Returns (o, lse) or (o, lse, m, l) -- lse/m/l are fp32 with shape q.shape[:-1]."""
+def flash_attn_fwd(q, k, v, causal: bool, precision: int = _lib.FA_PREC_AUTO, want_lm: bool = False, out=None):
+    """Returns (o, lse) or (o, lse, m, l) -- lse/m/l are fp32 with shape q.shape[:-1].
+    `out=(o, lse)` reuses preallocated outputs."""
     import torch
     lib = _lib.load_library()
     dt = _prep(q)
     assert _prep(k) == dt and _prep(v) == dt and k.shape == q.shape and v.shape == q.shape
     BH, T, d = _dims(q)
-    o = torch.empty_like(q)
-    lse = torch.empty(q.shape[:-1], dtype=torch.float32, device=q.device)
+    if out is not None:
+        o, lse = out
+    else:
+        o = torch.empty_like(q)
+        lse = torch.empty(q.shape[:-1], dtype=torch.float32, device=q.device)
     m = torch.empty_like(lse) if want_lm else None
     l = torch.empty_like(lse) if want_lm else None
     _lib.check(lib.fa_b200_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
