@@ -9,6 +9,7 @@
 //   warps 4-7   softmax group for Q tile 1
 //   warp  8     TMA producer (one lane): Q once, then the K/V ring
 //   warp  9     MMA issuer   (one lane): S_t = Q_t K_j^T and O_t += P_t V_j
+// (registers are moved from warps 8-11 to the softmax warps with setmaxnreg: 208 vs 80 per thread)
 // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [384,384+D).  P_t (bf16) overwrites the
 // first 64 columns of S_t and is consumed as the TMEM A operand of the PV MMA, so probabilities
 // never touch shared memory.  The MMA order  PV0(j) QK0(j+1) PV1(j) QK1(j+1)  keeps the tensor
@@ -31,7 +32,10 @@ namespace {
 
 constexpr int kBlockM = 128;  // rows per Q tile (= TMEM lanes)
 constexpr int kBlockN = 128;  // keys per K/V tile
-constexpr int kFwdThreads = 320;
+constexpr int kFwdThreads = 384;  // warps 0-7 softmax, 8 TMA, 9 MMA, 10-11 idle (complete the 4-warp group for setmaxnreg)
+#ifndef FA_FWD_PACKED
+#define FA_FWD_PACKED 1  // FFMA2 / FADD2 in the softmax inner loop (measured: +2 % over scalar)
+#endif
 
 struct FwdParams {
   int T, BH, causal;
@@ -126,6 +130,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
 
+  if (warp >= 8) {
+    // All four warps of this group must execute the SAME setmaxnreg instruction (one code location),
+    // and it must sit inside the role branch for ptxas to apply the budget to the right code.
+    reg_dealloc<80>();
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -215,8 +223,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
       }
     }
+  }
   } else {
     // ------------------------------------------------------------------ softmax groups
+    reg_alloc<208>();  // 256*208 + 128*80 <= 384*168 (the CTA register pool fixed at launch)
     const int t = warp >> 2;
     const int r = threadIdx.x & 127;
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
@@ -286,19 +296,47 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
       }
       const float nm = -m_ref * c2;
-      float l0 = 0.f, l1 = 0.f;
-      uint32_t pk[64];
+#if FA_FWD_PACKED
+      const float2 c2v = make_float2(c2, c2), nmv = make_float2(nm, nm);
+      float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+#else
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#endif
 #pragma unroll
-      for (int c = 0; c < 128; c += 2) {
-        const float p0 = ex2_approx(fmaf(s[c], c2, nm));
-        const float p1 = ex2_approx(fmaf(s[c + 1], c2, nm));
-        l0 += p0;
-        l1 += p1;
-        pk[c >> 1] = pack_bf16x2(p0, p1);
+      for (int q4 = 0; q4 < 4; ++q4) {  // 32 columns -> 16 packed TMEM columns at a time
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const int cc = q4 * 32 + c;
+#if FA_FWD_PACKED
+          const float2 x0 = ffma2(make_float2(s[cc], s[cc + 1]), c2v, nmv);
+          const float2 x1 = ffma2(make_float2(s[cc + 2], s[cc + 3]), c2v, nmv);
+          const float2 p0 = make_float2(ex2_mixed(x0.x, cc), ex2_mixed(x0.y, cc + 1));
+          const float2 p1 = make_float2(ex2_mixed(x1.x, cc + 2), ex2_mixed(x1.y, cc + 3));
+          la = fadd2(la, p0);
+          lb = fadd2(lb, p1);
+          pk[c >> 1] = pack_bf16x2(p0.x, p0.y);
+          pk[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+#else
+          const float p0 = ex2_mixed(fmaf(s[cc], c2, nm), cc);
+          const float p1 = ex2_mixed(fmaf(s[cc + 1], c2, nm), cc + 1);
+          const float p2 = ex2_mixed(fmaf(s[cc + 2], c2, nm), cc + 2);
+          const float p3 = ex2_mixed(fmaf(s[cc + 3], c2, nm), cc + 3);
+          l0 += p0;
+          l1 += p1;
+          l2 += p2;
+          l3 += p3;
+          pk[c >> 1] = pack_bf16x2(p0, p1);
+          pk[(c >> 1) + 1] = pack_bf16x2(p2, p3);
+#endif
+        }
+        tmem_st_x16(tS + q4 * 16, pk);
       }
-      l += l0 + l1;
-      tmem_st_x32(tS + 0, pk);
-      tmem_st_x32(tS + 32, pk + 32);
+#if FA_FWD_PACKED
+      l += (la.x + la.y) + (lb.x + lb.y);
+#else
+      l += (l0 + l1) + (l2 + l3);
+#endif
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();

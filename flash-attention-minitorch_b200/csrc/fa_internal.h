@@ -26,6 +26,7 @@ cudaError_t tc_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
                    float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st);
 
 bool tc_bwd_supported(int d);
+void tc_bwd_set_trace(long long* dev_buf);  // developer timeline buffer (256 int64), nullptr = off
 size_t tc_bwd_workspace_bytes(int BH, int T, int d);
 // dq/dk/dv are bf16 or fp32 (grads_f32).  workspace: tc_bwd_workspace_bytes() bytes of device memory.
 cudaError_t tc_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* o,

@@ -286,6 +286,48 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, rel. error ~1e-4, far below the
+// bf16 rounding of P).  The MUFU unit (16 ex2/clk/SM) is as scarce as the tensor pipe at head dim 128, so a
+// fixed fraction of the exponentials of every tile is evaluated here instead.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  float xi;  // floor(x) + 1.5 * 2^23 : the integer part sits in the low mantissa bits
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(xi) : "f"(x), "f"(12582912.f));
+  const float f = x - (xi - 12582912.f);  // fractional part in [0, 1)
+  const float p = fmaf(fmaf(fmaf(0.07711909f, f, 0.22756439f), f, 0.69514614f), f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xi) << 23));  // scale by 2^floor(x)
+}
+#ifndef FA_EX2_POLY_MASK
+#define FA_EX2_POLY_MASK 0x00  // bit i set: elements with index % 8 == i use the polynomial.  Measured on B200:
+                               // 0x00 (MUFU only) is fastest once the softmax warps have enough registers.
+#endif
+// element `idx` (compile-time after unrolling) of a tile row: MUFU or polynomial by a fixed interleave
+__device__ __forceinline__ float ex2_mixed(float x, int idx) {
+  return ((FA_EX2_POLY_MASK >> (idx & 7)) & 1) ? ex2_poly(x) : ex2_approx(x);
+}
+// packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2): one issue slot for two lanes
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

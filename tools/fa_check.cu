@@ -316,6 +316,52 @@ static int time_tc(int BH, int T, int d, int causal, int iters, bool do_bwd) {
   return 0;
 }
 
+extern "C" void fa_b200_debug_bwd_trace(void* dev_buf);
+
+static int trace_bwd(int BH, int T, int d, int causal) {
+  const size_t n = (size_t)BH * T * d, rows = (size_t)BH * T;
+  Dev dev;
+  __nv_bfloat16* t[8];
+  for (auto& p : t) p = dev.alloc<__nv_bfloat16>(n);
+  float* lse = dev.alloc<float>(rows);
+  std::vector<__nv_bfloat16> h(1 << 20);
+  for (auto& x : h) x = __float2bfloat16(urand());
+  for (int i = 0; i < 5; ++i)
+    for (size_t off = 0; off < n; off += h.size())
+      CK(cudaMemcpy(t[i] + off, h.data(), std::min(h.size(), n - off) * 2, cudaMemcpyHostToDevice));
+  size_t wb = fa_b200_bwd_workspace_bytes(FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d);
+  char* ws = dev.alloc<char>(wb);
+  long long* tr = dev.alloc<long long>(512);
+  FA(fa_b200_fwd(t[0], t[1], t[2], t[3], lse, nullptr, nullptr, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, nullptr));
+  FA(fa_b200_bwd(t[0], t[1], t[2], t[3], t[4], lse, t[5], t[6], t[7], FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, ws, wb, nullptr));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemset(tr, 0, 512 * 8));
+  fa_b200_debug_bwd_trace(tr);
+  FA(fa_b200_bwd(t[0], t[1], t[2], t[3], t[4], lse, t[5], t[6], t[7], FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, ws, wb, nullptr));
+  CK(cudaDeviceSynchronize());
+  fa_b200_debug_bwd_trace(nullptr);
+  std::vector<long long> hst(512);
+  CK(cudaMemcpy(hst.data(), tr, 512 * 8, cudaMemcpyDeviceToHost));
+  const char* names[2] = {"dK/dV kernel: compute{S_rdy P_done dP_rdy dS_done} | mma{iss_dV iss_S(i+1) iss_dK iss_dP(i+1)}",
+                          "dQ kernel:    compute{S_rdy P_done dP_rdy dS_done} | mma{iss_S(j+1) iss_dQ iss_dP(j+1)}"};
+  for (int kz = 0; kz < 2; ++kz) {
+    const long long* hh = hst.data() + kz * 256;
+    long long t0 = hh[0];
+    printf("%s  (clock64 of CTA(0,0), relative to first S ready)\n", names[kz]);
+    for (int il = 0; il < 16; ++il) {
+      printf("%3d |", il);
+      for (int e = 0; e < 11; ++e) {
+        if (e >= 4 && e <= 6) continue;
+        long long v = hh[il * 16 + e];
+        printf(" %7lld", v ? v - t0 : -1);
+        if (e == 3) printf(" |");
+      }
+      printf("\n");
+    }
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   std::string mode = argc > 1 ? argv[1] : "simt";
   int bad = 0;
@@ -333,6 +379,9 @@ int main(int argc, char** argv) {
       bad += check_tc(b, 2, 1024, 128, 1, 6.f);
       bad += check_tc(b, 2, 1024, 64, 0, 8.f);
     }
+  } else if (mode == "trace") {
+    return trace_bwd(argc > 2 ? atoi(argv[2]) : 512, argc > 3 ? atoi(argv[3]) : 4096, argc > 4 ? atoi(argv[4]) : 128,
+                     argc > 5 ? atoi(argv[5]) : 1);
   } else if (mode == "time") {
     int BH = argc > 2 ? atoi(argv[2]) : 512, T = argc > 3 ? atoi(argv[3]) : 4096, d = argc > 4 ? atoi(argv[4]) : 128;
     int causal = argc > 5 ? atoi(argv[5]) : 1, iters = argc > 6 ? atoi(argv[6]) : 10;
