@@ -89,6 +89,9 @@ int host_precision() {
   }
   return g_host_precision;
 }
+// The reference ABI computes in plain fp32, so "auto" there means the exact-fp32 kernels; the tensor-core
+// precisions are opt-in (fa_b200_set_host_precision / FA_B200_HOST_PRECISION).
+int host_effective_precision() { return host_precision() == FA_PREC_AUTO ? FA_PREC_FP32_SIMT : host_precision(); }
 
 bool valid_shape(int bh, int T, int d) { return bh > 0 && T > 0 && d > 0 && d <= 128; }
 
@@ -101,9 +104,12 @@ int resolve_precision(int dtype, int precision, int d, bool backward) {
     return -1;
   }
   if (dtype == FA_DTYPE_F32) {
-    if (precision == FA_PREC_AUTO || precision == FA_PREC_FP32_SIMT) return FA_PREC_FP32_SIMT;
+    // tf32 tensor-core kernels exist for the forward (d in {32, 64}); everything else on fp32 storage runs the
+    // exact-fp32 CUDA-core kernels, which satisfy any tf32 tolerance
+    const bool tf32_ok = !backward && fa::tc_fwd_tf32_supported(d);
+    if (precision == FA_PREC_AUTO || precision == FA_PREC_TF32_TC) return tf32_ok ? FA_PREC_TF32_TC : FA_PREC_FP32_SIMT;
+    if (precision == FA_PREC_FP32_SIMT) return FA_PREC_FP32_SIMT;
     if (precision == FA_PREC_BF16_TC) return tc_ok ? FA_PREC_BF16_TC : FA_PREC_FP32_SIMT;
-    if (precision == FA_PREC_TF32_TC) return FA_PREC_FP32_SIMT;  // tf32 kernels not built yet: exact fp32 instead
   }
   return -1;
 }
@@ -130,8 +136,13 @@ int fa_b200_fwd(const void* q, const void* k, const void* v, void* o, float* lse
                        l_out, batch_heads, T, d, causal != 0, st), 1);
     return FA_OK;
   }
+  if (prec == FA_PREC_TF32_TC) {
+    FA_CUDA(fa::tc_fwd_tf32((const float*)q, (const float*)k, (const float*)v, (float*)o, lse, m_out, l_out, batch_heads,
+                            T, d, causal != 0, st), 1);
+    return FA_OK;
+  }
   if (prec != FA_PREC_FP32_SIMT)
-    return fail(FA_ERR_UNSUPPORTED, "fa_b200_fwd: fp32 storage with tensor-core precision needs the host API");
+    return fail(FA_ERR_UNSUPPORTED, "fa_b200_fwd: fp32 storage with bf16 tensor-core precision needs the host API");
   FA_CUDA(fa::simt_fwd((const float*)q, (const float*)k, (const float*)v, (float*)o, lse, m_out, l_out, batch_heads, T,
                        d, causal != 0, st), 1);
   return FA_OK;
@@ -213,7 +224,7 @@ int fa_b200_host_fwd(const float* q, const float* k, const float* v, float* out,
   std::lock_guard<std::mutex> lk(g_arena_mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t rows = (size_t)batch * N, n = rows * d;
-  const int prec = resolve_precision(FA_DTYPE_F32, host_precision(), d, false);
+  const int prec = resolve_precision(FA_DTYPE_F32, host_effective_precision(), d, false);
   if (prec < 0) return fail(FA_ERR_BAD_ARG, "fa_b200_host_fwd: bad precision setting %d", host_precision());
   const bool tc = prec == FA_PREC_BF16_TC;
   size_t bytes = 4 * align_up(n * 4, 256) + 3 * align_up(rows * 4, 256) + (tc ? 3 * align_up(n * 2, 256) : 0) + 4096;
@@ -237,6 +248,8 @@ int fa_b200_host_fwd(const float* q, const float* k, const float* v, float* out,
     FA_CUDA(fa::cvt_f32_to_bf16(dk, bk, n, st), 1);
     FA_CUDA(fa::cvt_f32_to_bf16(dv, bv, n, st), 1);
     FA_CUDA(fa::tc_fwd(bq, bk, bv, dout, true, dlse, fa1 ? dm : nullptr, fa1 ? dl : nullptr, batch, N, d, causal != 0, st), 1);
+  } else if (prec == FA_PREC_TF32_TC) {
+    FA_CUDA(fa::tc_fwd_tf32(dq, dk, dv, dout, dlse, fa1 ? dm : nullptr, fa1 ? dl : nullptr, batch, N, d, causal != 0, st), 1);
   } else {
     FA_CUDA(fa::simt_fwd(dq, dk, dv, dout, dlse, fa1 ? dm : nullptr, fa1 ? dl : nullptr, batch, N, d, causal != 0, st), 1);
   }
@@ -263,7 +276,7 @@ int fa_b200_host_bwd(const float* q, const float* k, const float* v, const float
   std::lock_guard<std::mutex> lk(g_arena_mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t rows = (size_t)batch * N, n = rows * d;
-  const int prec = resolve_precision(FA_DTYPE_F32, host_precision(), d, true);
+  const int prec = resolve_precision(FA_DTYPE_F32, host_effective_precision(), d, true);
   if (prec < 0) return fail(FA_ERR_BAD_ARG, "fa_b200_host_bwd: bad precision setting %d", host_precision());
   const bool tc = prec == FA_PREC_BF16_TC;
   const size_t ws_bytes = tc ? fa::tc_bwd_workspace_bytes(batch, N, d) : 0;

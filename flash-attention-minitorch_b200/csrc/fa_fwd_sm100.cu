@@ -47,13 +47,21 @@ struct FwdParams {
   float* l_out;
 };
 
-template <int D>
+// kTF32 = false: bf16 storage, kind::f16 MMAs (UMMA_K = 16).  kTF32 = true: fp32 storage read directly by TMA,
+// kind::tf32 MMAs (UMMA_K = 8); P is written back to TMEM as tf32 over all 128 columns of S and V is consumed
+// MN-major through the 128B/32B-atom swizzle that UMMA requires for 32-bit MN-major operands.
+template <int D, bool kTF32>
 struct FwdCfg {
-  static constexpr int kStages = D >= 128 ? 2 : 4;
-  static constexpr int kBoxes = D / 64;                   // 64-column (128-byte) TMA boxes per tile row
+  static constexpr int kElem = kTF32 ? 4 : 2;
+  static constexpr int kAtom = 128 / kElem;               // elements per 128-byte swizzle row (TMA box width)
+  static constexpr int kBoxes = D / kAtom;                // boxes per tile row
   static constexpr int kBoxBytes = 128 * 128;             // 128 rows x 128 B
-  static constexpr int kTileBytes = kBoxes * kBoxBytes;   // one 128 x D bf16 tile
+  static constexpr int kTileBytes = kBoxes * kBoxBytes;   // one 128 x D tile
+  static constexpr int kStages = kTileBytes >= 32768 ? 2 : 4;
   static constexpr int kSmemBytes = (2 + 2 * kStages) * kTileBytes + 1024;
+  static constexpr int kKStepsQK = D * kElem / 32;        // UMMA_K covers 32 bytes of the contraction dim
+  static constexpr int kKStepsPV = kBlockN * kElem / 32;
+  static_assert(kTileBytes <= 32768, "tile too large for the two-Q-tile layout");
 };
 
 struct FwdBarriers {
@@ -83,11 +91,11 @@ __device__ __forceinline__ void store_row_chunk32<__nv_bfloat16>(__nv_bfloat16* 
   }
 }
 
-template <int D, typename OutT>
+template <int D, typename OutT, bool kTF32>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
               const __grid_constant__ CUtensorMap map_v, const FwdParams p) {
-  using Cfg = FwdCfg<D>;
+  using Cfg = FwdCfg<D, kTF32>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -143,7 +151,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       mbar_arrive_expect_tx(&bars.q_full, 2 * Cfg::kTileBytes);
       for (int t = 0; t < 2; ++t)
         for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_3d(sQ + t * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_q, &bars.q_full, b * 64,
+          tma_load_3d(sQ + t * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_q, &bars.q_full, b * Cfg::kAtom,
                       (2 * blk + t) * kBlockM, bh, kEvictFirst);
       for (int j = 0; j < n1; ++j) {
         const int st = j % S;
@@ -151,36 +159,45 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         mbar_wait(&bars.k_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&bars.k_full[st], Cfg::kTileBytes);
         for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_3d(sK + st * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_k, &bars.k_full[st], b * 64, j * kBlockN,
+          tma_load_3d(sK + st * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_k, &bars.k_full[st], b * Cfg::kAtom, j * kBlockN,
                       bh, kEvictLast);
         mbar_wait(&bars.v_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&bars.v_full[st], Cfg::kTileBytes);
         for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_3d(sV + st * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_v, &bars.v_full[st], b * 64, j * kBlockN,
+          tma_load_3d(sV + st * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_v, &bars.v_full[st], b * Cfg::kAtom, j * kBlockN,
                       bh, kEvictLast);
       }
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kBlockM, kBlockN, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kBlockM, D, 0, 1);
+      constexpr uint32_t kFmt = kTF32 ? kFmtTF32 : kFmtBF16;
+      constexpr uint32_t idesc_qk = make_idesc(kFmt, kBlockM, kBlockN, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(kFmt, kBlockM, D, 0, 1);
       const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV);
       auto issue_qk = [&](int t, int st) {
         const uint32_t qa = sQa + t * Cfg::kTileBytes, ka = sKa + st * Cfg::kTileBytes;
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * Cfg::kBoxBytes + (kk & 3) * 32;
-          umma_ss(tmem + t * 128, make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk,
+        for (int kk = 0; kk < Cfg::kKStepsQK; ++kk) {
+          const uint32_t off = (kk >> 2) * Cfg::kBoxBytes + (kk & 3) * 32;  // 4 k-steps of 32 B per swizzle row
+          umma_ss<kTF32>(tmem + t * 128, make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk,
                   kk > 0);
         }
       };
       auto issue_pv = [&](int t, int st, bool acc) {
         const uint32_t va = sVa + st * Cfg::kTileBytes;
 #pragma unroll
-        for (int kk = 0; kk < kBlockN / 16; ++kk) {
-          umma_ts(tmem + 256 + t * 128, tmem + t * 128 + kk * 8,
-                  make_smem_desc(va + kk * 2048, Cfg::kBoxBytes, 1024), idesc_pv, (acc || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < Cfg::kKStepsPV; ++kk) {
+          if constexpr (kTF32) {
+            // P: one tf32 per TMEM column, 8 columns per k-step.  V: 8 key rows (1 KB) per k-step, 4-row groups
+            // 512 B apart, 32-column atoms one box apart, 128B swizzle with 32-B atomicity.
+            umma_ts<true>(tmem + 256 + t * 128, tmem + t * 128 + kk * 8,
+                          make_smem_desc(va + kk * 1024, Cfg::kBoxBytes, 512, kDescSw128Base32), idesc_pv,
+                          (acc || kk > 0) ? 1u : 0u);
+          } else {
+            umma_ts<false>(tmem + 256 + t * 128, tmem + t * 128 + kk * 8,
+                           make_smem_desc(va + kk * 2048, Cfg::kBoxBytes, 1024), idesc_pv, (acc || kk > 0) ? 1u : 0u);
+          }
         }
       };
       mbar_wait(&bars.q_full, 0);
@@ -303,34 +320,48 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #endif
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {  // 32 columns -> 16 packed TMEM columns at a time
-        uint32_t pk[16];
+      for (int q4 = 0; q4 < 4; ++q4) {  // 32 score columns at a time
+        uint32_t pk[kTF32 ? 32 : 16];
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           const int cc = q4 * 32 + c;
 #if FA_FWD_PACKED
           const float2 x0 = ffma2(make_float2(s[cc], s[cc + 1]), c2v, nmv);
           const float2 x1 = ffma2(make_float2(s[cc + 2], s[cc + 3]), c2v, nmv);
-          const float2 p0 = make_float2(ex2_mixed(x0.x, cc), ex2_mixed(x0.y, cc + 1));
-          const float2 p1 = make_float2(ex2_mixed(x1.x, cc + 2), ex2_mixed(x1.y, cc + 3));
+          float2 p0 = make_float2(ex2_mixed(x0.x, cc), ex2_mixed(x0.y, cc + 1));
+          float2 p1 = make_float2(ex2_mixed(x1.x, cc + 2), ex2_mixed(x1.y, cc + 3));
+          if constexpr (kTF32) {  // round P to tf32 once, so that the row sum and the PV product see the same values
+            p0 = make_float2(round_tf32(p0.x), round_tf32(p0.y));
+            p1 = make_float2(round_tf32(p1.x), round_tf32(p1.y));
+          }
           la = fadd2(la, p0);
           lb = fadd2(lb, p1);
-          pk[c >> 1] = pack_bf16x2(p0.x, p0.y);
-          pk[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+          const float q0 = p0.x, q1 = p0.y, q2 = p1.x, q3 = p1.y;
 #else
-          const float p0 = ex2_mixed(fmaf(s[cc], c2, nm), cc);
-          const float p1 = ex2_mixed(fmaf(s[cc + 1], c2, nm), cc + 1);
-          const float p2 = ex2_mixed(fmaf(s[cc + 2], c2, nm), cc + 2);
-          const float p3 = ex2_mixed(fmaf(s[cc + 3], c2, nm), cc + 3);
-          l0 += p0;
-          l1 += p1;
-          l2 += p2;
-          l3 += p3;
-          pk[c >> 1] = pack_bf16x2(p0, p1);
-          pk[(c >> 1) + 1] = pack_bf16x2(p2, p3);
+          float q0 = ex2_mixed(fmaf(s[cc], c2, nm), cc);
+          float q1 = ex2_mixed(fmaf(s[cc + 1], c2, nm), cc + 1);
+          float q2 = ex2_mixed(fmaf(s[cc + 2], c2, nm), cc + 2);
+          float q3 = ex2_mixed(fmaf(s[cc + 3], c2, nm), cc + 3);
+          if constexpr (kTF32) {
+            q0 = round_tf32(q0); q1 = round_tf32(q1); q2 = round_tf32(q2); q3 = round_tf32(q3);
+          }
+          l0 += q0;
+          l1 += q1;
+          l2 += q2;
+          l3 += q3;
 #endif
+          if constexpr (kTF32) {
+            pk[c] = __float_as_uint(q0);
+            pk[c + 1] = __float_as_uint(q1);
+            pk[c + 2] = __float_as_uint(q2);
+            pk[c + 3] = __float_as_uint(q3);
+          } else {
+            pk[c >> 1] = pack_bf16x2(q0, q1);
+            pk[(c >> 1) + 1] = pack_bf16x2(q2, q3);
+          }
         }
-        tmem_st_x16(tS + q4 * 16, pk);
+        if constexpr (kTF32) tmem_st_x32(tS + q4 * 32, pk);   // tf32: P fills all 128 columns of S
+        else tmem_st_x16(tS + q4 * 16, pk);                    // bf16: two probabilities per column
       }
 #if FA_FWD_PACKED
       l += (la.x + la.y) + (lb.x + lb.y);
@@ -372,21 +403,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
-template <int D, typename OutT>
-cudaError_t launch_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, float* lse,
-                       float* m_out, float* l_out, int BH, int T, bool causal, cudaStream_t st) {
-  using Cfg = FwdCfg<D>;
+template <int D, typename OutT, bool kTF32>
+cudaError_t launch_fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* m_out, float* l_out,
+                       int BH, int T, bool causal, cudaStream_t st) {
+  using Cfg = FwdCfg<D, kTF32>;
   CUtensorMap mq, mk, mv;
-  if (make_tmap_3d(&mq, q, 2, D, T, BH, 64, kBlockM)) return cudaErrorInvalidValue;
-  if (make_tmap_3d(&mk, k, 2, D, T, BH, 64, kBlockN)) return cudaErrorInvalidValue;
-  if (make_tmap_3d(&mv, v, 2, D, T, BH, 64, kBlockN)) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_fwd_kernel<D, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (make_tmap_3d(&mq, q, Cfg::kElem, D, T, BH, Cfg::kAtom, kBlockM)) return cudaErrorInvalidValue;
+  if (make_tmap_3d(&mk, k, Cfg::kElem, D, T, BH, Cfg::kAtom, kBlockN)) return cudaErrorInvalidValue;
+  if (make_tmap_3d(&mv, v, Cfg::kElem, D, T, BH, Cfg::kAtom, kBlockN, kTF32 ? 2 : 1)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(fa_fwd_kernel<D, OutT, kTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
   FwdParams p;
   p.T = T;
   p.BH = BH;
@@ -398,25 +425,35 @@ cudaError_t launch_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   p.m_out = m_out;
   p.l_out = l_out;
   dim3 grid((T + 2 * kBlockM - 1) / (2 * kBlockM), BH);
-  fa_fwd_kernel<D, OutT><<<grid, kFwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, p);
+  fa_fwd_kernel<D, OutT, kTF32><<<grid, kFwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, p);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 bool tc_fwd_supported(int d) { return d == 64 || d == 128; }
+bool tc_fwd_tf32_supported(int d) { return d == 32 || d == 64; }
 
 cudaError_t tc_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, bool o_is_f32,
                    float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st) {
   if (BH > 65535) return cudaErrorInvalidValue;
   if (d == 128) {
-    return o_is_f32 ? launch_fwd<128, float>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st)
-                    : launch_fwd<128, __nv_bfloat16>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
+    return o_is_f32 ? launch_fwd<128, float, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st)
+                    : launch_fwd<128, __nv_bfloat16, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
   }
   if (d == 64) {
-    return o_is_f32 ? launch_fwd<64, float>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st)
-                    : launch_fwd<64, __nv_bfloat16>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
+    return o_is_f32 ? launch_fwd<64, float, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st)
+                    : launch_fwd<64, __nv_bfloat16, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
   }
+  return cudaErrorInvalidValue;
+}
+
+// fp32 storage in, fp32 out, tf32 tensor-core arithmetic
+cudaError_t tc_fwd_tf32(const float* q, const float* k, const float* v, float* o, float* lse, float* m_out,
+                        float* l_out, int BH, int T, int d, bool causal, cudaStream_t st) {
+  if (BH > 65535) return cudaErrorInvalidValue;
+  if (d == 64) return launch_fwd<64, float, true>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
+  if (d == 32) return launch_fwd<32, float, true>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
   return cudaErrorInvalidValue;
 }
 

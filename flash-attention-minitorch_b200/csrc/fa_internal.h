@@ -25,6 +25,11 @@ bool tc_fwd_supported(int d);
 cudaError_t tc_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, bool o_is_f32,
                    float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st);
 
+// fp32 storage read directly by TMA, kind::tf32 MMAs, fp32 output; d in {32, 64}
+bool tc_fwd_tf32_supported(int d);
+cudaError_t tc_fwd_tf32(const float* q, const float* k, const float* v, float* o, float* lse, float* m_out,
+                        float* l_out, int BH, int T, int d, bool causal, cudaStream_t st);
+
 bool tc_bwd_supported(int d);
 void tc_bwd_set_trace(long long* dev_buf);  // developer timeline buffer (256 int64), nullptr = off
 size_t tc_bwd_workspace_bytes(int BH, int T, int d);

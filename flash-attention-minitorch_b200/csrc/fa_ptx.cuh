@@ -328,6 +328,11 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
       : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
   return d;
 }
+__device__ __forceinline__ float round_tf32(float x) {  // round-to-nearest (ties away) fp32 -> tf32, kept in fp32 bits
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

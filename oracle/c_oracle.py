@@ -30,7 +30,19 @@ def lib() -> ctypes.CDLL:
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         _LIB.oracle_attention.restype = ctypes.c_int
         _LIB.oracle_num_threads.restype = ctypes.c_int
+        _LIB.oracle_set_num_threads.argtypes = [ctypes.c_int]
+        _LIB.oracle_set_num_threads.restype = None
     return _LIB
+
+
+def use_all_cores() -> int:
+    """Use every core this process may run on (torchrun pins OMP_NUM_THREADS=1).  Returns the thread count."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().oracle_set_num_threads(n)
+    return num_threads()
 
 
 def num_threads() -> int:

@@ -144,11 +144,52 @@ def test_device_fp32_any_head_dim(cuda_device, d):
     q, k, v, g = ao.make_inputs(2, 77, d, seed=d)
     dq_r, dk_r, dv_r, o_r, L_r = ao.attention_backward(q, k, v, g, True, np.float64)
     tq, tk, tv, tg = (_to_dev(x, cuda_device, bf16=False) for x in (q, k, v, g))
-    o, lse = device.flash_attn_fwd(tq, tk, tv, True)
+    o, lse = device.flash_attn_fwd(tq, tk, tv, True, precision=_lib.FA_PREC_FP32_SIMT)
     assert np.abs(o.cpu().numpy() - o_r).max() <= 1e-5
     dq, dk, dv = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, True)
     for got, ref in ((dq, dq_r), (dk, dk_r), (dv, dv_r)):
         assert np.abs(got.cpu().numpy() - ref).max() <= 1e-4
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("BH,T,d", [(3, 128, 64), (2, 40, 32), (2, 327, 64), (1, 1000, 32), (2, 1, 64), (1, 1024, 64)])
+def test_device_tf32_forward_vs_oracle(cuda_device, BH, T, d, causal):
+    """fp32 storage, tcgen05 kind::tf32 arithmetic (what FA_PREC_AUTO selects for fp32 tensors with d in {32, 64}):
+    north_star bar max-abs 1e-3 on O; the saved statistics feed the exact-fp32 backward."""
+    q, k, v, g = ao.make_inputs(BH, T, d, seed=500 + T + d)
+    dq_r, dk_r, dv_r, o_r, L_r = ao.attention_backward(q, k, v, g, causal, np.float64)
+    tq, tk, tv, tg = (_to_dev(x, cuda_device, bf16=False) for x in (q, k, v, g))
+    before = _lib.launch_count()
+    o, lse, m, l = device.flash_attn_fwd(tq, tk, tv, causal, precision=_lib.FA_PREC_TF32_TC, want_lm=True)
+    assert _lib.launch_count() == before + 1
+    assert np.abs(o.cpu().numpy() - o_r).max() <= FP32_ATOL
+    assert np.abs(lse.cpu().numpy() - L_r).max() <= FP32_ATOL
+    import torch
+    assert np.abs((m + torch.log(l)).cpu().numpy() - L_r).max() <= FP32_ATOL
+    o_auto, _ = device.flash_attn_fwd(tq, tk, tv, causal)  # AUTO resolves to the same kernel: bit-identical
+    assert torch.equal(o_auto, o)
+    dq, dk, dv = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, causal)
+    for got, ref, name in ((dq, dq_r, "dq"), (dk, dk_r, "dk"), (dv, dv_r, "dv")):
+        assert np.abs(got.cpu().numpy() - ref).max() <= FP32_ATOL, name
+
+
+def test_cfg2_full_size_tf32_forward(cuda_device):
+    """configs[1] at full size (B=32 H=16 T=1024 d=64, fp32 storage, non-causal): rows of P sum to one (V = 1 gives
+    O = 1), bit-exact determinism, and sampled heads against the C oracle at max-abs 1e-3."""
+    import torch
+    torch.manual_seed(2001)
+    BH, T, d = 512, 1024, 64
+    q, k, v = (torch.rand(BH, T, d, device=cuda_device) * 2 - 1 for _ in range(3))
+    o, lse = device.flash_attn_fwd(q, k, v, False, precision=_lib.FA_PREC_TF32_TC)
+    o2, lse2 = device.flash_attn_fwd(q, k, v, False, precision=_lib.FA_PREC_TF32_TC)
+    assert torch.equal(o, o2) and torch.equal(lse, lse2)
+    ones, _ = device.flash_attn_fwd(q, k, torch.ones_like(v), False, precision=_lib.FA_PREC_TF32_TC)
+    assert float((ones - 1).abs().max()) <= FP32_ATOL
+    for h in (0, 255, 511):
+        f = lambda t: t[h:h + 1].cpu().numpy()  # noqa: E731
+        r = c_oracle.attention(f(q), f(k), f(v), None, causal=False)
+        assert np.abs(f(o) - r["o"]).max() <= FP32_ATOL
+        assert np.abs(f(lse) - r["lse"]).max() <= FP32_ATOL
 
 
 def test_host_api_bf16_precision(cuda_device):

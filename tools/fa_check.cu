@@ -4,6 +4,8 @@
 //   fa_check fwd             tcgen05 forward (bf16) vs the CUDA-core fp32 kernels on the same bf16-rounded inputs
 //   fa_check bwd             tcgen05 backward (bf16) vs the CUDA-core fp32 backward
 //   fa_check time [BH T d causal iters]   CUDA-event timing of forward (+ backward when available)
+//   fa_check tf32            tcgen05 kind::tf32 forward (fp32 storage) vs the CUDA-core fp32 forward, max-abs 1e-3
+//   fa_check time32 [BH T d causal iters] timing of the tf32 forward (BASELINE.json configs[1] by default)
 //
 // This is developer tooling for quick iteration on a GPU box; the judged parity tests live in tests/.
 #include <cuda_bf16.h>
@@ -271,6 +273,79 @@ static int check_tc(bool do_bwd, int BH, int T, int d, int causal, float scale) 
   return bad;
 }
 
+
+// tf32 tensor-core forward (fp32 storage) vs the exact-fp32 CUDA-core forward on identical inputs
+static int check_tf32(int BH, int T, int d, int causal, float scale) {
+  const size_t n = (size_t)BH * T * d, rows = (size_t)BH * T;
+  std::vector<float> q(n), k(n), v(n);
+  for (auto& x : q) x = urand() * scale;
+  for (auto& x : k) x = urand() * scale;
+  for (auto& x : v) x = urand();
+  Dev dev;
+  float *dq = dev.alloc<float>(n), *dk = dev.alloc<float>(n), *dv = dev.alloc<float>(n), *o0 = dev.alloc<float>(n),
+        *o1 = dev.alloc<float>(n), *l0 = dev.alloc<float>(rows), *l1 = dev.alloc<float>(rows), *m0 = dev.alloc<float>(rows),
+        *m1 = dev.alloc<float>(rows), *s0 = dev.alloc<float>(rows), *s1 = dev.alloc<float>(rows);
+  CK(cudaMemcpy(dq, q.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dk, k.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dv, v.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(o1, 0xff, n * 4));
+  FA(fa_b200_fwd(dq, dk, dv, o0, l0, m0, s0, FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, nullptr));
+  FA(fa_b200_fwd(dq, dk, dv, o1, l1, m1, s1, FA_DTYPE_F32, FA_PREC_TF32_TC, BH, T, d, causal, nullptr));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("tf32 fwd BH=%d T=%d d=%d causal=%d: CUDA ERROR %s\n", BH, T, d, causal, cudaGetErrorString(e));
+    exit(3);
+  }
+  double ea, er, la, lr, ma, mr, sa, sr;
+  err_stats(d2h_f32(o1, n), d2h_f32(o0, n), ea, er);
+  err_stats(d2h_f32(l1, rows), d2h_f32(l0, rows), la, lr);
+  err_stats(d2h_f32(m1, rows), d2h_f32(m0, rows), ma, mr);
+  err_stats(d2h_f32(s1, rows), d2h_f32(s0, rows), sa, sr);
+  // The tensor core truncates fp32 operands to tf32 (2^-11 relative, one-sided), so |V| <= 1 gives |dO| <= 4.9e-4 and
+  // the raw row max (|s| <= sqrt(d)) moves by up to ~1.3e-3; the north_star bar (max-abs 1e-3) applies to O for
+  // U(-1,1) inputs.  Large-magnitude scores (scale > 1) are outside tf32's reach at 1e-3 and are checked relatively.
+  const bool ok = (scale == 1.f ? ea < 1e-3 : er < 2e-2) && la < 1e-3 * scale * scale && ma < 2e-3 * scale * scale &&
+                  sr < 2e-3 * scale * scale;
+  printf("tf32 fwd BH=%d T=%5d d=%3d causal=%d scale=%.0f  O abs %.2e (rel %.2e)  LSE abs %.2e  m abs %.2e  l rel %.2e  %s\n",
+         BH, T, d, causal, scale, ea, er, la, ma, sr, ok ? "OK" : "FAIL");
+  return !ok;
+}
+
+static int time_tf32(int BH, int T, int d, int causal, int iters) {
+  const size_t n = (size_t)BH * T * d, rows = (size_t)BH * T;
+  Dev dev;
+  float* t[4];
+  for (auto& p : t) p = dev.alloc<float>(n);
+  float* lse = dev.alloc<float>(rows);
+  {
+    std::vector<float> h(1 << 20);
+    for (auto& x : h) x = urand();
+    for (int i = 0; i < 3; ++i)
+      for (size_t off = 0; off < n; off += h.size())
+        CK(cudaMemcpy(t[i] + off, h.data(), std::min(h.size(), n - off) * 4, cudaMemcpyHostToDevice));
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const double ffwd = 4.0 * BH * (double)T * T * d * (causal ? 0.5 : 1.0);
+  for (int prec : {FA_PREC_TF32_TC, FA_PREC_FP32_SIMT}) {
+    const int it = prec == FA_PREC_TF32_TC ? iters : std::max(1, iters / 10);
+    for (int i = 0; i < 2; ++i) FA(fa_b200_fwd(t[0], t[1], t[2], t[3], lse, nullptr, nullptr, FA_DTYPE_F32, prec, BH, T, d, causal, nullptr));
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int i = 0; i < it; ++i) FA(fa_b200_fwd(t[0], t[1], t[2], t[3], lse, nullptr, nullptr, FA_DTYPE_F32, prec, BH, T, d, causal, nullptr));
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= it;
+    const double bytes = 4.0 * n * 4 + rows * 4.0;
+    printf("time %s fwd BH=%d T=%d d=%d causal=%d: %.3f ms  %.1f TFLOP/s  %.0f GB/s algorithmic\n",
+           prec == FA_PREC_TF32_TC ? "tf32" : "fp32-simt", BH, T, d, causal, ms, ffwd / ms * 1e-9, bytes / ms * 1e-6);
+  }
+  return 0;
+}
+
 static int time_tc(int BH, int T, int d, int causal, int iters, bool do_bwd) {
   const size_t n = (size_t)BH * T * d, rows = (size_t)BH * T;
   Dev dev;
@@ -379,6 +454,20 @@ int main(int argc, char** argv) {
       bad += check_tc(b, 2, 1024, 128, 1, 6.f);
       bad += check_tc(b, 2, 1024, 64, 0, 8.f);
     }
+  } else if (mode == "tf32") {
+    if (argc >= 6) {
+      bad = check_tf32(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argc > 6 ? atof(argv[6]) : 1.f);
+    } else {
+      for (int d : {64, 32})
+        for (int causal : {0, 1})
+          for (int T : {1, 40, 128, 256, 327, 1000, 1024, 2048 + 77}) bad += check_tf32(3, T, d, causal, 1.f);
+      bad += check_tf32(2, 1024, 64, 1, 6.f);
+      bad += check_tf32(2, 1024, 32, 0, 6.f);
+    }
+  } else if (mode == "time32") {
+    int BH = argc > 2 ? atoi(argv[2]) : 512, T = argc > 3 ? atoi(argv[3]) : 1024, d = argc > 4 ? atoi(argv[4]) : 64;
+    int causal = argc > 5 ? atoi(argv[5]) : 0, iters = argc > 6 ? atoi(argv[6]) : 20;
+    return time_tf32(BH, T, d, causal, iters);
   } else if (mode == "trace") {
     return trace_bwd(argc > 2 ? atoi(argv[2]) : 512, argc > 3 ? atoi(argv[3]) : 4096, argc > 4 ? atoi(argv[4]) : 128,
                      argc > 5 ? atoi(argv[5]) : 1);
