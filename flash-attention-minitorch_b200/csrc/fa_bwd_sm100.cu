@@ -42,6 +42,7 @@ struct BwdParams {
   const float* delta_pad;  // [BH][Tpad]  rowsum(dO o O); 0 on padding rows
   void* dk;
   void* dv;
+  Dropout drop;  // used by the kDrop instantiations only
 };
 
 template <int D>
@@ -93,7 +94,7 @@ __device__ __forceinline__ void store_chunk32<__nv_bfloat16>(__nv_bfloat16* dst,
   }
 }
 
-template <int D, typename OutT>
+template <int D, typename OutT, bool kDrop>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
               const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
@@ -274,6 +275,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const uint32_t tDP = tmem + Cfg::kColDP + lane_base;
     const float c2 = p.scale_log2;
     uint8_t* ds_row = sDS + g * kBoxBytes + r * 128;
+    // dropout: one 32-bit hash per 2 x 2 block of (query, key); this thread (one key row) uses the byte of its key
+    // parity in the low half (even query) and in the high half (odd query) -- the same bits the forward drew
+    const uint32_t kj = uint32_t(j * kTile + r);
+    const uint32_t drop_colkey = drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh) ^ ((kj >> 1) * kDropColMul);
+    const uint32_t drop_sh = (kj & 1) * 8;
+    const uint32_t drop_thr = p.drop.thr;
+    const float drop_scale = p.drop.keep_scale;
     for (int il = 0; il < n; ++il) {
       const int i = i0 + il;
       const float* sL = sStats + (il & 1) * 256 + g * 64;
@@ -303,10 +311,26 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         for (int c = 0; c < 64; ++c)
           if (g * 64 + c < r) pr[c] = 0.f;  // key index > query index
       }
+      uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;  // bit c: query column 64g + c of this key row is kept
+      if constexpr (kDrop) {
+        keep_lo = keep_hi = 0u;
+        const uint32_t i2 = uint32_t(i * kTile + g * 64) >> 1;
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          const uint32_t b = drop_mix(drop_colkey ^ ((i2 + (c >> 1)) * kDropRowMul)) >> drop_sh;
+          const uint32_t k0 = (b & 0xffu) >= drop_thr ? 1u : 0u, k1 = ((b >> 16) & 0xffu) >= drop_thr ? 1u : 0u;
+          if (c < 32) keep_lo |= (k0 << c) | (k1 << (c + 1));
+          else keep_hi |= (k0 << (c - 32)) | (k1 << (c - 31));
+        }
+      }
+      auto kept = [&](int c) { return ((c < 32 ? keep_lo >> c : keep_hi >> (c - 32)) & 1u) != 0u; };
       {
         uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) pk[c >> 1] = pack_bf16x2(pr[c], pr[c + 1]);
+        for (int c = 0; c < 64; c += 2) {
+          if constexpr (kDrop) pk[c >> 1] = pack_bf16x2(kept(c) ? pr[c] : 0.f, kept(c + 1) ? pr[c + 1] : 0.f);  // P^T o keep -> dV
+          else pk[c >> 1] = pack_bf16x2(pr[c], pr[c + 1]);
+        }
         // P^T of query columns [64g, 64g+64) goes to TMEM columns [64g, 64g+32): inside the S columns this
         // thread group has already consumed, so the two groups never touch each other's unread scores
         tmem_st_x32(tS + g * 64, pk);
@@ -332,6 +356,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < 8; e += 4) {
           const float4 D4 = *reinterpret_cast<const float4*>(sD + ch * 8 + e);
+          if constexpr (kDrop) {  // dP o Z with Z = keep / (1 - p); P itself stays undropped here
+            const int c = ch * 8 + e;
+            dp[c + 0] *= kept(c + 0) ? drop_scale : 0.f;
+            dp[c + 1] *= kept(c + 1) ? drop_scale : 0.f;
+            dp[c + 2] *= kept(c + 2) ? drop_scale : 0.f;
+            dp[c + 3] *= kept(c + 3) ? drop_scale : 0.f;
+          }
           ds[e + 0] = pr[ch * 8 + e + 0] * (dp[ch * 8 + e + 0] - D4.x) * p.tau;
           ds[e + 1] = pr[ch * 8 + e + 1] * (dp[ch * 8 + e + 1] - D4.y) * p.tau;
           ds[e + 2] = pr[ch * 8 + e + 2] * (dp[ch * 8 + e + 2] - D4.z) * p.tau;
@@ -361,6 +392,12 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       uint32_t rr[32];
       tmem_ld_x32(tAcc + c0, rr);
       tmem_wait_ld();
+      if constexpr (kDrop) {
+        if (g == 0) {  // dV accumulated (P o keep)^T dO: apply the 1/(1-p) of Z once here
+#pragma unroll
+          for (int x = 0; x < 32; ++x) rr[x] = __float_as_uint(__uint_as_float(rr[x]) * drop_scale);
+        }
+      }
       if (row_ok) store_chunk32<OutT>(out + c0, rr);
     }
   } else if (warp < 12) {
@@ -475,7 +512,7 @@ size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 template <int D, typename OutT>
 cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* o,
                        const __nv_bfloat16* dO, const float* lse, void* dq, void* dk, void* dv, bool accumulate_dq,
-                       void* workspace, int BH, int T, bool causal, cudaStream_t st) {
+                       void* workspace, int BH, int T, bool causal, Dropout drop, cudaStream_t st) {
   using Cfg = BwdCfg<D>;
   constexpr bool kF32 = sizeof(OutT) == 4;
   const size_t Tpad = pad_rows(T);
@@ -505,7 +542,9 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   if (make_tmap_3d(&mv, v, 2, D, T, BH, 64, kTile)) return cudaErrorInvalidValue;
   if (make_tmap_3d(&mdo, dO, 2, D, T, BH, 64, kTile)) return cudaErrorInvalidValue;
   if (make_tmap_3d(&mdq, dq_acc, 4, D, T, BH, 32, kTile)) return cudaErrorInvalidValue;
-  e = cudaFuncSetAttribute(fa_bwd_kernel<D, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  e = cudaFuncSetAttribute(fa_bwd_kernel<D, OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(fa_bwd_kernel<D, OutT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
   BwdParams p;
   p.T = T;
@@ -517,8 +556,10 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   p.delta_pad = delta_pad;
   p.dk = dk;
   p.dv = dv;
+  p.drop = drop;
   dim3 grid((unsigned)(Tpad / kTile), BH);
-  fa_bwd_kernel<D, OutT><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
+  if (drop.thr) fa_bwd_kernel<D, OutT, true><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
+  else fa_bwd_kernel<D, OutT, false><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (!kF32) {
@@ -540,15 +581,16 @@ size_t tc_bwd_workspace_bytes(int BH, int T, int d) {
 
 cudaError_t tc_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* o,
                    const __nv_bfloat16* dO, const float* lse, void* dq, void* dk, void* dv, bool grads_f32,
-                   bool accumulate_dq, void* workspace, int BH, int T, int d, bool causal, cudaStream_t st) {
+                   bool accumulate_dq, void* workspace, int BH, int T, int d, bool causal, cudaStream_t st,
+                   Dropout drop) {
   if (BH > 65535 || !workspace) return cudaErrorInvalidValue;
   if (d == 128) {
-    return grads_f32 ? launch_bwd<128, float>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, st)
-                     : launch_bwd<128, __nv_bfloat16>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, st);
+    return grads_f32 ? launch_bwd<128, float>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, drop, st)
+                     : launch_bwd<128, __nv_bfloat16>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, drop, st);
   }
   if (d == 64) {
-    return grads_f32 ? launch_bwd<64, float>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, st)
-                     : launch_bwd<64, __nv_bfloat16>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, st);
+    return grads_f32 ? launch_bwd<64, float>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, drop, st)
+                     : launch_bwd<64, __nv_bfloat16>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, drop, st);
   }
   return cudaErrorInvalidValue;
 }

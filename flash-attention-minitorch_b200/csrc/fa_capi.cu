@@ -122,8 +122,12 @@ int fa_b200_version(void) { return 100; }
 const char* fa_b200_last_error(void) { return g_err; }
 unsigned long long fa_b200_launch_count(void) { return g_launches.load(); }
 
-int fa_b200_fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* m_out, float* l_out,
-                int dtype, int precision, int batch_heads, int T, int d, int causal, void* stream) {
+}  // extern "C"
+
+namespace {
+
+int fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, float* m_out, float* l_out, int dtype,
+             int precision, int batch_heads, int T, int d, int causal, fa::Dropout drop, void* stream) {
   if (!q || !k || !v || !o) return fail(FA_ERR_BAD_ARG, "fa_b200_fwd: null tensor pointer");
   if (!valid_shape(batch_heads, T, d)) return fail(FA_ERR_BAD_ARG, "fa_b200_fwd: bad shape BH=%d T=%d d=%d", batch_heads, T, d);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -133,18 +137,53 @@ int fa_b200_fwd(const void* q, const void* k, const void* v, void* o, float* lse
     if (prec != FA_PREC_BF16_TC)
       return fail(FA_ERR_UNSUPPORTED, "fa_b200_fwd: bf16 storage needs d in {64,128} (got %d)", d);
     FA_CUDA(fa::tc_fwd((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, o, false, lse, m_out,
-                       l_out, batch_heads, T, d, causal != 0, st), 1);
+                       l_out, batch_heads, T, d, causal != 0, st, drop), 1);
     return FA_OK;
   }
   if (prec == FA_PREC_TF32_TC) {
     FA_CUDA(fa::tc_fwd_tf32((const float*)q, (const float*)k, (const float*)v, (float*)o, lse, m_out, l_out, batch_heads,
-                            T, d, causal != 0, st), 1);
+                            T, d, causal != 0, st, drop), 1);
     return FA_OK;
   }
   if (prec != FA_PREC_FP32_SIMT)
     return fail(FA_ERR_UNSUPPORTED, "fa_b200_fwd: fp32 storage with bf16 tensor-core precision needs the host API");
   FA_CUDA(fa::simt_fwd((const float*)q, (const float*)k, (const float*)v, (float*)o, lse, m_out, l_out, batch_heads, T,
-                       d, causal != 0, st), 1);
+                       d, causal != 0, st, drop), 1);
+  return FA_OK;
+}
+
+// p_drop in [0, 1): returns nonzero (and sets the error string) when out of range
+int check_p_drop(float p_drop, const char* who) {
+  if (!(p_drop >= 0.f) || !(p_drop < 1.f)) return fail(FA_ERR_BAD_ARG, "%s: p_drop %g outside [0, 1)", who, (double)p_drop);
+  return FA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fa_b200_fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* m_out, float* l_out,
+                int dtype, int precision, int batch_heads, int T, int d, int causal, void* stream) {
+  return fwd_impl(q, k, v, o, lse, m_out, l_out, dtype, precision, batch_heads, T, d, causal, fa::kNoDropout, stream);
+}
+
+int fa_b200_fwd_dropout(const void* q, const void* k, const void* v, void* o, float* lse, int dtype, int precision,
+                        int batch_heads, int T, int d, int causal, float p_drop, unsigned long long seed,
+                        void* stream) {
+  if (int rc = check_p_drop(p_drop, "fa_b200_fwd_dropout")) return rc;
+  return fwd_impl(q, k, v, o, lse, nullptr, nullptr, dtype, precision, batch_heads, T, d, causal,
+                  fa::make_dropout(p_drop, seed), stream);
+}
+
+float fa_b200_dropout_keep_scale(float p_drop) { return fa::make_dropout(p_drop, 0).keep_scale; }
+float fa_b200_dropout_effective_p(float p_drop) { return (float)fa::make_dropout(p_drop, 0).thr / 256.0f; }
+
+int fa_b200_dropout_mask(unsigned char* keep, int head_begin, int n_heads, int T, float p_drop,
+                         unsigned long long seed, void* stream) {
+  if (!keep || head_begin < 0 || n_heads <= 0 || n_heads > 65535 || T <= 0)
+    return fail(FA_ERR_BAD_ARG, "fa_b200_dropout_mask: bad argument");
+  if (int rc = check_p_drop(p_drop, "fa_b200_dropout_mask")) return rc;
+  FA_CUDA(fa::dropout_mask(keep, head_begin, n_heads, T, fa::make_dropout(p_drop, seed), static_cast<cudaStream_t>(stream)), 1);
   return FA_OK;
 }
 
@@ -158,9 +197,13 @@ size_t fa_b200_bwd_workspace_bytes(int dtype, int precision, int batch_heads, in
   return bytes;
 }
 
-int fa_b200_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_out, const float* lse,
-                void* dq, void* dk, void* dv, int dtype, int precision, int batch_heads, int T, int d, int causal,
-                int accumulate_dq, void* workspace, size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+namespace {
+
+int bwd_impl(const void* q, const void* k, const void* v, const void* o, const void* d_out, const float* lse, void* dq,
+             void* dk, void* dv, int dtype, int precision, int batch_heads, int T, int d, int causal, int accumulate_dq,
+             fa::Dropout drop, void* workspace, size_t workspace_bytes, void* stream) {
   if (!q || !k || !v || !o || !d_out || !lse || !dq || !dk || !dv)
     return fail(FA_ERR_BAD_ARG, "fa_b200_bwd: null tensor pointer");
   if (!valid_shape(batch_heads, T, d)) return fail(FA_ERR_BAD_ARG, "fa_b200_bwd: bad shape BH=%d T=%d d=%d", batch_heads, T, d);
@@ -176,7 +219,7 @@ int fa_b200_bwd(const void* q, const void* k, const void* v, const void* o, cons
   if (dtype == FA_DTYPE_BF16 && prec == FA_PREC_BF16_TC) {
     FA_CUDA(fa::tc_bwd((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                        (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_out, lse, dq, dk, dv, false, accumulate_dq != 0,
-                       workspace, batch_heads, T, d, causal != 0, st), 3);
+                       workspace, batch_heads, T, d, causal != 0, st, drop), 3);
     return FA_OK;
   }
   float* delta = reinterpret_cast<float*>(ws);
@@ -184,7 +227,7 @@ int fa_b200_bwd(const void* q, const void* k, const void* v, const void* o, cons
   if (dtype == FA_DTYPE_F32) {
     FA_CUDA(fa::simt_bwd_prep((const float*)o, (const float*)d_out, delta, nullptr, nullptr, nullptr, rows, d, st), 1);
     FA_CUDA(fa::simt_bwd((const float*)q, (const float*)k, (const float*)v, (const float*)d_out, lse, delta, (float*)dq,
-                         (float*)dk, (float*)dv, batch_heads, T, d, causal != 0, accumulate_dq != 0, st), 2);
+                         (float*)dk, (float*)dv, batch_heads, T, d, causal != 0, accumulate_dq != 0, st, drop), 2);
     return FA_OK;
   }
   // bf16 storage, head dim outside the tensor-core set: widen to fp32, run the CUDA-core kernels, narrow back
@@ -198,10 +241,30 @@ int fa_b200_bwd(const void* q, const void* k, const void* v, const void* o, cons
   if (accumulate_dq) FA_CUDA(fa::cvt_bf16_to_f32((const __nv_bfloat16*)dq, f[5], n, st), 1);
   FA_CUDA(fa::simt_bwd_prep(f[3], f[4], delta, nullptr, nullptr, nullptr, rows, d, st), 1);
   FA_CUDA(fa::simt_bwd(f[0], f[1], f[2], f[4], lse, delta, f[5], f[6], f[7], batch_heads, T, d, causal != 0,
-                       accumulate_dq != 0, st), 2);
+                       accumulate_dq != 0, st, drop), 2);
   void* dst[3] = {dq, dk, dv};
   for (int i = 0; i < 3; ++i) FA_CUDA(fa::cvt_f32_to_bf16(f[5 + i], (__nv_bfloat16*)dst[i], n, st), 1);
   return FA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fa_b200_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_out, const float* lse,
+                void* dq, void* dk, void* dv, int dtype, int precision, int batch_heads, int T, int d, int causal,
+                int accumulate_dq, void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_impl(q, k, v, o, d_out, lse, dq, dk, dv, dtype, precision, batch_heads, T, d, causal, accumulate_dq,
+                  fa::kNoDropout, workspace, workspace_bytes, stream);
+}
+
+int fa_b200_bwd_dropout(const void* q, const void* k, const void* v, const void* o, const void* d_out, const float* lse,
+                        void* dq, void* dk, void* dv, int dtype, int precision, int batch_heads, int T, int d,
+                        int causal, int accumulate_dq, float p_drop, unsigned long long seed, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (int rc = check_p_drop(p_drop, "fa_b200_bwd_dropout")) return rc;
+  return bwd_impl(q, k, v, o, d_out, lse, dq, dk, dv, dtype, precision, batch_heads, T, d, causal, accumulate_dq,
+                  fa::make_dropout(p_drop, seed), workspace, workspace_bytes, stream);
 }
 
 // developer hook (not declared in fa_b200.h): clock64 timeline of one backward CTA, see tools/fa_check.cu

@@ -45,6 +45,7 @@ struct FwdParams {
   float* lse;
   float* m_out;
   float* l_out;
+  Dropout drop;  // used by the kDrop instantiations only
 };
 
 // kTF32 = false: bf16 storage, kind::f16 MMAs (UMMA_K = 16).  kTF32 = true: fp32 storage read directly by TMA,
@@ -91,7 +92,7 @@ __device__ __forceinline__ void store_row_chunk32<__nv_bfloat16>(__nv_bfloat16* 
   }
 }
 
-template <int D, typename OutT, bool kTF32>
+template <int D, typename OutT, bool kTF32, bool kDrop>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
               const __grid_constant__ CUtensorMap map_v, const FwdParams p) {
@@ -256,6 +257,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     float m_ref = -INFINITY;   // reference max (raw S units) used in the exponent
     float m_true = -INFINITY;  // true running row max (only needed for the FA-1 statistics)
     float l = 0.f;
+    // dropout: one 32-bit hash per 2 x 2 block of (row, key); this thread uses the two bytes of its row parity
+    const uint32_t drop_rowkey = drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh) ^ ((uint32_t(row_g) >> 1) * kDropRowMul);
+    const uint32_t drop_sh = (row_g & 1) * 16;
+    const uint32_t drop_thr = p.drop.thr;
 
     for (int j = 0; j < nt; ++j) {
       mbar_wait(&bars.s_full[t], j & 1);
@@ -336,7 +341,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           }
           la = fadd2(la, p0);
           lb = fadd2(lb, p1);
-          const float q0 = p0.x, q1 = p0.y, q2 = p1.x, q3 = p1.y;
+          float q0 = p0.x, q1 = p0.y, q2 = p1.x, q3 = p1.y;
 #else
           float q0 = ex2_mixed(fmaf(s[cc], c2, nm), cc);
           float q1 = ex2_mixed(fmaf(s[cc + 1], c2, nm), cc + 1);
@@ -350,6 +355,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           l2 += q2;
           l3 += q3;
 #endif
+          if constexpr (kDrop) {  // l above is the undropped row sum; only P fed to the PV product is thinned
+            const uint32_t j2 = uint32_t(j * kBlockN + cc) >> 1;
+            const uint32_t b0 = drop_mix(drop_rowkey ^ (j2 * kDropColMul)) >> drop_sh;
+            const uint32_t b1 = drop_mix(drop_rowkey ^ ((j2 + 1) * kDropColMul)) >> drop_sh;
+            q0 = (b0 & 0xffu) >= drop_thr ? q0 : 0.f;
+            q1 = ((b0 >> 8) & 0xffu) >= drop_thr ? q1 : 0.f;
+            q2 = (b1 & 0xffu) >= drop_thr ? q2 : 0.f;
+            q3 = ((b1 >> 8) & 0xffu) >= drop_thr ? q3 : 0.f;
+          }
           if constexpr (kTF32) {
             pk[c] = __float_as_uint(q0);
             pk[c + 1] = __float_as_uint(q1);
@@ -377,7 +391,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // epilogue: O_t / l -> global, statistics
     mbar_wait(&bars.o_full[t], (nt - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.f / l;
+    const float inv_l = (kDrop ? p.drop.keep_scale : 1.f) / l;
     const bool row_ok = row_g < T;
     OutT* orow = reinterpret_cast<OutT*>(p.o) + ((size_t)bh * T + (row_ok ? row_g : 0)) * D;
 #pragma unroll
@@ -403,15 +417,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
-template <int D, typename OutT, bool kTF32>
-cudaError_t launch_fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* m_out, float* l_out,
-                       int BH, int T, bool causal, cudaStream_t st) {
+template <int D, typename OutT, bool kTF32, bool kDrop>
+cudaError_t launch_fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, float* m_out, float* l_out,
+                            int BH, int T, bool causal, Dropout drop, cudaStream_t st) {
   using Cfg = FwdCfg<D, kTF32>;
   CUtensorMap mq, mk, mv;
   if (make_tmap_3d(&mq, q, Cfg::kElem, D, T, BH, Cfg::kAtom, kBlockM)) return cudaErrorInvalidValue;
   if (make_tmap_3d(&mk, k, Cfg::kElem, D, T, BH, Cfg::kAtom, kBlockN)) return cudaErrorInvalidValue;
   if (make_tmap_3d(&mv, v, Cfg::kElem, D, T, BH, Cfg::kAtom, kBlockN, kTF32 ? 2 : 1)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(fa_fwd_kernel<D, OutT, kTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(fa_fwd_kernel<D, OutT, kTF32, kDrop>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
   FwdParams p;
@@ -424,9 +438,17 @@ cudaError_t launch_fwd(const void* q, const void* k, const void* v, void* o, flo
   p.lse = lse;
   p.m_out = m_out;
   p.l_out = l_out;
+  p.drop = drop;
   dim3 grid((T + 2 * kBlockM - 1) / (2 * kBlockM), BH);
-  fa_fwd_kernel<D, OutT, kTF32><<<grid, kFwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, p);
+  fa_fwd_kernel<D, OutT, kTF32, kDrop><<<grid, kFwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, p);
   return cudaGetLastError();
+}
+
+template <int D, typename OutT, bool kTF32>
+cudaError_t launch_fwd(const void* q, const void* k, const void* v, void* o, float* lse, float* m_out, float* l_out,
+                       int BH, int T, bool causal, Dropout drop, cudaStream_t st) {
+  return drop.thr ? launch_fwd_impl<D, OutT, kTF32, true>(q, k, v, o, lse, m_out, l_out, BH, T, causal, drop, st)
+                  : launch_fwd_impl<D, OutT, kTF32, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, drop, st);
 }
 
 }  // namespace
@@ -435,25 +457,26 @@ bool tc_fwd_supported(int d) { return d == 64 || d == 128; }
 bool tc_fwd_tf32_supported(int d) { return d == 32 || d == 64; }
 
 cudaError_t tc_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, bool o_is_f32,
-                   float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st) {
+                   float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st,
+                   Dropout drop) {
   if (BH > 65535) return cudaErrorInvalidValue;
   if (d == 128) {
-    return o_is_f32 ? launch_fwd<128, float, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st)
-                    : launch_fwd<128, __nv_bfloat16, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
+    return o_is_f32 ? launch_fwd<128, float, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, drop, st)
+                    : launch_fwd<128, __nv_bfloat16, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, drop, st);
   }
   if (d == 64) {
-    return o_is_f32 ? launch_fwd<64, float, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st)
-                    : launch_fwd<64, __nv_bfloat16, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
+    return o_is_f32 ? launch_fwd<64, float, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, drop, st)
+                    : launch_fwd<64, __nv_bfloat16, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, drop, st);
   }
   return cudaErrorInvalidValue;
 }
 
 // fp32 storage in, fp32 out, tf32 tensor-core arithmetic
 cudaError_t tc_fwd_tf32(const float* q, const float* k, const float* v, float* o, float* lse, float* m_out,
-                        float* l_out, int BH, int T, int d, bool causal, cudaStream_t st) {
+                        float* l_out, int BH, int T, int d, bool causal, cudaStream_t st, Dropout drop) {
   if (BH > 65535) return cudaErrorInvalidValue;
-  if (d == 64) return launch_fwd<64, float, true>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
-  if (d == 32) return launch_fwd<32, float, true>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
+  if (d == 64) return launch_fwd<64, float, true>(q, k, v, o, lse, m_out, l_out, BH, T, causal, drop, st);
+  if (d == 32) return launch_fwd<32, float, true>(q, k, v, o, lse, m_out, l_out, BH, T, causal, drop, st);
   return cudaErrorInvalidValue;
 }
 

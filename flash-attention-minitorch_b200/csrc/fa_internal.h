@@ -6,16 +6,20 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "fa_dropout.cuh"
+
 namespace fa {
+
+constexpr Dropout kNoDropout = {0u, 1.0f, 0u, 0u};
 
 // ---- fp32 CUDA-core path (fa_simt.cu) -------------------------------------------------------
 cudaError_t simt_fwd(const float* q, const float* k, const float* v, float* o, float* lse, float* m_out,
-                     float* l_out, int BH, int T, int d, bool causal, cudaStream_t st);
+                     float* l_out, int BH, int T, int d, bool causal, cudaStream_t st, Dropout drop = kNoDropout);
 cudaError_t simt_bwd_prep(const float* o, const float* dO, float* delta, const float* l_in, const float* m_in,
                           float* lse_out, size_t rows, int d, cudaStream_t st);
 cudaError_t simt_bwd(const float* q, const float* k, const float* v, const float* dO, const float* lse,
                      const float* delta, float* dq, float* dk, float* dv, int BH, int T, int d, bool causal,
-                     bool accumulate_dq, cudaStream_t st);
+                     bool accumulate_dq, cudaStream_t st, Dropout drop = kNoDropout);
 
 // ---- tcgen05 path (fa_fwd_sm100.cu / fa_bwd_sm100.cu) ---------------------------------------
 // bf16 Q/K/V laid out (BH, T, d) contiguous.  `o` is bf16 or fp32 depending on o_is_f32.
@@ -23,12 +27,13 @@ cudaError_t simt_bwd(const float* q, const float* k, const float* v, const float
 // FA-1 pair (row max of tau*S, sum exp(tau*S - m)).
 bool tc_fwd_supported(int d);
 cudaError_t tc_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, bool o_is_f32,
-                   float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st);
+                   float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st,
+                   Dropout drop = kNoDropout);
 
 // fp32 storage read directly by TMA, kind::tf32 MMAs, fp32 output; d in {32, 64}
 bool tc_fwd_tf32_supported(int d);
 cudaError_t tc_fwd_tf32(const float* q, const float* k, const float* v, float* o, float* lse, float* m_out,
-                        float* l_out, int BH, int T, int d, bool causal, cudaStream_t st);
+                        float* l_out, int BH, int T, int d, bool causal, cudaStream_t st, Dropout drop = kNoDropout);
 
 bool tc_bwd_supported(int d);
 void tc_bwd_set_trace(long long* dev_buf);  // developer timeline buffer (256 int64), nullptr = off
@@ -36,12 +41,15 @@ size_t tc_bwd_workspace_bytes(int BH, int T, int d);
 // dq/dk/dv are bf16 or fp32 (grads_f32).  workspace: tc_bwd_workspace_bytes() bytes of device memory.
 cudaError_t tc_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* o,
                    const __nv_bfloat16* dO, const float* lse, void* dq, void* dk, void* dv, bool grads_f32,
-                   bool accumulate_dq, void* workspace, int BH, int T, int d, bool causal, cudaStream_t st);
+                   bool accumulate_dq, void* workspace, int BH, int T, int d, bool causal, cudaStream_t st,
+                   Dropout drop = kNoDropout);
 
 // ---- elementwise helpers (fa_util.cu) -------------------------------------------------------
 cudaError_t cvt_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st);
 cudaError_t cvt_bf16_to_f32(const __nv_bfloat16* src, float* dst, size_t n, cudaStream_t st);
 // lse = m + log(l)   (FA-1 convention -> FA-2 convention)
 cudaError_t lse_from_lm(const float* l, const float* m, float* lse, size_t n, cudaStream_t st);
+// keep[h - head_begin][i][j] = 1/0 for heads [head_begin, head_begin + n_heads): the mask every kernel regenerates
+cudaError_t dropout_mask(unsigned char* keep, int head_begin, int n_heads, int T, Dropout drop, cudaStream_t st);
 
 }  // namespace fa

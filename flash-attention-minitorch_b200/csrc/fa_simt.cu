@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "fa_internal.h"
+#include "fa_dropout.cuh"
 
 namespace fa {
 
@@ -44,7 +45,7 @@ template <int DPAD, int NSPLIT>
 __global__ void __launch_bounds__(kRowsPerBlock* NSPLIT)
 simt_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                 float* __restrict__ o, float* __restrict__ lse, float* __restrict__ m_out,
-                float* __restrict__ l_out, int T, int d, int causal, float tau) {
+                float* __restrict__ l_out, int T, int d, int causal, float tau, Dropout drop) {
   constexpr int DC = DPAD / NSPLIT;
   constexpr int NT = kRowsPerBlock * NSPLIT;
   __shared__ float sK[kTile * DPAD];
@@ -67,6 +68,7 @@ simt_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
   float m = -INFINITY, l = 0.f;
   const int last_row = min(T, (int)(blockIdx.x + 1) * kRowsPerBlock) - 1;
   const int kv_end = causal ? min(T, last_row + 1) : T;
+  const uint32_t hkey = drop_head_key(drop.seed_lo, drop.seed_hi, bh);
 
   for (int j0 = 0; j0 < kv_end; j0 += kTile) {
     __syncthreads();
@@ -95,14 +97,15 @@ simt_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
 #pragma unroll
     for (int jj = 0; jj < kTile; ++jj) {
       float p = expf(s[jj] - m_new);
-      l += p;
+      l += p;  // the softmax statistics are those of the undropped scores
+      if (drop.thr && !drop_keep(hkey, row, j0 + jj, drop.thr)) p = 0.f;
 #pragma unroll
       for (int c = 0; c < DC; ++c) acc[c] = fmaf(p, sV[jj * DPAD + c * NSPLIT + h], acc[c]);
     }
     m = m_new;
   }
   if (row_ok) {
-    float inv = 1.f / l;
+    float inv = (drop.thr ? drop.keep_scale : 1.f) / l;
     float* ob = o + (size_t)bh * T * d + (size_t)row * d;
 #pragma unroll
     for (int c = 0; c < DC; ++c) {
@@ -139,7 +142,7 @@ template <int DPAD, int NSPLIT>
 __global__ void __launch_bounds__(kRowsPerBlock* NSPLIT)
 simt_bwd_dq_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                    const float* __restrict__ dO, const float* __restrict__ lse, const float* __restrict__ delta,
-                   float* __restrict__ dq, int T, int d, int causal, float tau, int accumulate) {
+                   float* __restrict__ dq, int T, int d, int causal, float tau, int accumulate, Dropout drop) {
   constexpr int DC = DPAD / NSPLIT;
   constexpr int NT = kRowsPerBlock * NSPLIT;
   __shared__ float sK[kTile * DPAD];
@@ -160,6 +163,7 @@ simt_bwd_dq_kernel(const float* __restrict__ q, const float* __restrict__ k, con
   }
   const float L = row_ok ? lse[(size_t)bh * T + row] : 0.f;
   const float Dl = row_ok ? delta[(size_t)bh * T + row] : 0.f;
+  const uint32_t hkey = drop_head_key(drop.seed_lo, drop.seed_hi, bh);
   const int last_row = min(T, (int)(blockIdx.x + 1) * kRowsPerBlock) - 1;
   const int kv_end = causal ? min(T, last_row + 1) : T;
   for (int j0 = 0; j0 < kv_end; j0 += kTile) {
@@ -180,6 +184,7 @@ simt_bwd_dq_kernel(const float* __restrict__ q, const float* __restrict__ k, con
       int col = j0 + jj;
       bool ok = row_ok && col < T && (!causal || col <= row);
       float p = ok ? expf(sv - L) : 0.f;
+      if (drop.thr) dp = drop_keep(hkey, row, col, drop.thr) ? dp * drop.keep_scale : 0.f;  // dP o Z
       float ds = p * (dp - Dl);
 #pragma unroll
       for (int c = 0; c < DC; ++c) acc[c] = fmaf(ds, sK[jj * DPAD + c * NSPLIT + h], acc[c]);
@@ -201,7 +206,7 @@ template <int DPAD, int NSPLIT>
 __global__ void __launch_bounds__(kRowsPerBlock* NSPLIT)
 simt_bwd_dkv_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                     const float* __restrict__ dO, const float* __restrict__ lse, const float* __restrict__ delta,
-                    float* __restrict__ dk, float* __restrict__ dv, int T, int d, int causal, float tau) {
+                    float* __restrict__ dk, float* __restrict__ dv, int T, int d, int causal, float tau, Dropout drop) {
   constexpr int DC = DPAD / NSPLIT;
   constexpr int NT = kRowsPerBlock * NSPLIT;
   __shared__ float sQ[kTile * DPAD];
@@ -222,6 +227,7 @@ simt_bwd_dkv_kernel(const float* __restrict__ q, const float* __restrict__ k, co
     dkacc[c] = 0.f;
     dvacc[c] = 0.f;
   }
+  const uint32_t hkey = drop_head_key(drop.seed_lo, drop.seed_hi, bh);
   const int first_key = blockIdx.x * kRowsPerBlock;
   const int i_begin = causal ? (first_key / kTile) * kTile : 0;
   for (int i0 = i_begin; i0 < T; i0 += kTile) {
@@ -247,10 +253,16 @@ simt_bwd_dkv_kernel(const float* __restrict__ q, const float* __restrict__ k, co
       int qi = i0 + ii;
       bool ok = row_ok && qi < T && (!causal || row <= qi);
       float p = ok ? expf(sv - sL[ii]) : 0.f;
+      float pz = p;  // P o Z feeds dV; the undropped P multiplies (dP o Z - delta)
+      if (drop.thr) {
+        const float z = drop_keep(hkey, qi, row, drop.thr) ? drop.keep_scale : 0.f;
+        pz = p * z;
+        dp *= z;
+      }
       float ds = p * (dp - sD[ii]);
 #pragma unroll
       for (int c = 0; c < DC; ++c) {
-        dvacc[c] = fmaf(p, sdO[ii * DPAD + c * NSPLIT + h], dvacc[c]);
+        dvacc[c] = fmaf(pz, sdO[ii * DPAD + c * NSPLIT + h], dvacc[c]);
         dkacc[c] = fmaf(ds, sQ[ii * DPAD + c * NSPLIT + h], dkacc[c]);
       }
     }
@@ -269,32 +281,32 @@ simt_bwd_dkv_kernel(const float* __restrict__ q, const float* __restrict__ k, co
 
 template <int DPAD, int NSPLIT>
 cudaError_t fwd_launch(const float* q, const float* k, const float* v, float* o, float* lse, float* m_out,
-                       float* l_out, int BH, int T, int d, bool causal, cudaStream_t st) {
+                       float* l_out, int BH, int T, int d, bool causal, Dropout drop, cudaStream_t st) {
   dim3 grid((T + kRowsPerBlock - 1) / kRowsPerBlock, BH);
   simt_fwd_kernel<DPAD, NSPLIT><<<grid, kRowsPerBlock * NSPLIT, 0, st>>>(q, k, v, o, lse, m_out, l_out, T, d,
-                                                                          causal ? 1 : 0, sqrtf(1.0f / d));
+                                                                          causal ? 1 : 0, sqrtf(1.0f / d), drop);
   return cudaGetLastError();
 }
 template <int DPAD, int NSPLIT>
 cudaError_t bwd_launch(const float* q, const float* k, const float* v, const float* dO, const float* lse,
                        const float* delta, float* dq, float* dk, float* dv, int BH, int T, int d, bool causal,
-                       bool accumulate_dq, cudaStream_t st) {
+                       bool accumulate_dq, Dropout drop, cudaStream_t st) {
   dim3 grid((T + kRowsPerBlock - 1) / kRowsPerBlock, BH);
   float tau = sqrtf(1.0f / d);
   simt_bwd_dq_kernel<DPAD, NSPLIT><<<grid, kRowsPerBlock * NSPLIT, 0, st>>>(q, k, v, dO, lse, delta, dq, T, d,
-                                                                             causal ? 1 : 0, tau, accumulate_dq);
+                                                                             causal ? 1 : 0, tau, accumulate_dq, drop);
   simt_bwd_dkv_kernel<DPAD, NSPLIT><<<grid, kRowsPerBlock * NSPLIT, 0, st>>>(q, k, v, dO, lse, delta, dk, dv, T, d,
-                                                                              causal ? 1 : 0, tau);
+                                                                              causal ? 1 : 0, tau, drop);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t simt_fwd(const float* q, const float* k, const float* v, float* o, float* lse, float* m_out,
-                     float* l_out, int BH, int T, int d, bool causal, cudaStream_t st) {
-  if (d <= 32) return fwd_launch<32, 1>(q, k, v, o, lse, m_out, l_out, BH, T, d, causal, st);
-  if (d <= 64) return fwd_launch<64, 2>(q, k, v, o, lse, m_out, l_out, BH, T, d, causal, st);
-  if (d <= 128) return fwd_launch<128, 4>(q, k, v, o, lse, m_out, l_out, BH, T, d, causal, st);
+                     float* l_out, int BH, int T, int d, bool causal, cudaStream_t st, Dropout drop) {
+  if (d <= 32) return fwd_launch<32, 1>(q, k, v, o, lse, m_out, l_out, BH, T, d, causal, drop, st);
+  if (d <= 64) return fwd_launch<64, 2>(q, k, v, o, lse, m_out, l_out, BH, T, d, causal, drop, st);
+  if (d <= 128) return fwd_launch<128, 4>(q, k, v, o, lse, m_out, l_out, BH, T, d, causal, drop, st);
   return cudaErrorInvalidValue;
 }
 
@@ -308,10 +320,10 @@ cudaError_t simt_bwd_prep(const float* o, const float* dO, float* delta, const f
 
 cudaError_t simt_bwd(const float* q, const float* k, const float* v, const float* dO, const float* lse,
                      const float* delta, float* dq, float* dk, float* dv, int BH, int T, int d, bool causal,
-                     bool accumulate_dq, cudaStream_t st) {
-  if (d <= 32) return bwd_launch<32, 1>(q, k, v, dO, lse, delta, dq, dk, dv, BH, T, d, causal, accumulate_dq, st);
-  if (d <= 64) return bwd_launch<64, 2>(q, k, v, dO, lse, delta, dq, dk, dv, BH, T, d, causal, accumulate_dq, st);
-  if (d <= 128) return bwd_launch<128, 4>(q, k, v, dO, lse, delta, dq, dk, dv, BH, T, d, causal, accumulate_dq, st);
+                     bool accumulate_dq, cudaStream_t st, Dropout drop) {
+  if (d <= 32) return bwd_launch<32, 1>(q, k, v, dO, lse, delta, dq, dk, dv, BH, T, d, causal, accumulate_dq, drop, st);
+  if (d <= 64) return bwd_launch<64, 2>(q, k, v, dO, lse, delta, dq, dk, dv, BH, T, d, causal, accumulate_dq, drop, st);
+  if (d <= 128) return bwd_launch<128, 4>(q, k, v, dO, lse, delta, dq, dk, dv, BH, T, d, causal, accumulate_dq, drop, st);
   return cudaErrorInvalidValue;
 }
 

@@ -46,6 +46,19 @@ __global__ void lse_from_lm_kernel(const float* __restrict__ l, const float* __r
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) lse[i] = m[i] + logf(l[i]);
 }
 
+// keep[bh][i][j] for the whole (T x T) square of every head (causal or not: the mask does not depend on it)
+__global__ void dropout_mask_kernel(unsigned char* __restrict__ keep, int head_begin, int T, Dropout drop) {
+  const uint32_t bh = blockIdx.y;
+  const uint32_t hkey = drop_head_key(drop.seed_lo, drop.seed_hi, head_begin + bh);
+  const size_t n = (size_t)T * T;
+  unsigned char* out = keep + (size_t)bh * n;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+    const uint32_t i = (uint32_t)(idx / T), j = (uint32_t)(idx - (size_t)i * T);
+    out[idx] = drop_keep(hkey, i, j, drop.thr) ? 1 : 0;
+  }
+}
+
 inline unsigned grid_for(size_t work_items, int threads) {
   size_t blocks = (work_items + threads - 1) / threads;
   const size_t cap = 148 * 8;
@@ -66,6 +79,12 @@ cudaError_t cvt_bf16_to_f32(const __nv_bfloat16* src, float* dst, size_t n, cuda
 }
 cudaError_t lse_from_lm(const float* l, const float* m, float* lse, size_t n, cudaStream_t st) {
   lse_from_lm_kernel<<<grid_for(n, 256), 256, 0, st>>>(l, m, lse, n);
+  return cudaGetLastError();
+}
+
+cudaError_t dropout_mask(unsigned char* keep, int head_begin, int n_heads, int T, Dropout drop, cudaStream_t st) {
+  dim3 grid(grid_for((size_t)T * T, 256), n_heads);
+  dropout_mask_kernel<<<grid, 256, 0, st>>>(keep, head_begin, T, drop);
   return cudaGetLastError();
 }
 

@@ -59,6 +59,17 @@ def load_library() -> ctypes.CDLL:
     lib.fa_b200_bwd_workspace_bytes.restype = sz
     lib.fa_b200_bwd.argtypes = [vp, vp, vp, vp, vp, f32p, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, sz, vp]
     lib.fa_b200_bwd.restype = ci
+    u64, f32 = ctypes.c_ulonglong, ctypes.c_float
+    lib.fa_b200_fwd_dropout.argtypes = [vp, vp, vp, vp, f32p, ci, ci, ci, ci, ci, ci, f32, u64, vp]
+    lib.fa_b200_fwd_dropout.restype = ci
+    lib.fa_b200_bwd_dropout.argtypes = [vp, vp, vp, vp, vp, f32p, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, f32, u64, vp, sz, vp]
+    lib.fa_b200_bwd_dropout.restype = ci
+    lib.fa_b200_dropout_mask.argtypes = [vp, ci, ci, ci, f32, u64, vp]
+    lib.fa_b200_dropout_mask.restype = ci
+    lib.fa_b200_dropout_keep_scale.argtypes = [f32]
+    lib.fa_b200_dropout_keep_scale.restype = f32
+    lib.fa_b200_dropout_effective_p.argtypes = [f32]
+    lib.fa_b200_dropout_effective_p.restype = f32
     lib.fa_b200_host_fwd.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
     lib.fa_b200_host_fwd.restype = ci
     lib.fa_b200_host_bwd.argtypes = [vp] * 10 + [ci, ci, ci, ci, ci, vp]

@@ -86,6 +86,29 @@ int fa_b200_bwd(const void* q, const void* k, const void* v, const void* o, cons
                 int accumulate_dq, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Attention dropout fused into the kernels (device-resident API).  The reference applies no dropout on its
+ * flash path; the convention is that of its Dropout module (minitorch/modules_basic.py:77-80): keep ~
+ * Bernoulli(1 - p), kept probabilities scaled by 1/(1 - p), applied to P after the softmax normalisation
+ * (lse is the logsumexp of the undropped scores).  The mask is a pure function of (seed, head, query, key)
+ * regenerated inside the backward -- nothing is stored.  p is quantised to 1/256: p_eff = round(256 p)/256.
+ *   fa_b200_fwd_dropout / fa_b200_bwd_dropout : as fa_b200_fwd / fa_b200_bwd with O = (P o Z) V
+ *   fa_b200_dropout_mask      : keep[n_heads][T][T] (1 = kept) for heads [head_begin, head_begin + n_heads) of the
+ *                               flattened batch*heads axis, exactly as the kernels draw it (debug / oracle)
+ *   fa_b200_dropout_keep_scale: the 1/(1 - p_eff) the kernels apply;  fa_b200_dropout_effective_p: p_eff
+ * ------------------------------------------------------------------------------------------ */
+int fa_b200_fwd_dropout(const void* q, const void* k, const void* v, void* o, float* lse, int dtype, int precision,
+                        int batch_heads, int T, int d, int causal, float p_drop, unsigned long long seed,
+                        void* stream);
+int fa_b200_bwd_dropout(const void* q, const void* k, const void* v, const void* o, const void* d_out, const float* lse,
+                        void* dq, void* dk, void* dv, int dtype, int precision, int batch_heads, int T, int d,
+                        int causal, int accumulate_dq, float p_drop, unsigned long long seed, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int fa_b200_dropout_mask(unsigned char* keep, int head_begin, int n_heads, int T, float p_drop,
+                         unsigned long long seed, void* stream);
+float fa_b200_dropout_keep_scale(float p_drop);
+float fa_b200_dropout_effective_p(float p_drop);
+
+/* ------------------------------------------------------------------------------------------
  * Host-pointer API: the reference ABI with an explicit convention and an error code.
  * All pointers are HOST fp32 buffers (pageable or pinned).  The call stages through a process-global
  * device arena, runs on `stream`, and returns after the outputs have landed in host memory.

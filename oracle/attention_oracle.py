@@ -81,6 +81,64 @@ def attention_backward(q, k, v, d_out, causal: bool, dtype=np.float64):
 
 
 # ----------------------------------------------------------------------------------------------
+# Attention dropout (not on the reference's flash path; convention of minitorch/modules_basic.py:77-80:
+# mask ~ Bernoulli(1 - p), x * mask * 1/(1 - p)), applied to P after the softmax normalisation.
+# dropout_keep_mask restates flash-attention-minitorch_b200/csrc/fa_dropout.cuh bit for bit.
+# ----------------------------------------------------------------------------------------------
+def _mix32(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint32, copy=True)
+    x ^= x >> np.uint32(16)
+    x *= np.uint32(0x7FEB352D)
+    x ^= x >> np.uint32(15)
+    x *= np.uint32(0x846CA68B)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def dropout_threshold(p: float) -> int:
+    """Byte threshold the kernels use: keep iff byte >= thr; p_eff = thr / 256."""
+    return 0 if not p > 0 else min(255, int(np.float32(p) * np.float32(256.0) + np.float32(0.5)))
+
+
+def dropout_keep_scale(p: float) -> float:
+    return float(np.float32(256.0) / (np.float32(256.0) - np.float32(dropout_threshold(p))))
+
+
+def dropout_keep_mask(seed: int, heads, T: int, p: float) -> np.ndarray:
+    """keep[len(heads), T, T] (bool) for the given head indices (b*H + h)."""
+    heads = np.atleast_1d(np.asarray(heads, dtype=np.uint32))
+    with np.errstate(over="ignore"):
+        lo, hi = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+        hkey = _mix32(lo ^ _mix32(hi + np.uint32(0x9E3779B9) * (heads + np.uint32(1))))
+        i = np.arange(T, dtype=np.uint32)
+        rterm = (i >> np.uint32(1)) * np.uint32(0x9E3779B1)
+        cterm = (i >> np.uint32(1)) * np.uint32(0x85EBCA77)
+        bits = _mix32(hkey[:, None, None] ^ rterm[None, :, None] ^ cterm[None, None, :])
+        sh = np.uint32(8) * ((i & np.uint32(1))[:, None] * np.uint32(2) + (i & np.uint32(1))[None, :])
+        byte = (bits >> sh[None]) & np.uint32(0xFF)
+    return byte >= np.uint32(dropout_threshold(p))
+
+
+def attention_dropout_backward(q, k, v, d_out, causal: bool, keep: np.ndarray, keep_scale: float, dtype=np.float64):
+    """Vanilla attention with dropout Z = keep * keep_scale on P.  Returns (dQ, dK, dV, O, L); L is the logsumexp
+    of the undropped scores.  O = (P o Z) V, dV = (P o Z)^T dO, dP = (dO V^T) o Z, dS = P o (dP - rowsum(dO o O))."""
+    q = np.asarray(q, dtype=dtype)
+    k = np.asarray(k, dtype=dtype)
+    v = np.asarray(v, dtype=dtype)
+    g = np.asarray(d_out, dtype=dtype)
+    tau = dtype(1.0 / np.sqrt(q.shape[-1]))
+    _, p, m, l, L = attention_forward(q, k, v, causal, dtype)
+    z = keep.astype(dtype) * dtype(keep_scale)
+    pz = p * z
+    o = pz @ v
+    dv = pz.transpose(0, 2, 1) @ g
+    dp = (g @ v.transpose(0, 2, 1)) * z
+    delta = (g * o).sum(axis=-1)
+    ds = p * (dp - delta[..., None])
+    return tau * (ds @ k), tau * (ds.transpose(0, 2, 1) @ q), dv, o, L
+
+
+# ----------------------------------------------------------------------------------------------
 # Tiled restatements of the reference's flash kernels (slow: pure numpy over tiles; small cases only)
 # ----------------------------------------------------------------------------------------------
 def _scores_tile(Qi, Kj, i0, j0, tau, causal, dtype):

@@ -29,6 +29,8 @@ def lib() -> ctypes.CDLL:
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         _LIB.oracle_attention.restype = ctypes.c_int
+        _LIB.oracle_attention_dropout.argtypes = list(_LIB.oracle_attention.argtypes) + [ctypes.c_void_p, ctypes.c_float]
+        _LIB.oracle_attention_dropout.restype = ctypes.c_int
         _LIB.oracle_num_threads.restype = ctypes.c_int
         _LIB.oracle_set_num_threads.argtypes = [ctypes.c_int]
         _LIB.oracle_set_num_threads.restype = None
@@ -49,8 +51,9 @@ def num_threads() -> int:
     return int(lib().oracle_num_threads())
 
 
-def attention(q, k, v, d_out=None, causal=False):
-    """fp32 vanilla attention on all host cores.  Returns dict(o, m, l, lse[, dq, dk, dv])."""
+def attention(q, k, v, d_out=None, causal=False, keep=None, keep_scale=1.0):
+    """fp32 vanilla attention on all host cores.  Returns dict(o, m, l, lse[, dq, dk, dv]).
+    keep (uint8 [BH,T,T], 1 = kept) + keep_scale apply dropout Z = keep * keep_scale to P."""
     q = np.ascontiguousarray(q, dtype=np.float32)
     k = np.ascontiguousarray(k, dtype=np.float32)
     v = np.ascontiguousarray(v, dtype=np.float32)
@@ -62,8 +65,15 @@ def attention(q, k, v, d_out=None, causal=False):
         g = np.ascontiguousarray(d_out, dtype=np.float32)
         out.update(dq=np.empty_like(q), dk=np.empty_like(q), dv=np.empty_like(q))
         gp, dqp, dkp, dvp = (a.ctypes.data_as(ctypes.c_void_p) for a in (g, out["dq"], out["dk"], out["dv"]))
-    rc = lib().oracle_attention(q, k, v, gp, out["o"], out["m"], out["l"], out["lse"], dqp, dkp, dvp,
-                                BH, T, d, 1 if causal else 0)
+    if keep is not None:
+        keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        assert keep.shape == (BH, T, T)
+        rc = lib().oracle_attention_dropout(q, k, v, gp, out["o"], out["m"], out["l"], out["lse"], dqp, dkp, dvp,
+                                            BH, T, d, 1 if causal else 0, keep.ctypes.data_as(ctypes.c_void_p),
+                                            float(keep_scale))
+    else:
+        rc = lib().oracle_attention(q, k, v, gp, out["o"], out["m"], out["l"], out["lse"], dqp, dkp, dvp,
+                                    BH, T, d, 1 if causal else 0)
     if rc != 0:
         raise MemoryError("oracle_attention: allocation failed")
     return out

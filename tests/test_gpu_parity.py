@@ -291,6 +291,114 @@ def test_cfg2_shape_fp32_forward_sampled(cuda_device):
 
 
 # ----------------------------------------------------------------------------------------------
+# 3b. fused attention dropout (BASELINE.json configs[3]): the kernels' mask is exported and fed to the oracle
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,p,seed,head_begin", [(1, 0.1, 1, 0), (77, 0.1, 4001, 0), (256, 0.5, 2**40 + 17, 3), (513, 0.03, 9, 500)])
+def test_dropout_mask_matches_oracle_restatement_bit_for_bit(cuda_device, T, p, seed, head_begin):
+    keep = device.dropout_mask(3, T, p, seed, device=cuda_device, head_begin=head_begin).cpu().numpy().astype(bool)
+    ref = ao.dropout_keep_mask(seed, np.arange(head_begin, head_begin + 3), T, p)
+    assert np.array_equal(keep, ref)
+    assert abs(device.dropout_keep_scale(p) - ao.dropout_keep_scale(p)) < 1e-7
+    if T >= 256:  # Bernoulli(1 - p_eff) within 5 sigma
+        p_eff = ao.dropout_threshold(p) / 256.0
+        assert abs(keep.mean() - (1 - p_eff)) <= 5 * np.sqrt(p_eff * (1 - p_eff) / keep.size)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("BH,T,d", [(2, 77, 32), (2, 130, 64), (1, 200, 100)])
+def test_dropout_fp32_path_vs_oracle(cuda_device, BH, T, d, causal):
+    """Exact-fp32 kernels with fused dropout against the oracle evaluated with the exported mask."""
+    p, seed = 0.1, 4001
+    q, k, v, g = ao.make_inputs(BH, T, d, seed=d + T)
+    keep = device.dropout_mask(BH, T, p, seed, device=cuda_device).cpu().numpy()
+    dq_r, dk_r, dv_r, o_r, L_r = ao.attention_dropout_backward(q, k, v, g, causal, keep, ao.dropout_keep_scale(p))
+    tq, tk, tv, tg = (_to_dev(x, cuda_device, bf16=False) for x in (q, k, v, g))
+    o, lse = device.flash_attn_fwd(tq, tk, tv, causal, precision=_lib.FA_PREC_FP32_SIMT, p_drop=p, seed=seed)
+    assert np.abs(o.cpu().numpy() - o_r).max() <= 1e-5
+    assert np.abs(lse.cpu().numpy() - L_r).max() <= 1e-5  # statistics of the undropped scores
+    dq, dk, dv = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, causal, precision=_lib.FA_PREC_FP32_SIMT, p_drop=p, seed=seed)
+    for got, ref in ((dq, dq_r), (dk, dk_r), (dv, dv_r)):
+        assert np.abs(got.cpu().numpy() - ref).max() <= 1e-4
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("BH,T,d,p", [(3, 128, 128, 0.1), (2, 300, 64, 0.1), (2, 1000, 128, 0.25), (4, 2, 64, 0.1), (2, 1024, 128, 0.1)])
+def test_dropout_bf16_tensor_core_path_vs_oracle(cuda_device, BH, T, d, p, causal):
+    """tcgen05 forward (thread = query row) and transposed backward (thread = key row) regenerate the same mask."""
+    seed = 4001 + T
+    q, k, v, g = _bf16_problem(BH, T, d, seed=200 + T + d)
+    keep = device.dropout_mask(BH, T, p, seed, device=cuda_device).cpu().numpy()
+    dq_r, dk_r, dv_r, o_r, L_r = ao.attention_dropout_backward(q, k, v, g, causal, keep, ao.dropout_keep_scale(p))
+    tq, tk, tv, tg = (_to_dev(x, cuda_device) for x in (q, k, v, g))
+    o, lse = device.flash_attn_fwd(tq, tk, tv, causal, p_drop=p, seed=seed)
+    assert rel_inf(o.float().cpu().numpy(), o_r) <= BF16_REL
+    assert np.abs(lse.cpu().numpy() - L_r).max() <= 2e-3
+    dq, dk, dv = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, causal, p_drop=p, seed=seed)
+    for got, ref, name in ((dq, dq_r, "dq"), (dk, dk_r, "dk"), (dv, dv_r, "dv")):
+        assert rel_inf(got.float().cpu().numpy(), ref) <= BF16_REL, name
+    # a different seed draws a different mask; p_drop = 0 is the plain kernel
+    o2, _ = device.flash_attn_fwd(tq, tk, tv, causal, p_drop=p, seed=seed + 1)
+    if T > 1:
+        assert not np.array_equal(o2.float().cpu().numpy(), o.float().cpu().numpy())
+
+
+def test_dropout_tf32_forward_vs_oracle(cuda_device):
+    p, seed, BH, T, d = 0.1, 77, 2, 333, 64
+    q, k, v, g = ao.make_inputs(BH, T, d, seed=12)
+    keep = device.dropout_mask(BH, T, p, seed, device=cuda_device).cpu().numpy()
+    _, _, _, o_r, L_r = ao.attention_dropout_backward(q, k, v, g, True, keep, ao.dropout_keep_scale(p))
+    tq, tk, tv = (_to_dev(x, cuda_device, bf16=False) for x in (q, k, v))
+    o, lse = device.flash_attn_fwd(tq, tk, tv, True, precision=_lib.FA_PREC_TF32_TC, p_drop=p, seed=seed)
+    assert np.abs(o.cpu().numpy() - o_r).max() <= FP32_ATOL and np.abs(lse.cpu().numpy() - L_r).max() <= FP32_ATOL
+
+
+@pytest.fixture(scope="module")
+def cfg4(cuda_device):
+    """configs[3]: B=4 H=32 T=16384 d=128 bf16 causal, dropout 0.1 (32 of the 128 heads, to bound test time)."""
+    import torch
+    torch.manual_seed(4001)
+    BH, T, d = 32, 16384, 128
+    mk = lambda: (torch.rand(BH, T, d, device=cuda_device) * 2 - 1).to(torch.bfloat16)  # noqa: E731
+    return dict(BH=BH, T=T, d=d, q=mk(), k=mk(), v=mk(), g=mk(), p=0.1, seed=4001)
+
+
+def test_cfg4_long_context_dropout_properties(cuda_device, cfg4):
+    """Size-independent properties at T = 16384: determinism, unbiasedness (V = 1 gives E[O] = 1 with the variance
+    of a Bernoulli thinning), backward linear in dO, and sum_j dV_j = sum_i Z-weighted dO."""
+    import torch
+    q, k, v, g, p, seed = (cfg4[x] for x in ("q", "k", "v", "g", "p", "seed"))
+    o1, l1 = device.flash_attn_fwd(q, k, v, True, p_drop=p, seed=seed)
+    o2, l2 = device.flash_attn_fwd(q, k, v, True, p_drop=p, seed=seed)
+    assert torch.equal(o1, o2) and torch.equal(l1, l2)
+    o0, l0 = device.flash_attn_fwd(q, k, v, True)
+    assert float((l1 - l0).abs().max()) == 0.0  # the statistics ignore dropout
+    ones, _ = device.flash_attn_fwd(q, k, torch.ones_like(v), True, p_drop=p, seed=seed)
+    late = ones[:, 4096:, 0].float()  # rows with >= 4096 keys: O = sum_j P_ij Z_ij, mean 1
+    assert abs(float(late.mean()) - 1.0) <= 2e-3
+    dq, dk, dv = device.flash_attn_bwd(q, k, v, o1, g, l1, True, p_drop=p, seed=seed)
+    dq2, dk2, dv2 = device.flash_attn_bwd(q, k, v, o1, (g.float() * 2).to(torch.bfloat16), l1, True, p_drop=p, seed=seed)
+    for a, b in ((dq2, dq), (dk2, dk), (dv2, dv)):
+        # doubling dO doubles delta too (delta = rowsum(dO o O)): the whole backward is linear in dO
+        assert float((a.float() - 2 * b.float()).abs().max() / b.float().abs().max()) <= BF16_REL
+
+
+def test_cfg4_sampled_head_vs_c_oracle_with_exported_mask(cuda_device, cfg4):
+    """One (b, h) slice of the long-context problem against the CPU oracle fed with the mask the kernels drew."""
+    q, k, v, g, p, seed, T = (cfg4[x] for x in ("q", "k", "v", "g", "p", "seed", "T"))
+    o, lse = device.flash_attn_fwd(q, k, v, True, p_drop=p, seed=seed)
+    dq, dk, dv = device.flash_attn_bwd(q, k, v, o, g, lse, True, p_drop=p, seed=seed)
+    h = 19
+    keep = device.dropout_mask(1, T, p, seed, device=cuda_device, head_begin=h).cpu().numpy()
+    f = lambda t: t[h:h + 1].float().cpu().numpy()  # noqa: E731
+    c_oracle.use_all_cores()
+    r = c_oracle.attention(f(q), f(k), f(v), f(g), causal=True, keep=keep, keep_scale=ao.dropout_keep_scale(p))
+    assert rel_inf(f(o), r["o"].astype(np.float64)) <= BF16_REL
+    assert np.abs(f(lse) - r["lse"]).max() <= 5e-3
+    for got, key in ((dq, "dq"), (dk, "dk"), (dv, "dv")):
+        assert rel_inf(f(got), r[key].astype(np.float64)) <= BF16_REL, key
+
+
+# ----------------------------------------------------------------------------------------------
 # 4. error behaviour and launch accounting
 # ----------------------------------------------------------------------------------------------
 def test_errors_are_reported_not_swallowed(cuda_device):

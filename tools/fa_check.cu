@@ -3,7 +3,8 @@
 //   fa_check simt            CUDA-core kernels vs an in-file CPU fp64 attention, small shapes
 //   fa_check fwd             tcgen05 forward (bf16) vs the CUDA-core fp32 kernels on the same bf16-rounded inputs
 //   fa_check bwd             tcgen05 backward (bf16) vs the CUDA-core fp32 backward
-//   fa_check time [BH T d causal iters]   CUDA-event timing of forward (+ backward when available)
+//   fa_check time [BH T d causal iters bwd p_drop]   CUDA-event timing of forward (+ backward)
+//   fa_check drop            fused dropout: tcgen05 forward/backward vs the CUDA-core kernels (same mask)
 //   fa_check tf32            tcgen05 kind::tf32 forward (fp32 storage) vs the CUDA-core fp32 forward, max-abs 1e-3
 //   fa_check time32 [BH T d causal iters] timing of the tf32 forward (BASELINE.json configs[1] by default)
 //
@@ -205,7 +206,8 @@ static std::vector<float> d2h_f32(const float* p, size_t n) {
 }
 
 // tcgen05 (bf16) vs CUDA-core fp32 on identical bf16-rounded inputs
-static int check_tc(bool do_bwd, int BH, int T, int d, int causal, float scale) {
+static const unsigned long long kSeed = 0x1234567887654321ull;
+static int check_tc(bool do_bwd, int BH, int T, int d, int causal, float scale, float p_drop = 0.f) {
   Problem pr;
   pr.init(BH, T, d, causal, scale);
   const size_t n = pr.n, rows = pr.rows;
@@ -226,8 +228,14 @@ static int check_tc(bool do_bwd, int BH, int T, int d, int causal, float scale) 
   CK(cudaMemcpy(bv, pr.vb.data(), n * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(bg, pr.gb.data(), n * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(bo, 0xff, n * 2));
-  FA(fa_b200_fwd(fq, fk, fv, fo, fl, fm, fs, FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, nullptr));
-  FA(fa_b200_fwd(bq, bk, bv, bo, bl, bm, bs, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, nullptr));
+  if (p_drop > 0.f) {
+    CK(cudaMemset(fm, 0, rows * 4)); CK(cudaMemset(fs, 0, rows * 4)); CK(cudaMemset(bm, 0, rows * 4)); CK(cudaMemset(bs, 0, rows * 4));
+    FA(fa_b200_fwd_dropout(fq, fk, fv, fo, fl, FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, p_drop, kSeed, nullptr));
+    FA(fa_b200_fwd_dropout(bq, bk, bv, bo, bl, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, p_drop, kSeed, nullptr));
+  } else {
+    FA(fa_b200_fwd(fq, fk, fv, fo, fl, fm, fs, FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, nullptr));
+    FA(fa_b200_fwd(bq, bk, bv, bo, bl, bm, bs, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, nullptr));
+  }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     printf("tc fwd BH=%d T=%d d=%d causal=%d: CUDA ERROR %s\n", BH, T, d, causal, cudaGetErrorString(e));
@@ -246,16 +254,21 @@ static int check_tc(bool do_bwd, int BH, int T, int d, int causal, float scale) 
     err_stats(gs, rs, sa, sr);
   }
   bool ok = er < 2e-2 && la < 2e-2 && ma < 2e-2 && sr < 2e-2;
-  printf("tc fwd BH=%d T=%5d d=%3d causal=%d scale=%.0f  O rel %.2e (abs %.2e)  LSE abs %.2e  m abs %.2e  l rel %.2e  %s\n",
-         BH, T, d, causal, scale, er, ea, la, ma, sr, ok ? "OK" : "FAIL");
+  printf("tc fwd BH=%d T=%5d d=%3d causal=%d scale=%.0f p_drop=%.2f  O rel %.2e (abs %.2e)  LSE abs %.2e  m abs %.2e  l rel %.2e  %s\n",
+         BH, T, d, causal, scale, p_drop, er, ea, la, ma, sr, ok ? "OK" : "FAIL");
   int bad = !ok;
   if (do_bwd) {
     size_t wf = fa_b200_bwd_workspace_bytes(FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d);
     size_t wb = fa_b200_bwd_workspace_bytes(FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d);
     char* wsf = dev.alloc<char>(wf);
     char* wsb = dev.alloc<char>(wb);
-    FA(fa_b200_bwd(fq, fk, fv, fo, fg, fl, fgq, fgk, fgv, FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, 0, wsf, wf, nullptr));
-    FA(fa_b200_bwd(bq, bk, bv, bo, bg, bl, bgq, bgk, bgv, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, wsb, wb, nullptr));
+    if (p_drop > 0.f) {
+      FA(fa_b200_bwd_dropout(fq, fk, fv, fo, fg, fl, fgq, fgk, fgv, FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, 0, p_drop, kSeed, wsf, wf, nullptr));
+      FA(fa_b200_bwd_dropout(bq, bk, bv, bo, bg, bl, bgq, bgk, bgv, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, p_drop, kSeed, wsb, wb, nullptr));
+    } else {
+      FA(fa_b200_bwd(fq, fk, fv, fo, fg, fl, fgq, fgk, fgv, FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, 0, wsf, wf, nullptr));
+      FA(fa_b200_bwd(bq, bk, bv, bo, bg, bl, bgq, bgk, bgv, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, wsb, wb, nullptr));
+    }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
       printf("tc bwd BH=%d T=%d d=%d causal=%d: CUDA ERROR %s\n", BH, T, d, causal, cudaGetErrorString(e));
@@ -346,7 +359,7 @@ static int time_tf32(int BH, int T, int d, int causal, int iters) {
   return 0;
 }
 
-static int time_tc(int BH, int T, int d, int causal, int iters, bool do_bwd) {
+static int time_tc(int BH, int T, int d, int causal, int iters, bool do_bwd, float p_drop = 0.f) {
   const size_t n = (size_t)BH * T * d, rows = (size_t)BH * T;
   Dev dev;
   __nv_bfloat16* t[9];
@@ -365,28 +378,28 @@ static int time_tc(int BH, int T, int d, int causal, int iters, bool do_bwd) {
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   const double ffwd = 4.0 * BH * (double)T * T * d * (causal ? 0.5 : 1.0);
-  for (int i = 0; i < 3; ++i) FA(fa_b200_fwd(t[0], t[1], t[2], t[3], lse, nullptr, nullptr, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, nullptr));
+  for (int i = 0; i < 3; ++i) FA(fa_b200_fwd_dropout(t[0], t[1], t[2], t[3], lse, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, p_drop, kSeed, nullptr));
   CK(cudaDeviceSynchronize());
   cudaEventRecord(e0);
-  for (int i = 0; i < iters; ++i) FA(fa_b200_fwd(t[0], t[1], t[2], t[3], lse, nullptr, nullptr, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, nullptr));
+  for (int i = 0; i < iters; ++i) FA(fa_b200_fwd_dropout(t[0], t[1], t[2], t[3], lse, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, p_drop, kSeed, nullptr));
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms;
   cudaEventElapsedTime(&ms, e0, e1);
   ms /= iters;
-  printf("time fwd BH=%d T=%d d=%d causal=%d: %.3f ms  %.1f TFLOP/s\n", BH, T, d, causal, ms, ffwd / ms * 1e-9);
+  printf("time fwd BH=%d T=%d d=%d causal=%d p_drop=%.2f: %.3f ms  %.1f TFLOP/s\n", BH, T, d, causal, p_drop, ms, ffwd / ms * 1e-9);
   if (do_bwd) {
     for (int i = 0; i < 2; ++i)
-      FA(fa_b200_bwd(t[0], t[1], t[2], t[3], t[4], lse, t[5], t[6], t[7], FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, ws, wb, nullptr));
+      FA(fa_b200_bwd_dropout(t[0], t[1], t[2], t[3], t[4], lse, t[5], t[6], t[7], FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, p_drop, kSeed, ws, wb, nullptr));
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
     for (int i = 0; i < iters; ++i)
-      FA(fa_b200_bwd(t[0], t[1], t[2], t[3], t[4], lse, t[5], t[6], t[7], FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, ws, wb, nullptr));
+      FA(fa_b200_bwd_dropout(t[0], t[1], t[2], t[3], t[4], lse, t[5], t[6], t[7], FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, p_drop, kSeed, ws, wb, nullptr));
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= iters;
-    printf("time bwd BH=%d T=%d d=%d causal=%d: %.3f ms  %.1f TFLOP/s\n", BH, T, d, causal, ms, 2.5 * ffwd / ms * 1e-9);
+    printf("time bwd BH=%d T=%d d=%d causal=%d p_drop=%.2f: %.3f ms  %.1f TFLOP/s\n", BH, T, d, causal, p_drop, ms, 2.5 * ffwd / ms * 1e-9);
   }
   return 0;
 }
@@ -454,6 +467,12 @@ int main(int argc, char** argv) {
       bad += check_tc(b, 2, 1024, 128, 1, 6.f);
       bad += check_tc(b, 2, 1024, 64, 0, 8.f);
     }
+  } else if (mode == "drop") {
+    // fused dropout: tcgen05 (bf16) vs CUDA-core fp32, same mask by construction
+    for (int d : {128, 64})
+      for (int causal : {0, 1})
+        for (int T : {128, 384, 1000, 2048 + 77}) bad += check_tc(true, 3, T, d, causal, 1.f, 0.1f);
+    bad += check_tc(true, 2, 512, 128, 1, 1.f, 0.5f);
   } else if (mode == "tf32") {
     if (argc >= 6) {
       bad = check_tf32(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argc > 6 ? atof(argv[6]) : 1.f);
@@ -475,7 +494,7 @@ int main(int argc, char** argv) {
     int BH = argc > 2 ? atoi(argv[2]) : 512, T = argc > 3 ? atoi(argv[3]) : 4096, d = argc > 4 ? atoi(argv[4]) : 128;
     int causal = argc > 5 ? atoi(argv[5]) : 1, iters = argc > 6 ? atoi(argv[6]) : 10;
     bool b = argc > 7 ? atoi(argv[7]) != 0 : false;
-    return time_tc(BH, T, d, causal, iters, b);
+    return time_tc(BH, T, d, causal, iters, b, argc > 8 ? atof(argv[8]) : 0.f);
   }
   printf("fa_check %s: %d failing cases\n", mode.c_str(), bad);
   return bad ? 1 : 0;
