@@ -22,6 +22,7 @@
 // d = 128 (dP(i+1) is only issued after dQ(i) has been drained) and a separate region when d = 64.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "fa_internal.h"
 #include "fa_ptx.cuh"
@@ -42,6 +43,8 @@ struct BwdParams {
   const float* delta_pad;  // [BH][Tpad]  rowsum(dO o O); 0 on padding rows
   void* dk;
   void* dv;
+  float* dq_acc;  // fp32 dQ accumulator [BH][T][D] (workspace, or the caller's fp32 q_grad)
+  int dq_red;     // 1: drain dQ with red.global.add.v2.f32 from registers; 0: smem staging + TMA reduce-add
   Dropout drop;  // used by the kDrop instantiations only
 };
 
@@ -408,6 +411,39 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const uint32_t tDQ = tmem + Cfg::kColDQ + (uint32_t(w * 32) << 16);
     const bool leader = (warp == 8 && lane == 0);
     uint32_t chunk_no = 0;
+    if (p.dq_red) {
+      // Fragment-layout drain: tcgen05.ld.16x256b hands each quad of lanes 32 contiguous bytes of one dQ row, so a
+      // warp-wide red.global.add.v2.f32 touches 8 complete 32-byte sectors -- no shared-memory staging at all.
+      float* gq = p.dq_acc + (size_t)bh * T * D + 2 * (lane & 3);
+      for (int il = 0; il < n; ++il) {
+        const int i = i0 + il;
+        mbar_wait(&bars.dq_full, il & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t rr[D / 32][16];
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) tmem_ld_16x256b_x4(tDQ + (uint32_t(h * 16) << 16) + c * 32, rr[c]);
+          tmem_wait_ld();
+          if (h == 1) {  // all of dQ(i) has left TMEM
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.dq_drained);
+          }
+          const int row0 = i * kTile + w * 32 + h * 16 + (lane >> 2), row1 = row0 + 8;
+          float* g0 = gq + (size_t)row0 * D;
+          float* g1 = gq + (size_t)row1 * D;
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c)
+#pragma unroll
+            for (int nn = 0; nn < 4; ++nn) {
+              const int col = c * 32 + nn * 8;
+              if (row0 < T) red_add_f32x2(g0 + col, __uint_as_float(rr[c][4 * nn]), __uint_as_float(rr[c][4 * nn + 1]));
+              if (row1 < T) red_add_f32x2(g1 + col, __uint_as_float(rr[c][4 * nn + 2]), __uint_as_float(rr[c][4 * nn + 3]));
+            }
+        }
+      }
+    } else
     for (int il = 0; il < n; ++il) {
       const int i = i0 + il;
       mbar_wait(&bars.dq_full, il & 1);
@@ -445,47 +481,48 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   if (warp == 13) tmem_dealloc(tmem, 512);
 }
 
-// delta = rowsum(dO o O), lse -> log2 domain, both padded to a multiple of 128 rows per head
+// delta = rowsum(dO o O), lse -> log2 domain, both padded to a multiple of 128 rows per head; the same pass
+// zero-fills the fp32 dQ accumulator (one kernel instead of a 1 GB memset plus a second launch).
+// D / 8 lanes own one row (16-byte loads), so a warp covers 256 / D rows... 32 / (D / 8) rows per pass.
 template <int D>
-__global__ void fa_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO,
-                                   const float* __restrict__ lse, float* __restrict__ lse_pad,
-                                   float* __restrict__ delta_pad, int T, int Tpad, size_t total_rows_pad) {
-  const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(256)
+fa_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO,
+                   const float* __restrict__ lse, float* __restrict__ lse_pad, float* __restrict__ delta_pad,
+                   float* __restrict__ dq_zero, int T, int Tpad, size_t total_rows_pad) {
+  constexpr int kLanesPerRow = D / 8;            // 16 (d = 128) or 8 (d = 64)
+  constexpr int kRowsPerWarp = 32 / kLanesPerRow;
   const int lane = threadIdx.x & 31;
-  if (row >= total_rows_pad) return;
-  const size_t bh = row / Tpad;
-  const int t = (int)(row - bh * Tpad);
-  if (t >= T) {
-    if (lane == 0) {
-      lse_pad[row] = INFINITY;
-      delta_pad[row] = 0.f;
-    }
-    return;
-  }
-  const size_t base = (bh * T + t) * D;
-  float acc = 0.f;
-  if constexpr (D == 128) {
-    const uint2 a = *reinterpret_cast<const uint2*>(o + base + lane * 4);
-    const uint2 b = *reinterpret_cast<const uint2*>(dO + base + lane * 4);
-    const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
-    const __nv_bfloat162* bh2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+  const int sub = lane / kLanesPerRow, li = lane % kLanesPerRow;
+  const size_t warp_global = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t row = warp_global * kRowsPerWarp + sub; row < total_rows_pad; row += nwarps * kRowsPerWarp) {
+    const size_t bh = row / Tpad;
+    const int t = (int)(row - bh * Tpad);
+    float acc = 0.f;
+    if (t < T) {
+      const size_t base = (bh * T + t) * D + li * 8;
+      const uint4 a = *reinterpret_cast<const uint4*>(o + base);
+      const uint4 b = *reinterpret_cast<const uint4*>(dO + base);
+      const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+      const __nv_bfloat162* bh2 = reinterpret_cast<const __nv_bfloat162*>(&b);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float2 x = __bfloat1622float2(ah[i]), y = __bfloat1622float2(bh2[i]);
-      acc = fmaf(x.x, y.x, acc);
-      acc = fmaf(x.y, y.y, acc);
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = __bfloat1622float2(ah[i]), y = __bfloat1622float2(bh2[i]);
+        acc = fmaf(x.x, y.x, acc);
+        acc = fmaf(x.y, y.y, acc);
+      }
+      if (dq_zero) {
+        float4* z = reinterpret_cast<float4*>(dq_zero + base);
+        z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-  } else {
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + base + lane * 2);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(dO + base + lane * 2);
-    const float2 x = __bfloat1622float2(a), y = __bfloat1622float2(b);
-    acc = fmaf(x.x, y.x, fmaf(x.y, y.y, 0.f));
-  }
 #pragma unroll
-  for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (lane == 0) {
-    delta_pad[row] = acc;
-    lse_pad[row] = lse[bh * T + t] * 1.4426950408889634f;
+    for (int off = kLanesPerRow / 2; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (li == 0) {
+      delta_pad[row] = t < T ? acc : 0.f;
+      lse_pad[row] = t < T ? lse[bh * T + t] * 1.4426950408889634f : INFINITY;
+    }
   }
 }
 
@@ -524,15 +561,14 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   ws += align256((size_t)BH * Tpad * 4);
   float* dq_acc = kF32 ? static_cast<float*>(dq) : reinterpret_cast<float*>(ws);
   cudaError_t e;
-  if (!kF32 || !accumulate_dq) {
-    e = cudaMemsetAsync(dq_acc, 0, n * 4, st);
-    if (e != cudaSuccess) return e;
-  }
   {
     const size_t rows = (size_t)BH * Tpad;
-    const int warps = 8;
-    fa_bwd_prep_kernel<D><<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, st>>>(o, dO, lse, lse_pad, delta_pad, T,
-                                                                                          (int)Tpad, rows);
+    const bool zero = !kF32 || !accumulate_dq;  // fp32 gradients with accumulate: reduce straight into the caller's q_grad
+    constexpr int kRowsPerBlock = 8 * (32 / (D / 8));
+    size_t blocks = (rows + kRowsPerBlock - 1) / kRowsPerBlock;
+    if (blocks > 148 * 32) blocks = 148 * 32;  // grid-stride beyond 32 blocks per SM
+    fa_bwd_prep_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(o, dO, lse, lse_pad, delta_pad, zero ? dq_acc : nullptr, T,
+                                                          (int)Tpad, rows);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -556,6 +592,17 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   p.delta_pad = delta_pad;
   p.dk = dk;
   p.dv = dv;
+  p.dq_acc = dq_acc;
+  {
+    static const int mode = [] {
+      // developer switch.  Default "tma": smem staging + cp.reduce.async.bulk (7.30 ms at config 3).  "red": fragment-
+      // layout tcgen05.ld + red.global.add.v2.f32 straight from registers -- no staging traffic, sector-complete, but
+      // measured slower (8.81 ms): 32-byte L2 reductions cost more than the TMA engine's line-sized ones.
+      const char* e = getenv("FA_B200_BWD_DQ");
+      return (e && e[0] == 'r') ? 1 : 0;
+    }();
+    p.dq_red = mode;
+  }
   p.drop = drop;
   dim3 grid((unsigned)(Tpad / kTile), BH);
   if (drop.thr) fa_bwd_kernel<D, OutT, true><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);

@@ -75,6 +75,58 @@ T* arena_take(size_t count) {
   return reinterpret_cast<T*>(static_cast<char*>(g_arena.base) + off);
 }
 
+// ---- copy/compute pipeline of the host-pointer API -------------------------------------------
+constexpr int kPipeBufs = 3;
+struct HostPipe {
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[kPipeBufs] = {}, ev_done[kPipeBufs] = {}, ev_free[kPipeBufs] = {};
+  int device = -1;
+  void destroy() {
+    if (device < 0) return;
+    for (int i = 0; i < kPipeBufs; ++i) {
+      if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+      if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+      if (ev_free[i]) cudaEventDestroy(ev_free[i]);
+      ev_in[i] = ev_done[i] = ev_free[i] = nullptr;
+    }
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
+    s_in = s_out = nullptr;
+    device = -1;
+  }
+  int ensure() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(FA_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    if (device == dev) return FA_OK;
+    destroy();
+    if ((e = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking)) != cudaSuccess)
+      return fail(FA_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    for (int i = 0; i < kPipeBufs; ++i)
+      if ((e = cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming)) != cudaSuccess)
+        return fail(FA_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+    device = dev;
+    return FA_OK;
+  }
+};
+HostPipe g_pipe;
+
+// heads per pipeline chunk: ~64 MB of fp32 per tensor (a few ms of PCIe), whole heads only
+int chunk_heads(int batch, size_t elems_per_head) {
+  size_t target = (size_t)16 << 20;  // elements
+  if (const char* e = getenv("FA_B200_HOST_CHUNK_ELEMS")) {  // test hook: force many small chunks
+    const long long v = atoll(e);
+    if (v > 0) target = (size_t)v;
+  }
+  size_t hc = target / (elems_per_head ? elems_per_head : 1);
+  if (hc < 1) hc = 1;
+  if (hc > (size_t)batch) hc = (size_t)batch;
+  return (int)hc;
+}
+
 int g_host_precision = -1;  // -1: not yet initialised from the environment
 int host_precision() {
   if (g_host_precision < 0) {
@@ -276,8 +328,14 @@ void fa_b200_release_arena(void) {
   std::lock_guard<std::mutex> lk(g_arena_mu);
   if (g_arena.base) cudaFree(g_arena.base);
   g_arena = Arena();
+  g_pipe.destroy();
 }
 
+// ---- host-pointer API -------------------------------------------------------------------------
+// The batch*heads axis is cut into chunks of whole heads (independent problems) that flow through a three-stage
+// pipeline on three streams -- H2D (copy-in stream), kernels (the caller's stream), D2H (copy-out stream) -- over
+// kPipeBufs rotating device buffers, so PCIe runs full duplex and the kernels hide under the copies.  The reference
+// launchers move everything in, run, move everything out (src/flash_attn2_fw.cu:331-352).
 int fa_b200_host_fwd(const float* q, const float* k, const float* v, float* out, float* l, float* m, int batch,
                      int N, int d, int causal, int convention, void* stream) {
   if (!q || !k || !v || !out || !l || !m) return fail(FA_ERR_BAD_ARG, "fa_b200_host_fwd: null pointer");
@@ -286,44 +344,64 @@ int fa_b200_host_fwd(const float* q, const float* k, const float* v, float* out,
     return fail(FA_ERR_BAD_ARG, "fa_b200_host_fwd: unknown convention %d", convention);
   std::lock_guard<std::mutex> lk(g_arena_mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t rows = (size_t)batch * N, n = rows * d;
   const int prec = resolve_precision(FA_DTYPE_F32, host_effective_precision(), d, false);
   if (prec < 0) return fail(FA_ERR_BAD_ARG, "fa_b200_host_fwd: bad precision setting %d", host_precision());
   const bool tc = prec == FA_PREC_BF16_TC;
-  size_t bytes = 4 * align_up(n * 4, 256) + 3 * align_up(rows * 4, 256) + (tc ? 3 * align_up(n * 2, 256) : 0) + 4096;
-  if (int rc = arena_reset(bytes)) return rc;
-  float* dq = arena_take<float>(n);
-  float* dk = arena_take<float>(n);
-  float* dv = arena_take<float>(n);
-  float* dout = arena_take<float>(n);
-  float* dlse = arena_take<float>(rows);
-  float* dm = arena_take<float>(rows);
-  float* dl = arena_take<float>(rows);
-  FA_CUDA(cudaMemcpyAsync(dq, q, n * 4, cudaMemcpyHostToDevice, st), 0);
-  FA_CUDA(cudaMemcpyAsync(dk, k, n * 4, cudaMemcpyHostToDevice, st), 0);
-  FA_CUDA(cudaMemcpyAsync(dv, v, n * 4, cudaMemcpyHostToDevice, st), 0);
   const bool fa1 = convention == FA_CONV_FA1;
-  if (tc) {
-    __nv_bfloat16* bq = arena_take<__nv_bfloat16>(n);
-    __nv_bfloat16* bk = arena_take<__nv_bfloat16>(n);
-    __nv_bfloat16* bv = arena_take<__nv_bfloat16>(n);
-    FA_CUDA(fa::cvt_f32_to_bf16(dq, bq, n, st), 1);
-    FA_CUDA(fa::cvt_f32_to_bf16(dk, bk, n, st), 1);
-    FA_CUDA(fa::cvt_f32_to_bf16(dv, bv, n, st), 1);
-    FA_CUDA(fa::tc_fwd(bq, bk, bv, dout, true, dlse, fa1 ? dm : nullptr, fa1 ? dl : nullptr, batch, N, d, causal != 0, st), 1);
-  } else if (prec == FA_PREC_TF32_TC) {
-    FA_CUDA(fa::tc_fwd_tf32(dq, dk, dv, dout, dlse, fa1 ? dm : nullptr, fa1 ? dl : nullptr, batch, N, d, causal != 0, st), 1);
-  } else {
-    FA_CUDA(fa::simt_fwd(dq, dk, dv, dout, dlse, fa1 ? dm : nullptr, fa1 ? dl : nullptr, batch, N, d, causal != 0, st), 1);
+  const size_t per_head = (size_t)N * d;
+  const int hc = chunk_heads(batch, per_head);
+  const int nchunks = (batch + hc - 1) / hc;
+  const int nbuf = nchunks < kPipeBufs ? nchunks : kPipeBufs;
+  const size_t cn = (size_t)hc * per_head, crows = (size_t)hc * N;
+  const size_t buf_bytes = 4 * align_up(cn * 4, 256) + 3 * align_up(crows * 4, 256) + (tc ? 3 * align_up(cn * 2, 256) : 0);
+  if (int rc = arena_reset(nbuf * buf_bytes + 4096)) return rc;
+  if (int rc = g_pipe.ensure()) return rc;
+  struct Buf {
+    float *q, *k, *v, *o, *lse, *m, *l;
+    __nv_bfloat16 *bq, *bk, *bv;
+  } bufs[kPipeBufs];
+  for (int b = 0; b < nbuf; ++b) {
+    Buf& B = bufs[b];
+    B.q = arena_take<float>(cn); B.k = arena_take<float>(cn); B.v = arena_take<float>(cn); B.o = arena_take<float>(cn);
+    B.lse = arena_take<float>(crows); B.m = arena_take<float>(crows); B.l = arena_take<float>(crows);
+    B.bq = B.bk = B.bv = nullptr;
+    if (tc) { B.bq = arena_take<__nv_bfloat16>(cn); B.bk = arena_take<__nv_bfloat16>(cn); B.bv = arena_take<__nv_bfloat16>(cn); }
   }
-  FA_CUDA(cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, st), 0);
-  if (fa1) {
-    FA_CUDA(cudaMemcpyAsync(l, dl, rows * 4, cudaMemcpyDeviceToHost, st), 0);
-    FA_CUDA(cudaMemcpyAsync(m, dm, rows * 4, cudaMemcpyDeviceToHost, st), 0);
-  } else {
-    // FA-2 libraries return the logsumexp in `l` and never write `m` (src/flash_attn2_fw.cu:283-289)
-    FA_CUDA(cudaMemcpyAsync(l, dlse, rows * 4, cudaMemcpyDeviceToHost, st), 0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int b = c % nbuf, h0 = c * hc, hn = (batch - h0 < hc) ? batch - h0 : hc;
+    const size_t off = (size_t)h0 * per_head, roff = (size_t)h0 * N, n = (size_t)hn * per_head, rows = (size_t)hn * N;
+    Buf& B = bufs[b];
+    if (c >= nbuf) FA_CUDA(cudaStreamWaitEvent(g_pipe.s_in, g_pipe.ev_free[b], 0), 0);  // previous tenant copied out
+    FA_CUDA(cudaMemcpyAsync(B.q, q + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
+    FA_CUDA(cudaMemcpyAsync(B.k, k + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
+    FA_CUDA(cudaMemcpyAsync(B.v, v + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
+    FA_CUDA(cudaEventRecord(g_pipe.ev_in[b], g_pipe.s_in), 0);
+    FA_CUDA(cudaStreamWaitEvent(st, g_pipe.ev_in[b], 0), 0);
+    if (tc) {
+      FA_CUDA(fa::cvt_f32_to_bf16(B.q, B.bq, n, st), 1);
+      FA_CUDA(fa::cvt_f32_to_bf16(B.k, B.bk, n, st), 1);
+      FA_CUDA(fa::cvt_f32_to_bf16(B.v, B.bv, n, st), 1);
+      FA_CUDA(fa::tc_fwd(B.bq, B.bk, B.bv, B.o, true, B.lse, fa1 ? B.m : nullptr, fa1 ? B.l : nullptr, hn, N, d, causal != 0, st), 1);
+    } else if (prec == FA_PREC_TF32_TC) {
+      FA_CUDA(fa::tc_fwd_tf32(B.q, B.k, B.v, B.o, B.lse, fa1 ? B.m : nullptr, fa1 ? B.l : nullptr, hn, N, d, causal != 0, st), 1);
+    } else {
+      FA_CUDA(fa::simt_fwd(B.q, B.k, B.v, B.o, B.lse, fa1 ? B.m : nullptr, fa1 ? B.l : nullptr, hn, N, d, causal != 0, st), 1);
+    }
+    FA_CUDA(cudaEventRecord(g_pipe.ev_done[b], st), 0);
+    FA_CUDA(cudaStreamWaitEvent(g_pipe.s_out, g_pipe.ev_done[b], 0), 0);
+    FA_CUDA(cudaMemcpyAsync(out + off, B.o, n * 4, cudaMemcpyDeviceToHost, g_pipe.s_out), 0);
+    if (fa1) {
+      FA_CUDA(cudaMemcpyAsync(l + roff, B.l, rows * 4, cudaMemcpyDeviceToHost, g_pipe.s_out), 0);
+      FA_CUDA(cudaMemcpyAsync(m + roff, B.m, rows * 4, cudaMemcpyDeviceToHost, g_pipe.s_out), 0);
+    } else {
+      // FA-2 libraries return the logsumexp in `l` and never write `m` (src/flash_attn2_fw.cu:283-289)
+      FA_CUDA(cudaMemcpyAsync(l + roff, B.lse, rows * 4, cudaMemcpyDeviceToHost, g_pipe.s_out), 0);
+    }
+    FA_CUDA(cudaEventRecord(g_pipe.ev_free[b], g_pipe.s_out), 0);
   }
+  // the caller's stream "owns" the result: later work on it sees the outputs, and the call returns complete
+  FA_CUDA(cudaStreamWaitEvent(st, g_pipe.ev_free[(nchunks - 1) % nbuf], 0), 0);
+  FA_CUDA(cudaStreamSynchronize(g_pipe.s_out), 0);
   FA_CUDA(cudaStreamSynchronize(st), 0);
   return FA_OK;
 }
@@ -338,57 +416,73 @@ int fa_b200_host_bwd(const float* q, const float* k, const float* v, const float
     return fail(FA_ERR_BAD_ARG, "fa_b200_host_bwd: unknown convention %d", convention);
   std::lock_guard<std::mutex> lk(g_arena_mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t rows = (size_t)batch * N, n = rows * d;
   const int prec = resolve_precision(FA_DTYPE_F32, host_effective_precision(), d, true);
   if (prec < 0) return fail(FA_ERR_BAD_ARG, "fa_b200_host_bwd: bad precision setting %d", host_precision());
   const bool tc = prec == FA_PREC_BF16_TC;
-  const size_t ws_bytes = tc ? fa::tc_bwd_workspace_bytes(batch, N, d) : 0;
-  size_t bytes = 8 * align_up(n * 4, 256) + 4 * align_up(rows * 4, 256) + (tc ? 5 * align_up(n * 2, 256) : 0) +
-                 align_up(ws_bytes, 256) + 4096;
-  if (int rc = arena_reset(bytes)) return rc;
-  float* dq = arena_take<float>(n);
-  float* dk = arena_take<float>(n);
-  float* dv = arena_take<float>(n);
-  float* dout = arena_take<float>(n);
-  float* ddo = arena_take<float>(n);
-  float* gq = arena_take<float>(n);
-  float* gk = arena_take<float>(n);
-  float* gv = arena_take<float>(n);
-  float* dl = arena_take<float>(rows);
-  float* dm = arena_take<float>(rows);
-  float* dlse = arena_take<float>(rows);
-  float* ddelta = arena_take<float>(rows);
-  FA_CUDA(cudaMemcpyAsync(dq, q, n * 4, cudaMemcpyHostToDevice, st), 0);
-  FA_CUDA(cudaMemcpyAsync(dk, k, n * 4, cudaMemcpyHostToDevice, st), 0);
-  FA_CUDA(cudaMemcpyAsync(dv, v, n * 4, cudaMemcpyHostToDevice, st), 0);
-  FA_CUDA(cudaMemcpyAsync(dout, out, n * 4, cudaMemcpyHostToDevice, st), 0);
-  FA_CUDA(cudaMemcpyAsync(ddo, out_grad, n * 4, cudaMemcpyHostToDevice, st), 0);
-  // the reference accumulates into whatever the caller put in q_grad (src/flash_attn2_bw.cu:228)
-  FA_CUDA(cudaMemcpyAsync(gq, q_grad, n * 4, cudaMemcpyHostToDevice, st), 0);
-  FA_CUDA(cudaMemcpyAsync(dl, l, rows * 4, cudaMemcpyHostToDevice, st), 0);
   const bool fa1 = convention == FA_CONV_FA1;
-  const float* lse = dl;
-  if (fa1) {
-    FA_CUDA(cudaMemcpyAsync(dm, m, rows * 4, cudaMemcpyHostToDevice, st), 0);
-    FA_CUDA(fa::lse_from_lm(dl, dm, dlse, rows, st), 1);
-    lse = dlse;
-  }
-  if (tc) {
+  const size_t per_head = (size_t)N * d;
+  const int hc = chunk_heads(batch, per_head);
+  const int nchunks = (batch + hc - 1) / hc;
+  const int nbuf = nchunks < kPipeBufs ? nchunks : kPipeBufs;
+  const size_t cn = (size_t)hc * per_head, crows = (size_t)hc * N;
+  const size_t ws_bytes = tc ? fa::tc_bwd_workspace_bytes(hc, N, d) : 0;
+  const size_t buf_bytes = 8 * align_up(cn * 4, 256) + 4 * align_up(crows * 4, 256) + (tc ? 5 * align_up(cn * 2, 256) : 0) +
+                           align_up(ws_bytes, 256) + 256;
+  if (int rc = arena_reset(nbuf * buf_bytes + 4096)) return rc;
+  if (int rc = g_pipe.ensure()) return rc;
+  struct Buf {
+    float *q, *k, *v, *o, *g, *gq, *gk, *gv, *l, *m, *lse, *delta;
     __nv_bfloat16* b[5];
-    const float* src[5] = {dq, dk, dv, dout, ddo};
-    for (int i = 0; i < 5; ++i) {
-      b[i] = arena_take<__nv_bfloat16>(n);
-      FA_CUDA(fa::cvt_f32_to_bf16(src[i], b[i], n, st), 1);
-    }
-    void* ws = ws_bytes ? arena_take<char>(ws_bytes) : nullptr;
-    FA_CUDA(fa::tc_bwd(b[0], b[1], b[2], b[3], b[4], lse, gq, gk, gv, true, true, ws, batch, N, d, causal != 0, st), 2);
-  } else {
-    FA_CUDA(fa::simt_bwd_prep(dout, ddo, ddelta, nullptr, nullptr, nullptr, rows, d, st), 1);
-    FA_CUDA(fa::simt_bwd(dq, dk, dv, ddo, lse, ddelta, gq, gk, gv, batch, N, d, causal != 0, true, st), 2);
+    void* ws;
+  } bufs[kPipeBufs];
+  for (int i = 0; i < nbuf; ++i) {
+    Buf& B = bufs[i];
+    B.q = arena_take<float>(cn); B.k = arena_take<float>(cn); B.v = arena_take<float>(cn); B.o = arena_take<float>(cn);
+    B.g = arena_take<float>(cn); B.gq = arena_take<float>(cn); B.gk = arena_take<float>(cn); B.gv = arena_take<float>(cn);
+    B.l = arena_take<float>(crows); B.m = arena_take<float>(crows); B.lse = arena_take<float>(crows);
+    B.delta = arena_take<float>(crows);
+    for (int j = 0; j < 5; ++j) B.b[j] = tc ? arena_take<__nv_bfloat16>(cn) : nullptr;
+    B.ws = ws_bytes ? arena_take<char>(ws_bytes) : nullptr;
   }
-  FA_CUDA(cudaMemcpyAsync(q_grad, gq, n * 4, cudaMemcpyDeviceToHost, st), 0);
-  FA_CUDA(cudaMemcpyAsync(k_grad, gk, n * 4, cudaMemcpyDeviceToHost, st), 0);
-  FA_CUDA(cudaMemcpyAsync(v_grad, gv, n * 4, cudaMemcpyDeviceToHost, st), 0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int b = c % nbuf, h0 = c * hc, hn = (batch - h0 < hc) ? batch - h0 : hc;
+    const size_t off = (size_t)h0 * per_head, roff = (size_t)h0 * N, n = (size_t)hn * per_head, rows = (size_t)hn * N;
+    Buf& B = bufs[b];
+    if (c >= nbuf) FA_CUDA(cudaStreamWaitEvent(g_pipe.s_in, g_pipe.ev_free[b], 0), 0);
+    FA_CUDA(cudaMemcpyAsync(B.q, q + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
+    FA_CUDA(cudaMemcpyAsync(B.k, k + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
+    FA_CUDA(cudaMemcpyAsync(B.v, v + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
+    FA_CUDA(cudaMemcpyAsync(B.o, out + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
+    FA_CUDA(cudaMemcpyAsync(B.g, out_grad + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
+    // the reference accumulates into whatever the caller put in q_grad (src/flash_attn2_bw.cu:228)
+    FA_CUDA(cudaMemcpyAsync(B.gq, q_grad + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
+    FA_CUDA(cudaMemcpyAsync(B.l, l + roff, rows * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
+    if (fa1) FA_CUDA(cudaMemcpyAsync(B.m, m + roff, rows * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
+    FA_CUDA(cudaEventRecord(g_pipe.ev_in[b], g_pipe.s_in), 0);
+    FA_CUDA(cudaStreamWaitEvent(st, g_pipe.ev_in[b], 0), 0);
+    const float* lse = B.l;
+    if (fa1) {
+      FA_CUDA(fa::lse_from_lm(B.l, B.m, B.lse, rows, st), 1);
+      lse = B.lse;
+    }
+    if (tc) {
+      const float* src[5] = {B.q, B.k, B.v, B.o, B.g};
+      for (int j = 0; j < 5; ++j) FA_CUDA(fa::cvt_f32_to_bf16(src[j], B.b[j], n, st), 1);
+      FA_CUDA(fa::tc_bwd(B.b[0], B.b[1], B.b[2], B.b[3], B.b[4], lse, B.gq, B.gk, B.gv, true, true, B.ws, hn, N, d,
+                         causal != 0, st), 2);
+    } else {
+      FA_CUDA(fa::simt_bwd_prep(B.o, B.g, B.delta, nullptr, nullptr, nullptr, rows, d, st), 1);
+      FA_CUDA(fa::simt_bwd(B.q, B.k, B.v, B.g, lse, B.delta, B.gq, B.gk, B.gv, hn, N, d, causal != 0, true, st), 2);
+    }
+    FA_CUDA(cudaEventRecord(g_pipe.ev_done[b], st), 0);
+    FA_CUDA(cudaStreamWaitEvent(g_pipe.s_out, g_pipe.ev_done[b], 0), 0);
+    FA_CUDA(cudaMemcpyAsync(q_grad + off, B.gq, n * 4, cudaMemcpyDeviceToHost, g_pipe.s_out), 0);
+    FA_CUDA(cudaMemcpyAsync(k_grad + off, B.gk, n * 4, cudaMemcpyDeviceToHost, g_pipe.s_out), 0);
+    FA_CUDA(cudaMemcpyAsync(v_grad + off, B.gv, n * 4, cudaMemcpyDeviceToHost, g_pipe.s_out), 0);
+    FA_CUDA(cudaEventRecord(g_pipe.ev_free[b], g_pipe.s_out), 0);
+  }
+  FA_CUDA(cudaStreamWaitEvent(st, g_pipe.ev_free[(nchunks - 1) % nbuf], 0), 0);
+  FA_CUDA(cudaStreamSynchronize(g_pipe.s_out), 0);
   FA_CUDA(cudaStreamSynchronize(st), 0);
   return FA_OK;
 }

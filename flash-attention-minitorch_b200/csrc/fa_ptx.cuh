@@ -254,6 +254,27 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
       : FA_R4(r, 0), FA_R4(r, 4), FA_R4(r, 8), FA_R4(r, 12), FA_R4(r, 16), FA_R4(r, 20), FA_R4(r, 24), FA_R4(r, 28)
       : "r"(taddr));
 }
+// Shape 16x256b (the classic accumulator-fragment layout): one instruction reads 16 TMEM lanes starting at the
+// lane in taddr; repeat n covers columns [8n, 8n+8).  Thread t gets, per repeat, {row t/4: cols 2(t%4), +1} in
+// regs 4n, 4n+1 and {row t/4 + 8: same cols} in regs 4n+2, 4n+3 -- i.e. each quad owns 32 contiguous bytes of a row.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : FA_R4(r, 0), FA_R4(r, 4), FA_R4(r, 8), FA_R4(r, 12)
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : FA_R4(r, 0), FA_R4(r, 4), FA_R4(r, 8), FA_R4(r, 12), FA_R4(r, 16), FA_R4(r, 20), FA_R4(r, 24), FA_R4(r, 28)
+      : "r"(taddr));
+}
+// fp32 pair reduction into global memory (no return value): RED.ADD.F32x2
+__device__ __forceinline__ void red_add_f32x2(float* gptr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gptr), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void tmem_st_x2(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
 }

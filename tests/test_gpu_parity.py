@@ -96,6 +96,42 @@ def test_backward_accumulates_into_q_grad_like_reference(cuda_device):
     assert np.abs(kg - dk_ref).max() <= FP32_ATOL and np.abs(vg - dv_ref).max() <= FP32_ATOL
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_host_api_chunk_pipeline_equals_single_shot(cuda_device, monkeypatch, prec):
+    """The host-pointer ABI streams heads through a 3-buffer H2D / kernel / D2H pipeline; forcing 1-head chunks (7
+    chunks over 3 buffers, ragged last use) must give bit-identical results to the single-chunk call."""
+    lib = _lib.load_library()
+    BH, T, d = 7, 200, 64
+    q, k, v, g = ao.make_inputs(BH, T, d, seed=21)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    prev = lib.fa_b200_get_host_precision()
+    lib.fa_b200_set_host_precision(_lib.FA_PREC_BF16_TC if prec == "bf16" else _lib.FA_PREC_FP32_SIMT)
+    try:
+        res = []
+        for chunk in (None, str(T * d)):
+            if chunk is None:
+                monkeypatch.delenv("FA_B200_HOST_CHUNK_ELEMS", raising=False)
+            else:
+                monkeypatch.setenv("FA_B200_HOST_CHUNK_ELEMS", chunk)
+            out = np.zeros_like(q)
+            l = np.zeros((BH, T), np.float32)
+            m = np.full((BH, T), -np.finfo(np.float32).max, np.float32)
+            _lib.check(lib.fa_b200_host_fwd(p(q), p(k), p(v), p(out), p(l), p(m), BH, T, d, 1, _lib.FA_CONV_FA1, None))
+            qg, kg, vg = np.full_like(q, 0.5), np.zeros_like(q), np.zeros_like(q)
+            _lib.check(lib.fa_b200_host_bwd(p(q), p(k), p(v), p(out), p(g), p(qg), p(kg), p(vg), p(l), p(m), BH, T, d, 1,
+                                            _lib.FA_CONV_FA1, None))
+            res.append((out, l, m, kg, vg, qg))
+        for a, b in zip(res[0][:5], res[1][:5]):
+            assert np.array_equal(a, b)
+        # dQ goes through fp32 reductions whose order is not fixed on the tensor-core path
+        assert np.abs(res[0][5] - res[1][5]).max() <= (0 if prec == "fp32" else 1e-5)
+        dq_r, dk_r, dv_r, o_r, _ = ao.attention_backward(q, k, v, g, True, np.float64)
+        tol = FP32_ATOL if prec == "fp32" else 2e-2
+        assert np.abs(res[1][0] - o_r).max() <= tol and np.abs(res[1][5] - (dq_r + 0.5)).max() <= tol
+    finally:
+        lib.fa_b200_set_host_precision(prev)
+
+
 # ----------------------------------------------------------------------------------------------
 # 2. device-resident API, bf16 tensor-core path vs the oracle on the same bf16-rounded inputs
 # ----------------------------------------------------------------------------------------------

@@ -254,8 +254,80 @@ static int run_case(const char* name, int a_form, int b_form, int N, int K, int 
   return maxerr < 1e-2 ? 0 : 3;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05.ld.16x256b register mapping (used by the backward's dQ drain: fragment layout gives each
+// quad of lanes 32 contiguous bytes of one row, i.e. sector-complete red.global.add.v2.f32).
+// Every TMEM cell (lane, col) is first written with lane * 256 + col through the 32x32b shape.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) ldshape_kernel(uint32_t* __restrict__ out) {
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t mine = tmem + (uint32_t(warp * 32) << 16);
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    uint32_t r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = threadIdx.x * 256 + c0 + i;
+    tmem_st_x32(mine + c0, r);
+  }
+  tmem_wait_st();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  for (int h = 0; h < 2; ++h) {
+    uint32_t r[16];
+    tmem_ld_16x256b_x4(tmem + (uint32_t(warp * 32 + h * 16) << 16) + 8, r);  // columns [8, 40)
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[((warp * 2 + h) * 32 + lane) * 16 + i] = r[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static int run_ldshape() {
+  uint32_t* d;
+  cudaMalloc(&d, 4 * 2 * 32 * 16 * 4);
+  ldshape_kernel<<<1, 128>>>(d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("ldshape: CUDA ERROR %s\n", cudaGetErrorString(e));
+    return 1;
+  }
+  std::vector<uint32_t> h(4 * 2 * 32 * 16);
+  cudaMemcpy(h.data(), d, h.size() * 4, cudaMemcpyDeviceToHost);
+  int bad = 0;
+  for (int w = 0; w < 4; ++w)
+    for (int hf = 0; hf < 2; ++hf)
+      for (int t = 0; t < 32; ++t)
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t v = h[((w * 2 + hf) * 32 + t) * 16 + i];
+          const int lane = v >> 8, col = v & 255;
+          // hypothesis: repeat n = i / 4 covers columns [8n, 8n+8); regs 4n+{0,1}: row t/4, regs 4n+{2,3}: row t/4 + 8;
+          // column pair 2 * (t % 4) + (i & 1)
+          const int n = i / 4, exp_lane = w * 32 + hf * 16 + t / 4 + ((i & 2) ? 8 : 0), exp_col = 8 + 8 * n + 2 * (t % 4) + (i & 1);
+          if (lane != exp_lane || col != exp_col) {
+            if (bad < 24) printf("ldshape mismatch w=%d h=%d t=%2d reg=%2d: got (lane %3d, col %3d) expected (%3d, %3d)\n", w, hf, t, i, lane, col, exp_lane, exp_col);
+            ++bad;
+          }
+        }
+  printf("tcgen05.ld.16x256b.x4 fragment mapping: %s (%d mismatches)\n", bad ? "DIFFERENT FROM HYPOTHESIS" : "OK", bad);
+  cudaFree(d);
+  return bad != 0;
+}
+
 int main(int argc, char** argv) {
   int fails = 0;
+  fails += run_ldshape();
   typedef __nv_bfloat16 bf;
   const bool full = argc > 1;
   if (full) {
