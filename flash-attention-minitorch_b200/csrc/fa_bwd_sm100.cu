@@ -282,7 +282,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // parity in the low half (even query) and in the high half (odd query) -- the same bits the forward drew
     const uint32_t kj = uint32_t(j * kTile + r);
     const uint32_t drop_colkey = drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh) ^ ((kj >> 1) * kDropColMul);
-    const uint32_t drop_sh = (kj & 1) * 8;
+    const uint32_t drop_b0 = kj & 1;  // byte b0: even query of the block, byte b0 + 2: odd query
+    const uint32_t drop_sel2 = drop_sel_pair(drop_b0, drop_b0 + 2);
+    const uint32_t drop_sh = 7 + 8 * drop_b0;
     const uint32_t drop_thr = p.drop.thr;
     const float drop_scale = p.drop.keep_scale;
     for (int il = 0; il < n; ++il) {
@@ -314,25 +316,31 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         for (int c = 0; c < 64; ++c)
           if (g * 64 + c < r) pr[c] = 0.f;  // key index > query index
       }
-      uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;  // bit c: query column 64g + c of this key row is kept
-      if constexpr (kDrop) {
-        keep_lo = keep_hi = 0u;
-        const uint32_t i2 = uint32_t(i * kTile + g * 64) >> 1;
-#pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          const uint32_t b = drop_mix(drop_colkey ^ ((i2 + (c >> 1)) * kDropRowMul)) >> drop_sh;
-          const uint32_t k0 = (b & 0xffu) >= drop_thr ? 1u : 0u, k1 = ((b >> 16) & 0xffu) >= drop_thr ? 1u : 0u;
-          if (c < 32) keep_lo |= (k0 << c) | (k1 << (c + 1));
-          else keep_hi |= (k0 << (c - 32)) | (k1 << (c - 31));
-        }
-      }
-      auto kept = [&](int c) { return ((c < 32 ? keep_lo >> c : keep_hi >> (c - 32)) & 1u) != 0u; };
+      // keep bits of this key row: query pair pi = c >> 1 of each 32-column half sits at bit (15 - pi % 16) for the
+      // even query and bit (31 - pi % 16) for the odd one (shift-in order), halves 0 / 1 in keep_a / keep_b
+      uint32_t keep_a = 0u, keep_b = 0u;
+      auto kept = [&](int c) {
+        const int pos = 15 - ((c >> 1) & 15) + 16 * (c & 1);
+        return (((c < 32 ? keep_a : keep_b) >> pos) & 1u) != 0u;
+      };
       {
         uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          if constexpr (kDrop) pk[c >> 1] = pack_bf16x2(kept(c) ? pr[c] : 0.f, kept(c + 1) ? pr[c + 1] : 0.f);  // P^T o keep -> dV
-          else pk[c >> 1] = pack_bf16x2(pr[c], pr[c + 1]);
+        for (int c = 0; c < 64; c += 2) pk[c >> 1] = pack_bf16x2(pr[c], pr[c + 1]);
+        if constexpr (kDrop) {  // P^T o keep feeds dV; pr[] itself stays undropped for dS
+          const uint32_t i2 = uint32_t(i * kTile + g * 64) >> 1;
+#pragma unroll
+          for (int c = 0; c < 64; c += 4) {
+            // the two lanes of a key pair need the same block words: each hashes one, a shuffle gives the other
+            const uint32_t mine = drop_keep_word(drop_mix(drop_colkey ^ ((i2 + (c >> 1) + (lane & 1)) * kDropRowMul)), drop_thr);
+            const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
+            const uint32_t w0 = (lane & 1) ? theirs : mine, w1 = (lane & 1) ? mine : theirs;  // queries c,c+1 | c+2,c+3
+            pk[c >> 1] &= drop_prmt(w0, drop_sel2);
+            pk[(c >> 1) + 1] &= drop_prmt(w1, drop_sel2);
+            uint32_t& acc = c < 32 ? keep_a : keep_b;
+            acc = (acc << 1) | ((w0 >> drop_sh) & 0x00010001u);
+            acc = (acc << 1) | ((w1 >> drop_sh) & 0x00010001u);
+          }
         }
         // P^T of query columns [64g, 64g+64) goes to TMEM columns [64g, 64g+32): inside the S columns this
         // thread group has already consumed, so the two groups never touch each other's unread scores

@@ -228,7 +228,7 @@ int fa_b200_fwd_dropout(const void* q, const void* k, const void* v, void* o, fl
 }
 
 float fa_b200_dropout_keep_scale(float p_drop) { return fa::make_dropout(p_drop, 0).keep_scale; }
-float fa_b200_dropout_effective_p(float p_drop) { return (float)fa::make_dropout(p_drop, 0).thr / 256.0f; }
+float fa_b200_dropout_effective_p(float p_drop) { return (float)fa::make_dropout(p_drop, 0).thr / 128.0f; }
 
 int fa_b200_dropout_mask(unsigned char* keep, int head_begin, int n_heads, int T, float p_drop,
                          unsigned long long seed, void* stream) {

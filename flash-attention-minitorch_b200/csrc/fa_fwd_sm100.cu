@@ -259,8 +259,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     float l = 0.f;
     // dropout: one 32-bit hash per 2 x 2 block of (row, key); this thread uses the two bytes of its row parity
     const uint32_t drop_rowkey = drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh) ^ ((uint32_t(row_g) >> 1) * kDropRowMul);
-    const uint32_t drop_sh = (row_g & 1) * 16;
     const uint32_t drop_thr = p.drop.thr;
+    const uint32_t drop_b0 = (row_g & 1) * 2;  // bytes b0, b0 + 1 of a block word belong to this row
+    const uint32_t drop_sel2 = drop_sel_pair(drop_b0, drop_b0 + 1), drop_selA = drop_sel_word(drop_b0),
+                   drop_selB = drop_sel_word(drop_b0 + 1);
 
     for (int j = 0; j < nt; ++j) {
       mbar_wait(&bars.s_full[t], j & 1);
@@ -355,15 +357,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           l2 += q2;
           l3 += q3;
 #endif
-          if constexpr (kDrop) {  // l above is the undropped row sum; only P fed to the PV product is thinned
-            const uint32_t j2 = uint32_t(j * kBlockN + cc) >> 1;
-            const uint32_t b0 = drop_mix(drop_rowkey ^ (j2 * kDropColMul)) >> drop_sh;
-            const uint32_t b1 = drop_mix(drop_rowkey ^ ((j2 + 1) * kDropColMul)) >> drop_sh;
-            q0 = (b0 & 0xffu) >= drop_thr ? q0 : 0.f;
-            q1 = ((b0 >> 8) & 0xffu) >= drop_thr ? q1 : 0.f;
-            q2 = (b1 & 0xffu) >= drop_thr ? q2 : 0.f;
-            q3 = ((b1 >> 8) & 0xffu) >= drop_thr ? q3 : 0.f;
-          }
           if constexpr (kTF32) {
             pk[c] = __float_as_uint(q0);
             pk[c + 1] = __float_as_uint(q1);
@@ -372,6 +365,22 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           } else {
             pk[c >> 1] = pack_bf16x2(q0, q1);
             pk[(c >> 1) + 1] = pack_bf16x2(q2, q3);
+          }
+          if constexpr (kDrop) {  // l above is the undropped row sum; only P fed to the PV product is thinned
+            // the two lanes of a row pair need the same two block words: each hashes one, a shuffle gives the other
+            const uint32_t j2 = (uint32_t(j * kBlockN + cc) >> 1) + (lane & 1);
+            const uint32_t mine = drop_keep_word(drop_mix(drop_rowkey ^ (j2 * kDropColMul)), drop_thr);
+            const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
+            const uint32_t w0 = (lane & 1) ? theirs : mine, w1 = (lane & 1) ? mine : theirs;  // columns cc,cc+1 | cc+2,cc+3
+            if constexpr (kTF32) {
+              pk[c] &= drop_prmt(w0, drop_selA);
+              pk[c + 1] &= drop_prmt(w0, drop_selB);
+              pk[c + 2] &= drop_prmt(w1, drop_selA);
+              pk[c + 3] &= drop_prmt(w1, drop_selB);
+            } else {
+              pk[c >> 1] &= drop_prmt(w0, drop_sel2);
+              pk[(c >> 1) + 1] &= drop_prmt(w1, drop_sel2);
+            }
           }
         }
         if constexpr (kTF32) tmem_st_x32(tS + q4 * 32, pk);   // tf32: P fills all 128 columns of S

@@ -90,7 +90,7 @@ int fa_b200_bwd(const void* q, const void* k, const void* v, const void* o, cons
  * flash path; the convention is that of its Dropout module (minitorch/modules_basic.py:77-80): keep ~
  * Bernoulli(1 - p), kept probabilities scaled by 1/(1 - p), applied to P after the softmax normalisation
  * (lse is the logsumexp of the undropped scores).  The mask is a pure function of (seed, head, query, key)
- * regenerated inside the backward -- nothing is stored.  p is quantised to 1/256: p_eff = round(256 p)/256.
+ * regenerated inside the backward -- nothing is stored.  p is quantised to 1/128: p_eff = round(128 p)/128.
  *   fa_b200_fwd_dropout / fa_b200_bwd_dropout : as fa_b200_fwd / fa_b200_bwd with O = (P o Z) V
  *   fa_b200_dropout_mask      : keep[n_heads][T][T] (1 = kept) for heads [head_begin, head_begin + n_heads) of the
  *                               flattened batch*heads axis, exactly as the kernels draw it (debug / oracle)

@@ -96,12 +96,12 @@ def _mix32(x: np.ndarray) -> np.ndarray:
 
 
 def dropout_threshold(p: float) -> int:
-    """Byte threshold the kernels use: keep iff byte >= thr; p_eff = thr / 256."""
-    return 0 if not p > 0 else min(255, int(np.float32(p) * np.float32(256.0) + np.float32(0.5)))
+    """7-bit threshold the kernels use: keep iff (byte & 0x7f) >= thr; p_eff = thr / 128."""
+    return 0 if not p > 0 else min(127, int(np.float32(p) * np.float32(128.0) + np.float32(0.5)))
 
 
 def dropout_keep_scale(p: float) -> float:
-    return float(np.float32(256.0) / (np.float32(256.0) - np.float32(dropout_threshold(p))))
+    return float(np.float32(128.0) / (np.float32(128.0) - np.float32(dropout_threshold(p))))
 
 
 def dropout_keep_mask(seed: int, heads, T: int, p: float) -> np.ndarray:
@@ -115,7 +115,7 @@ def dropout_keep_mask(seed: int, heads, T: int, p: float) -> np.ndarray:
         cterm = (i >> np.uint32(1)) * np.uint32(0x85EBCA77)
         bits = _mix32(hkey[:, None, None] ^ rterm[None, :, None] ^ cterm[None, None, :])
         sh = np.uint32(8) * ((i & np.uint32(1))[:, None] * np.uint32(2) + (i & np.uint32(1))[None, :])
-        byte = (bits >> sh[None]) & np.uint32(0xFF)
+        byte = (bits >> sh[None]) & np.uint32(0x7F)
     return byte >= np.uint32(dropout_threshold(p))
 
 

@@ -336,7 +336,7 @@ def test_dropout_mask_matches_oracle_restatement_bit_for_bit(cuda_device, T, p, 
     assert np.array_equal(keep, ref)
     assert abs(device.dropout_keep_scale(p) - ao.dropout_keep_scale(p)) < 1e-7
     if T >= 256:  # Bernoulli(1 - p_eff) within 5 sigma
-        p_eff = ao.dropout_threshold(p) / 256.0
+        p_eff = ao.dropout_threshold(p) / 128.0
         assert abs(keep.mean() - (1 - p_eff)) <= 5 * np.sqrt(p_eff * (1 - p_eff) / keep.size)
 
 
