@@ -30,8 +30,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "flash-attention-minitorch_b200"))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(name="cfg3: FA-2 fw+bw causal B=32 H=16 T=4096 d=128 bf16 (BASELINE.json configs[2])",
-                B=32, H=16, T=4096, d=128, causal=True)
+# cfg3 is the configuration BASELINE.json's metric is quoted on and the only one the default run measures; cfg2 and
+# cfg4 (--workload) are the other single-GPU configurations of BASELINE.json, kept for profiles/ -- not bench lines.
+WORKLOADS = {
+    "cfg3": dict(name="cfg3: FA-2 fw+bw causal B=32 H=16 T=4096 d=128 bf16 (BASELINE.json configs[2])",
+                 B=32, H=16, T=4096, d=128, causal=True, dtype="bf16", backward=True, p_drop=0.0),
+    "cfg2": dict(name="cfg2: flash-attn forward non-causal B=32 H=16 T=1024 d=64 fp32 storage / tf32 MMA (BASELINE.json configs[1])",
+                 B=32, H=16, T=1024, d=64, causal=False, dtype="f32", backward=False, p_drop=0.0),
+    "cfg4": dict(name="cfg4: FA-2 fw+bw causal B=4 H=32 T=16384 d=128 bf16 dropout 0.1 (BASELINE.json configs[3])",
+                 B=4, H=32, T=16384, d=128, causal=True, dtype="bf16", backward=True, p_drop=0.1),
+}
+WORKLOAD = WORKLOADS["cfg3"]
 METRIC = "attention fw+bw TFLOP/s (whole job)"
 
 
@@ -69,6 +78,17 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def wait_first_sample(self, timeout_s: float = 5.0):
+        """nvidia-smi needs a few hundred ms to start: make sure it is sampling before the timed region begins."""
+        t0 = time.time()
+        while self.proc is not None and time.time() - t0 < timeout_s:
+            try:
+                if os.path.getsize(self.tmp.name) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -105,7 +125,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU legs (the only places that touch oracle/)
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_sample(heads: int, T: int, d: int, causal: bool, repeats: int = 1):
+def cpu_reference_sample(heads: int, T: int, d: int, causal: bool, repeats: int = 1, backward: bool = True):
     """Reference CPU attention path (C restatement, all host cores) on `heads` heads of the workload."""
     import numpy as np
     from oracle import c_oracle
@@ -115,9 +135,9 @@ def cpu_reference_sample(heads: int, T: int, d: int, causal: bool, repeats: int 
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
-        c_oracle.attention(q, k, v, g, causal)
+        c_oracle.attention(q, k, v, g if backward else None, causal)
         best = min(best, time.perf_counter() - t0)
-    fl = 3.5 * flops_fwd(heads, T, d, causal)
+    fl = (3.5 if backward else 1.0) * flops_fwd(heads, T, d, causal)
     return dict(seconds=best, tflops=fl / best * 1e-12, cores=c_oracle.num_threads())
 
 
@@ -167,18 +187,29 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load_library()
 
-    w = WORKLOAD
+    w = WORKLOADS[args.workload]
     BH, T, d, causal = w["B"] * w["H"], w["T"], w["d"], w["causal"]
+    do_bwd, p_drop, seed = w["backward"], w["p_drop"], 4001
+    tdt = torch.bfloat16 if w["dtype"] == "bf16" else torch.float32
     torch.manual_seed(3001 + rank)
-    mk = lambda: (torch.rand(BH, T, d, device=dev) * 2 - 1).to(torch.bfloat16)  # noqa: E731
-    q, k, v, g = mk(), mk(), mk(), mk()
-    grads = (torch.empty_like(q), torch.empty_like(q), torch.empty_like(q))
+    mk = lambda: (torch.rand(BH, T, d, device=dev) * 2 - 1).to(tdt)  # noqa: E731
+    q, k, v = mk(), mk(), mk()
     outs = (torch.empty_like(q), torch.empty(BH, T, dtype=torch.float32, device=dev))
-    ws = device.bwd_workspace(q)
+    if do_bwd:
+        g = mk()
+        grads = (torch.empty_like(q), torch.empty_like(q), torch.empty_like(q))
+        ws = device.bwd_workspace(q)
+
+    def fwd():
+        return device.flash_attn_fwd(q, k, v, causal, out=outs, p_drop=p_drop, seed=seed)
+
+    def bwd(o, lse):
+        device.flash_attn_bwd(q, k, v, o, g, lse, causal, workspace=ws, out=grads, p_drop=p_drop, seed=seed)
 
     def step():
-        o, lse = device.flash_attn_fwd(q, k, v, causal, out=outs)
-        device.flash_attn_bwd(q, k, v, o, g, lse, causal, workspace=ws, out=grads)
+        o, lse = fwd()
+        if do_bwd:
+            bwd(o, lse)
         return o, lse
 
     def barrier():
@@ -186,11 +217,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.wait_first_sample()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -210,13 +242,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     a.record()
     for _ in range(reps):
-        device.flash_attn_fwd(q, k, v, causal, out=outs)
+        fwd()
     b.record()
-    for _ in range(reps):
-        device.flash_attn_bwd(q, k, v, o, g, lse, causal, workspace=ws, out=grads)
+    for _ in range(reps if do_bwd else 0):
+        bwd(o, lse)
     c.record()
     torch.cuda.synchronize()
-    fw_ms, bw_ms = [a.elapsed_time(b) / reps], [b.elapsed_time(c) / reps]
+    fw_ms, bw_ms = [a.elapsed_time(b) / reps], [b.elapsed_time(c) / reps if do_bwd else 0.0]
     clocks = sampler.stop()
 
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -224,15 +256,23 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    f_step = 3.5 * flops_fwd(BH, T, d, causal)
+    f_step = (3.5 if do_bwd else 1.0) * flops_fwd(BH, T, d, causal)
     value = f_step * world / (ms_step * 1e-3) * 1e-12
 
     # ---- e2e: reference-facing host-pointer ABI, pinned fp32 host buffers, copies inside the timed region
-    e2e = run_e2e(lib, dev, BH, T, d, causal, steps=min(args.steps, 2), world=world)
+    if p_drop > 0:
+        e2e = {"value": None, "unit": "TFLOP/s", "note": "the reference's host-pointer ABI has no dropout argument; "
+               "dropout is a device-API feature (fa_b200_fwd_dropout / fa_b200_bwd_dropout)"}
+    else:
+        e2e = run_e2e(lib, dev, BH, T, d, causal, steps=min(args.steps, 2), world=world, do_bwd=do_bwd,
+                      prec=_lib.FA_PREC_BF16_TC if w["dtype"] == "bf16" else _lib.FA_PREC_TF32_TC)
 
     line = None
     if rank == 0:
         peaks = measured_peaks()
+        if w["dtype"] != "bf16":  # kind::tf32 runs at half the bf16 rate; no separate measured tf32 peak exists
+            peaks["tflops"] *= 0.5
+            peaks["source"] += " / 2 for tf32"
         fw, bw = statistics.mean(fw_ms), statistics.mean(bw_ms)
         dom_is_bw = bw >= fw
         dom_ms = bw if dom_is_bw else fw
@@ -242,17 +282,20 @@ def run_ours(args):
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("bwd" if dom_is_bw else "fwd")
+                traffic = json.load(open(tpath)).get(args.workload, {}).get("bwd" if dom_is_bw else "fwd")
             except Exception:
                 traffic = None
         # CPU baseline: rank 0 at N=1 only (the reference arm, --impl reference, covers N>1)
-        cpu = cpu_reference_sample(16, T, d, causal) if world == 1 else None
+        cpu_heads = max(1, min(16, int(16 * (4096 / T) ** 2)))  # ~3 s of CPU work at any T
+        cpu = cpu_reference_sample(cpu_heads, T, d, causal, backward=do_bwd) if world == 1 else None
         line = {"metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "vs_baseline": None, "dtype": "bf16" if w["dtype"] == "bf16" else "tf32", "data": "synthetic",
                 "config": {"workload": w["name"], "batch_heads_per_gpu": BH, "global_batch_heads": BH * world, "seq_len": T,
-                           "head_dim": d, "causal": causal, "parallelism": f"batch*heads sharded x{world}, no collective",
-                           "l2": "inputs (8 x 537 MB per GPU) exceed the 126 MB L2; no flush between iterations",
+                           "head_dim": d, "causal": causal, "dropout": p_drop,
+                           "parallelism": f"batch*heads sharded x{world}, no collective",
+                           "l2": f"inputs ({q.numel() * q.element_size() / 1e6:.0f} MB per tensor per GPU) exceed the 126 MB L2; "
+                                 "no flush between iterations",
                            "flops_per_step_per_gpu": f_step},
                 "per_gpu_tflops": value / world,
                 "frac_of_spec_bf16_2250": value / world / 2250.0,
@@ -264,7 +307,7 @@ def run_ours(args):
                                          "frac": flops_fwd(BH, T, d, causal) / (fw * 1e-3) * 1e-12 / peaks["tflops"]}},
                 "cpu_baseline": None if cpu is None else {
                     "value": cpu["tflops"], "unit": "TFLOP/s", "cores": cpu["cores"], "kind": "port",
-                    "sample": f"16 of {BH} (b,h) problems, fw+bw, fp32, {cpu['seconds']:.2f} s"},
+                    "sample": f"{cpu_heads} of {BH} (b,h) problems, {'fw+bw' if do_bwd else 'fw'}, fp32, {cpu['seconds']:.2f} s"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -273,7 +316,7 @@ def run_ours(args):
     return 0
 
 
-def run_e2e(lib, dev, BH, T, d, causal, steps, world):
+def run_e2e(lib, dev, BH, T, d, causal, steps, world, do_bwd=True, prec=None):
     """Same workload through fa_b200_host_fwd/bwd (what launch_flash_attn_fw/_bw forward to): pinned fp32 host
     buffers in, fp32 host buffers out, bf16 tensor-core arithmetic on the device.  Returns the e2e object."""
     import torch
@@ -284,20 +327,23 @@ def run_e2e(lib, dev, BH, T, d, causal, steps, world):
     hq, hk, hv, hg = pin(n), pin(n), pin(n), pin(n)
     for h in (hq, hk, hv, hg):  # fill on the device (fast), land in pinned host memory
         h.copy_((torch.rand(n, device=dev) * 2 - 1).to(torch.bfloat16).float())
-    ho, hgq, hgk, hgv = pin(n), pin(n), pin(n), pin(n)
+    ho = pin(n)
+    hgq, hgk, hgv = (pin(n), pin(n), pin(n)) if do_bwd else (ho, ho, ho)
     hl, hm = pin(rows), pin(rows)
-    hgq.zero_()
+    if do_bwd:
+        hgq.zero_()
     hm.fill_(-3.4028234663852886e38)
     torch.cuda.synchronize()
     prev = lib.fa_b200_get_host_precision()
-    lib.fa_b200_set_host_precision(_lib.FA_PREC_BF16_TC)
+    lib.fa_b200_set_host_precision(_lib.FA_PREC_BF16_TC if prec is None else prec)
     stream = torch.cuda.current_stream().cuda_stream
     P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
 
     def step():
         _lib.check(lib.fa_b200_host_fwd(P(hq), P(hk), P(hv), P(ho), P(hl), P(hm), BH, T, d, int(causal), _lib.FA_CONV_FA2, stream))
-        _lib.check(lib.fa_b200_host_bwd(P(hq), P(hk), P(hv), P(ho), P(hg), P(hgq), P(hgk), P(hgv), P(hl), P(hm), BH, T, d,
-                                        int(causal), _lib.FA_CONV_FA2, stream))
+        if do_bwd:
+            _lib.check(lib.fa_b200_host_bwd(P(hq), P(hk), P(hv), P(ho), P(hg), P(hgq), P(hgk), P(hgv), P(hl), P(hm), BH, T, d,
+                                            int(causal), _lib.FA_CONV_FA2, stream))
     try:
         step()  # warm-up: arena allocation, first-touch
         if world > 1:
@@ -317,12 +363,14 @@ def run_e2e(lib, dev, BH, T, d, causal, steps, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    f_step = 3.5 * flops_fwd(BH, T, d, causal)
-    h2d = (3 * n + 6 * n + rows) * 4   # fwd: q,k,v ; bwd: q,k,v,out,out_grad,q_grad + L
-    d2h = (n + rows + 3 * n) * 4       # fwd: out, L ; bwd: q_grad,k_grad,v_grad
+    f_step = (3.5 if do_bwd else 1.0) * flops_fwd(BH, T, d, causal)
+    h2d = (3 * n + (6 * n + rows if do_bwd else 0)) * 4   # fwd: q,k,v ; bwd: q,k,v,out,out_grad,q_grad + L
+    d2h = (n + rows + (3 * n if do_bwd else 0)) * 4       # fwd: out, L ; bwd: q_grad,k_grad,v_grad
     return {"value": f_step * world / (ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": ms, "steps": steps,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "api": "fa_b200_host_fwd + fa_b200_host_bwd (reference ABI launch_flash_attn_fw/_bw), pinned fp32 host buffers, bf16 tensor-core arithmetic"}
+            "api": "fa_b200_host_fwd" + (" + fa_b200_host_bwd" if do_bwd else "") + " (reference ABI launch_flash_attn_fw/_bw), pinned fp32 "
+                   "host buffers streamed through a 3-buffer H2D/kernel/D2H pipeline, "
+                   + ("bf16" if prec in (None, _lib.FA_PREC_BF16_TC) else "tf32") + " tensor-core arithmetic"}
 
 
 def main():
@@ -331,6 +379,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg3",
+                    help="cfg3 (default) is the headline configuration; cfg2 / cfg4 are recorded under profiles/ only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -1,0 +1,180 @@
+"""Decoder-only Pre-LN transformer of the reference's machine-translation run, device-resident.
+
+Same module tree, parameter names, shapes and initialisation as the reference (minitorch/modules_transfomer.py,
+modules_basic.py), so a state dict maps one to one:
+
+    DecoderLM(n_vocab, n_embd, n_head, n_positions, p_dropout, ln_eps, bias)      modules_transfomer.py:253-357
+      token_embeddings / position_embeddings : Embedding(n_vocab, n_embd), N(0,1)  modules_basic.py:17-53
+      t_layer_1..4 : TransformerLayer  (x + attn(ln_1(x)); out + ff(ln_2(out)))    modules_transfomer.py:204-250
+        attention  : MultiHeadAttention, causal, flash path                        modules_transfomer.py:14-157
+        ff         : FeedForward(n_embd, middle_dim=256): linear, GELU, dropout, linear   modules_transfomer.py:160-201
+      dropout, ln (LayerNorm1d), lm_head : Linear(n_embd, n_vocab)
+    Linear weights are (in, out), U(-1/sqrt(in), 1/sqrt(in)) (RParam, modules_basic.py:82-85)
+
+`attention_fn(q, k, v, causal)` defaults to this repo's CUDA kernels; tests on a CPU-only box inject a plain
+restatement to exercise the host logic (the product path itself has no CPU attention).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Iterator, List, Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+class Parameter:
+    def __init__(self, value: torch.Tensor):
+        self.value = value.requires_grad_(True)
+
+
+class Module:
+    training = True
+
+    def named_parameters(self, prefix: str = "") -> Iterator[Tuple[str, Parameter]]:
+        for name, v in vars(self).items():
+            if isinstance(v, Parameter):
+                yield prefix + name, v
+            elif isinstance(v, Module):
+                yield from v.named_parameters(prefix + name + ".")
+
+    def parameters(self) -> List[Parameter]:
+        return [p for _, p in self.named_parameters()]
+
+    def modules(self):
+        yield self
+        for v in vars(self).values():
+            if isinstance(v, Module):
+                yield from v.modules()
+
+    def train(self):
+        for m in self.modules():
+            m.training = True
+
+    def eval(self):
+        for m in self.modules():
+            m.training = False
+
+    def __call__(self, *a, **kw):
+        return self.forward(*a, **kw)
+
+
+def _rparam(in_size: int, shape, device, dtype, gen) -> Parameter:
+    r = (2.0 / math.sqrt(in_size)) * (torch.rand(shape, generator=gen, dtype=torch.float32) - 0.5)
+    return Parameter(r.to(device=device, dtype=dtype))
+
+
+class Embedding(Module):
+    def __init__(self, num_embeddings, embedding_dim, device, dtype, gen):
+        self.weights = Parameter(torch.randn((num_embeddings, embedding_dim), generator=gen).to(device=device, dtype=dtype))
+
+    def forward(self, idx):
+        return ops.embedding(idx, self.weights.value)
+
+
+class Linear(Module):
+    def __init__(self, in_size, out_size, bias, device, dtype, gen):
+        self.weights = _rparam(in_size, (in_size, out_size), device, dtype, gen)
+        if bias:
+            self.bias = _rparam(in_size, (out_size,), device, dtype, gen)
+        self.has_bias = bool(bias)
+
+    def forward(self, x):
+        return ops.linear(x, self.weights.value, self.bias.value if self.has_bias else None)
+
+
+class LayerNorm1d(Module):
+    def __init__(self, dim, eps, device, dtype):
+        self.eps = eps
+        self.weights = Parameter(torch.ones(dim, device=device, dtype=dtype))
+        self.bias = Parameter(torch.zeros(dim, device=device, dtype=dtype))
+
+    def forward(self, x):
+        return ops.layernorm(x, self.weights.value, self.bias.value, self.eps)
+
+
+class MultiHeadAttention(Module):
+    def __init__(self, n_embd, n_head, causal, bias, device, dtype, gen, attention_fn):
+        self.n_embd, self.n_head, self.causal = n_embd, n_head, causal
+        self.attn_hidden_dim = n_embd // n_head
+        self.q_projection = Linear(n_embd, n_embd, bias, device, dtype, gen)
+        self.k_projection = Linear(n_embd, n_embd, bias, device, dtype, gen)
+        self.v_projection = Linear(n_embd, n_embd, bias, device, dtype, gen)
+        self.out_projection = Linear(n_embd, n_embd, bias, device, dtype, gen)
+        self.attention_fn = attention_fn
+
+    def forward(self, x):
+        B, T, E = x.shape
+        H, d = self.n_head, self.attn_hidden_dim
+        x2 = x.reshape(B * T, E)
+        # flash path of project_to_query_key_value: K keeps the (B, H, T, d) layout (modules_transfomer.py:83-84)
+        q = self.q_projection(x2).view(B, T, H, d).permute(0, 2, 1, 3).contiguous()
+        k = self.k_projection(x2).view(B, T, H, d).permute(0, 2, 1, 3).contiguous()
+        v = self.v_projection(x2).view(B, T, H, d).permute(0, 2, 1, 3).contiguous()
+        o = self.attention_fn(q, k, v, self.causal)
+        o = o.permute(0, 2, 1, 3).contiguous().view(B * T, E)
+        return self.out_projection(o).view(B, T, E)
+
+
+class FeedForward(Module):
+    def __init__(self, n_embd, middle_dim, p_dropout, bias, device, dtype, gen):
+        self.linear_in = Linear(n_embd, middle_dim, bias, device, dtype, gen)
+        self.linear_out = Linear(middle_dim, n_embd, bias, device, dtype, gen)
+        self.p_dropout = p_dropout
+
+    def forward(self, x):
+        B, T, E = x.shape
+        h = ops.gelu(self.linear_in(x.reshape(B * T, E)))
+        h = ops.dropout(h, self.p_dropout, self.training)
+        return self.linear_out(h).view(B, T, E)
+
+
+class TransformerLayer(Module):
+    def __init__(self, n_embd, n_head, p_dropout, ln_eps, bias, device, dtype, gen, attention_fn):
+        self.ln_1 = LayerNorm1d(n_embd, ln_eps, device, dtype)
+        self.ln_2 = LayerNorm1d(n_embd, ln_eps, device, dtype)
+        self.attention = MultiHeadAttention(n_embd, n_head, True, bias, device, dtype, gen, attention_fn)
+        self.ff = FeedForward(n_embd, 256, p_dropout, bias, device, dtype, gen)
+
+    def forward(self, x):
+        B, T, E = x.shape
+        out = x + self.attention(self.ln_1(x.reshape(B * T, E)).view(B, T, E))
+        return out + self.ff(self.ln_2(out.reshape(B * T, E)).view(B, T, E))
+
+
+class DecoderLM(Module):
+    def __init__(self, n_vocab: int, n_embd: int, n_head: int, n_positions: int, p_dropout: float = 0.1,
+                 ln_eps: float = 1e-5, bias: bool = True, device="cuda", dtype=torch.float32, seed: int = 11111,
+                 attention_fn: Optional[Callable] = None):
+        gen = torch.Generator().manual_seed(seed)
+        attention_fn = attention_fn or ops.flash_attention
+        self.n_vocab, self.n_embd, self.n_positions, self.p_dropout = n_vocab, n_embd, n_positions, p_dropout
+        self.token_embeddings = Embedding(n_vocab, n_embd, device, dtype, gen)
+        self.position_embeddings = Embedding(n_vocab, n_embd, device, dtype, gen)  # sized n_vocab, as in the reference
+        self.t_layer_1 = TransformerLayer(n_embd, n_head, p_dropout, ln_eps, bias, device, dtype, gen, attention_fn)
+        self.t_layer_2 = TransformerLayer(n_embd, n_head, p_dropout, ln_eps, bias, device, dtype, gen, attention_fn)
+        self.t_layer_3 = TransformerLayer(n_embd, n_head, p_dropout, ln_eps, bias, device, dtype, gen, attention_fn)
+        self.t_layer_4 = TransformerLayer(n_embd, n_head, p_dropout, ln_eps, bias, device, dtype, gen, attention_fn)
+        self.ln = LayerNorm1d(n_embd, ln_eps, device, dtype)
+        self.lm_head = Linear(n_embd, n_vocab, bias, device, dtype, gen)
+
+    def forward(self, idx):
+        B, T = idx.shape
+        pos = torch.arange(T, device=idx.device).view(1, T)
+        x = ops.dropout(self.token_embeddings(idx) + self.position_embeddings(pos), self.p_dropout, self.training)
+        for layer in (self.t_layer_1, self.t_layer_2, self.t_layer_3, self.t_layer_4):
+            x = layer(x)
+        x = self.ln(x.reshape(B * T, self.n_embd))
+        return self.lm_head(x).view(B, T, self.n_vocab)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {n: p.value.detach() for n, p in self.named_parameters()}
+
+
+def loss_fn(batch, model: DecoderLM):
+    """MLE loss averaged over all positions (project/run_machine_translation.py:158-177)."""
+    logits = model(batch["input_ids"])
+    B, T, V = logits.shape
+    loss = ops.softmax_loss(logits.view(B * T, V), batch["labels"].view(B * T))
+    return (loss * batch["label_token_weights"].view(B * T)).mean()
