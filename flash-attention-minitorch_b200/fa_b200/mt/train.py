@@ -1,0 +1,158 @@
+"""Training loop of the machine-translation run on synthetic token batches, data-parallel over ranks.
+
+Mirrors project/run_machine_translation.py: model/optimizer construction (:332-365), the per-rank batch size
+int((128*40 + L) / L) (:385), loss_fn (:158-177) and the train() loop with its forward / backward / optimizer
+timers accumulated over iterations 2..9 of 10 (:180-221).  The IWSLT corpus and the BPE tokenizer are not
+available offline, so batches are uniform random token ids of the same shape.
+
+Data parallelism: one process per GPU, identical initial weights (same seed), per-rank batches, and ONE
+collective per step -- an all-reduce(sum)/world of the flattened gradients over NCCL (NVLink 5 / NVSwitch).
+The attention path itself has no collective (heads are independent).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import time
+from typing import Callable, Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .model import DecoderLM, loss_fn
+from .optim import Adam
+
+
+def synthetic_batch(batch_size: int, seq_len: int, n_vocab: int, device, gen: torch.Generator) -> Dict[str, torch.Tensor]:
+    """Random token ids; labels are the inputs shifted by one; every label position weighted 1 (collate_batch,
+    run_machine_translation.py:107-155, without the source/target split of real sentence pairs)."""
+    tokens = torch.randint(0, n_vocab, (batch_size, seq_len + 1), generator=gen).to(device)
+    return {"input_ids": tokens[:, :-1].contiguous(), "labels": tokens[:, 1:].contiguous(),
+            "label_token_weights": torch.ones(batch_size, seq_len, device=device)}
+
+
+class GradAllReducer:
+    """One flat bucket for all gradients: a single all-reduce per step (payload ~36 MB at the reference config,
+    latency-bound on NVSwitch, so one launch beats per-parameter calls)."""
+
+    def __init__(self, params: List, world: int):
+        self.params, self.world = params, world
+        self.numel = sum(p.value.numel() for p in params)
+        self.flat: Optional[torch.Tensor] = None
+
+    def __call__(self) -> None:
+        if self.world == 1:
+            return
+        p0 = self.params[0].value
+        if self.flat is None:
+            self.flat = torch.empty(self.numel, device=p0.device, dtype=p0.dtype)
+        off = 0
+        for p in self.params:
+            n = p.value.numel()
+            g = p.value.grad
+            if g is None:
+                self.flat[off:off + n].zero_()
+            else:
+                self.flat[off:off + n].copy_(g.reshape(-1))
+            off += n
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        self.flat.div_(self.world)
+        off = 0
+        for p in self.params:
+            n = p.value.numel()
+            p.value.grad = self.flat[off:off + n].view_as(p.value).clone()
+            off += n
+
+
+def train(model: DecoderLM, optimizer: Adam, n_iters: int, batch_size: int, seq_len: int, rank: int, world: int,
+          sync: Callable[[], None], seed: int = 0, log: Optional[Callable[[str], None]] = None) -> Dict[str, float]:
+    """Runs n_iters steps and returns the reference-style timers (iterations >= 2) plus tokens/s and losses."""
+    model.train()
+    device = next(iter(model.parameters())).value.device
+    gen = torch.Generator().manual_seed(1000 * (rank + 1) + seed)
+    reducer = GradAllReducer(model.parameters(), world)
+    fw = bw = comm = opt = 0.0
+    timed_tokens, timed_s, losses = 0, 0.0, []
+    for it in range(n_iters):
+        batch = synthetic_batch(batch_size, seq_len, model.n_vocab, device, gen)
+        sync()
+        t0 = time.perf_counter()
+        optimizer.zero_grad()
+        loss = loss_fn(batch, model)
+        sync()
+        t1 = time.perf_counter()
+        loss.backward()
+        sync()
+        t2 = time.perf_counter()
+        reducer()
+        sync()
+        t3 = time.perf_counter()
+        optimizer.step()
+        sync()
+        t4 = time.perf_counter()
+        losses.append(float(loss.item()))
+        if it > 1:  # the reference skips its first two iterations (run_machine_translation.py:207-210)
+            fw += t1 - t0
+            bw += t2 - t1
+            comm += t3 - t2
+            opt += t4 - t3
+            timed_tokens += batch_size * seq_len
+            timed_s += t4 - t0
+        if log:
+            log(f"iter {it} loss {losses[-1]:.4f} tokens/s/rank {batch_size * seq_len / (t4 - t0):.0f}")
+    return {"forward_s": fw, "backward_s": bw, "allreduce_s": comm, "opt_s": opt, "tokens_per_s_per_rank": timed_tokens / max(timed_s, 1e-9),
+            "timed_iters": max(n_iters - 2, 0), "loss_first": losses[0], "loss_last": losses[-1], "losses": losses}
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(description="decoder-only LM training with B200 flash attention (synthetic tokens)")
+    ap.add_argument("--model-max-length", type=int, default=512)
+    ap.add_argument("--use-flash-attention", type=lambda s: s.lower() in ("1", "true", "yes"), default=True)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--n-vocab", type=int, default=10000)
+    ap.add_argument("--n-embd", type=int, default=256)
+    ap.add_argument("--n-head", type=int, default=8)
+    ap.add_argument("--learning-rate", type=float, default=0.02)
+    ap.add_argument("--p-dropout", type=float, default=0.1)
+    ap.add_argument("--seed", type=int, default=11111)
+    args = ap.parse_args(argv)
+    if not args.use_flash_attention:
+        raise SystemExit("only the flash-attention path exists here (the vanilla path is the reference's CPU oracle)")
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: this trainer has no CPU path")
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    L = args.model_max_length
+    batch_size = int((128 * 40 + L) / L)  # run_machine_translation.py:385, per rank
+    model = DecoderLM(n_vocab=args.n_vocab, n_embd=args.n_embd, n_head=args.n_head, n_positions=L, p_dropout=args.p_dropout,
+                      ln_eps=1e-5, bias=True, device=device, seed=args.seed)
+    optimizer = Adam(model.parameters(), lr=args.learning_rate)
+
+    def sync():
+        torch.cuda.synchronize()
+
+    res = train(model, optimizer, args.iters, batch_size, L, rank, world, sync,
+                log=(lambda s: print(s, flush=True)) if rank == 0 else None)
+    t = torch.tensor([res["tokens_per_s_per_rank"]], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        # same line the reference prints (run_machine_translation.py:221), plus the job-level throughput
+        print("N: {}, Forward Time: {}, Backward Time: {}, Opt Time: {}".format(L, res["forward_s"], res["backward_s"], res["opt_s"]))
+        print(json.dumps({"metric": "decoder LM training tokens/s (whole job)", "value": float(t.item()) * world, "unit": "tokens/s",
+                          "n_gpus": world, "seq_len": L, "batch_per_rank": batch_size, "iters_timed": res["timed_iters"],
+                          "forward_s": res["forward_s"], "backward_s": res["backward_s"], "allreduce_s": res["allreduce_s"],
+                          "opt_s": res["opt_s"], "loss_first": res["loss_first"], "loss_last": res["loss_last"],
+                          "data": "synthetic uniform tokens", "params": sum(p.value.numel() for p in model.parameters())}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
