@@ -319,6 +319,23 @@ int fa_b200_bwd_dropout(const void* q, const void* k, const void* v, const void*
                   fa::make_dropout(p_drop, seed), workspace, workspace_bytes, stream);
 }
 
+// ---- decoder-LM operators (device pointers, fp32) ------------------------------------------
+int fa_b200_gemm_tf32(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, int a_mn_major,
+                      int b_mn_major, int accumulate, void* stream) {
+  if (!a || !b || !c) return fail(FA_ERR_BAD_ARG, "fa_b200_gemm_tf32: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0 || (M & 3) || (N & 3) || (K & 3))
+    return fail(FA_ERR_BAD_ARG, "fa_b200_gemm_tf32: M, N, K must be positive multiples of 4 (got %d %d %d)", M, N, K);
+  FA_CUDA(fa::gemm_tf32(a, b, c, bias, M, N, K, a_mn_major != 0, b_mn_major != 0, accumulate != 0,
+                        static_cast<cudaStream_t>(stream)), 1);
+  return FA_OK;
+}
+
+int fa_b200_colsum_f32(const float* x, float* out, int M, int N, int accumulate, void* stream) {
+  if (!x || !out || M <= 0 || N <= 0) return fail(FA_ERR_BAD_ARG, "fa_b200_colsum_f32: bad argument");
+  FA_CUDA(fa::colsum_f32(x, out, M, N, accumulate != 0, static_cast<cudaStream_t>(stream)), 1);
+  return FA_OK;
+}
+
 // developer hook (not declared in fa_b200.h): clock64 timeline of one backward CTA, see tools/fa_check.cu
 void fa_b200_debug_bwd_trace(void* dev_buf) { fa::tc_bwd_set_trace(static_cast<long long*>(dev_buf)); }
 

@@ -1,0 +1,215 @@
+// fa_gemm_sm100.cu -- fp32-storage / tf32 tensor-core GEMM for the decoder-LM linear layers.
+//
+// Replaces, for the Linear layers of the model path, the reference's MatrixMultiplyKernel (src/combine.cu:318-407:
+// a 32 x 32 shared-memory-tiled fp32 FMA kernel driven through host staging, minitorch/cuda_kernel_ops.py:302-380):
+//     C[M x N] = A[M x K] * B[K x N]  (+ bias[N])         fp32 in HBM, tcgen05.mma kind::tf32, fp32 accumulate in TMEM
+// Each operand may be stored with either dimension contiguous, which covers the three products of a Linear layer
+// without any transposition pass (W is (in, out) row-major as in minitorch/modules_basic.py:82-122):
+//     forward   Y  = X  W        A = X  (K contiguous)        B = W  (N contiguous)
+//     backward  dX = dY W^T      A = dY (K contiguous)        B = W  viewed (N' = in, K' = out): K contiguous
+//               dW = X^T dY      A = X  viewed (M' = in, K' = tokens): M contiguous;  B = dY: N contiguous
+// "K contiguous" operands are K-major UMMA operands (128-byte swizzle); "M/N contiguous" operands are MN-major and use
+// the 128B swizzle with 32-byte atomicity that UMMA requires for 32-bit MN-major data (verified by tools/umma_probe).
+//
+// One CTA computes one 128 x 128 tile: warp 4 = TMA producer (6-stage ring of 128 x 32 operand slabs), warp 5 = MMA
+// issuer (4 k-steps of 8 per slab), warps 0-3 = epilogue (TMEM -> registers -> + bias -> global, row per thread).
+// TMA zero-fills out-of-range rows / columns, so M, N, K only need to be multiples of 4 (16-byte global strides).
+#include <cuda.h>
+#include <math.h>
+
+#include "fa_internal.h"
+#include "fa_ptx.cuh"
+#include "fa_tma_host.h"
+
+namespace fa {
+
+namespace {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32;  // tile; kBK fp32 = one 128-byte swizzle row
+constexpr int kStages = 6;
+constexpr int kSlabBytes = 128 * 128;           // 128 x 32 fp32, either orientation
+constexpr int kGemmThreads = 192;
+constexpr int kGemmSmem = 2 * kStages * kSlabBytes + 1024;
+
+struct GemmParams {
+  int M, N, K;
+  float* c;
+  const float* bias;  // nullptr = none
+  int accumulate;     // C += A B instead of C = A B
+};
+
+struct GemmBarriers {
+  uint64_t full[kStages], empty[kStages], acc_full;
+};
+
+// kAMn / kBMn: operand stored with its M / N dimension contiguous (MN-major) instead of K contiguous (K-major)
+template <bool kAMn, bool kBMn>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kSlabBytes;
+  __shared__ GemmBarriers bars;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const int nk = (p.K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bars.full[i], 1);
+      mbar_init(&bars.empty[i], 1);
+    }
+    mbar_init(&bars.acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(&tmem_slot, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_a);
+      tma_prefetch_desc(&map_b);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int st = kb % kStages;
+        mbar_wait(&bars.empty[st], ((kb / kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars.full[st], 2 * kSlabBytes);
+        uint8_t* a = sA + st * kSlabBytes;
+        uint8_t* b = sB + st * kSlabBytes;
+        if constexpr (kAMn) {  // global [K][M]: four boxes of (32 m) x (32 k rows)
+          for (int x = 0; x < 4; ++x) tma_load_3d(a + x * 4096, &map_a, &bars.full[st], m0 + 32 * x, kb * kBK, 0, kEvictNormal);
+        } else {               // global [M][K]: one box of (32 k) x (128 m rows)
+          tma_load_3d(a, &map_a, &bars.full[st], kb * kBK, m0, 0, kEvictNormal);
+        }
+        if constexpr (kBMn) {
+          for (int x = 0; x < 4; ++x) tma_load_3d(b + x * 4096, &map_b, &bars.full[st], n0 + 32 * x, kb * kBK, 0, kEvictNormal);
+        } else {
+          tma_load_3d(b, &map_b, &bars.full[st], kb * kBK, n0, 0, kEvictNormal);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kFmtTF32, kBM, kBN, kAMn ? 1 : 0, kBMn ? 1 : 0);
+      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int st = kb % kStages;
+        mbar_wait(&bars.full[st], (kb / kStages) & 1);
+        tc_fence_after();
+        const uint32_t a = a0 + st * kSlabBytes, b = b0 + st * kSlabBytes;
+#pragma unroll
+        for (int kk = 0; kk < kBK / 8; ++kk) {
+          // K-major: 8 tf32 = 32 bytes along the swizzle row, 8-row groups 1024 B apart.  MN-major: 8 k-rows = 1 KB,
+          // 4-row groups 512 B apart, 32-element MN atoms one 4 KB box apart, 32-byte-atom swizzle.
+          const uint64_t da = kAMn ? make_smem_desc(a + kk * 1024, 4096, 512, kDescSw128Base32) : make_smem_desc(a + kk * 32, 16, 1024);
+          const uint64_t db = kBMn ? make_smem_desc(b + kk * 1024, 4096, 512, kDescSw128Base32) : make_smem_desc(b + kk * 32, 16, 1024);
+          umma_ss<true>(tmem, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&bars.empty[st]);
+      }
+      umma_commit(&bars.acc_full);
+    }
+  } else {
+    // epilogue: thread = one output row (TMEM lane), 128 fp32 columns
+    mbar_wait(&bars.acc_full, 0);
+    tc_fence_after();
+    const int row = m0 + warp * 32 + lane;
+    const uint32_t tacc = tmem + (uint32_t(warp * 32) << 16);
+    float* crow = p.c + (size_t)(row < p.M ? row : 0) * p.N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kBN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_x32(tacc + c0, r);
+      tmem_wait_ld();
+      if (row < p.M) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const int col = n0 + c0 + i;
+          if (col < p.N) {  // N is a multiple of 4: a float4 is entirely inside or outside
+            float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+            if (p.bias) {
+              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
+              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            }
+            float4* dst = reinterpret_cast<float4*>(crow + col);
+            if (p.accumulate) {
+              const float4 o = *dst;
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *dst = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 128);
+}
+
+template <bool kAMn, bool kBMn>
+cudaError_t launch_gemm(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, bool accumulate,
+                        cudaStream_t st) {
+  CUtensorMap ma, mb;
+  // K-major operand [rows][K]: box (32 k, 128 rows), 128B swizzle.  MN-major operand [K][cols]: box (32 cols, 32 k rows),
+  // 128B swizzle with 32-byte atoms.
+  if (kAMn ? make_tmap_3d(&ma, a, 4, M, K, 1, 32, 32, 2) : make_tmap_3d(&ma, a, 4, K, M, 1, 32, 128, 1)) return cudaErrorInvalidValue;
+  if (kBMn ? make_tmap_3d(&mb, b, 4, N, K, 1, 32, 32, 2) : make_tmap_3d(&mb, b, 4, K, N, 1, 32, 128, 1)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(fa_gemm_tf32_kernel<kAMn, kBMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+  if (e != cudaSuccess) return e;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.c = c; p.bias = bias; p.accumulate = accumulate ? 1 : 0;
+  dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM);
+  fa_gemm_tf32_kernel<kAMn, kBMn><<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, p);
+  return cudaGetLastError();
+}
+
+// out[n] (+)= sum_m x[m][n]   (bias gradient)
+__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int accumulate) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __shared__ float part[8][33];
+  float acc = 0.f;
+  if (n < N)
+    for (int m = blockIdx.y * nw + w; m < M; m += nw * gridDim.y) acc += x[(size_t)m * N + n];
+  part[w][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (w == 0 && n < N) {
+    float s = 0.f;
+    for (int i = 0; i < nw; ++i) s += part[i][threadIdx.x & 31];
+    if (gridDim.y > 1 || accumulate) atomicAdd(out + n, s);
+    else out[n] = s;
+  }
+}
+
+}  // namespace
+
+cudaError_t gemm_tf32(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, bool a_mn_major,
+                      bool b_mn_major, bool accumulate, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0 || (M & 3) || (N & 3) || (K & 3)) return cudaErrorInvalidValue;
+  if (a_mn_major) return b_mn_major ? launch_gemm<true, true>(a, b, c, bias, M, N, K, accumulate, st)
+                                    : launch_gemm<true, false>(a, b, c, bias, M, N, K, accumulate, st);
+  return b_mn_major ? launch_gemm<false, true>(a, b, c, bias, M, N, K, accumulate, st)
+                    : launch_gemm<false, false>(a, b, c, bias, M, N, K, accumulate, st);
+}
+
+cudaError_t colsum_f32(const float* x, float* out, int M, int N, bool accumulate, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return cudaErrorInvalidValue;
+  const int ysplit = M >= 4096 ? 16 : 1;
+  if (ysplit > 1 && !accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * 4, st);
+    if (e != cudaSuccess) return e;
+  }
+  colsum_kernel<<<dim3((N + 31) / 32, ysplit), 256, 0, st>>>(x, out, M, N, accumulate ? 1 : 0);
+  return cudaGetLastError();
+}
+
+}  // namespace fa

@@ -52,4 +52,11 @@ cudaError_t lse_from_lm(const float* l, const float* m, float* lse, size_t n, cu
 // keep[h - head_begin][i][j] = 1/0 for heads [head_begin, head_begin + n_heads): the mask every kernel regenerates
 cudaError_t dropout_mask(unsigned char* keep, int head_begin, int n_heads, int T, Dropout drop, cudaStream_t st);
 
+// ---- decoder-LM operators around the attention path (fa_gemm_sm100.cu, fa_lm_kernels.cu) --------
+// C[M x N] (+)= A * B (+ bias[N]); fp32 storage, tf32 tensor cores.  a_mn_major: A stored [K][M] (M contiguous) instead
+// of [M][K]; b_mn_major: B stored [K][N] (N contiguous) instead of [N][K].  M, N, K multiples of 4.
+cudaError_t gemm_tf32(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, bool a_mn_major,
+                      bool b_mn_major, bool accumulate, cudaStream_t st);
+cudaError_t colsum_f32(const float* x, float* out, int M, int N, bool accumulate, cudaStream_t st);
+
 }  // namespace fa

@@ -70,6 +70,10 @@ def load_library() -> ctypes.CDLL:
     lib.fa_b200_dropout_keep_scale.restype = f32
     lib.fa_b200_dropout_effective_p.argtypes = [f32]
     lib.fa_b200_dropout_effective_p.restype = f32
+    lib.fa_b200_gemm_tf32.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+    lib.fa_b200_gemm_tf32.restype = ci
+    lib.fa_b200_colsum_f32.argtypes = [vp, vp, ci, ci, ci, vp]
+    lib.fa_b200_colsum_f32.restype = ci
     lib.fa_b200_host_fwd.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
     lib.fa_b200_host_fwd.restype = ci
     lib.fa_b200_host_bwd.argtypes = [vp] * 10 + [ci, ci, ci, ci, ci, vp]

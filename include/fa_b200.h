@@ -126,6 +126,20 @@ int fa_b200_get_host_precision(void);
 void fa_b200_release_arena(void);
 
 /* ------------------------------------------------------------------------------------------
+ * Operators of the decoder-only LM around the attention path ("next" rows), device pointers,
+ * fp32.  They replace, for the model path of project/run_machine_translation.py, the reference's host-staged
+ * kernels of src/combine.cu (MatrixMultiplyKernel :318-407, reduceKernel :409-470).
+ *   fa_b200_gemm_tf32 : C[M x N] (+)= A[M x K] B[K x N] (+ bias[N]) on tcgen05 kind::tf32, fp32 accumulate.
+ *       a_mn_major = 0: A stored [M][K];  1: A stored [K][M].   b_mn_major = 0: B stored [N][K];  1: B stored [K][N].
+ *       Linear (W is (in, out)):  Y = X W: (0, 1);  dX = dY W^T: (0, 0) with B = W;  dW = X^T dY: (1, 1).
+ *       M, N, K multiples of 4.
+ *   fa_b200_colsum_f32: out[N] (+)= column sums of x[M][N]  (bias gradients)
+ * ------------------------------------------------------------------------------------------ */
+int fa_b200_gemm_tf32(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, int a_mn_major,
+                      int b_mn_major, int accumulate, void* stream);
+int fa_b200_colsum_f32(const float* x, float* out, int M, int N, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * The reference entry points themselves.  Exported by the six shim libraries (not by libfa_b200.so,
  * where the two conventions would collide on one symbol name).  `stream` is a cudaStream_t.
  * On failure they print to stderr and exit(EXIT_FAILURE), as the reference does
