@@ -336,6 +336,65 @@ int fa_b200_colsum_f32(const float* x, float* out, int M, int N, int accumulate,
   return FA_OK;
 }
 
+#define FA_ST static_cast<cudaStream_t>(stream)
+int fa_b200_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, int rows,
+                          int dim, float eps, void* stream) {
+  if (!x || !w || !b || !y || !mean || !rstd) return fail(FA_ERR_BAD_ARG, "fa_b200_layernorm_fwd: null pointer");
+  FA_CUDA(fa::layernorm_fwd(x, w, b, y, mean, rstd, rows, dim, eps, FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_layernorm_bwd(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
+                          float* dw, float* db, int rows, int dim, void* stream) {
+  if (!x || !w || !dy || !mean || !rstd || !dx || !dw || !db) return fail(FA_ERR_BAD_ARG, "fa_b200_layernorm_bwd: null pointer");
+  FA_CUDA(fa::layernorm_bwd(x, w, dy, mean, rstd, dx, dw, db, rows, dim, FA_ST), 2);
+  return FA_OK;
+}
+int fa_b200_gelu_fwd(const float* x, float* y, size_t n, void* stream) {
+  if (!x || !y) return fail(FA_ERR_BAD_ARG, "fa_b200_gelu_fwd: null pointer");
+  FA_CUDA(fa::gelu(x, nullptr, y, n, false, FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_gelu_bwd(const float* x, const float* dy, float* dx, size_t n, void* stream) {
+  if (!x || !dy || !dx) return fail(FA_ERR_BAD_ARG, "fa_b200_gelu_bwd: null pointer");
+  FA_CUDA(fa::gelu(x, dy, dx, n, true, FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_dropout_apply(const float* x, float* y, size_t n, float p_drop, unsigned long long seed, void* stream) {
+  if (!x || !y) return fail(FA_ERR_BAD_ARG, "fa_b200_dropout_apply: null pointer");
+  if (int rc = check_p_drop(p_drop, "fa_b200_dropout_apply")) return rc;
+  FA_CUDA(fa::dropout_apply(x, y, n, fa::make_dropout(p_drop, seed), FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_embedding_fwd(const long long* idx, const float* w, float* y, size_t n_idx, int dim, void* stream) {
+  if (!idx || !w || !y) return fail(FA_ERR_BAD_ARG, "fa_b200_embedding_fwd: null pointer");
+  FA_CUDA(fa::embedding_fwd(idx, w, y, n_idx, dim, FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, void* stream) {
+  if (!idx || !dy || !dw) return fail(FA_ERR_BAD_ARG, "fa_b200_embedding_bwd: null pointer");
+  FA_CUDA(fa::embedding_bwd(idx, dy, dw, n_idx, dim, vocab, FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_softmax_loss_fwd(const float* logits, const long long* target, float* loss, float* lse, int rows, int n_classes,
+                             void* stream) {
+  if (!logits || !target || !loss || !lse) return fail(FA_ERR_BAD_ARG, "fa_b200_softmax_loss_fwd: null pointer");
+  FA_CUDA(fa::softmax_loss_fwd(logits, target, loss, lse, rows, n_classes, FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_softmax_loss_bwd(const float* logits, const long long* target, const float* lse, const float* gscale,
+                             float* dlogits, int rows, int n_classes, void* stream) {
+  if (!logits || !target || !lse || !gscale || !dlogits) return fail(FA_ERR_BAD_ARG, "fa_b200_softmax_loss_bwd: null pointer");
+  FA_CUDA(fa::softmax_loss_bwd(logits, target, lse, gscale, dlogits, rows, n_classes, FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_adam_step(float* p, const float* g, float* m, float* v, size_t n, float step_size, float beta1, float beta2,
+                      float v_coef, float eps, void* stream) {
+  if (!p || !g || !m || !v) return fail(FA_ERR_BAD_ARG, "fa_b200_adam_step: null pointer");
+  FA_CUDA(fa::adam_step(p, g, m, v, n, step_size, beta1, beta2, v_coef, eps, FA_ST), 1);
+  return FA_OK;
+}
+#undef FA_ST
+
 // developer hook (not declared in fa_b200.h): clock64 timeline of one backward CTA, see tools/fa_check.cu
 void fa_b200_debug_bwd_trace(void* dev_buf) { fa::tc_bwd_set_trace(static_cast<long long*>(dev_buf)); }
 

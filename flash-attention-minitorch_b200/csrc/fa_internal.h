@@ -58,5 +58,20 @@ cudaError_t dropout_mask(unsigned char* keep, int head_begin, int n_heads, int T
 cudaError_t gemm_tf32(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, bool a_mn_major,
                       bool b_mn_major, bool accumulate, cudaStream_t st);
 cudaError_t colsum_f32(const float* x, float* out, int M, int N, bool accumulate, cudaStream_t st);
+// fa_lm_kernels.cu: one fused pass per operator (dims multiples of 4; dw/db/embedding-dw are zeroed inside)
+cudaError_t layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, int rows,
+                          int dim, float eps, cudaStream_t st);
+cudaError_t layernorm_bwd(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
+                          float* dw, float* db, int rows, int dim, cudaStream_t st);
+cudaError_t gelu(const float* x, const float* dy, float* y, size_t n, bool backward, cudaStream_t st);
+cudaError_t dropout_apply(const float* x, float* y, size_t n, Dropout drop, cudaStream_t st);
+cudaError_t embedding_fwd(const long long* idx, const float* w, float* y, size_t n_idx, int dim, cudaStream_t st);
+cudaError_t embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, cudaStream_t st);
+cudaError_t softmax_loss_fwd(const float* logits, const long long* target, float* loss, float* lse, int rows, int C,
+                             cudaStream_t st);
+cudaError_t softmax_loss_bwd(const float* logits, const long long* target, const float* lse, const float* gscale,
+                             float* dlogits, int rows, int C, cudaStream_t st);
+cudaError_t adam_step(float* p, const float* g, float* m, float* v, size_t n, float step_size, float b1, float b2,
+                      float v_coef, float eps, cudaStream_t st);
 
 }  // namespace fa

@@ -1,0 +1,327 @@
+// fa_lm_kernels.cu -- HBM-bound operators of the decoder-LM slice: LayerNorm,
+// GELU, dropout, embedding, softmax cross-entropy and the optimizer step, device-resident and fused per operator.
+//
+// What they replace in the reference (each of which stages through host numpy storage, one elementwise
+// map/zip/reduce launch per arithmetic op, minitorch/cuda_kernel_ops.py:60-200 over src/combine.cu:150-734):
+//   LayerNorm1d.forward     mean, (x-mean)^2 mean, +eps, ^0.5, /, *w, +b  (8 launches)   minitorch/modules_basic.py:166-175
+//   GELU                    tanh approximation (9 launches)                              minitorch/nn.py:208-214
+//   Dropout.forward         host np.random.binomial mask, 2 launches                     minitorch/modules_basic.py:77-80
+//   Embedding.forward       one_hot (host) @ weights                                     minitorch/modules_basic.py:46-53
+//   softmax_loss            logsumexp - sum(one_hot * logits)                            minitorch/nn.py:217-274
+//   Adam.step               ~12 launches per parameter                                   minitorch/optim.py:44-76
+// All are memory-bound: one pass over the data, 16-byte accesses where the layout allows, grids sized in multiples
+// of the SM count.  Row reductions use one warp (LayerNorm, dim <= 8192) or one CTA (loss, any class count) per row.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "fa_dropout.cuh"
+#include "fa_internal.h"
+
+namespace fa {
+
+namespace {
+
+constexpr int kSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+__device__ __forceinline__ float warp_max(float x) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+
+// ---------------------------------------------------------------- LayerNorm (one warp per row)
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                     float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                     int rows, int dim, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * dim;
+  float s = 0.f;
+  for (int c = lane * 4; c < dim; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(s) / dim;
+  float q = 0.f;
+  for (int c = lane * 4; c < dim; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float a = v.x - mean, bb = v.y - mean, cc = v.z - mean, d = v.w - mean;
+    q += (a * a + bb * bb) + (cc * cc + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / dim + eps);  // biased variance, as ((x - mean) ** 2).mean()
+  float* yr = y + (size_t)row * dim;
+  for (int c = lane * 4; c < dim; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float4 ww = *reinterpret_cast<const float4*>(w + c);
+    const float4 bv = *reinterpret_cast<const float4*>(b + c);
+    *reinterpret_cast<float4*>(yr + c) = make_float4(ww.x * (v.x - mean) * rstd + bv.x, ww.y * (v.y - mean) * rstd + bv.y,
+                                                     ww.z * (v.z - mean) * rstd + bv.z, ww.w * (v.w - mean) * rstd + bv.w);
+  }
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+// dx = rstd * (w dy - mean(w dy) - xhat mean(w dy xhat));  one warp per row
+__global__ void layernorm_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ dy,
+                                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                        float* __restrict__ dx, int rows, int dim) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * dim;
+  const float* gr = dy + (size_t)row * dim;
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane * 4; c < dim; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float4 g = *reinterpret_cast<const float4*>(gr + c);
+    const float4 ww = *reinterpret_cast<const float4*>(w + c);
+    const float g0 = g.x * ww.x, g1 = g.y * ww.y, g2 = g.z * ww.z, g3 = g.w * ww.w;
+    s1 += (g0 + g1) + (g2 + g3);
+    s2 += (g0 * (v.x - mean) + g1 * (v.y - mean) + g2 * (v.z - mean) + g3 * (v.w - mean)) * rstd;
+  }
+  s1 = warp_sum(s1) / dim;
+  s2 = warp_sum(s2) / dim;
+  float* dr = dx + (size_t)row * dim;
+  for (int c = lane * 4; c < dim; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float4 g = *reinterpret_cast<const float4*>(gr + c);
+    const float4 ww = *reinterpret_cast<const float4*>(w + c);
+    *reinterpret_cast<float4*>(dr + c) = make_float4(rstd * (g.x * ww.x - s1 - (v.x - mean) * rstd * s2),
+                                                     rstd * (g.y * ww.y - s1 - (v.y - mean) * rstd * s2),
+                                                     rstd * (g.z * ww.z - s1 - (v.z - mean) * rstd * s2),
+                                                     rstd * (g.w * ww.w - s1 - (v.w - mean) * rstd * s2));
+  }
+}
+
+// dw[c] += sum_rows dy xhat, db[c] += sum_rows dy: thread = column, block = strip of rows, one atomic per column per block
+__global__ void layernorm_bwd_dwdb_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                          float* __restrict__ dw, float* __restrict__ db, int rows, int dim, int rows_per_block) {
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < dim; c += gridDim.x * blockDim.x) {
+    float aw = 0.f, ab = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const float g = dy[(size_t)r * dim + c];
+      aw += g * (x[(size_t)r * dim + c] - mean_in[r]) * rstd_in[r];
+      ab += g;
+    }
+    atomicAdd(dw + c, aw);
+    atomicAdd(db + c, ab);
+  }
+}
+
+// ---------------------------------------------------------------- GELU (tanh approximation)
+__device__ __forceinline__ float gelu_f(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.f + tanhf(u));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  const float t = tanhf(u);
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * 0.7978845608028654f * (1.f + 3.f * 0.044715f * x * x);
+}
+// mode 0: y = gelu(x);  mode 1: y = dy * gelu'(x)
+__global__ void gelu_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ y, size_t n4,
+                            int mode) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 o;
+    if (mode == 0) {
+      o = make_float4(gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w));
+    } else {
+      const float4 g = reinterpret_cast<const float4*>(dy)[i];
+      o = make_float4(g.x * gelu_grad_f(v.x), g.y * gelu_grad_f(v.y), g.z * gelu_grad_f(v.z), g.w * gelu_grad_f(v.w));
+    }
+    reinterpret_cast<float4*>(y)[i] = o;
+  }
+}
+
+// ---------------------------------------------------------------- dropout: y = x * keep / (1 - p), keep = f(seed, index)
+// The same call serves forward and backward (the op is linear in x): nothing is stored between them.
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n4, uint32_t key, uint32_t thr,
+                               float scale) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    // one hash word per four elements: byte e (7 bits) >= thr keeps element e
+    const uint32_t w = drop_keep_word(drop_mix(key ^ ((uint32_t)i * kDropRowMul) ^ ((uint32_t)(i >> 32) * kDropColMul)), thr);
+    reinterpret_cast<float4*>(y)[i] = make_float4((w & 0x80u) ? v.x * scale : 0.f, (w & 0x8000u) ? v.y * scale : 0.f,
+                                                  (w & 0x800000u) ? v.z * scale : 0.f, (w & 0x80000000u) ? v.w * scale : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------- embedding
+__global__ void embedding_fwd_kernel(const long long* __restrict__ idx, const float* __restrict__ w, float* __restrict__ y,
+                                     size_t n_idx, int dim4) {
+  const size_t total = n_idx * dim4, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / dim4;
+    const int c = (int)(i - r * dim4);
+    reinterpret_cast<float4*>(y)[i] = reinterpret_cast<const float4*>(w)[(size_t)idx[r] * dim4 + c];
+  }
+}
+__global__ void embedding_bwd_kernel(const long long* __restrict__ idx, const float* __restrict__ dy, float* __restrict__ dw,
+                                     size_t n_idx, int dim) {
+  const size_t total = n_idx * dim, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / dim;
+    const int c = (int)(i - r * dim);
+    atomicAdd(dw + (size_t)idx[r] * dim + c, dy[i]);
+  }
+}
+
+// ---------------------------------------------------------------- softmax cross-entropy (one CTA per row)
+__device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[w] = v;
+  __syncthreads();
+  float r = is_max ? -INFINITY : 0.f;
+  for (int i = 0; i < nw; ++i) r = is_max ? fmaxf(r, sh[i]) : r + sh[i];
+  return r;
+}
+// loss[i] = logsumexp(logits[i]) - logits[i][target[i]];  lse saved for the backward
+__global__ void softmax_loss_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                        float* __restrict__ loss, float* __restrict__ lse_out, int C) {
+  __shared__ float sh[32];
+  const float* row = logits + (size_t)blockIdx.x * C;
+  float m = -INFINITY;
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  m = block_reduce(m, sh, true);
+  float s = 0.f;
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    s += (__expf(v.x - m) + __expf(v.y - m)) + (__expf(v.z - m) + __expf(v.w - m));
+  }
+  s = block_reduce(s, sh, false);
+  if (threadIdx.x == 0) {
+    const float lse = m + logf(s);
+    lse_out[blockIdx.x] = lse;
+    loss[blockIdx.x] = lse - row[target[blockIdx.x]];
+  }
+}
+// dlogits[i][j] = gscale[i] * (exp(logits[i][j] - lse[i]) - [j == target[i]])
+__global__ void softmax_loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                        const float* __restrict__ lse, const float* __restrict__ gscale,
+                                        float* __restrict__ dlogits, int C) {
+  const float* row = logits + (size_t)blockIdx.x * C;
+  float* out = dlogits + (size_t)blockIdx.x * C;
+  const float L = lse[blockIdx.x], g = gscale[blockIdx.x];
+  const int t = (int)target[blockIdx.x];
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    float4 o = make_float4(g * __expf(v.x - L), g * __expf(v.y - L), g * __expf(v.z - L), g * __expf(v.w - L));
+    if (t >= c && t < c + 4) (&o.x)[t - c] -= g;
+    *reinterpret_cast<float4*>(out + c) = o;
+  }
+}
+
+// ---------------------------------------------------------------- Adam over one flat parameter buffer
+// m = b1 m + (1-b1) g;  v = b2 v + (1-b1) g^2  (sic: the reference uses 1-beta1 here, minitorch/optim.py:68);
+// p -= step_size * m / (sqrt(v) + eps),  step_size = lr sqrt(1-b2^t) / (1-b1^t) computed by the host.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            size_t n4, float step_size, float b1, float b2, float v_coef, float eps) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define FA_ADAM1(c)                                    \
+  mm.c = b1 * mm.c + (1.f - b1) * gg.c;                \
+  vv.c = b2 * vv.c + v_coef * gg.c * gg.c;             \
+  pp.c -= step_size * mm.c / (sqrtf(vv.c) + eps);
+    FA_ADAM1(x) FA_ADAM1(y) FA_ADAM1(z) FA_ADAM1(w)
+#undef FA_ADAM1
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+}
+
+inline unsigned ew_grid(size_t items, int threads) {
+  size_t b = (items + threads - 1) / threads;
+  if (b > (size_t)kSMs * 16) b = (size_t)kSMs * 16;
+  return (unsigned)(b ? b : 1);
+}
+
+}  // namespace
+
+cudaError_t layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, int rows,
+                          int dim, float eps, cudaStream_t st) {
+  if (rows <= 0 || dim <= 0 || (dim & 3)) return cudaErrorInvalidValue;
+  layernorm_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, w, b, y, mean, rstd, rows, dim, eps);
+  return cudaGetLastError();
+}
+cudaError_t layernorm_bwd(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
+                          float* dw, float* db, int rows, int dim, cudaStream_t st) {
+  if (rows <= 0 || dim <= 0 || (dim & 3)) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(dw, 0, (size_t)dim * 4, st)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(db, 0, (size_t)dim * 4, st)) != cudaSuccess) return e;
+  layernorm_bwd_dx_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, w, dy, mean, rstd, dx, rows, dim);
+  const int col_blocks = (dim + 255) / 256;
+  int strips = (kSMs * 2) / col_blocks;
+  if (strips < 1) strips = 1;
+  if (strips > rows) strips = rows;
+  const int rpb = (rows + strips - 1) / strips;
+  layernorm_bwd_dwdb_kernel<<<dim3(col_blocks, (rows + rpb - 1) / rpb), 256, 0, st>>>(x, dy, mean, rstd, dw, db, rows, dim, rpb);
+  return cudaGetLastError();
+}
+cudaError_t gelu(const float* x, const float* dy, float* y, size_t n, bool backward, cudaStream_t st) {
+  if (n & 3) return cudaErrorInvalidValue;
+  gelu_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(x, dy, y, n / 4, backward ? 1 : 0);
+  return cudaGetLastError();
+}
+cudaError_t dropout_apply(const float* x, float* y, size_t n, Dropout drop, cudaStream_t st) {
+  if (n & 3) return cudaErrorInvalidValue;
+  const uint32_t key = drop_head_key(drop.seed_lo, drop.seed_hi, 0xE1E7u);
+  dropout_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(x, y, n / 4, key, drop.thr, drop.keep_scale);
+  return cudaGetLastError();
+}
+cudaError_t embedding_fwd(const long long* idx, const float* w, float* y, size_t n_idx, int dim, cudaStream_t st) {
+  if (dim <= 0 || (dim & 3)) return cudaErrorInvalidValue;
+  embedding_fwd_kernel<<<ew_grid(n_idx * (dim / 4), 256), 256, 0, st>>>(idx, w, y, n_idx, dim / 4);
+  return cudaGetLastError();
+}
+cudaError_t embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(dw, 0, vocab * dim * 4, st);
+  if (e != cudaSuccess) return e;
+  embedding_bwd_kernel<<<ew_grid(n_idx * dim, 256), 256, 0, st>>>(idx, dy, dw, n_idx, dim);
+  return cudaGetLastError();
+}
+cudaError_t softmax_loss_fwd(const float* logits, const long long* target, float* loss, float* lse, int rows, int C,
+                             cudaStream_t st) {
+  if (rows <= 0 || C <= 0 || (C & 3)) return cudaErrorInvalidValue;
+  softmax_loss_fwd_kernel<<<rows, 256, 0, st>>>(logits, target, loss, lse, C);
+  return cudaGetLastError();
+}
+cudaError_t softmax_loss_bwd(const float* logits, const long long* target, const float* lse, const float* gscale,
+                             float* dlogits, int rows, int C, cudaStream_t st) {
+  if (rows <= 0 || C <= 0 || (C & 3)) return cudaErrorInvalidValue;
+  softmax_loss_bwd_kernel<<<rows, 256, 0, st>>>(logits, target, lse, gscale, dlogits, C);
+  return cudaGetLastError();
+}
+cudaError_t adam_step(float* p, const float* g, float* m, float* v, size_t n, float step_size, float b1, float b2,
+                      float v_coef, float eps, cudaStream_t st) {
+  if (n & 3) return cudaErrorInvalidValue;
+  adam_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(p, g, m, v, n / 4, step_size, b1, b2, v_coef, eps);
+  return cudaGetLastError();
+}
+
+}  // namespace fa

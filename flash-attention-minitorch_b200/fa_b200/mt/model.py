@@ -59,6 +59,25 @@ class Module:
     def __call__(self, *a, **kw):
         return self.forward(*a, **kw)
 
+    def flatten_parameters(self):
+        """Move every parameter into ONE flat buffer (values) with a twin flat buffer for gradients; each
+        Parameter.value becomes a view of the first and its .grad a view of the second (autograd accumulates into it
+        in place).  One optimizer kernel and one all-reduce then cover the whole model.  Returns (values, grads)."""
+        params = self.parameters()
+        sizes = [p.value.numel() for p in params]
+        total = (sum(sizes) + 3) // 4 * 4  # the elementwise kernels move float4s
+        ref = params[0].value
+        flat = torch.zeros(total, device=ref.device, dtype=ref.dtype)
+        gflat = torch.zeros_like(flat)
+        off = 0
+        for p, n in zip(params, sizes):
+            flat[off:off + n].copy_(p.value.detach().reshape(-1))
+            p.value = flat[off:off + n].view(p.value.shape).requires_grad_(True)
+            p.value.grad = gflat[off:off + n].view(p.value.shape)
+            off += n
+        self._flat = (flat, gflat)
+        return self._flat
+
 
 def _rparam(in_size: int, shape, device, dtype, gen) -> Parameter:
     r = (2.0 / math.sqrt(in_size)) * (torch.rand(shape, generator=gen, dtype=torch.float32) - 0.5)

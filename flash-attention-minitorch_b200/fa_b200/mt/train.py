@@ -34,15 +34,21 @@ def synthetic_batch(batch_size: int, seq_len: int, n_vocab: int, device, gen: to
 
 class GradAllReducer:
     """One flat bucket for all gradients: a single all-reduce per step (payload ~36 MB at the reference config,
-    latency-bound on NVSwitch, so one launch beats per-parameter calls)."""
+    latency-bound on NVSwitch, so one launch beats per-parameter calls).  With flattened parameters
+    (Module.flatten_parameters) the bucket IS the gradient storage: no packing copies."""
 
-    def __init__(self, params: List, world: int):
+    def __init__(self, params: List, world: int, flat_grads: Optional[torch.Tensor] = None):
         self.params, self.world = params, world
         self.numel = sum(p.value.numel() for p in params)
         self.flat: Optional[torch.Tensor] = None
+        self.flat_grads = flat_grads
 
     def __call__(self) -> None:
         if self.world == 1:
+            return
+        if self.flat_grads is not None:
+            dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM)
+            self.flat_grads.div_(self.world)
             return
         p0 = self.params[0].value
         if self.flat is None:
@@ -71,7 +77,7 @@ def train(model: DecoderLM, optimizer: Adam, n_iters: int, batch_size: int, seq_
     model.train()
     device = next(iter(model.parameters())).value.device
     gen = torch.Generator().manual_seed(1000 * (rank + 1) + seed)
-    reducer = GradAllReducer(model.parameters(), world)
+    reducer = GradAllReducer(model.parameters(), world, optimizer.flat[1] if optimizer.flat is not None else None)
     fw = bw = comm = opt = 0.0
     timed_tokens, timed_s, losses = 0, 0.0, []
     for it in range(n_iters):
@@ -130,7 +136,7 @@ def main(argv=None) -> int:
     batch_size = int((128 * 40 + L) / L)  # run_machine_translation.py:385, per rank
     model = DecoderLM(n_vocab=args.n_vocab, n_embd=args.n_embd, n_head=args.n_head, n_positions=L, p_dropout=args.p_dropout,
                       ln_eps=1e-5, bias=True, device=device, seed=args.seed)
-    optimizer = Adam(model.parameters(), lr=args.learning_rate)
+    optimizer = Adam(model.parameters(), lr=args.learning_rate, flat=model.flatten_parameters())
 
     def sync():
         torch.cuda.synchronize()

@@ -138,6 +138,33 @@ void fa_b200_release_arena(void);
 int fa_b200_gemm_tf32(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, int a_mn_major,
                       int b_mn_major, int accumulate, void* stream);
 int fa_b200_colsum_f32(const float* x, float* out, int M, int N, int accumulate, void* stream);
+/* One fused, device-resident pass per operator of the model path (reference formulas in parentheses); fp32, row-major,
+ * inner dimensions and element counts multiples of 4.
+ *   layernorm : y = w (x - mean) / sqrt(var + eps) + b, biased variance (minitorch/modules_basic.py:166-175);
+ *               fwd saves mean / rstd per row; bwd overwrites dx, dw, db
+ *   gelu      : tanh approximation (minitorch/nn.py:208-214)
+ *   dropout   : y = x * keep / (1 - p_eff), keep = f(seed, element index) -- call it again on dy for the backward
+ *               (minitorch/modules_basic.py:77-80; p quantised as in fa_b200_fwd_dropout)
+ *   embedding : y[i] = w[idx[i]]  (one_hot @ weights, minitorch/modules_basic.py:46-53); bwd overwrites dw[vocab][dim]
+ *   softmax_loss : loss[i] = logsumexp(logits[i]) - logits[i][target[i]] (minitorch/nn.py:256-274); lse saved;
+ *               bwd: dlogits[i][j] = gscale[i] (softmax(logits[i])[j] - [j == target[i]])
+ *   adam_step : m = b1 m + (1-b1) g; v = b2 v + v_coef g^2; p -= step_size m / (sqrt(v) + eps) over one flat buffer
+ *               (minitorch/optim.py:44-76, whose v_coef is 1 - beta1; step_size = lr sqrt(1-b2^t)/(1-b1^t)) */
+int fa_b200_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, int rows,
+                          int dim, float eps, void* stream);
+int fa_b200_layernorm_bwd(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
+                          float* dw, float* db, int rows, int dim, void* stream);
+int fa_b200_gelu_fwd(const float* x, float* y, size_t n, void* stream);
+int fa_b200_gelu_bwd(const float* x, const float* dy, float* dx, size_t n, void* stream);
+int fa_b200_dropout_apply(const float* x, float* y, size_t n, float p_drop, unsigned long long seed, void* stream);
+int fa_b200_embedding_fwd(const long long* idx, const float* w, float* y, size_t n_idx, int dim, void* stream);
+int fa_b200_embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, void* stream);
+int fa_b200_softmax_loss_fwd(const float* logits, const long long* target, float* loss, float* lse, int rows, int n_classes,
+                             void* stream);
+int fa_b200_softmax_loss_bwd(const float* logits, const long long* target, const float* lse, const float* gscale,
+                             float* dlogits, int rows, int n_classes, void* stream);
+int fa_b200_adam_step(float* p, const float* g, float* m, float* v, size_t n, float step_size, float beta1, float beta2,
+                      float v_coef, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * The reference entry points themselves.  Exported by the six shim libraries (not by libfa_b200.so,

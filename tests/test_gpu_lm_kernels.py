@@ -60,3 +60,90 @@ def test_colsum(cuda_device):
         assert float((out.double() - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
         _lib.check(lib.fa_b200_colsum_f32(x.data_ptr(), out.data_ptr(), M, N, 1, torch.cuda.current_stream().cuda_stream))
         assert float((out.double() - 2 * ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
+# ----------------------------------------------------------------------------------------------
+# fused HBM-bound operators vs their reference formulas in fp64 (the fixtures of the CPU suite pin those formulas
+# to the reference's own modules)
+# ----------------------------------------------------------------------------------------------
+from fa_b200.mt import ops  # noqa: E402
+from fa_b200.mt.optim import Adam  # noqa: E402
+from fa_b200.mt.model import Parameter  # noqa: E402
+
+
+def _grads(fn, inputs, gy):
+    outs = fn(*inputs)
+    (outs * gy).sum().backward()
+    return outs, [t.grad for t in inputs if t.requires_grad]
+
+
+@pytest.mark.parametrize("rows,dim", [(5632, 256), (77, 64), (3, 1024)])
+def test_layernorm_kernels(cuda_device, rows, dim):
+    torch.manual_seed(rows + dim)
+    x = (torch.randn(rows, dim) * 2 + 0.5)
+    w, b, gy = torch.rand(dim) + 0.5, torch.rand(dim) - 0.5, torch.rand(rows, dim) * 2 - 1
+    ref_in = [t.double().requires_grad_(True) for t in (x, w, b)]
+    y_ref, g_ref = _grads(lambda a, ww, bb: ops.layernorm(a, ww, bb, 1e-5), ref_in, gy.double())
+    dev_in = [t.to(cuda_device).requires_grad_(True) for t in (x, w, b)]
+    y, g = _grads(lambda a, ww, bb: ops.layernorm(a, ww, bb, 1e-5), dev_in, gy.to(cuda_device))
+    assert float((y.double().cpu() - y_ref).abs().max()) <= 1e-5
+    for got, ref in zip(g, g_ref):
+        assert float((got.double().cpu() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_gelu_dropout_embedding_kernels(cuda_device):
+    torch.manual_seed(4)
+    x, gy = torch.randn(1000, 256) * 2, torch.rand(1000, 256) * 2 - 1
+    xr = x.double().requires_grad_(True)
+    y_ref, (g_ref,) = _grads(ops.gelu, [xr], gy.double())
+    xd = x.to(cuda_device).requires_grad_(True)
+    y, (g,) = _grads(ops.gelu, [xd], gy.to(cuda_device))
+    assert float((y.double().cpu() - y_ref).abs().max()) <= 2e-6 and float((g.double().cpu() - g_ref).abs().max()) <= 2e-6
+    # dropout: inverted Bernoulli, same mask regenerated in the backward, fresh mask per call
+    xd = torch.ones(2048, 512, device=cuda_device, requires_grad=True)
+    y1 = ops.dropout(xd, 0.1, True)
+    y1.sum().backward()
+    keep = float((y1 != 0).float().mean())
+    p_eff = 13 / 128
+    assert abs(keep - (1 - p_eff)) <= 5 * (p_eff * (1 - p_eff) / y1.numel()) ** 0.5
+    assert abs(float(y1.max()) - 1 / (1 - p_eff)) < 1e-6 and torch.equal(xd.grad, y1.detach())  # dy = 1: dx = mask * scale
+    assert not torch.equal(ops.dropout(xd, 0.1, True), y1) and ops.dropout(xd, 0.1, False) is xd
+    # embedding: gather forward, scatter-add backward with repeated indices
+    w = torch.randn(300, 64)
+    idx = torch.randint(0, 300, (7, 33))
+    ge = torch.randn(7, 33, 64)
+    wr = w.double().requires_grad_(True)
+    (wr[idx] * ge.double()).sum().backward()
+    wd = w.to(cuda_device).requires_grad_(True)
+    yd = ops.embedding(idx.to(cuda_device), wd)
+    (yd * ge.to(cuda_device)).sum().backward()
+    assert torch.equal(yd.cpu(), w[idx]) and float((wd.grad.double().cpu() - wr.grad).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("rows,C", [(5632, 10000), (9, 36), (64, 300)])
+def test_softmax_loss_kernels(cuda_device, rows, C):
+    torch.manual_seed(C)
+    logits, target, gw = torch.randn(rows, C) * 3, torch.randint(0, C, (rows,)), torch.rand(rows)
+    lr = logits.double().requires_grad_(True)
+    loss_ref = ops.softmax_loss(lr, target)
+    (loss_ref * gw.double()).sum().backward()
+    ld = logits.to(cuda_device).requires_grad_(True)
+    loss = ops.softmax_loss(ld, target.to(cuda_device))
+    (loss * gw.to(cuda_device)).sum().backward()
+    assert float((loss.double().cpu() - loss_ref).abs().max()) <= 2e-5
+    assert float((ld.grad.double().cpu() - lr.grad).abs().max()) <= 2e-6
+
+
+def test_fused_adam_kernel_matches_reference_formula(cuda_device):
+    torch.manual_seed(1)
+    p0, grads = torch.rand(1000) * 2 - 1, torch.randn(4, 1000)
+    ref = Parameter(p0.double().clone())
+    oref = Adam([ref], lr=0.02)
+    flat, gflat = p0.to(cuda_device).clone(), torch.zeros(1000, device=cuda_device)
+    odev = Adam([], lr=0.02, flat=(flat, gflat))
+    for g in grads:
+        ref.value.grad = g.double()
+        oref.step()
+        gflat.copy_(g)
+        odev.step()
+    assert float((flat.double().cpu() - ref.value.detach()).abs().max()) <= 2e-6

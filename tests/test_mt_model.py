@@ -176,3 +176,19 @@ def test_two_rank_gloo_data_parallel_equals_single_process_on_the_union_batch():
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "dp==single True ranks_equal True" in outs[0], outs
+
+
+def test_flat_parameter_adam_equals_per_parameter_adam():
+    a, b = small_model(), small_model()
+    oa = Adam(a.parameters(), lr=0.02)
+    ob = Adam(b.parameters(), lr=0.02, flat=b.flatten_parameters())
+    batch = synthetic_batch(2, 8, 40, "cpu", torch.Generator().manual_seed(1))
+    for _ in range(3):
+        for m, o in ((a, oa), (b, ob)):
+            o.zero_grad()
+            loss_fn(batch, m).backward()
+            o.step()
+    fa = torch.cat([p.value.detach().reshape(-1) for p in a.parameters()])
+    fb = torch.cat([p.value.detach().reshape(-1) for p in b.parameters()])
+    assert torch.equal(fa, fb)
+    assert b.parameters()[0].value.grad.data_ptr() == ob.flat[1].data_ptr()  # gradients live in the flat bucket
