@@ -359,10 +359,11 @@ int fa_b200_gelu_bwd(const float* x, const float* dy, float* dx, size_t n, void*
   FA_CUDA(fa::gelu(x, dy, dx, n, true, FA_ST), 1);
   return FA_OK;
 }
-int fa_b200_dropout_apply(const float* x, float* y, size_t n, float p_drop, unsigned long long seed, void* stream) {
+int fa_b200_dropout_apply(const float* x, float* y, size_t n, float p_drop, unsigned long long seed,
+                          const unsigned long long* seed_offset_dev, void* stream) {
   if (!x || !y) return fail(FA_ERR_BAD_ARG, "fa_b200_dropout_apply: null pointer");
   if (int rc = check_p_drop(p_drop, "fa_b200_dropout_apply")) return rc;
-  FA_CUDA(fa::dropout_apply(x, y, n, fa::make_dropout(p_drop, seed), FA_ST), 1);
+  FA_CUDA(fa::dropout_apply(x, y, n, fa::make_dropout(p_drop, seed), seed_offset_dev, FA_ST), 1);
   return FA_OK;
 }
 int fa_b200_embedding_fwd(const long long* idx, const float* w, float* y, size_t n_idx, int dim, void* stream) {

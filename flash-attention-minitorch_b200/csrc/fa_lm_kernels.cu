@@ -150,7 +150,13 @@ __global__ void gelu_kernel(const float* __restrict__ x, const float* __restrict
 // ---------------------------------------------------------------- dropout: y = x * keep / (1 - p), keep = f(seed, index)
 // The same call serves forward and backward (the op is linear in x): nothing is stored between them.
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n4, uint32_t key, uint32_t thr,
-                               float scale) {
+                               float scale, const unsigned long long* __restrict__ seed_offset) {
+  // seed_offset (optional, device memory): a step counter mixed into the key, so that a captured CUDA graph draws a
+  // fresh mask on every replay without any host-side parameter change
+  if (seed_offset) {
+    const unsigned long long o = *seed_offset;
+    key = drop_mix(key ^ drop_mix((uint32_t)o + 0x9E3779B9u * (uint32_t)(o >> 32)));
+  }
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -288,10 +294,11 @@ cudaError_t gelu(const float* x, const float* dy, float* y, size_t n, bool backw
   gelu_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(x, dy, y, n / 4, backward ? 1 : 0);
   return cudaGetLastError();
 }
-cudaError_t dropout_apply(const float* x, float* y, size_t n, Dropout drop, cudaStream_t st) {
+cudaError_t dropout_apply(const float* x, float* y, size_t n, Dropout drop, const unsigned long long* seed_offset,
+                          cudaStream_t st) {
   if (n & 3) return cudaErrorInvalidValue;
   const uint32_t key = drop_head_key(drop.seed_lo, drop.seed_hi, 0xE1E7u);
-  dropout_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(x, y, n / 4, key, drop.thr, drop.keep_scale);
+  dropout_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(x, y, n / 4, key, drop.thr, drop.keep_scale, seed_offset);
   return cudaGetLastError();
 }
 cudaError_t embedding_fwd(const long long* idx, const float* w, float* y, size_t n_idx, int dim, cudaStream_t st) {

@@ -165,33 +165,54 @@ def gelu(x):
 
 
 class _Dropout(torch.autograd.Function):
-    """Mask = f(seed, element index), regenerated in the backward: no mask tensor is ever materialised."""
+    """Mask = f(seed, step counter, element index), regenerated in the backward: no mask tensor is ever materialised."""
 
     @staticmethod
-    def forward(ctx, x, p, seed):
+    def forward(ctx, x, p, seed, step):
         x = x.contiguous()
         y = torch.empty_like(x)
-        _lib.check(_lib.load_library().fa_b200_dropout_apply(x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed), _st()))
-        ctx.p, ctx.seed = float(p), int(seed)
+        _lib.check(_lib.load_library().fa_b200_dropout_apply(x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed),
+                                                             step.data_ptr() if step is not None else None, _st()))
+        ctx.p, ctx.seed, ctx.step = float(p), int(seed), step
         return y
 
     @staticmethod
     def backward(ctx, dy):
         dy = dy.contiguous()
         dx = torch.empty_like(dy)
-        _lib.check(_lib.load_library().fa_b200_dropout_apply(dy.data_ptr(), dx.data_ptr(), dy.numel(), ctx.p, ctx.seed, _st()))
-        return dx, None, None
+        _lib.check(_lib.load_library().fa_b200_dropout_apply(dy.data_ptr(), dx.data_ptr(), dy.numel(), ctx.p, ctx.seed,
+                                                             ctx.step.data_ptr() if ctx.step is not None else None, _st()))
+        return dx, None, None, None
 
 
-_dropout_calls = [0]
+class DropoutState:
+    """Seeds of the fused dropout.  Every call site gets its own (base seed, call index) pair; `step` is a device-side
+    counter mixed in by the kernel, so a captured CUDA graph (fixed call indices) still draws fresh masks per replay:
+    the trainer bumps it once per step."""
+
+    def __init__(self):
+        self.base_seed = 0x5EED
+        self.calls = 0
+        self.step = None  # torch.int64 tensor of one element on the device, or None
+
+    def begin_step(self):
+        self.calls = 0
+        if self.step is not None:
+            self.step.add_(1)
 
 
-def dropout(x, p: float, training: bool, generator=None, seed: int = 0x5EED):
+dropout_state = DropoutState()
+
+
+def dropout(x, p: float, training: bool, generator=None):
     if not training or p <= 0.0:
         return x
     if _on_kernels(x) and x.numel() % 4 == 0:
-        _dropout_calls[0] += 1  # a fresh mask per call: (seed, call counter) keys the hash
-        return _Dropout.apply(x, p, (seed << 32) ^ _dropout_calls[0])
+        st = dropout_state
+        st.calls += 1
+        if st.step is None:
+            st.step = torch.zeros(1, dtype=torch.int64, device=x.device)
+        return _Dropout.apply(x, p, (st.base_seed << 32) ^ st.calls, st.step)
     mask = (torch.rand(x.shape, device=x.device, generator=generator) < (1.0 - p)).to(x.dtype)
     return (x * mask) * (1.0 / (1.0 - p))
 

@@ -71,26 +71,76 @@ class GradAllReducer:
             off += n
 
 
+class GraphedStep:
+    """zero_grad + forward + backward of one training step captured ONCE into a CUDA graph and replayed per step.
+
+    The eager step is launch-bound (a few hundred kernels of a few microseconds each behind Python dispatch); the graph
+    replays them back to back.  What makes the step capturable: parameters and gradients live in two flat static
+    buffers (Module.flatten_parameters), batches are copied into static input tensors, workspaces come from the graph's
+    private pool, and the dropout masks take their per-step variation from a device-side counter
+    (ops.dropout_state.step) instead of a host-side seed.  The gradient all-reduce (NCCL) and the fused Adam launch
+    stay outside the graph (Adam's bias-corrected step size changes every step)."""
+
+    def __init__(self, model: DecoderLM, optimizer: Adam, batch: Dict[str, torch.Tensor], warmup: int = 3):
+        from . import ops
+        assert optimizer.flat is not None, "graph capture needs flattened parameters"
+        self.model, self.optimizer, self.ops = model, optimizer, ops
+        self.static = {k: v.clone() for k, v in batch.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up off the capture: lazy initialisations, autotuning, arena growth
+            for _ in range(warmup):
+                optimizer.zero_grad()
+                loss_fn(self.static, model).backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
+            optimizer.zero_grad()
+            self.loss = loss_fn(self.static, model)
+            self.loss.backward()
+
+    def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        for k, v in batch.items():
+            self.static[k].copy_(v)
+        self.ops.dropout_state.begin_step()
+        self.graph.replay()
+        return self.loss
+
+
 def train(model: DecoderLM, optimizer: Adam, n_iters: int, batch_size: int, seq_len: int, rank: int, world: int,
-          sync: Callable[[], None], seed: int = 0, log: Optional[Callable[[str], None]] = None) -> Dict[str, float]:
-    """Runs n_iters steps and returns the reference-style timers (iterations >= 2) plus tokens/s and losses."""
+          sync: Callable[[], None], seed: int = 0, log: Optional[Callable[[str], None]] = None,
+          cuda_graph: bool = False) -> Dict[str, float]:
+    """Runs n_iters steps and returns the reference-style timers (iterations >= 2) plus tokens/s and losses.
+    With cuda_graph the forward and backward are one graph replay, reported together as `backward_s` = 0."""
+    from . import ops
     model.train()
     device = next(iter(model.parameters())).value.device
     gen = torch.Generator().manual_seed(1000 * (rank + 1) + seed)
+    ops.dropout_state.base_seed = 0x5EED + 7919 * rank  # different masks on different ranks
     reducer = GradAllReducer(model.parameters(), world, optimizer.flat[1] if optimizer.flat is not None else None)
+    graphed = None
     fw = bw = comm = opt = 0.0
     timed_tokens, timed_s, losses = 0, 0.0, []
     for it in range(n_iters):
         batch = synthetic_batch(batch_size, seq_len, model.n_vocab, device, gen)
+        if cuda_graph and graphed is None:
+            graphed = GraphedStep(model, optimizer, batch)
         sync()
         t0 = time.perf_counter()
-        optimizer.zero_grad()
-        loss = loss_fn(batch, model)
-        sync()
-        t1 = time.perf_counter()
-        loss.backward()
-        sync()
-        t2 = time.perf_counter()
+        if graphed is not None:
+            loss = graphed(batch)
+            sync()
+            t1 = t2 = time.perf_counter()
+        else:
+            ops.dropout_state.begin_step()
+            optimizer.zero_grad()
+            loss = loss_fn(batch, model)
+            sync()
+            t1 = time.perf_counter()
+            loss.backward()
+            sync()
+            t2 = time.perf_counter()
         reducer()
         sync()
         t3 = time.perf_counter()
@@ -122,6 +172,8 @@ def main(argv=None) -> int:
     ap.add_argument("--learning-rate", type=float, default=0.02)
     ap.add_argument("--p-dropout", type=float, default=0.1)
     ap.add_argument("--seed", type=int, default=11111)
+    ap.add_argument("--cuda-graph", type=lambda s: s.lower() in ("1", "true", "yes"), default=True,
+                    help="capture forward+backward into a CUDA graph (default); False gives the reference's fw/bw split timers")
     args = ap.parse_args(argv)
     if not args.use_flash_attention:
         raise SystemExit("only the flash-attention path exists here (the vanilla path is the reference's CPU oracle)")
@@ -142,7 +194,7 @@ def main(argv=None) -> int:
         torch.cuda.synchronize()
 
     res = train(model, optimizer, args.iters, batch_size, L, rank, world, sync,
-                log=(lambda s: print(s, flush=True)) if rank == 0 else None)
+                log=(lambda s: print(s, flush=True)) if rank == 0 else None, cuda_graph=args.cuda_graph)
     t = torch.tensor([res["tokens_per_s_per_rank"]], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -151,6 +203,7 @@ def main(argv=None) -> int:
         print("N: {}, Forward Time: {}, Backward Time: {}, Opt Time: {}".format(L, res["forward_s"], res["backward_s"], res["opt_s"]))
         print(json.dumps({"metric": "decoder LM training tokens/s (whole job)", "value": float(t.item()) * world, "unit": "tokens/s",
                           "n_gpus": world, "seq_len": L, "batch_per_rank": batch_size, "iters_timed": res["timed_iters"],
+                          "cuda_graph": bool(args.cuda_graph),
                           "forward_s": res["forward_s"], "backward_s": res["backward_s"], "allreduce_s": res["allreduce_s"],
                           "opt_s": res["opt_s"], "loss_first": res["loss_first"], "loss_last": res["loss_last"],
                           "data": "synthetic uniform tokens", "params": sum(p.value.numel() for p in model.parameters())}), flush=True)

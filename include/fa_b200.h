@@ -144,7 +144,9 @@ int fa_b200_colsum_f32(const float* x, float* out, int M, int N, int accumulate,
  *               fwd saves mean / rstd per row; bwd overwrites dx, dw, db
  *   gelu      : tanh approximation (minitorch/nn.py:208-214)
  *   dropout   : y = x * keep / (1 - p_eff), keep = f(seed, element index) -- call it again on dy for the backward
- *               (minitorch/modules_basic.py:77-80; p quantised as in fa_b200_fwd_dropout)
+ *               (minitorch/modules_basic.py:77-80; p quantised as in fa_b200_fwd_dropout).  seed_offset_dev (optional,
+ *               device memory) is a step counter mixed into the seed at run time: a captured CUDA graph then draws
+ *               a fresh mask on every replay
  *   embedding : y[i] = w[idx[i]]  (one_hot @ weights, minitorch/modules_basic.py:46-53); bwd overwrites dw[vocab][dim]
  *   softmax_loss : loss[i] = logsumexp(logits[i]) - logits[i][target[i]] (minitorch/nn.py:256-274); lse saved;
  *               bwd: dlogits[i][j] = gscale[i] (softmax(logits[i])[j] - [j == target[i]])
@@ -156,7 +158,8 @@ int fa_b200_layernorm_bwd(const float* x, const float* w, const float* dy, const
                           float* dw, float* db, int rows, int dim, void* stream);
 int fa_b200_gelu_fwd(const float* x, float* y, size_t n, void* stream);
 int fa_b200_gelu_bwd(const float* x, const float* dy, float* dx, size_t n, void* stream);
-int fa_b200_dropout_apply(const float* x, float* y, size_t n, float p_drop, unsigned long long seed, void* stream);
+int fa_b200_dropout_apply(const float* x, float* y, size_t n, float p_drop, unsigned long long seed,
+                          const unsigned long long* seed_offset_dev, void* stream);
 int fa_b200_embedding_fwd(const long long* idx, const float* w, float* y, size_t n_idx, int dim, void* stream);
 int fa_b200_embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, void* stream);
 int fa_b200_softmax_loss_fwd(const float* logits, const long long* target, float* loss, float* lse, int rows, int n_classes,

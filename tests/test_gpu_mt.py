@@ -100,3 +100,34 @@ def test_flat_parameters_fused_adam_training_step(cuda_device):
         losses.append(float(loss))
     assert losses[-1] < 0.8 * losses[0], losses
     assert m.parameters()[0].value.grad.data_ptr() == flat[1].data_ptr()  # autograd accumulated in place
+
+
+def test_cuda_graph_step_equals_eager_step_and_redraws_dropout(cuda_device):
+    """One captured graph replayed per step: without dropout it reproduces the eager trajectory; with dropout every
+    replay draws a fresh mask (device-side step counter), so two replays on the same batch give different losses."""
+    from fa_b200.mt.train import GraphedStep
+    gen = torch.Generator().manual_seed(3)
+    batches = [synthetic_batch(4, 96, 300, cuda_device, gen) for _ in range(4)]
+    traj = {}
+    for mode in ("eager", "graph"):
+        m = build(cuda_device, ops.flash_attention, p_dropout=0.0)
+        opt = Adam(m.parameters(), lr=0.01, flat=m.flatten_parameters())
+        step = GraphedStep(m, opt, batches[0]) if mode == "graph" else None
+        losses = []
+        for b in batches:
+            if step is not None:
+                loss = step(b)
+            else:
+                opt.zero_grad()
+                loss = loss_fn(b, m)
+                loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        traj[mode] = (losses, opt.flat[0].clone())
+    assert max(abs(a - b) for a, b in zip(*[traj[k][0] for k in ("eager", "graph")])) <= 1e-4
+    assert float((traj["eager"][1] - traj["graph"][1]).abs().max()) <= 1e-4
+    m = build(cuda_device, ops.flash_attention, p_dropout=0.1)
+    opt = Adam(m.parameters(), lr=0.0, flat=m.flatten_parameters())
+    step = GraphedStep(m, opt, batches[0])
+    l1, l2 = float(step(batches[0])), float(step(batches[0]))
+    assert l1 != l2
