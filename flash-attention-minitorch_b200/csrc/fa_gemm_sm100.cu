@@ -36,6 +36,7 @@ struct GemmParams {
   float* c;
   const float* bias;  // nullptr = none
   int accumulate;     // C += A B instead of C = A B
+  int k_blocks_per_split;  // split-K: CTA z reduces k-blocks [z * this, (z + 1) * this) and red.adds into a zeroed C
 };
 
 struct GemmBarriers {
@@ -55,7 +56,10 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
-  const int nk = (p.K + kBK - 1) / kBK;
+  const int nk_total = (p.K + kBK - 1) / kBK;
+  const int kb_begin = blockIdx.z * p.k_blocks_per_split;
+  const int nk = min(p.k_blocks_per_split, nk_total - kb_begin);  // >= 1 by construction of the grid
+  const bool split = gridDim.z > 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -80,19 +84,20 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tma_prefetch_desc(&map_b);
       for (int kb = 0; kb < nk; ++kb) {
         const int st = kb % kStages;
+        const int k0 = (kb_begin + kb) * kBK;
         mbar_wait(&bars.empty[st], ((kb / kStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&bars.full[st], 2 * kSlabBytes);
         uint8_t* a = sA + st * kSlabBytes;
         uint8_t* b = sB + st * kSlabBytes;
         if constexpr (kAMn) {  // global [K][M]: four boxes of (32 m) x (32 k rows)
-          for (int x = 0; x < 4; ++x) tma_load_3d(a + x * 4096, &map_a, &bars.full[st], m0 + 32 * x, kb * kBK, 0, kEvictNormal);
+          for (int x = 0; x < 4; ++x) tma_load_3d(a + x * 4096, &map_a, &bars.full[st], m0 + 32 * x, k0, 0, kEvictNormal);
         } else {               // global [M][K]: one box of (32 k) x (128 m rows)
-          tma_load_3d(a, &map_a, &bars.full[st], kb * kBK, m0, 0, kEvictNormal);
+          tma_load_3d(a, &map_a, &bars.full[st], k0, m0, 0, kEvictNormal);
         }
         if constexpr (kBMn) {
-          for (int x = 0; x < 4; ++x) tma_load_3d(b + x * 4096, &map_b, &bars.full[st], n0 + 32 * x, kb * kBK, 0, kEvictNormal);
+          for (int x = 0; x < 4; ++x) tma_load_3d(b + x * 4096, &map_b, &bars.full[st], n0 + 32 * x, k0, 0, kEvictNormal);
         } else {
-          tma_load_3d(b, &map_b, &bars.full[st], kb * kBK, n0, 0, kEvictNormal);
+          tma_load_3d(b, &map_b, &bars.full[st], k0, n0, 0, kEvictNormal);
         }
       }
     }
@@ -135,11 +140,16 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const int col = n0 + c0 + i;
           if (col < p.N) {  // N is a multiple of 4: a float4 is entirely inside or outside
             float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-            if (p.bias) {
+            if (p.bias && blockIdx.z == 0) {
               const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
               v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
             }
             float4* dst = reinterpret_cast<float4*>(crow + col);
+            if (split) {  // partial sum over this CTA's k range: fp32 reduction into C (zeroed by the launcher)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                           : "memory");
+              continue;
+            }
             if (p.accumulate) {
               const float4 o = *dst;
               v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -167,26 +177,49 @@ cudaError_t launch_gemm(const float* a, const float* b, float* c, const float* b
   if (e != cudaSuccess) return e;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.c = c; p.bias = bias; p.accumulate = accumulate ? 1 : 0;
-  dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM);
+  // split-K when the output has too few tiles to fill the 148 SMs (weight gradients: 256 x 256 outputs reduced over
+  // thousands of tokens): each split keeps at least 8 k-blocks, partial tiles are red.added into a zeroed C
+  const int tiles = ((N + kBN - 1) / kBN) * ((M + kBM - 1) / kBM);
+  const int nk_total = (K + kBK - 1) / kBK;
+  int splits = 1;
+  if (tiles < 74) {
+    splits = 148 / tiles;
+    if (splits > nk_total / 8) splits = nk_total / 8;
+    if (splits < 1) splits = 1;
+  }
+  p.k_blocks_per_split = (nk_total + splits - 1) / splits;
+  splits = (nk_total + p.k_blocks_per_split - 1) / p.k_blocks_per_split;  // no empty split
+  if (splits > 1 && !accumulate) {
+    e = cudaMemsetAsync(c, 0, (size_t)M * N * sizeof(float), st);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
   fa_gemm_tf32_kernel<kAMn, kBMn><<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, p);
   return cudaGetLastError();
 }
 
-// out[n] (+)= sum_m x[m][n]   (bias gradient)
-__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int accumulate) {
-  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  __shared__ float part[8][33];
-  float acc = 0.f;
-  if (n < N)
-    for (int m = blockIdx.y * nw + w; m < M; m += nw * gridDim.y) acc += x[(size_t)m * N + n];
+// out[n] (+)= sum_m x[m][n]   (bias gradient).  Block = 32 column-quads x 8 row lanes (float4 loads), grid.y strips of
+// rows; the 8 row lanes meet in shared memory and each block issues one atomic per column.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N) {
+  const int cq = blockIdx.x * 32 + (threadIdx.x & 31);  // column quad
+  const int w = threadIdx.x >> 5;
+  __shared__ float4 part[8][32];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cq * 4 < N)
+    for (int m = blockIdx.y * 8 + w; m < M; m += 8 * gridDim.y) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (size_t)m * N + cq * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
   part[w][threadIdx.x & 31] = acc;
   __syncthreads();
-  if (w == 0 && n < N) {
-    float s = 0.f;
-    for (int i = 0; i < nw; ++i) s += part[i][threadIdx.x & 31];
-    if (gridDim.y > 1 || accumulate) atomicAdd(out + n, s);
-    else out[n] = s;
+  if (w == 0 && cq * 4 < N) {
+    float4 s = part[0][threadIdx.x];
+    for (int i = 1; i < 8; ++i) {
+      const float4 v = part[i][threadIdx.x];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* o = out + cq * 4;
+    atomicAdd(o, s.x); atomicAdd(o + 1, s.y); atomicAdd(o + 2, s.z); atomicAdd(o + 3, s.w);
   }
 }
 
@@ -202,13 +235,15 @@ cudaError_t gemm_tf32(const float* a, const float* b, float* c, const float* bia
 }
 
 cudaError_t colsum_f32(const float* x, float* out, int M, int N, bool accumulate, cudaStream_t st) {
-  if (M <= 0 || N <= 0) return cudaErrorInvalidValue;
-  const int ysplit = M >= 4096 ? 16 : 1;
-  if (ysplit > 1 && !accumulate) {
+  if (M <= 0 || N <= 0 || (N & 3)) return cudaErrorInvalidValue;
+  if (!accumulate) {
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * 4, st);
     if (e != cudaSuccess) return e;
   }
-  colsum_kernel<<<dim3((N + 31) / 32, ysplit), 256, 0, st>>>(x, out, M, N, accumulate ? 1 : 0);
+  const int col_blocks = (N / 4 + 31) / 32;
+  int strips = (148 * 2 + col_blocks - 1) / col_blocks;
+  if (strips > (M + 7) / 8) strips = (M + 7) / 8;
+  colsum_kernel<<<dim3(col_blocks, strips), 256, 0, st>>>(x, out, M, N);
   return cudaGetLastError();
 }
 

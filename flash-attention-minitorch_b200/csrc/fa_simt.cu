@@ -321,7 +321,8 @@ cudaError_t simt_bwd_prep(const float* o, const float* dO, float* delta, const f
 cudaError_t simt_bwd(const float* q, const float* k, const float* v, const float* dO, const float* lse,
                      const float* delta, float* dq, float* dk, float* dv, int BH, int T, int d, bool causal,
                      bool accumulate_dq, cudaStream_t st, Dropout drop) {
-  if (d <= 32) return bwd_launch<32, 1>(q, k, v, dO, lse, delta, dq, dk, dv, BH, T, d, causal, accumulate_dq, drop, st);
+  // four lanes per row also at d <= 32: one lane per row leaves the SMs with ~10 resident warps at the MT model's sizes
+  if (d <= 32) return bwd_launch<32, 4>(q, k, v, dO, lse, delta, dq, dk, dv, BH, T, d, causal, accumulate_dq, drop, st);
   if (d <= 64) return bwd_launch<64, 2>(q, k, v, dO, lse, delta, dq, dk, dv, BH, T, d, causal, accumulate_dq, drop, st);
   if (d <= 128) return bwd_launch<128, 4>(q, k, v, dO, lse, delta, dq, dk, dv, BH, T, d, causal, accumulate_dq, drop, st);
   return cudaErrorInvalidValue;
