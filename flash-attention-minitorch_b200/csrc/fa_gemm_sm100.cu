@@ -1,6 +1,6 @@
 // fa_gemm_sm100.cu -- fp32-storage / tf32 tensor-core GEMM for the decoder-LM linear layers.
 //
-// Replaces, for the Linear layers of the model path, the reference's MatrixMultiplyKernel (src/combine.cu:318-407:
+// Replaces, for the Linear layers of the model path, the reference's MatrixMultiplyKernel (src/combine.cu:150-253, 467-535:
 // a 32 x 32 shared-memory-tiled fp32 FMA kernel driven through host staging, minitorch/cuda_kernel_ops.py:302-380):
 //     C[M x N] = A[M x K] * B[K x N]  (+ bias[N])         fp32 in HBM, tcgen05.mma kind::tf32, fp32 accumulate in TMEM
 // Each operand may be stored with either dimension contiguous, which covers the three products of a Linear layer
