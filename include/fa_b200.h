@@ -128,7 +128,7 @@ void fa_b200_release_arena(void);
 /* ------------------------------------------------------------------------------------------
  * Operators of the decoder-only LM around the attention path ("next" rows), device pointers,
  * fp32.  They replace, for the model path of project/run_machine_translation.py, the reference's host-staged
- * kernels of src/combine.cu (MatrixMultiplyKernel :318-407, reduceKernel :409-470).
+ * kernels of src/combine.cu (MatrixMultiplyKernel :150-253, reduceKernel :315-387).
  *   fa_b200_gemm_tf32 : C[M x N] (+)= A[M x K] B[K x N] (+ bias[N]) on tcgen05 kind::tf32, fp32 accumulate.
  *       a_mn_major = 0: A stored [M][K];  1: A stored [K][M].   b_mn_major = 0: B stored [N][K];  1: B stored [K][N].
  *       Linear (W is (in, out)):  Y = X W: (0, 1);  dX = dY W^T: (0, 0) with B = W;  dW = X^T dY: (1, 1).
