@@ -24,6 +24,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "fa_internal.h"
 #include "fa_ptx.cuh"
 #include "fa_tma_host.h"
@@ -45,6 +47,11 @@ struct BwdParams {
   void* dv;
   float* dq_acc;  // fp32 dQ accumulator [BH][T][D] (workspace, or the caller's fp32 q_grad)
   int dq_red;     // 1: drain dQ with red.global.add.v2.f32 from registers; 0: smem staging + TMA reduce-add
+  // bf16 gradients, fused conversion: the CTA that delivers the LAST partial sum of a Q tile converts that tile from the
+  // fp32 accumulator (still in L2) to bf16 -- no separate conversion pass over HBM.  tile_counters[bh][i] counts arrivals.
+  int* tile_counters;  // nullptr = conversion by fa_bwd_dq_convert_kernel after the main kernel
+  __nv_bfloat16* dq_out;
+  int accumulate_dq;
   Dropout drop;  // used by the kDrop instantiations only
 };
 
@@ -419,6 +426,59 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const uint32_t tDQ = tmem + Cfg::kColDQ + (uint32_t(w * 32) << 16);
     const bool leader = (warp == 8 && lane == 0);
     uint32_t chunk_no = 0;
+    int& s_last_arriver = *reinterpret_cast<int*>(smem + Cfg::kOffBars + 200);  // (static smem would not fit at d = 128)
+    // Called once the reduce-adds of Q tile `tile` have been issued; `kNewer` = bulk groups committed after them.
+    auto finish_tile = [&](int tile, auto newer_groups) {
+      constexpr int kNewer = decltype(newer_groups)::value;
+      if (leader) {
+        tma_store_wait_all<kNewer>();  // every reduce-add of `tile` has been performed, not just read from smem
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __threadfence();
+        const int expected = p.causal ? min(tile + 1, (int)gridDim.x) : (int)gridDim.x;
+        s_last_arriver = atomicAdd(p.tile_counters + (size_t)bh * gridDim.x + tile, 1) == expected - 1;
+      }
+      named_bar_sync(1, 128);
+      if (s_last_arriver) {
+        __threadfence();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        const int t128 = threadIdx.x & 127;
+        const int rows = min(kTile, T - tile * kTile);
+        const float* src = p.dq_acc + ((size_t)bh * T + (size_t)tile * kTile) * D;
+        __nv_bfloat16* dst = p.dq_out + ((size_t)bh * T + (size_t)tile * kTile) * D;
+        const int limit = rows * (D / 4);
+        constexpr int kBatch = 8;  // independent 16-byte L2 loads in flight per thread (latency-bound otherwise)
+#pragma unroll 1
+        for (int base = 0; base < kTile * (D / 4); base += 128 * kBatch) {
+          float4 a[kBatch];
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            const int idx = base + u * 128 + t128;
+            if (idx < limit) a[u] = __ldcg(reinterpret_cast<const float4*>(src) + idx);  // L2: never in this SM's L1
+          }
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            const int idx = base + u * 128 + t128;
+            if (idx < limit) {
+              uint2* o2 = reinterpret_cast<uint2*>(dst) + idx;
+              if (p.accumulate_dq) {
+                const uint2 old = *o2;
+                const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old);
+                const float2 x = __bfloat1622float2(oh[0]), y = __bfloat1622float2(oh[1]);
+                a[u].x += x.x; a[u].y += x.y; a[u].z += y.x; a[u].w += y.y;
+              }
+              *o2 = make_uint2(pack_bf16x2(a[u].x, a[u].y), pack_bf16x2(a[u].z, a[u].w));
+            }
+          }
+        }
+      }
+      named_bar_sync(1, 128);  // s_last_arriver may be rewritten
+    };
+    const bool fused_cvt = p.tile_counters != nullptr;
+    // Reduce-adds take microseconds to be performed at L2; their tile is only counted kLag tile pairs later, when
+    // waiting for them costs nothing (pending[] = tiles issued but not yet counted, oldest first).
+    constexpr int kLag = 3;
+    int pending[kLag];
+    int n_pending = 0;
     if (p.dq_red) {
       // Fragment-layout drain: tcgen05.ld.16x256b hands each quad of lanes 32 contiguous bytes of one dQ row, so a
       // warp-wide red.global.add.v2.f32 touches 8 complete 32-byte sectors -- no shared-memory staging at all.
@@ -480,6 +540,20 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           tma_store_commit();
         }
       }
+      if (fused_cvt) {
+        if (n_pending == kLag) {
+          finish_tile(pending[0], std::integral_constant<int, kLag * (D / 32)>{});
+#pragma unroll
+          for (int x = 0; x + 1 < kLag; ++x) pending[x] = pending[x + 1];
+          --n_pending;
+        }
+        pending[n_pending++] = i;
+      }
+    }
+    if (fused_cvt) {
+#pragma unroll
+      for (int x = 0; x < kLag; ++x)
+        if (x < n_pending) finish_tile(pending[x], std::integral_constant<int, 0>{});
     }
     if (leader) tma_store_wait_all<0>();
   }
@@ -496,7 +570,9 @@ template <int D>
 __global__ void __launch_bounds__(256)
 fa_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO,
                    const float* __restrict__ lse, float* __restrict__ lse_pad, float* __restrict__ delta_pad,
-                   float* __restrict__ dq_zero, int T, int Tpad, size_t total_rows_pad) {
+                   float* __restrict__ dq_zero, int T, int Tpad, size_t total_rows_pad, int* __restrict__ counters,
+                   int n_counters) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_counters; i += gridDim.x * blockDim.x) counters[i] = 0;
   constexpr int kLanesPerRow = D / 8;            // 16 (d = 128) or 8 (d = 64)
   constexpr int kRowsPerWarp = 32 / kLanesPerRow;
   const int lane = threadIdx.x & 31;
@@ -551,6 +627,19 @@ __global__ void fa_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfl
   }
 }
 
+// developer switches, read per call.  FA_B200_BWD_CVT=fused converts dQ to bf16 inside the main kernel (the CTA that
+// delivers the last partial of a Q tile converts it from L2): correct, one launch and 1 GB of HBM reads fewer, but
+// measured SLOWER (8.12 ms vs 7.31 ms at config 3): waiting for reduce-adds to be *performed* (cp.async.bulk.wait_group
+// without .read) and the two extra barriers per tile sit on the drain warps' critical path.  Default: separate pass.
+bool bwd_fused_convert_enabled() {
+  const char* e = getenv("FA_B200_BWD_CVT");
+  return e && e[0] == 'f';
+}
+bool bwd_dq_red_enabled() {
+  const char* e = getenv("FA_B200_BWD_DQ");
+  return e && e[0] == 'r';
+}
+
 size_t pad_rows(int T) { return (size_t)((T + kTile - 1) / kTile) * kTile; }
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -568,6 +657,10 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   float* delta_pad = reinterpret_cast<float*>(ws);
   ws += align256((size_t)BH * Tpad * 4);
   float* dq_acc = kF32 ? static_cast<float*>(dq) : reinterpret_cast<float*>(ws);
+  ws += align256(n * 4);
+  int* counters = reinterpret_cast<int*>(ws);  // [BH][Tpad / 128] arrival counters of the fused dQ conversion
+  const int n_counters = (int)((size_t)BH * (Tpad / kTile));
+  const bool fused_env = bwd_fused_convert_enabled();
   cudaError_t e;
   {
     const size_t rows = (size_t)BH * Tpad;
@@ -576,7 +669,7 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
     size_t blocks = (rows + kRowsPerBlock - 1) / kRowsPerBlock;
     if (blocks > 148 * 32) blocks = 148 * 32;  // grid-stride beyond 32 blocks per SM
     fa_bwd_prep_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(o, dO, lse, lse_pad, delta_pad, zero ? dq_acc : nullptr, T,
-                                                          (int)Tpad, rows);
+                                                          (int)Tpad, rows, counters, n_counters);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -601,9 +694,11 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   p.dk = dk;
   p.dv = dv;
   p.dq_acc = dq_acc;
+  p.accumulate_dq = accumulate_dq ? 1 : 0;
+  p.dq_out = kF32 ? nullptr : static_cast<__nv_bfloat16*>(dq);
   {
-    static const int mode = [] {
-      // developer switch.  Default "tma": smem staging + cp.reduce.async.bulk (7.30 ms at config 3).  "red": fragment-
+    const int mode = [] {
+      // developer switch (read per call so that tests can flip it).  Default "tma": smem staging + cp.reduce.async.bulk (7.30 ms at config 3).  "red": fragment-
       // layout tcgen05.ld + red.global.add.v2.f32 straight from registers -- no staging traffic, sector-complete, but
       // measured slower (8.81 ms): 32-byte L2 reductions cost more than the TMA engine's line-sized ones.
       const char* e = getenv("FA_B200_BWD_DQ");
@@ -611,13 +706,15 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
     }();
     p.dq_red = mode;
   }
+  const bool fused_cvt = !kF32 && fused_env && !p.dq_red;
+  p.tile_counters = fused_cvt ? counters : nullptr;
   p.drop = drop;
   dim3 grid((unsigned)(Tpad / kTile), BH);
   if (drop.thr) fa_bwd_kernel<D, OutT, true><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
   else fa_bwd_kernel<D, OutT, false><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (!kF32) {
+  if (!kF32 && !fused_cvt) {
     fa_bwd_dq_convert_kernel<<<148 * 8, 256, 0, st>>>(dq_acc, static_cast<__nv_bfloat16*>(dq), n, accumulate_dq ? 1 : 0);
     e = cudaGetLastError();
   }
@@ -627,11 +724,16 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
 }  // namespace
 
 bool tc_bwd_supported(int d) { return d == 64 || d == 128; }
+// kernels one tc_bwd call launches: prep + main (+ the dQ conversion pass when it is not fused into the main kernel)
+int tc_bwd_num_launches(bool grads_f32) {
+  return (grads_f32 || (bwd_fused_convert_enabled() && !bwd_dq_red_enabled())) ? 2 : 3;
+}
 void tc_bwd_set_trace(long long*) {}
 
 size_t tc_bwd_workspace_bytes(int BH, int T, int d) {
-  // lse_pad + delta_pad + fp32 dQ accumulator (the latter only used for bf16 gradients)
-  return 2 * align256((size_t)BH * pad_rows(T) * 4) + align256((size_t)BH * T * d * 4);
+  // lse_pad + delta_pad + fp32 dQ accumulator (the latter only used for bf16 gradients) + per-Q-tile arrival counters
+  return 2 * align256((size_t)BH * pad_rows(T) * 4) + align256((size_t)BH * T * d * 4) +
+         align256((size_t)BH * (pad_rows(T) / kTile) * 4);
 }
 
 cudaError_t tc_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* o,

@@ -271,7 +271,7 @@ int bwd_impl(const void* q, const void* k, const void* v, const void* o, const v
   if (dtype == FA_DTYPE_BF16 && prec == FA_PREC_BF16_TC) {
     FA_CUDA(fa::tc_bwd((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                        (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_out, lse, dq, dk, dv, false, accumulate_dq != 0,
-                       workspace, batch_heads, T, d, causal != 0, st, drop), 3);
+                       workspace, batch_heads, T, d, causal != 0, st, drop), fa::tc_bwd_num_launches(false));
     return FA_OK;
   }
   float* delta = reinterpret_cast<float*>(ws);
