@@ -46,10 +46,32 @@ class _FlashAttn2(torch.autograd.Function):
 
 
 def flash_attention(q, k, v, causal: bool = True, p_drop: float = 0.0, seed: int = 0):
-    """softmax(q k^T / sqrt(d) [+ causal mask]) v on the B200 kernels; q, k, v: (B, H, T, d) CUDA tensors."""
+    """softmax(q k^T / sqrt(d) [+ causal mask]) v on the B200 kernels; q, k, v: (B, H, T, d) CUDA tensors.
+    fp32 tensors take the fp32 path (tf32 tensor-core forward where covered, exact-fp32 backward; 1e-3 bar)."""
     if not q.is_cuda:
         raise RuntimeError("flash_attention needs CUDA tensors: the product has no CPU attention path")
     return _FlashAttn2.apply(q, k, v, causal, p_drop, seed)
+
+
+def flash_attention_bf16(q, k, v, causal: bool = True, p_drop: float = 0.0, seed: int = 0):
+    """The bf16 tensor-core path for fp32 model tensors (2e-2 relative bar): cast to bf16, run forward AND backward on
+    tcgen05, cast back.  Head dims below 64 are zero-padded to 64 (the scores and the softmax scale are computed for
+    the padded dim, so q is pre-multiplied by sqrt(64 / d)); the padding columns of O and of the gradients are zero
+    and sliced away."""
+    if not q.is_cuda:
+        raise RuntimeError("flash_attention needs CUDA tensors: the product has no CPU attention path")
+    d = q.shape[-1]
+    if d in (64, 128):
+        qb, kb, vb = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
+        return _FlashAttn2.apply(qb, kb, vb, causal, p_drop, seed).to(q.dtype)
+    if d > 64:
+        raise ValueError(f"bf16 tensor-core path needs d <= 64 or d = 128 (got {d})")
+    pad = 64 - d
+    fix = math.sqrt(64.0 / d)  # kernels scale by 1/sqrt(64); the model's scale is 1/sqrt(d)
+    qb = torch.nn.functional.pad(q * fix, (0, pad)).to(torch.bfloat16)
+    kb = torch.nn.functional.pad(k, (0, pad)).to(torch.bfloat16)
+    vb = torch.nn.functional.pad(v, (0, pad)).to(torch.bfloat16)
+    return _FlashAttn2.apply(qb, kb, vb, causal, p_drop, seed)[..., :d].to(q.dtype)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -172,6 +172,9 @@ def main(argv=None) -> int:
     ap.add_argument("--learning-rate", type=float, default=0.02)
     ap.add_argument("--p-dropout", type=float, default=0.1)
     ap.add_argument("--seed", type=int, default=11111)
+    ap.add_argument("--attention-precision", choices=["fp32", "bf16"], default="fp32",
+                    help="fp32: tf32 tensor-core forward + exact-fp32 backward (1e-3 bar, default); bf16: forward and "
+                         "backward on the bf16 tensor-core kernels (2e-2 bar)")
     ap.add_argument("--cuda-graph", type=lambda s: s.lower() in ("1", "true", "yes"), default=True,
                     help="capture forward+backward into a CUDA graph (default); False gives the reference's fw/bw split timers")
     args = ap.parse_args(argv)
@@ -186,8 +189,10 @@ def main(argv=None) -> int:
         dist.init_process_group("nccl", device_id=device)
     L = args.model_max_length
     batch_size = int((128 * 40 + L) / L)  # run_machine_translation.py:385, per rank
+    from . import ops
     model = DecoderLM(n_vocab=args.n_vocab, n_embd=args.n_embd, n_head=args.n_head, n_positions=L, p_dropout=args.p_dropout,
-                      ln_eps=1e-5, bias=True, device=device, seed=args.seed)
+                      ln_eps=1e-5, bias=True, device=device, seed=args.seed,
+                      attention_fn=ops.flash_attention_bf16 if args.attention_precision == "bf16" else ops.flash_attention)
     optimizer = Adam(model.parameters(), lr=args.learning_rate, flat=model.flatten_parameters())
 
     def sync():
@@ -203,7 +208,7 @@ def main(argv=None) -> int:
         print("N: {}, Forward Time: {}, Backward Time: {}, Opt Time: {}".format(L, res["forward_s"], res["backward_s"], res["opt_s"]))
         print(json.dumps({"metric": "decoder LM training tokens/s (whole job)", "value": float(t.item()) * world, "unit": "tokens/s",
                           "n_gpus": world, "seq_len": L, "batch_per_rank": batch_size, "iters_timed": res["timed_iters"],
-                          "cuda_graph": bool(args.cuda_graph),
+                          "cuda_graph": bool(args.cuda_graph), "attention_precision": args.attention_precision,
                           "forward_s": res["forward_s"], "backward_s": res["backward_s"], "allreduce_s": res["allreduce_s"],
                           "opt_s": res["opt_s"], "loss_first": res["loss_first"], "loss_last": res["loss_last"],
                           "data": "synthetic uniform tokens", "params": sum(p.value.numel() for p in model.parameters())}), flush=True)

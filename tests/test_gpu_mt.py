@@ -135,3 +135,18 @@ def test_cuda_graph_step_equals_eager_step_and_redraws_dropout(cuda_device):
     step = GraphedStep(m, opt, batches[0])
     l1, l2 = float(step(batches[0])), float(step(batches[0]))
     assert l1 != l2
+
+
+@pytest.mark.parametrize("n_embd,n_head", [(64, 2), (128, 2), (256, 2)])  # head dims 32 (padded to 64), 64, 128
+def test_bf16_attention_path_of_the_model_within_the_bf16_bar(cuda_device, n_embd, n_head):
+    """fp32 model tensors through the bf16 tensor-core attention (forward and backward on tcgen05): gradients of every
+    parameter within 2e-2 of the tensor max against the same model on vanilla fp32 attention."""
+    fast = build(cuda_device, ops.flash_attention_bf16, n_embd, n_head)
+    plain = build(cuda_device, vanilla_attention, n_embd, n_head)
+    batch = synthetic_batch(3, 96, 300, cuda_device, torch.Generator().manual_seed(9))
+    lf, lp = loss_fn(batch, fast), loss_fn(batch, plain)
+    lf.backward()
+    lp.backward()
+    assert abs(float(lf) - float(lp)) <= 2e-3 * abs(float(lp))
+    for (name, a), (_, b) in zip(fast.named_parameters(), plain.named_parameters()):
+        assert float((a.value.grad - b.value.grad).abs().max()) <= 2e-2 * float(b.value.grad.abs().max()) + 1e-5, name
