@@ -185,6 +185,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        from fa_b200 import sharding
+        sharding.bind_to_gpu_numa(local)  # pinned e2e buffers land on the GPU's own NUMA node
     lib = _lib.load_library()
 
     w = WORKLOADS[args.workload]

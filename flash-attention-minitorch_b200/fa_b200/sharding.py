@@ -15,3 +15,24 @@ def shard_bounds(batch_heads: int, rank: int, world: int) -> tuple[int, int]:
 
 def shard_sizes(batch_heads: int, world: int) -> list[int]:
     return [e - b for b, e in (shard_bounds(batch_heads, r, world) for r in range(world))]
+
+
+def bind_to_gpu_numa(gpu_index: int) -> int:
+    """Pin this process to the CPUs NVML reports as local to `gpu_index` (best effort; returns the number of CPUs bound
+    to, 0 if nothing was changed).  One process per GPU: pinned host buffers allocated afterwards are first-touched on
+    the GPU's own NUMA node, so host<->device copies of different ranks do not meet on the inter-socket link."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
