@@ -12,8 +12,11 @@
 // the 128B swizzle with 32-byte atomicity that UMMA requires for 32-bit MN-major data (verified by tools/umma_probe).
 //
 // One CTA computes one 128 x 128 tile: warp 4 = TMA producer (6-stage ring of 128 x 32 operand slabs), warp 5 = MMA
-// issuer (4 k-steps of 8 per slab), warps 0-3 = epilogue (TMEM -> registers -> + bias -> global, row per thread).
-// TMA zero-fills out-of-range rows / columns, so M, N, K only need to be multiples of 4 (16-byte global strides).
+// issuer (4 k-steps of 8 per slab), warps 0-3 = epilogue: TMEM -> registers (+ bias) -> 128B-swizzled shared memory ->
+// TMA store (or TMA reduce-add for C += / split-K) of 128 x 32 column slabs, double buffered.  A thread owns one output
+// row, so direct global stores would touch 32 different lines per instruction; the TMA engine writes full lines and
+// clips the tile at the matrix edge.  TMA zero-fills out-of-range operand rows / columns, so M, N, K only need to be
+// multiples of 4 (16-byte global strides).
 #include <cuda.h>
 #include <math.h>
 
@@ -26,10 +29,13 @@ namespace fa {
 namespace {
 
 constexpr int kBM = 128, kBN = 128, kBK = 32;  // tile; kBK fp32 = one 128-byte swizzle row
-constexpr int kStages = 6;
 constexpr int kSlabBytes = 128 * 128;           // 128 x 32 fp32, either orientation
 constexpr int kGemmThreads = 192;
-constexpr int kGemmSmem = 2 * kStages * kSlabBytes + 1024;
+// operand ring + two output staging slabs.  Six stages (225 KB, one CTA per SM) for long reductions; two stages (97 KB,
+// two CTAs per SM, so one CTA's epilogue overlaps the other's main loop) when a CTA has at most 16 k-blocks -- the
+// model's forward GEMMs have K = 256, i.e. 8 k-blocks followed by a 64 KB epilogue.
+constexpr int gemm_smem(int stages) { return (2 * stages + 2) * kSlabBytes + 1024; }
+constexpr int kMaxStages = 6;
 
 struct GemmParams {
   int M, N, K;
@@ -40,18 +46,19 @@ struct GemmParams {
 };
 
 struct GemmBarriers {
-  uint64_t full[kStages], empty[kStages], acc_full;
+  uint64_t full[kMaxStages], empty[kMaxStages], acc_full;
 };
 
 // kAMn / kBMn: operand stored with its M / N dimension contiguous (MN-major) instead of K contiguous (K-major)
-template <bool kAMn, bool kBMn>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <bool kAMn, bool kBMn, int kStages>
+__global__ void __launch_bounds__(kGemmThreads, kStages <= 2 ? 2 : 1)
 fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kSlabBytes;
+  uint8_t* sC = smem + 2 * kStages * kSlabBytes;
   __shared__ GemmBarriers bars;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,42 +130,49 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       umma_commit(&bars.acc_full);
     }
   } else {
-    // epilogue: thread = one output row (TMEM lane), 128 fp32 columns
+    // epilogue: thread = one output row (TMEM lane); four 32-column slabs through two staging buffers
     mbar_wait(&bars.acc_full, 0);
     tc_fence_after();
-    const int row = m0 + warp * 32 + lane;
+    const int r = warp * 32 + lane;
     const uint32_t tacc = tmem + (uint32_t(warp * 32) << 16);
-    float* crow = p.c + (size_t)(row < p.M ? row : 0) * p.N;
+    const bool leader = threadIdx.x == 0;
+    const bool reduce = split || p.accumulate;
+    const bool add_bias = p.bias && blockIdx.z == 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < kBN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_x32(tacc + c0, r);
+    for (int c = 0; c < kBN / 32; ++c) {
+      if (n0 + c * 32 >= p.N) break;  // slab entirely outside the matrix (uniform across the CTA)
+      uint8_t* buf = sC + (c & 1) * kSlabBytes;
+      uint32_t rr[32];
+      tmem_ld_x32(tacc + c * 32, rr);
       tmem_wait_ld();
-      if (row < p.M) {
+      if (add_bias) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const int col = n0 + c0 + i;
+          const int col = n0 + c * 32 + i;
           if (col < p.N) {  // N is a multiple of 4: a float4 is entirely inside or outside
-            float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-            if (p.bias && blockIdx.z == 0) {
-              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
-              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            }
-            float4* dst = reinterpret_cast<float4*>(crow + col);
-            if (split) {  // partial sum over this CTA's k range: fp32 reduction into C (zeroed by the launcher)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                           : "memory");
-              continue;
-            }
-            if (p.accumulate) {
-              const float4 o = *dst;
-              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-            }
-            *dst = v;
+            const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
+            rr[i] = __float_as_uint(__uint_as_float(rr[i]) + b4.x);
+            rr[i + 1] = __float_as_uint(__uint_as_float(rr[i + 1]) + b4.y);
+            rr[i + 2] = __float_as_uint(__uint_as_float(rr[i + 2]) + b4.z);
+            rr[i + 3] = __float_as_uint(__uint_as_float(rr[i + 3]) + b4.w);
           }
         }
       }
+      if (leader && c >= 2) tma_store_wait_read<1>();  // the buffer's previous store has been read out
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        *reinterpret_cast<uint4*>(buf + r * 128 + ((ch ^ (r & 7)) << 4)) =
+            make_uint4(rr[ch * 4], rr[ch * 4 + 1], rr[ch * 4 + 2], rr[ch * 4 + 3]);
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (leader) {
+        if (reduce) tma_reduce_add_3d(&map_c, buf, n0 + c * 32, m0, 0);
+        else tma_store_3d(&map_c, buf, n0 + c * 32, m0, 0);
+        tma_store_commit();
+      }
     }
+    if (leader) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -173,8 +187,9 @@ cudaError_t launch_gemm(const float* a, const float* b, float* c, const float* b
   // 128B swizzle with 32-byte atoms.
   if (kAMn ? make_tmap_3d(&ma, a, 4, M, K, 1, 32, 32, 2) : make_tmap_3d(&ma, a, 4, K, M, 1, 32, 128, 1)) return cudaErrorInvalidValue;
   if (kBMn ? make_tmap_3d(&mb, b, 4, N, K, 1, 32, 32, 2) : make_tmap_3d(&mb, b, 4, K, N, 1, 32, 128, 1)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(fa_gemm_tf32_kernel<kAMn, kBMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
-  if (e != cudaSuccess) return e;
+  CUtensorMap mc;  // C [M][N]: slabs of (32 columns, 128 rows), 128B swizzle, clipped at the edges by the TMA engine
+  if (make_tmap_3d(&mc, c, 4, N, M, 1, 32, 128, 1)) return cudaErrorInvalidValue;
+  cudaError_t e;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.c = c; p.bias = bias; p.accumulate = accumulate ? 1 : 0;
   // split-K when the output has too few tiles to fill the 148 SMs (weight gradients: 256 x 256 outputs reduced over
@@ -194,7 +209,15 @@ cudaError_t launch_gemm(const float* a, const float* b, float* c, const float* b
     if (e != cudaSuccess) return e;
   }
   dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
-  fa_gemm_tf32_kernel<kAMn, kBMn><<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, p);
+  if (p.k_blocks_per_split <= 16) {
+    e = cudaFuncSetAttribute(fa_gemm_tf32_kernel<kAMn, kBMn, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(2));
+    if (e != cudaSuccess) return e;
+    fa_gemm_tf32_kernel<kAMn, kBMn, 2><<<grid, kGemmThreads, gemm_smem(2), st>>>(ma, mb, mc, p);
+  } else {
+    e = cudaFuncSetAttribute(fa_gemm_tf32_kernel<kAMn, kBMn, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(6));
+    if (e != cudaSuccess) return e;
+    fa_gemm_tf32_kernel<kAMn, kBMn, 6><<<grid, kGemmThreads, gemm_smem(6), st>>>(ma, mb, mc, p);
+  }
   return cudaGetLastError();
 }
 
@@ -205,11 +228,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   const int w = threadIdx.x >> 5;
   __shared__ float4 part[8][32];
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (cq * 4 < N)
-    for (int m = blockIdx.y * 8 + w; m < M; m += 8 * gridDim.y) {
+  if (cq * 4 < N) {
+    const int step = 8 * gridDim.y;
+    int m = blockIdx.y * 8 + w;
+    for (; m + 3 * step < M; m += 4 * step) {  // four independent 16-byte loads in flight
+      const float4 v0 = *reinterpret_cast<const float4*>(x + (size_t)m * N + cq * 4);
+      const float4 v1 = *reinterpret_cast<const float4*>(x + (size_t)(m + step) * N + cq * 4);
+      const float4 v2 = *reinterpret_cast<const float4*>(x + (size_t)(m + 2 * step) * N + cq * 4);
+      const float4 v3 = *reinterpret_cast<const float4*>(x + (size_t)(m + 3 * step) * N + cq * 4);
+      acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+      acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; m < M; m += step) {
       const float4 v = *reinterpret_cast<const float4*>(x + (size_t)m * N + cq * 4);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
+  }
   part[w][threadIdx.x & 31] = acc;
   __syncthreads();
   if (w == 0 && cq * 4 < N) {
@@ -241,7 +275,7 @@ cudaError_t colsum_f32(const float* x, float* out, int M, int N, bool accumulate
     if (e != cudaSuccess) return e;
   }
   const int col_blocks = (N / 4 + 31) / 32;
-  int strips = (148 * 2 + col_blocks - 1) / col_blocks;
+  int strips = (148 * 8 + col_blocks - 1) / col_blocks;
   if (strips > (M + 7) / 8) strips = (M + 7) / 8;
   colsum_kernel<<<dim3(col_blocks, strips), 256, 0, st>>>(x, out, M, N);
   return cudaGetLastError();
