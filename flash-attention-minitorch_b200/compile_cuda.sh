@@ -24,7 +24,9 @@ for f in fa_simt fa_util fa_capi fa_fwd_sm100 fa_bwd_sm100 fa_gemm_sm100 fa_lm_k
     pids+=($!)
   fi
 done
-for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+fail=0
+for p in "${pids[@]:-}"; do [ -n "$p" ] && { wait "$p" || fail=1; }; done
+[ "$fail" = 0 ] || { echo "compile_cuda.sh: compilation failed" >&2; exit 1; }
 
 $NVCC $ARCH -shared -o "$LIB/libfa_b200.so" "$OBJ"/fa_simt.o "$OBJ"/fa_util.o "$OBJ"/fa_capi.o "$OBJ"/fa_fwd_sm100.o \
   "$OBJ"/fa_bwd_sm100.o "$OBJ"/fa_gemm_sm100.o "$OBJ"/fa_lm_kernels.o -lcudart

@@ -336,7 +336,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           const float2 x0 = ffma2(make_float2(s[cc], s[cc + 1]), c2v, nmv);
           const float2 x1 = ffma2(make_float2(s[cc + 2], s[cc + 3]), c2v, nmv);
           float2 p0 = make_float2(ex2_mixed(x0.x, cc), ex2_mixed(x0.y, cc + 1));
-          float2 p1 = make_float2(ex2_mixed(x1.x, cc + 2), ex2_mixed(x1.y, cc + 3));
+          float2 p1;
+          if (FA_EX2_POLY2_PERIOD > 0 && ((cc >> 2) % (FA_EX2_POLY2_PERIOD > 0 ? FA_EX2_POLY2_PERIOD : 1)) == 0) p1 = ex2_poly2(x1);
+          else p1 = make_float2(ex2_mixed(x1.x, cc + 2), ex2_mixed(x1.y, cc + 3));
           if constexpr (kTF32) {  // round P to tf32 once, so that the row sum and the PV product see the same values
             p0 = make_float2(round_tf32(p0.x), round_tf32(p0.y));
             p1 = make_float2(round_tf32(p1.x), round_tf32(p1.y));

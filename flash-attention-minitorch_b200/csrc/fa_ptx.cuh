@@ -318,6 +318,9 @@ __device__ __forceinline__ float ex2_poly(float x) {
   const float p = fmaf(fmaf(fmaf(0.07711909f, f, 0.22756439f), f, 0.69514614f), f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(xi) << 23));  // scale by 2^floor(x)
 }
+#ifndef FA_EX2_POLY2_PERIOD
+#define FA_EX2_POLY2_PERIOD 0  // n > 0: of every n groups of four scores, one pair goes to ex2_poly2 (fraction 1/(2n))
+#endif
 #ifndef FA_EX2_POLY_MASK
 #define FA_EX2_POLY_MASK 0x00  // bit i set: elements with index % 8 == i use the polynomial.  Measured on B200:
                                // 0x00 (MUFU only) is fastest once the softmax warps have enough registers.
@@ -348,6 +351,22 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
       : "=l"(reinterpret_cast<unsigned long long&>(d))
       : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
   return d;
+}
+// Packed variant: two exponentials per issue slot on the FMA pipe.  x = j + f with j = round(x) (magic-number add),
+// f in [-1/2, 1/2]; 2^f by a near-minimax degree-3 polynomial (max rel. error 7.5e-5, far below bf16's 2^-9);
+// 2^j by adding j to the exponent field.  6 packed FP ops + 2 clamps + 4 integer ops per pair.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);  // 1.5 * 2^23: the integer lands in the low mantissa bits
+  const float2 jm = fadd2(x, magic);
+  const float2 j = fadd2(jm, make_float2(-12582912.f, -12582912.f));
+  const float2 f = fadd2(x, make_float2(-j.x, -j.y));
+  float2 p = ffma2(make_float2(0.05517164f, 0.05517164f), f, make_float2(0.24261113f, 0.24261113f));
+  p = ffma2(p, f, make_float2(0.69326097f, 0.69326097f));
+  p = ffma2(p, f, make_float2(0.99992806f, 0.99992806f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(jm.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(jm.y) << 23)));
 }
 __device__ __forceinline__ float round_tf32(float x) {  // round-to-nearest (ties away) fp32 -> tf32, kept in fp32 bits
   uint32_t r;
