@@ -330,6 +330,26 @@ int fa_b200_gemm_tf32(const float* a, const float* b, float* c, const float* bia
   return FA_OK;
 }
 
+int fa_b200_gemm_tf32_heads(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, int a_mn_major,
+                            int b_mn_major, int accumulate, int a_heads, int b_heads, int c_heads, int T, int H, int d,
+                            void* stream) {
+  if (!a || !b || !c) return fail(FA_ERR_BAD_ARG, "fa_b200_gemm_tf32_heads: null pointer");
+  const fa::HeadLayout hl = {a_heads != 0, b_heads != 0, c_heads != 0, T, H, d};
+  cudaError_t e = fa::gemm_tf32(a, b, c, bias, M, N, K, a_mn_major != 0, b_mn_major != 0, accumulate != 0,
+                                static_cast<cudaStream_t>(stream), hl);
+  if (e == cudaErrorInvalidValue)
+    return fail(FA_ERR_BAD_ARG, "fa_b200_gemm_tf32_heads: unsupported shape M=%d N=%d K=%d T=%d H=%d d=%d (needs multiples of 4, "
+                "T %% 128 == 0, d %% 32 == 0, head-layout operand width H*d)", M, N, K, T, H, d);
+  FA_CUDA(e, 1);
+  return FA_OK;
+}
+
+int fa_b200_colsum_heads_f32(const float* x, float* out, int B, int H, int T, int d, int accumulate, void* stream) {
+  if (!x || !out) return fail(FA_ERR_BAD_ARG, "fa_b200_colsum_heads_f32: null pointer");
+  FA_CUDA(fa::colsum_heads_f32(x, out, B, H, T, d, accumulate != 0, static_cast<cudaStream_t>(stream)), 1);
+  return FA_OK;
+}
+
 int fa_b200_colsum_f32(const float* x, float* out, int M, int N, int accumulate, void* stream) {
   if (!x || !out || M <= 0 || N <= 0) return fail(FA_ERR_BAD_ARG, "fa_b200_colsum_f32: bad argument");
   FA_CUDA(fa::colsum_f32(x, out, M, N, accumulate != 0, static_cast<cudaStream_t>(stream)), 1);

@@ -43,7 +43,21 @@ struct GemmParams {
   const float* bias;  // nullptr = none
   int accumulate;     // C += A B instead of C = A B
   int k_blocks_per_split;  // split-K: CTA z reduces k-blocks [z * this, (z + 1) * this) and red.adds into a zeroed C
+  // "Head layout" operands: a logical [tokens = B*T][E = H*d] matrix that physically lives as (B, H, T, d) -- the layout
+  // the attention kernels consume and produce.  Its tensor map is {d, T, B*H}; a 32-column slab is (part of) one head and a
+  // row tile stays inside one batch (T % 128 == 0), so the TMA engine does the (B,T,H,d) <-> (B,H,T,d) permutation for free:
+  // the projections write Q/K/V straight into attention layout and read O / dQ / dK / dV straight out of it.
+  int a_heads, b_heads, c_heads;
+  int T, H, d;
 };
+
+// coordinates of the 32-wide slab starting at column `e` / row `m` of a head-layout matrix in its {d, T, B*H} tensor map
+struct HeadCoord {
+  int c0, c1, c2;
+};
+__device__ __forceinline__ HeadCoord head_coord(const GemmParams& p, int e, int m) {
+  return {e % p.d, m % p.T, (m / p.T) * p.H + e / p.d};
+}
 
 struct GemmBarriers {
   uint64_t full[kMaxStages], empty[kMaxStages], acc_full;
@@ -97,12 +111,31 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint8_t* a = sA + st * kSlabBytes;
         uint8_t* b = sB + st * kSlabBytes;
         if constexpr (kAMn) {  // global [K][M]: four boxes of (32 m) x (32 k rows)
-          for (int x = 0; x < 4; ++x) tma_load_3d(a + x * 4096, &map_a, &bars.full[st], m0 + 32 * x, k0, 0, kEvictNormal);
+          for (int x = 0; x < 4; ++x) {
+            if (p.a_heads) {  // [tokens][E] in head layout, tokens = the reduction dimension
+              const HeadCoord h = head_coord(p, m0 + 32 * x, k0);
+              tma_load_3d(a + x * 4096, &map_a, &bars.full[st], h.c0, h.c1, h.c2, kEvictNormal);
+            } else {
+              tma_load_3d(a + x * 4096, &map_a, &bars.full[st], m0 + 32 * x, k0, 0, kEvictNormal);
+            }
+          }
         } else {               // global [M][K]: one box of (32 k) x (128 m rows)
-          tma_load_3d(a, &map_a, &bars.full[st], k0, m0, 0, kEvictNormal);
+          if (p.a_heads) {
+            const HeadCoord h = head_coord(p, k0, m0);
+            tma_load_3d(a, &map_a, &bars.full[st], h.c0, h.c1, h.c2, kEvictNormal);
+          } else {
+            tma_load_3d(a, &map_a, &bars.full[st], k0, m0, 0, kEvictNormal);
+          }
         }
         if constexpr (kBMn) {
-          for (int x = 0; x < 4; ++x) tma_load_3d(b + x * 4096, &map_b, &bars.full[st], n0 + 32 * x, k0, 0, kEvictNormal);
+          for (int x = 0; x < 4; ++x) {
+            if (p.b_heads) {
+              const HeadCoord h = head_coord(p, n0 + 32 * x, k0);
+              tma_load_3d(b + x * 4096, &map_b, &bars.full[st], h.c0, h.c1, h.c2, kEvictNormal);
+            } else {
+              tma_load_3d(b + x * 4096, &map_b, &bars.full[st], n0 + 32 * x, k0, 0, kEvictNormal);
+            }
+          }
         } else {
           tma_load_3d(b, &map_b, &bars.full[st], k0, n0, 0, kEvictNormal);
         }
@@ -167,8 +200,10 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
       if (leader) {
-        if (reduce) tma_reduce_add_3d(&map_c, buf, n0 + c * 32, m0, 0);
-        else tma_store_3d(&map_c, buf, n0 + c * 32, m0, 0);
+        HeadCoord h = {n0 + c * 32, m0, 0};
+        if (p.c_heads) h = head_coord(p, n0 + c * 32, m0);
+        if (reduce) tma_reduce_add_3d(&map_c, buf, h.c0, h.c1, h.c2);
+        else tma_store_3d(&map_c, buf, h.c0, h.c1, h.c2);
         tma_store_commit();
       }
     }
@@ -181,17 +216,25 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
 template <bool kAMn, bool kBMn>
 cudaError_t launch_gemm(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, bool accumulate,
-                        cudaStream_t st) {
+                        const HeadLayout& hl, cudaStream_t st) {
   CUtensorMap ma, mb;
   // K-major operand [rows][K]: box (32 k, 128 rows), 128B swizzle.  MN-major operand [K][cols]: box (32 cols, 32 k rows),
-  // 128B swizzle with 32-byte atoms.
-  if (kAMn ? make_tmap_3d(&ma, a, 4, M, K, 1, 32, 32, 2) : make_tmap_3d(&ma, a, 4, K, M, 1, 32, 128, 1)) return cudaErrorInvalidValue;
-  if (kBMn ? make_tmap_3d(&mb, b, 4, N, K, 1, 32, 32, 2) : make_tmap_3d(&mb, b, 4, K, N, 1, 32, 128, 1)) return cudaErrorInvalidValue;
+  // 128B swizzle with 32-byte atoms.  Head-layout operands: {d, T, B*H} with the same boxes.
+  const uint64_t tokens = kAMn ? (uint64_t)K : (uint64_t)M;  // token count of a head-layout A (its other dim is H*d)
+  const uint64_t BH_a = hl.a ? tokens / hl.T * hl.H : 0;
+  if (hl.a ? make_tmap_3d(&ma, a, 4, hl.d, hl.T, BH_a, 32, kAMn ? 32 : 128, kAMn ? 2 : 1)
+           : (kAMn ? make_tmap_3d(&ma, a, 4, M, K, 1, 32, 32, 2) : make_tmap_3d(&ma, a, 4, K, M, 1, 32, 128, 1)))
+    return cudaErrorInvalidValue;
+  if (hl.b ? make_tmap_3d(&mb, b, 4, hl.d, hl.T, (uint64_t)K / hl.T * hl.H, 32, 32, 2)  // only the MN-major B (dW = X^T dY_heads)
+           : (kBMn ? make_tmap_3d(&mb, b, 4, N, K, 1, 32, 32, 2) : make_tmap_3d(&mb, b, 4, K, N, 1, 32, 128, 1)))
+    return cudaErrorInvalidValue;
   CUtensorMap mc;  // C [M][N]: slabs of (32 columns, 128 rows), 128B swizzle, clipped at the edges by the TMA engine
-  if (make_tmap_3d(&mc, c, 4, N, M, 1, 32, 128, 1)) return cudaErrorInvalidValue;
+  if (hl.c ? make_tmap_3d(&mc, c, 4, hl.d, hl.T, (uint64_t)M / hl.T * hl.H, 32, 128, 1) : make_tmap_3d(&mc, c, 4, N, M, 1, 32, 128, 1))
+    return cudaErrorInvalidValue;
   cudaError_t e;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.c = c; p.bias = bias; p.accumulate = accumulate ? 1 : 0;
+  p.a_heads = hl.a; p.b_heads = hl.b; p.c_heads = hl.c; p.T = hl.T > 0 ? hl.T : 1; p.H = hl.H; p.d = hl.d > 0 ? hl.d : 1;
   // split-K when the output has too few tiles to fill the 148 SMs (weight gradients: 256 x 256 outputs reduced over
   // thousands of tokens): each split keeps at least 8 k-blocks, partial tiles are red.added into a zeroed C
   const int tiles = ((N + kBN - 1) / kBN) * ((M + kBM - 1) / kBM);
@@ -257,15 +300,57 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   }
 }
 
+// out[h * d + dd] += sum over (b, t) of x[b][h][t][dd]   (bias gradient of a projection whose output is in head layout)
+__global__ void __launch_bounds__(256) colsum_heads_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H,
+                                                          int T, int d) {
+  const int h = blockIdx.x, dd = threadIdx.x % d, lanes = blockDim.x / d, r = threadIdx.x / d;
+  __shared__ float part[256];
+  float acc = 0.f;
+  if (r < lanes)
+    for (int row = blockIdx.y * lanes + r; row < B * T; row += lanes * gridDim.y) {
+      const int b = row / T, t = row - b * T;
+      acc += x[(((size_t)b * H + h) * T + t) * d + dd];
+    }
+  part[threadIdx.x] = r < lanes ? acc : 0.f;
+  __syncthreads();
+  if (threadIdx.x < d) {
+    float s = 0.f;
+    for (int i = 0; i < lanes; ++i) s += part[i * d + threadIdx.x];
+    atomicAdd(out + h * d + threadIdx.x, s);
+  }
+}
+
 }  // namespace
 
 cudaError_t gemm_tf32(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, bool a_mn_major,
-                      bool b_mn_major, bool accumulate, cudaStream_t st) {
+                      bool b_mn_major, bool accumulate, cudaStream_t st, HeadLayout hl) {
   if (M <= 0 || N <= 0 || K <= 0 || (M & 3) || (N & 3) || (K & 3)) return cudaErrorInvalidValue;
-  if (a_mn_major) return b_mn_major ? launch_gemm<true, true>(a, b, c, bias, M, N, K, accumulate, st)
-                                    : launch_gemm<true, false>(a, b, c, bias, M, N, K, accumulate, st);
-  return b_mn_major ? launch_gemm<false, true>(a, b, c, bias, M, N, K, accumulate, st)
-                    : launch_gemm<false, false>(a, b, c, bias, M, N, K, accumulate, st);
+  if (hl.a || hl.b || hl.c) {
+    // head-layout operands: whole 32-column slabs per head, row tiles inside one batch
+    if (hl.T <= 0 || hl.H <= 0 || hl.d <= 0 || hl.d % 32 || hl.T % 128) return cudaErrorInvalidValue;
+    if (hl.b && !b_mn_major) return cudaErrorInvalidValue;
+    const int E = hl.H * hl.d;
+    if (hl.a && (a_mn_major ? (M != E || K % hl.T) : (K != E || M % hl.T))) return cudaErrorInvalidValue;
+    if (hl.b && (N != E || K % hl.T)) return cudaErrorInvalidValue;
+    if (hl.c && (N != E || M % hl.T)) return cudaErrorInvalidValue;
+  }
+  if (a_mn_major) return b_mn_major ? launch_gemm<true, true>(a, b, c, bias, M, N, K, accumulate, hl, st)
+                                    : launch_gemm<true, false>(a, b, c, bias, M, N, K, accumulate, hl, st);
+  return b_mn_major ? launch_gemm<false, true>(a, b, c, bias, M, N, K, accumulate, hl, st)
+                    : launch_gemm<false, false>(a, b, c, bias, M, N, K, accumulate, hl, st);
+}
+
+cudaError_t colsum_heads_f32(const float* x, float* out, int B, int H, int T, int d, bool accumulate, cudaStream_t st) {
+  if (B <= 0 || H <= 0 || T <= 0 || d <= 0 || d > 256) return cudaErrorInvalidValue;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)H * d * 4, st);
+    if (e != cudaSuccess) return e;
+  }
+  int strips = (148 * 4 + H - 1) / H;
+  const int lanes = 256 / d;
+  if (strips > (B * T + lanes - 1) / lanes) strips = (B * T + lanes - 1) / lanes;
+  colsum_heads_kernel<<<dim3(H, strips), 256, 0, st>>>(x, out, B, H, T, d);
+  return cudaGetLastError();
 }
 
 cudaError_t colsum_f32(const float* x, float* out, int M, int N, bool accumulate, cudaStream_t st) {

@@ -56,8 +56,15 @@ cudaError_t dropout_mask(unsigned char* keep, int head_begin, int n_heads, int T
 // ---- decoder-LM operators around the attention path (fa_gemm_sm100.cu, fa_lm_kernels.cu) --------
 // C[M x N] (+)= A * B (+ bias[N]); fp32 storage, tf32 tensor cores.  a_mn_major: A stored [K][M] (M contiguous) instead
 // of [M][K]; b_mn_major: B stored [K][N] (N contiguous) instead of [N][K].  M, N, K multiples of 4.
+// HeadLayout: which operands are logical [B*T][H*d] matrices stored as (B, H, T, d) (T % 128 == 0, d % 32 == 0)
+struct HeadLayout {
+  int a, b, c;  // flags
+  int T, H, d;
+};
+constexpr HeadLayout kNoHeads = {0, 0, 0, 0, 0, 0};
 cudaError_t gemm_tf32(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, bool a_mn_major,
-                      bool b_mn_major, bool accumulate, cudaStream_t st);
+                      bool b_mn_major, bool accumulate, cudaStream_t st, HeadLayout hl = kNoHeads);
+cudaError_t colsum_heads_f32(const float* x, float* out, int B, int H, int T, int d, bool accumulate, cudaStream_t st);
 cudaError_t colsum_f32(const float* x, float* out, int M, int N, bool accumulate, cudaStream_t st);
 // fa_lm_kernels.cu: one fused pass per operator (dims multiples of 4; dw/db/embedding-dw are zeroed inside)
 cudaError_t layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, int rows,

@@ -127,13 +127,15 @@ class MultiHeadAttention(Module):
         B, T, E = x.shape
         H, d = self.n_head, self.attn_hidden_dim
         x2 = x.reshape(B * T, E)
-        # flash path of project_to_query_key_value: K keeps the (B, H, T, d) layout (modules_transfomer.py:83-84)
-        q = self.q_projection(x2).view(B, T, H, d).permute(0, 2, 1, 3).contiguous()
-        k = self.k_projection(x2).view(B, T, H, d).permute(0, 2, 1, 3).contiguous()
-        v = self.v_projection(x2).view(B, T, H, d).permute(0, 2, 1, 3).contiguous()
+        # flash path of project_to_query_key_value: K keeps the (B, H, T, d) layout (modules_transfomer.py:83-84).
+        # ops.linear_to_heads / linear_from_heads write / read that layout directly when T % 128 == 0 and d % 32 == 0
+        # (the GEMM's tensor maps permute); otherwise they are linear + permute + contiguous as in the reference.
+        bias = lambda lin: lin.bias.value if lin.has_bias else None  # noqa: E731
+        q = ops.linear_to_heads(x2, self.q_projection.weights.value, bias(self.q_projection), B, T, H, d)
+        k = ops.linear_to_heads(x2, self.k_projection.weights.value, bias(self.k_projection), B, T, H, d)
+        v = ops.linear_to_heads(x2, self.v_projection.weights.value, bias(self.v_projection), B, T, H, d)
         o = self.attention_fn(q, k, v, self.causal)
-        o = o.permute(0, 2, 1, 3).contiguous().view(B * T, E)
-        return self.out_projection(o).view(B, T, E)
+        return ops.linear_from_heads(o, self.out_projection.weights.value, bias(self.out_projection)).view(B, T, E)
 
 
 class FeedForward(Module):

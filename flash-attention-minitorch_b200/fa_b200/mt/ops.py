@@ -130,6 +130,94 @@ def linear(x, weight, bias=None):
     return y if bias is None else y + bias
 
 
+def _gemm_heads(a, b, c, bias, M, N, K, a_mn, b_mn, a_h, b_h, c_h, T, H, d):
+    _lib.check(_lib.load_library().fa_b200_gemm_tf32_heads(a.data_ptr(), b.data_ptr(), c.data_ptr(),
+                                                           bias.data_ptr() if bias is not None else None, M, N, K, a_mn, b_mn, 0,
+                                                           a_h, b_h, c_h, T, H, d, _st()))
+    return c
+
+
+def heads_layout_ok(x, T: int, d: int) -> bool:
+    """The TMA-permuting GEMM needs whole 32-column slabs per head and row tiles inside one batch."""
+    return x.is_cuda and x.dtype == torch.float32 and T % 128 == 0 and d % 32 == 0
+
+
+class _LinearToHeads(torch.autograd.Function):
+    """(B*T, in) @ W(in, H*d) + b written DIRECTLY as (B, H, T, d): the projection and the
+    .view(B,T,H,d).permute(0,2,1,3).contiguous() of project_to_query_key_value (modules_transfomer.py:79-89) in one
+    kernel -- the output tensor map does the permutation.  Backward reads dY out of head layout the same way."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, B, T, H, d):
+        x, w = x.contiguous(), w.contiguous()
+        M, K = x.shape
+        y = torch.empty(B, H, T, d, device=x.device, dtype=torch.float32)
+        _gemm_heads(x, w, y, b.contiguous() if b is not None else None, M, H * d, K, 0, 1, 0, 0, 1, T, H, d)
+        ctx.save_for_backward(x, w)
+        ctx.dims, ctx.has_bias = (B, T, H, d), b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        B, T, H, d = ctx.dims
+        dy = dy.contiguous()
+        M, K = x.shape
+        E = H * d
+        dx = _gemm_heads(dy, w, torch.empty(M, K, device=x.device, dtype=torch.float32), None, M, K, E, 0, 0, 1, 0, 0, T, H, d)
+        dw = _gemm_heads(x, dy, torch.empty(K, E, device=x.device, dtype=torch.float32), None, K, E, M, 1, 1, 0, 1, 0, T, H, d)
+        db = None
+        if ctx.has_bias:
+            db = torch.empty(E, device=x.device, dtype=torch.float32)
+            _lib.check(_lib.load_library().fa_b200_colsum_heads_f32(dy.data_ptr(), db.data_ptr(), B, H, T, d, 0, _st()))
+        return dx, dw, db, None, None, None, None
+
+
+class _LinearFromHeads(torch.autograd.Function):
+    """O(B, H, T, d) read as (B*T, H*d) @ W + b: the permute(0,2,1,3).contiguous().view of MultiHeadAttention.forward
+    (modules_transfomer.py:154-157) folded into the A-operand tensor map; backward writes dO straight into head layout."""
+
+    @staticmethod
+    def forward(ctx, o, w, b):
+        o, w = o.contiguous(), w.contiguous()
+        B, H, T, d = o.shape
+        M, E, N = B * T, H * d, w.shape[1]
+        y = torch.empty(M, N, device=o.device, dtype=torch.float32)
+        _gemm_heads(o, w, y, b.contiguous() if b is not None else None, M, N, E, 0, 1, 1, 0, 0, T, H, d)
+        ctx.save_for_backward(o, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        o, w = ctx.saved_tensors
+        B, H, T, d = o.shape
+        M, E, N = B * T, H * d, w.shape[1]
+        dy = dy.contiguous()
+        do = _gemm_heads(dy, w, torch.empty_like(o), None, M, E, N, 0, 0, 0, 0, 1, T, H, d)
+        dw = _gemm_heads(o, dy, torch.empty(E, N, device=o.device, dtype=torch.float32), None, E, N, M, 1, 1, 1, 0, 0, T, H, d)
+        db = None
+        if ctx.has_bias:
+            db = torch.empty(N, device=o.device, dtype=torch.float32)
+            _lib.check(_lib.load_library().fa_b200_colsum_f32(dy.data_ptr(), db.data_ptr(), M, N, 0, _st()))
+        return do, dw, db
+
+
+def linear_to_heads(x, weight, bias, B: int, T: int, H: int, d: int):
+    """x (B*T, in) -> (B, H, T, d) = heads of x @ W + b.  Fused (no permute copy) when the layout allows it."""
+    if heads_layout_ok(x, T, d) and _on_kernels(x, weight) and x.shape[1] % 4 == 0:
+        return _LinearToHeads.apply(x, weight, bias, B, T, H, d)
+    return linear(x, weight, bias).view(B, T, H, d).permute(0, 2, 1, 3).contiguous()
+
+
+def linear_from_heads(o, weight, bias):
+    """o (B, H, T, d) -> (B*T, out) = merge_heads(o) @ W + b."""
+    B, H, T, d = o.shape
+    if heads_layout_ok(o, T, d) and _on_kernels(o, weight) and weight.shape[1] % 4 == 0:
+        return _LinearFromHeads.apply(o, weight, bias)
+    return linear(o.permute(0, 2, 1, 3).contiguous().view(B * T, H * d), weight, bias)
+
+
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, eps):

@@ -138,6 +138,16 @@ void fa_b200_release_arena(void);
 int fa_b200_gemm_tf32(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, int a_mn_major,
                       int b_mn_major, int accumulate, void* stream);
 int fa_b200_colsum_f32(const float* x, float* out, int M, int N, int accumulate, void* stream);
+/* The same GEMM with "head layout" operands: a logical [B*T][H*d] matrix stored as (B, H, T, d), the layout of the
+ * attention kernels.  The TMA tensor maps do the (B,T,H,d) <-> (B,H,T,d) permutation, so the q/k/v projections write
+ * straight into attention layout and the output projection / the projection gradients read straight out of it --
+ * the three .contiguous() copies per layer of minitorch/modules_transfomer.py:79-89,115-117 disappear.
+ * a_heads / b_heads / c_heads flag which operands use it (b_heads needs b_mn_major); T % 128 == 0, d % 32 == 0.
+ * fa_b200_colsum_heads_f32: out[h*d + dd] (+)= sum_{b,t} x[b][h][t][dd]. */
+int fa_b200_gemm_tf32_heads(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, int a_mn_major,
+                            int b_mn_major, int accumulate, int a_heads, int b_heads, int c_heads, int T, int H, int d,
+                            void* stream);
+int fa_b200_colsum_heads_f32(const float* x, float* out, int B, int H, int T, int d, int accumulate, void* stream);
 /* One fused, device-resident pass per operator of the model path (reference formulas in parentheses); fp32, row-major,
  * inner dimensions and element counts multiples of 4.
  *   layernorm : y = w (x - mean) / sqrt(var + eps) + b, biased variance (minitorch/modules_basic.py:166-175);

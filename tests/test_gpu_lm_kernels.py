@@ -147,3 +147,39 @@ def test_fused_adam_kernel_matches_reference_formula(cuda_device):
         gflat.copy_(g)
         odev.step()
     assert float((flat.double().cpu() - ref.value.detach()).abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize("B,T,H,d,K", [(2, 128, 2, 32, 64), (3, 256, 8, 32, 256), (1, 128, 2, 64, 128), (2, 128, 1, 128, 64)])
+def test_head_layout_projections_equal_linear_plus_permute(cuda_device, B, T, H, d, K):
+    """linear_to_heads / linear_from_heads (the GEMM's tensor maps write / read (B,H,T,d) directly) against the
+    reference sequence linear -> view -> permute -> contiguous on the same kernels: same products, same k order, so
+    outputs and input gradients agree to fp32 rounding; weight gradients (split-K reductions) to 1e-5 relative."""
+    torch.manual_seed(B * T + d)
+    E = H * d
+    x = torch.randn(B * T, K, device=cuda_device)
+    w, b = torch.randn(K, E, device=cuda_device) / K ** 0.5, torch.randn(E, device=cuda_device)
+    wo, bo = torch.randn(E, K, device=cuda_device) / E ** 0.5, torch.randn(K, device=cuda_device)
+    gy = torch.randn(B * T, K, device=cuda_device)
+
+    def run(fused):
+        leaves = [t.clone().requires_grad_(True) for t in (x, w, b, wo, bo)]
+        xx, ww, bb, wwo, bbo = leaves
+        if fused:
+            assert ops.heads_layout_ok(xx, T, d)
+            heads = ops.linear_to_heads(xx, ww, bb, B, T, H, d)
+            y = ops.linear_from_heads(heads * 1.5, wwo, bbo)
+        else:
+            heads = ops.linear(xx, ww, bb).view(B, T, H, d).permute(0, 2, 1, 3).contiguous()
+            y = ops.linear((heads * 1.5).permute(0, 2, 1, 3).contiguous().view(B * T, E), wwo, bbo)
+        (y * gy).sum().backward()
+        return [heads.detach(), y.detach()] + [t.grad for t in leaves]
+
+    before = _lib.launch_count()
+    fused = run(True)
+    assert _lib.launch_count() - before >= 8  # 2 forward GEMMs, 4 backward GEMMs, 2 bias reductions: all ours
+    plain = run(False)
+    for name, a, c in zip(("heads", "y", "dx", "dw", "db", "dwo", "dbo"), fused, plain):
+        assert a.shape == c.shape and float((a - c).abs().max()) <= 1e-5 * max(1.0, float(c.abs().max())), name
+    # and against fp64 on the CPU within the tf32 bar
+    ref = (x.double().cpu() @ w.double().cpu() + b.double().cpu()).view(B, T, H, d).permute(0, 2, 1, 3)
+    assert float((fused[0].double().cpu() - ref).abs().max()) <= 3e-3 * K ** 0.5
