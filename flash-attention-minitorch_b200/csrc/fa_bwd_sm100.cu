@@ -35,6 +35,7 @@ namespace fa {
 namespace {
 
 constexpr int kTile = 128;
+long long* g_bwd_trace = nullptr;  // developer timeline buffer (tc_bwd_set_trace)
 constexpr int kBwdThreads = 512;
 constexpr int kBoxBytes = 128 * 128;  // 128 rows x 128 B
 
@@ -42,7 +43,7 @@ struct BwdParams {
   int T, Tpad, causal;
   float tau, scale_log2;
   const float* lse_pad;    // [BH][Tpad]  lse * log2(e); +inf on padding rows (=> P = 0 there)
-  const float* delta_pad;  // [BH][Tpad]  rowsum(dO o O); 0 on padding rows
+  const float* delta_pad;  // [BH][Tpad]  -rowsum(dO o O) (negated: the main loop adds it with one packed FADD2); 0 on padding rows
   void* dk;
   void* dv;
   float* dq_acc;  // fp32 dQ accumulator [BH][T][D] (workspace, or the caller's fp32 q_grad)
@@ -53,6 +54,8 @@ struct BwdParams {
   __nv_bfloat16* dq_out;
   int accumulate_dq;
   Dropout drop;  // used by the kDrop instantiations only
+  int dq_debug;      // timing experiments only (FA_B200_BWD_DEBUG_DQ): 1 = skip the reduce-adds, 2 = plain TMA stores
+  long long* trace;  // developer timeline (tools/fa_check trace): clock64 stamps of CTA (0, 0), 16 slots per Q tile
 };
 
 template <int D>
@@ -130,6 +133,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   const int nq = (T + kTile - 1) / kTile;
   const int i0 = p.causal ? j : 0;
   const int n = nq - i0;  // number of Q tiles this CTA visits (>= 1)
+  long long* const tr = (blockIdx.x == 0 && blockIdx.y == 0) ? p.trace : nullptr;
+#define FA_TR(il_, e_) do { if (tr && (il_) < 16 && lane == 0) tr[(il_) * 16 + (e_)] = clock64(); } while (0)
+#define FA_TR2(il_, e_) do { if (tr && (il_) < 16 && lane == 0 && warp == 0) tr[256 + (il_) * 16 + (e_)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
     mbar_init(&bars.kv_full, 1);
@@ -193,91 +199,103 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       }
     }
   } else if (warp == 13) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer: the whole warp runs the issue code
+    // (uniform-register descriptors, see fa_ptx.cuh `_w` forms); one elected lane issues each MMA / commit
+    {
       constexpr uint32_t idesc_sT = make_idesc(kFmtBF16, 128, 128, 0, 0);  // K-major x K-major
       constexpr uint32_t idesc_acc = make_idesc(kFmtBF16, 128, D, 0, 1);   // (TMEM | K-major) x MN-major
       constexpr uint32_t idesc_dq = make_idesc(kFmtBF16, 128, D, 1, 1);    // MN-major x MN-major
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sDO), aDS = smem_u32(sDS);
-      // [128 x D] tile, K-major operand, k-step kk of 16 elements
-      auto kmaj = [](uint32_t base, int kk) { return make_smem_desc(base + (kk >> 2) * kBoxBytes + (kk & 3) * 32, 16, 1024); };
-      // tile viewed MN-major: 16 "K" rows per step, MN atoms (64 elements) one box apart
-      auto mnmaj = [](uint32_t base, int kk) { return make_smem_desc(base + kk * 2048, kBoxBytes, 1024); };
-      auto issue_sT = [&](uint32_t a_tile, uint32_t b_tile, uint32_t col) {  // S^T or dP^T
+      // One base descriptor per (tile, major-ness); a k-step only adds a compile-time constant to its low word.
+      // K-major view of a [128 x D] tile: k-step kk of 16 elements = 32 B inside the 128-B swizzle row, boxes of 64 elements.
+      // MN-major view: 16 "K" rows (2 KB) per step, MN atoms (64 elements) one box apart.
+      auto kmaj0 = [](uint32_t base) { return make_smem_desc(base, 16, 1024); };
+      auto mnmaj0 = [](uint32_t base) { return make_smem_desc(base, kBoxBytes, 1024); };
+      auto kstep = [](uint64_t d0, int kk) { return desc_advance(d0, (kk >> 2) * kBoxBytes + (kk & 3) * 32); };
+      auto mnstep = [](uint64_t d0, int kk) { return desc_advance(d0, kk * 2048); };
+      const uint64_t dK_k = kmaj0(aK), dK_mn = mnmaj0(aK), dV_k = kmaj0(aV), dDS_k = kmaj0(aDS), dDS_mn = mnmaj0(aDS);
+      auto issue_sT = [&](uint64_t a0, uint64_t b0, uint32_t col) {  // S^T or dP^T: K-major x K-major
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) umma_ss(tmem + col, kmaj(a_tile, kk), kmaj(b_tile, kk), idesc_sT, kk > 0);
+        for (int kk = 0; kk < D / 16; ++kk) umma_ss_w(tmem + col, kstep(a0, kk), kstep(b0, kk), idesc_sT, kk > 0);
       };
-      auto issue_dv = [&](uint32_t do_tile, bool acc) {
+      auto issue_dv = [&](uint64_t do_mn, bool acc) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_ts(tmem + Cfg::kColDV, tmem + Cfg::kColS + (kk >> 2) * 64 + (kk & 3) * 8, mnmaj(do_tile, kk), idesc_acc,
-                  (acc || kk > 0) ? 1u : 0u);
+          umma_ts_w(tmem + Cfg::kColDV, tmem + Cfg::kColS + (kk >> 2) * 64 + (kk & 3) * 8, mnstep(do_mn, kk), idesc_acc,
+                    (acc || kk > 0) ? 1u : 0u);
       };
-      auto issue_dk = [&](uint32_t q_tile, bool acc) {
+      auto issue_dk = [&](uint64_t q_mn, bool acc) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_ss(tmem + Cfg::kColDK, kmaj(aDS, kk), mnmaj(q_tile, kk), idesc_acc, (acc || kk > 0) ? 1u : 0u);
+          umma_ss_w(tmem + Cfg::kColDK, kstep(dDS_k, kk), mnstep(q_mn, kk), idesc_acc, (acc || kk > 0) ? 1u : 0u);
       };
       auto issue_dq = [&]() {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_ss(tmem + Cfg::kColDQ, mnmaj(aDS, kk), mnmaj(aK, kk), idesc_dq, kk > 0);
+        for (int kk = 0; kk < 8; ++kk) umma_ss_w(tmem + Cfg::kColDQ, mnstep(dDS_mn, kk), mnstep(dK_mn, kk), idesc_dq, kk > 0);
       };
       auto q_tile = [&](int il) { return aQ + (il & 1) * Cfg::kTileBytes; };
       auto do_tile = [&](int il) { return aDO + (il % Cfg::kDoStages) * Cfg::kTileBytes; };
 
-      mbar_wait(&bars.kv_full, 0);
-      mbar_wait(&bars.q_full[0], 0);
+      mbar_wait_w(&bars.kv_full, 0);
+      mbar_wait_w(&bars.q_full[0], 0);
       tc_fence_after();
-      issue_sT(aK, q_tile(0), Cfg::kColS);
-      umma_commit(&bars.s_full);
-      mbar_wait(&bars.do_full[0], 0);
+      issue_sT(dK_k, kmaj0(q_tile(0)), Cfg::kColS);
+      umma_commit_w(&bars.s_full);
+      mbar_wait_w(&bars.do_full[0], 0);
       tc_fence_after();
-      issue_sT(aV, do_tile(0), Cfg::kColDP);
-      umma_commit(&bars.dp_full);
-      mbar_wait(&bars.p_full, 0);
+      issue_sT(dV_k, kmaj0(do_tile(0)), Cfg::kColDP);
+      umma_commit_w(&bars.dp_full);
+      mbar_wait_w(&bars.p_full, 0);
       tc_fence_after();
-      issue_dv(do_tile(0), false);
-      umma_commit(&bars.do_empty[0]);
+      issue_dv(mnmaj0(do_tile(0)), false);
+      umma_commit_w(&bars.do_empty[0]);
       if (n > 1) {
-        mbar_wait(&bars.q_full[1], 0);
+        mbar_wait_w(&bars.q_full[1], 0);
         tc_fence_after();
-        issue_sT(aK, q_tile(1), Cfg::kColS);
-        umma_commit(&bars.s_full);
+        issue_sT(dK_k, kmaj0(q_tile(1)), Cfg::kColS);
+        umma_commit_w(&bars.s_full);
       }
       for (int il = 0; il < n; ++il) {
-        mbar_wait(&bars.ds_full, il & 1);
-        if (!Cfg::kAliasDq && il > 0) mbar_wait(&bars.dq_drained, (il - 1) & 1);
+        mbar_wait_w(&bars.ds_full, il & 1);
+        if (!Cfg::kAliasDq && il > 0) mbar_wait_w(&bars.dq_drained, (il - 1) & 1);
         tc_fence_after();
+        FA_TR(il, 8);
         issue_dq();
-        umma_commit(&bars.dq_full);
-        issue_dk(q_tile(il), il > 0);
-        umma_commit(&bars.ds_empty);
-        umma_commit(&bars.q_empty[il & 1]);
+        umma_commit_w(&bars.dq_full);
+        issue_dk(mnmaj0(q_tile(il)), il > 0);
+        umma_commit_w(&bars.ds_empty);
+        umma_commit_w(&bars.q_empty[il & 1]);
+        FA_TR(il, 9);
         if (il + 1 < n) {
           const int nx = il + 1;
-          if (Cfg::kAliasDq) mbar_wait(&bars.dq_drained, il & 1);
-          mbar_wait(&bars.do_full[nx % Cfg::kDoStages], (nx / Cfg::kDoStages) & 1);
+          if (Cfg::kAliasDq) mbar_wait_w(&bars.dq_drained, il & 1);
+          mbar_wait_w(&bars.do_full[nx % Cfg::kDoStages], (nx / Cfg::kDoStages) & 1);
           tc_fence_after();
-          issue_sT(aV, do_tile(nx), Cfg::kColDP);
-          umma_commit(&bars.dp_full);
-          mbar_wait(&bars.p_full, nx & 1);
+          FA_TR(il, 10);
+          issue_sT(dV_k, kmaj0(do_tile(nx)), Cfg::kColDP);
+          umma_commit_w(&bars.dp_full);
+          FA_TR(il, 11);
+          mbar_wait_w(&bars.p_full, nx & 1);
           tc_fence_after();
-          issue_dv(do_tile(nx), true);
-          umma_commit(&bars.do_empty[nx % Cfg::kDoStages]);
+          FA_TR(il, 12);
+          issue_dv(mnmaj0(do_tile(nx)), true);
+          umma_commit_w(&bars.do_empty[nx % Cfg::kDoStages]);
+          FA_TR(il, 13);
           if (il + 2 < n) {
             const int n2 = il + 2;
-            mbar_wait(&bars.q_full[n2 & 1], (n2 >> 1) & 1);
+            mbar_wait_w(&bars.q_full[n2 & 1], (n2 >> 1) & 1);
             tc_fence_after();
-            issue_sT(aK, q_tile(n2), Cfg::kColS);
-            umma_commit(&bars.s_full);
+            issue_sT(dK_k, kmaj0(q_tile(n2)), Cfg::kColS);
+            umma_commit_w(&bars.s_full);
+            FA_TR(il, 14);
           }
         }
       }
-      umma_commit(&bars.dkv_full);
+      umma_commit_w(&bars.dkv_full);
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ compute warps
-    reg_alloc<168>();
+    reg_alloc<136>();  // 8 x 136 + 4 x 152 (drain) + 4 x 88 = the 128 registers per thread the CTA was launched with
     const int g = warp >> 2;                 // which half of the 128 query columns
     const int r = (warp & 3) * 32 + lane;    // key row within the tile == TMEM lane
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
@@ -302,6 +320,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       mbar_wait(&bars.q_full[il & 1], (il >> 1) & 1);  // L / delta of this Q tile have landed
       mbar_wait(&bars.s_full, il & 1);
       tc_fence_after();
+      if (warp == 0) FA_TR(il, 0);
       float pr[64];
       {
         uint32_t* u = reinterpret_cast<uint32_t*>(pr);
@@ -309,6 +328,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         tmem_ld_x32(tS + g * 64 + 32, u + 32);
         tmem_wait_ld();
       }
+      FA_TR2(il, 0);
       const bool diag = p.causal && (i == j);
 #pragma unroll
       for (int c = 0; c < 64; c += 4) {
@@ -325,6 +345,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       }
       // keep bits of this key row: query pair pi = c >> 1 of each 32-column half sits at bit (15 - pi % 16) for the
       // even query and bit (31 - pi % 16) for the odd one (shift-in order), halves 0 / 1 in keep_a / keep_b
+      FA_TR2(il, 1);
       uint32_t keep_a = 0u, keep_b = 0u;
       auto kept = [&](int c) {
         const int pos = 15 - ((c >> 1) & 15) + 16 * (c & 1);
@@ -351,52 +372,75 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
         // P^T of query columns [64g, 64g+64) goes to TMEM columns [64g, 64g+32): inside the S columns this
         // thread group has already consumed, so the two groups never touch each other's unread scores
+        FA_TR2(il, 2);
         tmem_st_x32(tS + g * 64, pk);
+        // tau is folded into the kept P values here, where the MUFU pipe is the limiter and the FMA pipe has slack:
+        // dS^T = (tau P^T) o (dP^T - delta) then costs one FADD2 + one FMUL2 per pair on the critical dS phase
+        const float2 tau2 = make_float2(p.tau, p.tau);
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          const float2 t2 = fmul2(make_float2(pr[c], pr[c + 1]), tau2);
+          pr[c] = t2.x;
+          pr[c + 1] = t2.y;
+        }
+        FA_TR2(il, 3);
         tmem_wait_st();
       }
+      FA_TR2(il, 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.p_full);
+      if (warp == 0) FA_TR(il, 1);
       // ---- dS^T = tau * P^T o (dP^T - delta)
       mbar_wait(&bars.dp_full, il & 1);
       tc_fence_after();
-      float dp[64];
-      {
-        uint32_t* u = reinterpret_cast<uint32_t*>(dp);
-        tmem_ld_x32(tDP + g * 64, u);
-        tmem_ld_x32(tDP + g * 64 + 32, u + 32);
+      if (warp == 0) FA_TR(il, 2);
+      // dP^T is consumed in two 32-column halves (32 live registers instead of 64: the drain warps need the registers to
+      // pull a whole dQ tile out of TMEM at once)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float dp[32];
+        tmem_ld_x32(tDP + g * 64 + hf * 32, reinterpret_cast<uint32_t*>(dp));
         tmem_wait_ld();
-      }
-      if (il > 0) mbar_wait(&bars.ds_empty, (il - 1) & 1);  // dK(i-1) / dQ(i-1) have finished reading dS
+        FA_TR2(il, 5 + 3 * hf);
+        if (hf == 0 && il > 0) mbar_wait(&bars.ds_empty, (il - 1) & 1);  // dK(i-1) / dQ(i-1) have finished reading dS
+        FA_TR2(il, 6 + 3 * hf);
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        float ds[8];
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const int ch = hf * 4 + c8;  // 16-byte chunk of this thread's 128-byte dS^T row
+          float ds[8];
 #pragma unroll
-        for (int e = 0; e < 8; e += 4) {
-          const float4 D4 = *reinterpret_cast<const float4*>(sD + ch * 8 + e);
-          if constexpr (kDrop) {  // dP o Z with Z = keep / (1 - p); P itself stays undropped here
-            const int c = ch * 8 + e;
-            dp[c + 0] *= kept(c + 0) ? drop_scale : 0.f;
-            dp[c + 1] *= kept(c + 1) ? drop_scale : 0.f;
-            dp[c + 2] *= kept(c + 2) ? drop_scale : 0.f;
-            dp[c + 3] *= kept(c + 3) ? drop_scale : 0.f;
+          for (int e = 0; e < 8; e += 4) {
+            const float4 D4 = *reinterpret_cast<const float4*>(sD + ch * 8 + e);
+            const int c = ch * 8 + e, cl = c8 * 8 + e;
+            if constexpr (kDrop) {  // dP o Z with Z = keep / (1 - p); P itself stays undropped here
+              dp[cl + 0] *= kept(c + 0) ? drop_scale : 0.f;
+              dp[cl + 1] *= kept(c + 1) ? drop_scale : 0.f;
+              dp[cl + 2] *= kept(c + 2) ? drop_scale : 0.f;
+              dp[cl + 3] *= kept(c + 3) ? drop_scale : 0.f;
+            }
+            const float2 a = fmul2(make_float2(pr[c + 0], pr[c + 1]), fadd2(make_float2(dp[cl + 0], dp[cl + 1]), make_float2(D4.x, D4.y)));
+            const float2 b = fmul2(make_float2(pr[c + 2], pr[c + 3]), fadd2(make_float2(dp[cl + 2], dp[cl + 3]), make_float2(D4.z, D4.w)));
+            ds[e + 0] = a.x;
+            ds[e + 1] = a.y;
+            ds[e + 2] = b.x;
+            ds[e + 3] = b.y;
           }
-          ds[e + 0] = pr[ch * 8 + e + 0] * (dp[ch * 8 + e + 0] - D4.x) * p.tau;
-          ds[e + 1] = pr[ch * 8 + e + 1] * (dp[ch * 8 + e + 1] - D4.y) * p.tau;
-          ds[e + 2] = pr[ch * 8 + e + 2] * (dp[ch * 8 + e + 2] - D4.z) * p.tau;
-          ds[e + 3] = pr[ch * 8 + e + 3] * (dp[ch * 8 + e + 3] - D4.w) * p.tau;
+          uint4 v;
+          v.x = pack_bf16x2(ds[0], ds[1]);
+          v.y = pack_bf16x2(ds[2], ds[3]);
+          v.z = pack_bf16x2(ds[4], ds[5]);
+          v.w = pack_bf16x2(ds[6], ds[7]);
+          *reinterpret_cast<uint4*>(ds_row + ((ch ^ (r & 7)) << 4)) = v;
         }
-        uint4 v;
-        v.x = pack_bf16x2(ds[0], ds[1]);
-        v.y = pack_bf16x2(ds[2], ds[3]);
-        v.z = pack_bf16x2(ds[4], ds[5]);
-        v.w = pack_bf16x2(ds[6], ds[7]);
-        *reinterpret_cast<uint4*>(ds_row + ((ch ^ (r & 7)) << 4)) = v;
+        FA_TR2(il, 7 + 3 * hf);
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.ds_full);
+      if (warp == 0) FA_TR(il, 3);
+      if (warp == 7) FA_TR(il, 4);
     }
     // ---- epilogue: group 0 stores dV_j, group 1 stores dK_j
     mbar_wait(&bars.dkv_full, 0);
@@ -420,7 +464,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else if (warp < 12) {
     // ------------------------------------------------------------------ dQ drain warps
-    reg_dealloc<88>();
+    reg_alloc<152>();
     const int w = warp - 8;
     const int r = w * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t tDQ = tmem + Cfg::kColDQ + (uint32_t(w * 32) << 16);
@@ -516,30 +560,36 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const int i = i0 + il;
       mbar_wait(&bars.dq_full, il & 1);
       tc_fence_after();
-#pragma unroll 1
+      if (warp == 8) FA_TR(il, 5);
+      // The whole dQ tile leaves TMEM at once (D registers per thread), so that dP(i+1) -- which aliases these columns
+      // at d = 128 and sits on the critical chain dS -> dQ -> dP -> dS -- is released after one TMEM read instead of after
+      // three staging rounds; the staging / reduce-adds below then overlap the next tile pair.
+      uint32_t rr[D];
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) tmem_ld_x32(tDQ + c * 32, rr + c * 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.dq_drained);
+      if (warp == 8) FA_TR(il, 6);
+#pragma unroll
       for (int c = 0; c < D / 32; ++c, ++chunk_no) {
         uint8_t* buf = sStage + (chunk_no & 1) * kBoxBytes;
-        uint32_t rr[32];
-        tmem_ld_x32(tDQ + c * 32, rr);
-        tmem_wait_ld();
-        if (c == D / 32 - 1) {  // all of dQ(i) is in registers: the TMEM region may be overwritten
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars.dq_drained);
-        }
         if (leader && chunk_no >= 2) tma_store_wait_read<1>();  // staging buffer no longer being read
         named_bar_sync(1, 128);
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch)
           *reinterpret_cast<uint4*>(buf + r * 128 + ((ch ^ (r & 7)) << 4)) =
-              make_uint4(rr[ch * 4], rr[ch * 4 + 1], rr[ch * 4 + 2], rr[ch * 4 + 3]);
+              make_uint4(rr[c * 32 + ch * 4], rr[c * 32 + ch * 4 + 1], rr[c * 32 + ch * 4 + 2], rr[c * 32 + ch * 4 + 3]);
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (leader) {
-          tma_reduce_add_3d(&map_dq, buf, c * 32, i * kTile, bh);
+          if (p.dq_debug == 0) tma_reduce_add_3d(&map_dq, buf, c * 32, i * kTile, bh);
+          else if (p.dq_debug == 2) tma_store_3d(&map_dq, buf, c * 32, i * kTile, bh);
           tma_store_commit();
         }
       }
+      if (warp == 8) FA_TR(il, 7);
       if (fused_cvt) {
         if (n_pending == kLag) {
           finish_tile(pending[0], std::integral_constant<int, kLag * (D / 32)>{});
@@ -604,7 +654,7 @@ fa_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __r
 #pragma unroll
     for (int off = kLanesPerRow / 2; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (li == 0) {
-      delta_pad[row] = t < T ? acc : 0.f;
+      delta_pad[row] = t < T ? -acc : 0.f;
       lse_pad[row] = t < T ? lse[bh * T + t] * 1.4426950408889634f : INFINITY;
     }
   }
@@ -709,6 +759,11 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   const bool fused_cvt = !kF32 && fused_env && !p.dq_red;
   p.tile_counters = fused_cvt ? counters : nullptr;
   p.drop = drop;
+  p.trace = g_bwd_trace;
+  {
+    const char* e = getenv("FA_B200_BWD_DEBUG_DQ");  // timing experiments only: results are wrong when set
+    p.dq_debug = !e ? 0 : e[0] == 's' && e[1] == 'k' ? 1 : e[0] == 's' && e[1] == 't' ? 2 : 0;
+  }
   dim3 grid((unsigned)(Tpad / kTile), BH);
   if (drop.thr) fa_bwd_kernel<D, OutT, true><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
   else fa_bwd_kernel<D, OutT, false><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
@@ -728,7 +783,7 @@ bool tc_bwd_supported(int d) { return d == 64 || d == 128; }
 int tc_bwd_num_launches(bool grads_f32) {
   return (grads_f32 || (bwd_fused_convert_enabled() && !bwd_dq_red_enabled())) ? 2 : 3;
 }
-void tc_bwd_set_trace(long long*) {}
+void tc_bwd_set_trace(long long* buf) { g_bwd_trace = buf; }
 
 size_t tc_bwd_workspace_bytes(int BH, int T, int d) {
   // lse_pad + delta_pad + fp32 dQ accumulator (the latter only used for bf16 gradients) + per-Q-tile arrival counters

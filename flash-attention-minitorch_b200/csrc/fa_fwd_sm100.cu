@@ -170,74 +170,71 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       }
     }
   } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer: the whole warp runs the issue code
+    // (warp-uniform descriptors, one elected lane issues each MMA / commit: the `_w` forms of fa_ptx.cuh)
+    {
       constexpr uint32_t kFmt = kTF32 ? kFmtTF32 : kFmtBF16;
       constexpr uint32_t idesc_qk = make_idesc(kFmt, kBlockM, kBlockN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(kFmt, kBlockM, D, 0, 1);
       const uint32_t sQa = smem_u32(sQ), sKa = smem_u32(sK), sVa = smem_u32(sV);
+      // one base descriptor per tile, a k-step adds a compile-time constant to its low word (desc_advance)
       auto issue_qk = [&](int t, int st) {
-        const uint32_t qa = sQa + t * Cfg::kTileBytes, ka = sKa + st * Cfg::kTileBytes;
+        const uint64_t q0 = make_smem_desc(sQa + t * Cfg::kTileBytes, 16, 1024);
+        const uint64_t k0 = make_smem_desc(sKa + st * Cfg::kTileBytes, 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < Cfg::kKStepsQK; ++kk) {
           const uint32_t off = (kk >> 2) * Cfg::kBoxBytes + (kk & 3) * 32;  // 4 k-steps of 32 B per swizzle row
-          umma_ss<kTF32>(tmem + t * 128, make_smem_desc(qa + off, 16, 1024), make_smem_desc(ka + off, 16, 1024), idesc_qk,
-                  kk > 0);
+          umma_ss_w<kTF32>(tmem + t * 128, desc_advance(q0, off), desc_advance(k0, off), idesc_qk, kk > 0);
         }
       };
       auto issue_pv = [&](int t, int st, bool acc) {
         const uint32_t va = sVa + st * Cfg::kTileBytes;
+        // bf16: 16 key rows (2 KB) per k-step, 64-column atoms one box apart, 128B swizzle.
+        // tf32: P is one tf32 per TMEM column, 8 columns per k-step; V: 8 key rows (1 KB) per k-step, 4-row groups
+        // 512 B apart, 32-column atoms one box apart, 128B swizzle with 32-B atomicity.
+        const uint64_t v0 = kTF32 ? make_smem_desc(va, Cfg::kBoxBytes, 512, kDescSw128Base32) : make_smem_desc(va, Cfg::kBoxBytes, 1024);
 #pragma unroll
-        for (int kk = 0; kk < Cfg::kKStepsPV; ++kk) {
-          if constexpr (kTF32) {
-            // P: one tf32 per TMEM column, 8 columns per k-step.  V: 8 key rows (1 KB) per k-step, 4-row groups
-            // 512 B apart, 32-column atoms one box apart, 128B swizzle with 32-B atomicity.
-            umma_ts<true>(tmem + 256 + t * 128, tmem + t * 128 + kk * 8,
-                          make_smem_desc(va + kk * 1024, Cfg::kBoxBytes, 512, kDescSw128Base32), idesc_pv,
-                          (acc || kk > 0) ? 1u : 0u);
-          } else {
-            umma_ts<false>(tmem + 256 + t * 128, tmem + t * 128 + kk * 8,
-                           make_smem_desc(va + kk * 2048, Cfg::kBoxBytes, 1024), idesc_pv, (acc || kk > 0) ? 1u : 0u);
-          }
-        }
+        for (int kk = 0; kk < Cfg::kKStepsPV; ++kk)
+          umma_ts_w<kTF32>(tmem + 256 + t * 128, tmem + t * 128 + kk * 8, desc_advance(v0, kk * (kTF32 ? 1024 : 2048)), idesc_pv,
+                           (acc || kk > 0) ? 1u : 0u);
       };
-      mbar_wait(&bars.q_full, 0);
-      mbar_wait(&bars.k_full[0], 0);
+      mbar_wait_w(&bars.q_full, 0);
+      mbar_wait_w(&bars.k_full[0], 0);
       tc_fence_after();
       issue_qk(0, 0);
-      umma_commit(&bars.s_full[0]);
+      umma_commit_w(&bars.s_full[0]);
       issue_qk(1, 0);
-      umma_commit(&bars.s_full[1]);
-      umma_commit(&bars.k_empty[0]);
+      umma_commit_w(&bars.s_full[1]);
+      umma_commit_w(&bars.k_empty[0]);
       for (int j = 0; j < n1; ++j) {
         const int st = j % S;
         const uint32_t ph = (j / S) & 1;
         const int jn = j + 1, stn = jn % S;
         const uint32_t phn = (jn / S) & 1;
-        mbar_wait(&bars.v_full[st], ph);
+        mbar_wait_w(&bars.v_full[st], ph);
         if (j < n0) {
-          mbar_wait(&bars.p_full[0], j & 1);
+          mbar_wait_w(&bars.p_full[0], j & 1);
           tc_fence_after();
           issue_pv(0, st, j > 0);
-          umma_commit(&bars.o_full[0]);
+          umma_commit_w(&bars.o_full[0]);
         }
         if (jn < n0) {
-          mbar_wait(&bars.k_full[stn], phn);
+          mbar_wait_w(&bars.k_full[stn], phn);
           tc_fence_after();
           issue_qk(0, stn);
-          umma_commit(&bars.s_full[0]);
+          umma_commit_w(&bars.s_full[0]);
         }
-        mbar_wait(&bars.p_full[1], j & 1);
+        mbar_wait_w(&bars.p_full[1], j & 1);
         tc_fence_after();
         issue_pv(1, st, j > 0);
-        umma_commit(&bars.o_full[1]);
-        umma_commit(&bars.v_empty[st]);
+        umma_commit_w(&bars.o_full[1]);
+        umma_commit_w(&bars.v_empty[st]);
         if (jn < n1) {
-          mbar_wait(&bars.k_full[stn], phn);
+          mbar_wait_w(&bars.k_full[stn], phn);
           tc_fence_after();
           issue_qk(1, stn);
-          umma_commit(&bars.s_full[1]);
-          umma_commit(&bars.k_empty[stn]);
+          umma_commit_w(&bars.s_full[1]);
+          umma_commit_w(&bars.k_empty[stn]);
         }
       }
     }

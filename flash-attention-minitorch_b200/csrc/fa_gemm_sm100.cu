@@ -142,25 +142,26 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    // the whole warp runs the issue code (warp-uniform descriptors, one elected lane issues: `_w` forms of fa_ptx.cuh)
+    {
       constexpr uint32_t idesc = make_idesc(kFmtTF32, kBM, kBN, kAMn ? 1 : 0, kBMn ? 1 : 0);
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
       for (int kb = 0; kb < nk; ++kb) {
         const int st = kb % kStages;
-        mbar_wait(&bars.full[st], (kb / kStages) & 1);
+        mbar_wait_w(&bars.full[st], (kb / kStages) & 1);
         tc_fence_after();
+        // K-major: 8 tf32 = 32 bytes along the swizzle row, 8-row groups 1024 B apart.  MN-major: 8 k-rows = 1 KB,
+        // 4-row groups 512 B apart, 32-element MN atoms one 4 KB box apart, 32-byte-atom swizzle.
         const uint32_t a = a0 + st * kSlabBytes, b = b0 + st * kSlabBytes;
+        const uint64_t da0 = kAMn ? make_smem_desc(a, 4096, 512, kDescSw128Base32) : make_smem_desc(a, 16, 1024);
+        const uint64_t db0 = kBMn ? make_smem_desc(b, 4096, 512, kDescSw128Base32) : make_smem_desc(b, 16, 1024);
 #pragma unroll
-        for (int kk = 0; kk < kBK / 8; ++kk) {
-          // K-major: 8 tf32 = 32 bytes along the swizzle row, 8-row groups 1024 B apart.  MN-major: 8 k-rows = 1 KB,
-          // 4-row groups 512 B apart, 32-element MN atoms one 4 KB box apart, 32-byte-atom swizzle.
-          const uint64_t da = kAMn ? make_smem_desc(a + kk * 1024, 4096, 512, kDescSw128Base32) : make_smem_desc(a + kk * 32, 16, 1024);
-          const uint64_t db = kBMn ? make_smem_desc(b + kk * 1024, 4096, 512, kDescSw128Base32) : make_smem_desc(b + kk * 32, 16, 1024);
-          umma_ss<true>(tmem, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
-        }
-        umma_commit(&bars.empty[st]);
+        for (int kk = 0; kk < kBK / 8; ++kk)
+          umma_ss_w<true>(tmem, desc_advance(da0, kk * (kAMn ? 1024 : 32)), desc_advance(db0, kk * (kBMn ? 1024 : 32)), idesc,
+                          (kb > 0 || kk > 0) ? 1u : 0u);
+        umma_commit_w(&bars.empty[st]);
       }
-      umma_commit(&bars.acc_full);
+      umma_commit_w(&bars.acc_full);
     }
   } else {
     // epilogue: thread = one output row (TMEM lane); four 32-column slabs through two staging buffers

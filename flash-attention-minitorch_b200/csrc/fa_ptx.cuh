@@ -181,6 +181,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
          (uint64_t((sbo_bytes >> 4) & 0x3fff) << 32);
 }
 
+// Descriptor of the same tile advanced by `bytes` (a multiple of 16 that stays inside the 256 KB window of the 14-bit
+// address field): one 32-bit add on the low word instead of re-encoding -- what the MMA issue loops use per k-step.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) {
+  return (desc & 0xffffffff00000000ull) | uint64_t(uint32_t(desc) + (bytes >> 4));
+}
+
 // Instruction descriptor (32 bit) for kind::f16 / kind::tf32 with fp32 accumulation.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt  [10,13) B fmt  (0 f16, 1 bf16, 2 tf32)
 //   [15] A major (0 = K, 1 = MN)  [16] B major  [17,23) N>>3  [24,29) M>>4
@@ -225,6 +231,70 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-collective issue (the `_w` forms): called by ALL 32 lanes of a converged warp, one lane elected inside the asm
+// issues the instruction.  Why: every operand of UTCHMMA / UTCBAR lives in a uniform register.  Inside `if (lane == 0)`
+// ptxas cannot prove the descriptors warp-uniform, so it builds them in vector registers and wraps EVERY tcgen05.mma
+// into R2UR moves plus an ELECT / BRA.U.ANY loop -- measured 115-140 cycles per 128x128x16 MMA in the attention
+// kernels against 66-68 for the same MMAs issued from uniform registers (tools/umma_rate.cu).  With the whole warp
+// executing the issue code, the descriptor arithmetic runs on the uniform datapath and the MMAs are emitted back to
+// back.  elect.sync picks the same lane on every call of a converged warp, which is what tcgen05.commit needs (it
+// tracks the MMAs of the issuing thread).
+// ---------------------------------------------------------------------------------------------
+template <bool kTF32 = false>
+__device__ __forceinline__ void umma_ss_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  if constexpr (kTF32) {
+    asm volatile(
+        "{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+template <bool kTF32 = false>
+__device__ __forceinline__ void umma_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  if constexpr (kTF32) {
+    asm volatile(
+        "{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+  asm volatile(
+      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+// mbarrier wait by a whole warp that must stay converged afterwards: the loop condition is a warp vote, i.e. uniform,
+// so ptxas keeps treating the code after the wait as convergent (uniform-datapath descriptor arithmetic, bare UTCHMMAs).
+__device__ __forceinline__ void mbar_wait_w(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if ((++spins & 0x3ff) == 0) {  // same watchdog as mbar_wait: trap after ~4 s instead of hanging the GPU
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
   }
 }
 

@@ -29,7 +29,8 @@ class FaError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(LIB_DIR, "libfa_b200.so")
+    # FA_B200_LIB: developer override used for same-box A/B runs of two builds (tools/lm_bench.py, bench.py)
+    return os.environ.get("FA_B200_LIB") or os.path.join(LIB_DIR, "libfa_b200.so")
 
 
 def shim_path(name: str) -> str:

@@ -430,22 +430,33 @@ static int trace_bwd(int BH, int T, int d, int causal) {
   fa_b200_debug_bwd_trace(nullptr);
   std::vector<long long> hst(512);
   CK(cudaMemcpy(hst.data(), tr, 512 * 8, cudaMemcpyDeviceToHost));
-  const char* names[2] = {"dK/dV kernel: compute{S_rdy P_done dP_rdy dS_done} | mma{iss_dV iss_S(i+1) iss_dK iss_dP(i+1)}",
-                          "dQ kernel:    compute{S_rdy P_done dP_rdy dS_done} | mma{iss_S(j+1) iss_dQ iss_dP(j+1)}"};
-  for (int kz = 0; kz < 2; ++kz) {
-    const long long* hh = hst.data() + kz * 256;
-    long long t0 = hh[0];
-    printf("%s  (clock64 of CTA(0,0), relative to first S ready)\n", names[kz]);
-    for (int il = 0; il < 16; ++il) {
-      printf("%3d |", il);
-      for (int e = 0; e < 11; ++e) {
-        if (e >= 4 && e <= 6) continue;
-        long long v = hh[il * 16 + e];
-        printf(" %7lld", v ? v - t0 : -1);
-        if (e == 3) printf(" |");
-      }
-      printf("\n");
+  // slots per Q tile il: 0-4 compute warps {S ready, P stored, dP ready, dS stored (warp 0), dS stored (warp 7)},
+  // 5-7 drain warps {dQ ready, dQ in registers (TMEM released), reduce-adds issued}, 8-14 MMA warp {dS ready, dQ+dK issued,
+  // dQ drained & dO landed, dP issued, P ready, dV issued, S(i+2) issued}
+  const long long* hh = hst.data();
+  const long long t0 = hh[0];
+  printf("bwd timeline of CTA(0,0), cycles relative to first S ready\n");
+  printf(" il | CW: S_rdy  P_done  dP_rdy dS_w0   dS_w7 | DW: dQ_rdy drained  staged | MMA: dS_rdy iss_dQK drained  iss_dP   P_rdy  iss_dV   iss_S\n");
+  for (int il = 0; il < 16; ++il) {
+    printf("%3d |", il);
+    for (int e = 0; e < 15; ++e) {
+      const long long v = hh[il * 16 + e];
+      printf(" %7lld", v ? v - t0 : -1);
+      if (e == 4 || e == 7) printf(" |");
     }
+    printf("\n");
+  }
+  // second table: inside the compute warp 0 (slots 256 + il * 16 + e)
+  printf(" il | CW0: S_ld'd   exp'd  packed   tau'd   st'd | dP0ld'd ds_empty  half0 | dP1ld'd    -     half1   (relative to S_rdy of the same il)\n");
+  for (int il = 0; il < 16; ++il) {
+    printf("%3d |", il);
+    const long long base = hh[il * 16 + 0];
+    for (int e = 0; e < 11; ++e) {
+      const long long v = hh[256 + il * 16 + e];
+      printf(" %7lld", v ? v - base : -1);
+      if (e == 4 || e == 7) printf(" |");
+    }
+    printf("   dP_rdy %lld\n", hh[il * 16 + 2] - base);
   }
   return 0;
 }
