@@ -30,6 +30,13 @@
 #include "fa_ptx.cuh"
 #include "fa_tma_host.h"
 
+// A/B switch for same-box experiments (tools/build_variant.sh + tools/ab.sh).  Fetching -delta into registers before the
+// wait for dP (to take the shared-memory load latency off the dS phase) measured 2.5 % SLOWER than loading it chunk by
+// chunk (6.64 vs 6.48 ms at config 3): the 32 extra live registers cost more than the latency they hide.
+#ifndef FA_BWD_DELTA_PREFETCH
+#define FA_BWD_DELTA_PREFETCH 0
+#endif
+
 namespace fa {
 
 namespace {
@@ -47,12 +54,6 @@ struct BwdParams {
   void* dk;
   void* dv;
   float* dq_acc;  // fp32 dQ accumulator [BH][T][D] (workspace, or the caller's fp32 q_grad)
-  int dq_red;     // 1: drain dQ with red.global.add.v2.f32 from registers; 0: smem staging + TMA reduce-add
-  // bf16 gradients, fused conversion: the CTA that delivers the LAST partial sum of a Q tile converts that tile from the
-  // fp32 accumulator (still in L2) to bf16 -- no separate conversion pass over HBM.  tile_counters[bh][i] counts arrivals.
-  int* tile_counters;  // nullptr = conversion by fa_bwd_dq_convert_kernel after the main kernel
-  __nv_bfloat16* dq_out;
-  int accumulate_dq;
   Dropout drop;  // used by the kDrop instantiations only
   int dq_debug;      // timing experiments only (FA_B200_BWD_DEBUG_DQ): 1 = skip the reduce-adds, 2 = plain TMA stores
   long long* trace;  // developer timeline (tools/fa_check trace): clock64 stamps of CTA (0, 0), 16 slots per Q tile
@@ -62,6 +63,11 @@ template <int D>
 struct BwdCfg {
   static constexpr int kBoxes = D / 64;
   static constexpr int kTileBytes = kBoxes * kBoxBytes;
+  // setmaxnreg split of the 128 registers per thread the CTA is launched with (x 32 lanes: 8 compute, 4 drain, 4 other
+  // warps).  Without dropout the drain warps take a whole dQ tile (D registers) out of TMEM at once; the dropout variant
+  // needs ~24 more registers in the compute warps (mask words), so its drain works in two halves.
+  static constexpr int kRegCompute = 136, kRegDrain = 152, kRegMisc = 88;       // 8*136 + 4*152 + 4*88 = 16*128
+  static constexpr int kRegComputeDrop = 160, kRegDrainDrop = 104;              // 8*160 + 4*104 + 4*88 <= 16*128
   static constexpr int kQStages = 2;
   static constexpr int kDoStages = D >= 128 ? 1 : 2;
   static constexpr bool kAliasDq = D >= 128;
@@ -165,7 +171,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   const uint32_t tmem = *tmem_slot;
 
   if (warp >= 12) {
-    reg_dealloc<88>();
+    reg_dealloc<Cfg::kRegMisc>();
   }
   if (warp == 12) {
     // ------------------------------------------------------------------ TMA producer
@@ -295,7 +301,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ compute warps
-    reg_alloc<136>();  // 8 x 136 + 4 x 152 (drain) + 4 x 88 = the 128 registers per thread the CTA was launched with
+    reg_alloc<kDrop ? Cfg::kRegComputeDrop : Cfg::kRegCompute>();
     const int g = warp >> 2;                 // which half of the 128 query columns
     const int r = (warp & 3) * 32 + lane;    // key row within the tile == TMEM lane
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
@@ -391,7 +397,16 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.p_full);
       if (warp == 0) FA_TR(il, 1);
-      // ---- dS^T = tau * P^T o (dP^T - delta)
+      // ---- dS^T = (tau P^T) o (dP^T - delta)
+      // -delta of the first 32 query columns is fetched BEFORE waiting for dP: a shared-memory load takes ~150 cycles while
+      // the tensor pipe streams operands, and the compiler cannot hoist these loads over the dS stores below (both are
+      // shared memory) -- left in program order they cost one exposed load latency per 16-byte chunk of dS.  The second
+      // half's values are fetched into the same registers as soon as the first half's are consumed, ahead of that chunk's store.
+      float4 dl[8];
+#if FA_BWD_DELTA_PREFETCH
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dl[q] = *reinterpret_cast<const float4*>(sD + q * 4);
+#endif
       mbar_wait(&bars.dp_full, il & 1);
       tc_fence_after();
       if (warp == 0) FA_TR(il, 2);
@@ -411,7 +426,11 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           float ds[8];
 #pragma unroll
           for (int e = 0; e < 8; e += 4) {
+#if FA_BWD_DELTA_PREFETCH
+            const float4 D4 = dl[c8 * 2 + (e >> 2)];
+#else
             const float4 D4 = *reinterpret_cast<const float4*>(sD + ch * 8 + e);
+#endif
             const int c = ch * 8 + e, cl = c8 * 8 + e;
             if constexpr (kDrop) {  // dP o Z with Z = keep / (1 - p); P itself stays undropped here
               dp[cl + 0] *= kept(c + 0) ? drop_scale : 0.f;
@@ -425,6 +444,10 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             ds[e + 1] = a.y;
             ds[e + 2] = b.x;
             ds[e + 3] = b.y;
+          }
+          if (FA_BWD_DELTA_PREFETCH && hf == 0) {  // refill with the second half's -delta before this chunk's store
+            dl[c8 * 2] = *reinterpret_cast<const float4*>(sD + 32 + c8 * 8);
+            dl[c8 * 2 + 1] = *reinterpret_cast<const float4*>(sD + 32 + c8 * 8 + 4);
           }
           uint4 v;
           v.x = pack_bf16x2(ds[0], ds[1]);
@@ -464,98 +487,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else if (warp < 12) {
     // ------------------------------------------------------------------ dQ drain warps
-    reg_alloc<152>();
+    if constexpr (kDrop) reg_dealloc<Cfg::kRegDrainDrop>();  // below the launch value: a decrease
+    else reg_alloc<Cfg::kRegDrain>();
     const int w = warp - 8;
     const int r = w * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t tDQ = tmem + Cfg::kColDQ + (uint32_t(w * 32) << 16);
     const bool leader = (warp == 8 && lane == 0);
     uint32_t chunk_no = 0;
-    int& s_last_arriver = *reinterpret_cast<int*>(smem + Cfg::kOffBars + 200);  // (static smem would not fit at d = 128)
-    // Called once the reduce-adds of Q tile `tile` have been issued; `kNewer` = bulk groups committed after them.
-    auto finish_tile = [&](int tile, auto newer_groups) {
-      constexpr int kNewer = decltype(newer_groups)::value;
-      if (leader) {
-        tma_store_wait_all<kNewer>();  // every reduce-add of `tile` has been performed, not just read from smem
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        __threadfence();
-        const int expected = p.causal ? min(tile + 1, (int)gridDim.x) : (int)gridDim.x;
-        s_last_arriver = atomicAdd(p.tile_counters + (size_t)bh * gridDim.x + tile, 1) == expected - 1;
-      }
-      named_bar_sync(1, 128);
-      if (s_last_arriver) {
-        __threadfence();
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        const int t128 = threadIdx.x & 127;
-        const int rows = min(kTile, T - tile * kTile);
-        const float* src = p.dq_acc + ((size_t)bh * T + (size_t)tile * kTile) * D;
-        __nv_bfloat16* dst = p.dq_out + ((size_t)bh * T + (size_t)tile * kTile) * D;
-        const int limit = rows * (D / 4);
-        constexpr int kBatch = 8;  // independent 16-byte L2 loads in flight per thread (latency-bound otherwise)
-#pragma unroll 1
-        for (int base = 0; base < kTile * (D / 4); base += 128 * kBatch) {
-          float4 a[kBatch];
-#pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            const int idx = base + u * 128 + t128;
-            if (idx < limit) a[u] = __ldcg(reinterpret_cast<const float4*>(src) + idx);  // L2: never in this SM's L1
-          }
-#pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            const int idx = base + u * 128 + t128;
-            if (idx < limit) {
-              uint2* o2 = reinterpret_cast<uint2*>(dst) + idx;
-              if (p.accumulate_dq) {
-                const uint2 old = *o2;
-                const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old);
-                const float2 x = __bfloat1622float2(oh[0]), y = __bfloat1622float2(oh[1]);
-                a[u].x += x.x; a[u].y += x.y; a[u].z += y.x; a[u].w += y.y;
-              }
-              *o2 = make_uint2(pack_bf16x2(a[u].x, a[u].y), pack_bf16x2(a[u].z, a[u].w));
-            }
-          }
-        }
-      }
-      named_bar_sync(1, 128);  // s_last_arriver may be rewritten
-    };
-    const bool fused_cvt = p.tile_counters != nullptr;
-    // Reduce-adds take microseconds to be performed at L2; their tile is only counted kLag tile pairs later, when
-    // waiting for them costs nothing (pending[] = tiles issued but not yet counted, oldest first).
-    constexpr int kLag = 3;
-    int pending[kLag];
-    int n_pending = 0;
-    if (p.dq_red) {
-      // Fragment-layout drain: tcgen05.ld.16x256b hands each quad of lanes 32 contiguous bytes of one dQ row, so a
-      // warp-wide red.global.add.v2.f32 touches 8 complete 32-byte sectors -- no shared-memory staging at all.
-      float* gq = p.dq_acc + (size_t)bh * T * D + 2 * (lane & 3);
-      for (int il = 0; il < n; ++il) {
-        const int i = i0 + il;
-        mbar_wait(&bars.dq_full, il & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t rr[D / 32][16];
-#pragma unroll
-          for (int c = 0; c < D / 32; ++c) tmem_ld_16x256b_x4(tDQ + (uint32_t(h * 16) << 16) + c * 32, rr[c]);
-          tmem_wait_ld();
-          if (h == 1) {  // all of dQ(i) has left TMEM
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.dq_drained);
-          }
-          const int row0 = i * kTile + w * 32 + h * 16 + (lane >> 2), row1 = row0 + 8;
-          float* g0 = gq + (size_t)row0 * D;
-          float* g1 = gq + (size_t)row1 * D;
-#pragma unroll
-          for (int c = 0; c < D / 32; ++c)
-#pragma unroll
-            for (int nn = 0; nn < 4; ++nn) {
-              const int col = c * 32 + nn * 8;
-              if (row0 < T) red_add_f32x2(g0 + col, __uint_as_float(rr[c][4 * nn]), __uint_as_float(rr[c][4 * nn + 1]));
-              if (row1 < T) red_add_f32x2(g1 + col, __uint_as_float(rr[c][4 * nn + 2]), __uint_as_float(rr[c][4 * nn + 3]));
-            }
-        }
-      }
-    } else
     for (int il = 0; il < n; ++il) {
       const int i = i0 + il;
       mbar_wait(&bars.dq_full, il & 1);
@@ -563,47 +501,40 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       if (warp == 8) FA_TR(il, 5);
       // The whole dQ tile leaves TMEM at once (D registers per thread), so that dP(i+1) -- which aliases these columns
       // at d = 128 and sits on the critical chain dS -> dQ -> dP -> dS -- is released after one TMEM read instead of after
-      // three staging rounds; the staging / reduce-adds below then overlap the next tile pair.
-      uint32_t rr[D];
+      // three staging rounds; the staging / reduce-adds below then overlap the next tile pair.  (Dropout variant: two
+      // halves, the compute warps need the registers.)
+      constexpr int kParts = kDrop ? 2 : 1, kColsPart = D / kParts;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) tmem_ld_x32(tDQ + c * 32, rr + c * 32);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.dq_drained);
-      if (warp == 8) FA_TR(il, 6);
+      for (int part = 0; part < kParts; ++part) {
+        uint32_t rr[kColsPart];
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c, ++chunk_no) {
-        uint8_t* buf = sStage + (chunk_no & 1) * kBoxBytes;
-        if (leader && chunk_no >= 2) tma_store_wait_read<1>();  // staging buffer no longer being read
-        named_bar_sync(1, 128);
+        for (int c = 0; c < kColsPart / 32; ++c) tmem_ld_x32(tDQ + part * kColsPart + c * 32, rr + c * 32);
+        tmem_wait_ld();
+        if (part == kParts - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.dq_drained);
+          if (warp == 8) FA_TR(il, 6);
+        }
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          *reinterpret_cast<uint4*>(buf + r * 128 + ((ch ^ (r & 7)) << 4)) =
-              make_uint4(rr[c * 32 + ch * 4], rr[c * 32 + ch * 4 + 1], rr[c * 32 + ch * 4 + 2], rr[c * 32 + ch * 4 + 3]);
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (leader) {
-          if (p.dq_debug == 0) tma_reduce_add_3d(&map_dq, buf, c * 32, i * kTile, bh);
-          else if (p.dq_debug == 2) tma_store_3d(&map_dq, buf, c * 32, i * kTile, bh);
-          tma_store_commit();
+        for (int c = 0; c < kColsPart / 32; ++c, ++chunk_no) {
+          uint8_t* buf = sStage + (chunk_no & 1) * kBoxBytes;
+          if (leader && chunk_no >= 2) tma_store_wait_read<1>();  // staging buffer no longer being read
+          named_bar_sync(1, 128);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<uint4*>(buf + r * 128 + ((ch ^ (r & 7)) << 4)) =
+                make_uint4(rr[c * 32 + ch * 4], rr[c * 32 + ch * 4 + 1], rr[c * 32 + ch * 4 + 2], rr[c * 32 + ch * 4 + 3]);
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (leader) {
+            if (p.dq_debug == 0) tma_reduce_add_3d(&map_dq, buf, part * kColsPart + c * 32, i * kTile, bh);
+            else if (p.dq_debug == 2) tma_store_3d(&map_dq, buf, part * kColsPart + c * 32, i * kTile, bh);
+            tma_store_commit();
+          }
         }
       }
       if (warp == 8) FA_TR(il, 7);
-      if (fused_cvt) {
-        if (n_pending == kLag) {
-          finish_tile(pending[0], std::integral_constant<int, kLag * (D / 32)>{});
-#pragma unroll
-          for (int x = 0; x + 1 < kLag; ++x) pending[x] = pending[x + 1];
-          --n_pending;
-        }
-        pending[n_pending++] = i;
-      }
-    }
-    if (fused_cvt) {
-#pragma unroll
-      for (int x = 0; x < kLag; ++x)
-        if (x < n_pending) finish_tile(pending[x], std::integral_constant<int, 0>{});
     }
     if (leader) tma_store_wait_all<0>();
   }
@@ -620,9 +551,7 @@ template <int D>
 __global__ void __launch_bounds__(256)
 fa_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO,
                    const float* __restrict__ lse, float* __restrict__ lse_pad, float* __restrict__ delta_pad,
-                   float* __restrict__ dq_zero, int T, int Tpad, size_t total_rows_pad, int* __restrict__ counters,
-                   int n_counters) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_counters; i += gridDim.x * blockDim.x) counters[i] = 0;
+                   float* __restrict__ dq_zero, int T, int Tpad, size_t total_rows_pad) {
   constexpr int kLanesPerRow = D / 8;            // 16 (d = 128) or 8 (d = 64)
   constexpr int kRowsPerWarp = 32 / kLanesPerRow;
   const int lane = threadIdx.x & 31;
@@ -677,19 +606,6 @@ __global__ void fa_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfl
   }
 }
 
-// developer switches, read per call.  FA_B200_BWD_CVT=fused converts dQ to bf16 inside the main kernel (the CTA that
-// delivers the last partial of a Q tile converts it from L2): correct, one launch and 1 GB of HBM reads fewer, but
-// measured SLOWER (8.12 ms vs 7.31 ms at config 3): waiting for reduce-adds to be *performed* (cp.async.bulk.wait_group
-// without .read) and the two extra barriers per tile sit on the drain warps' critical path.  Default: separate pass.
-bool bwd_fused_convert_enabled() {
-  const char* e = getenv("FA_B200_BWD_CVT");
-  return e && e[0] == 'f';
-}
-bool bwd_dq_red_enabled() {
-  const char* e = getenv("FA_B200_BWD_DQ");
-  return e && e[0] == 'r';
-}
-
 size_t pad_rows(int T) { return (size_t)((T + kTile - 1) / kTile) * kTile; }
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -707,10 +623,6 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   float* delta_pad = reinterpret_cast<float*>(ws);
   ws += align256((size_t)BH * Tpad * 4);
   float* dq_acc = kF32 ? static_cast<float*>(dq) : reinterpret_cast<float*>(ws);
-  ws += align256(n * 4);
-  int* counters = reinterpret_cast<int*>(ws);  // [BH][Tpad / 128] arrival counters of the fused dQ conversion
-  const int n_counters = (int)((size_t)BH * (Tpad / kTile));
-  const bool fused_env = bwd_fused_convert_enabled();
   cudaError_t e;
   {
     const size_t rows = (size_t)BH * Tpad;
@@ -719,7 +631,7 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
     size_t blocks = (rows + kRowsPerBlock - 1) / kRowsPerBlock;
     if (blocks > 148 * 32) blocks = 148 * 32;  // grid-stride beyond 32 blocks per SM
     fa_bwd_prep_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(o, dO, lse, lse_pad, delta_pad, zero ? dq_acc : nullptr, T,
-                                                          (int)Tpad, rows, counters, n_counters);
+                                                          (int)Tpad, rows);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -744,20 +656,6 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   p.dk = dk;
   p.dv = dv;
   p.dq_acc = dq_acc;
-  p.accumulate_dq = accumulate_dq ? 1 : 0;
-  p.dq_out = kF32 ? nullptr : static_cast<__nv_bfloat16*>(dq);
-  {
-    const int mode = [] {
-      // developer switch (read per call so that tests can flip it).  Default "tma": smem staging + cp.reduce.async.bulk (7.30 ms at config 3).  "red": fragment-
-      // layout tcgen05.ld + red.global.add.v2.f32 straight from registers -- no staging traffic, sector-complete, but
-      // measured slower (8.81 ms): 32-byte L2 reductions cost more than the TMA engine's line-sized ones.
-      const char* e = getenv("FA_B200_BWD_DQ");
-      return (e && e[0] == 'r') ? 1 : 0;
-    }();
-    p.dq_red = mode;
-  }
-  const bool fused_cvt = !kF32 && fused_env && !p.dq_red;
-  p.tile_counters = fused_cvt ? counters : nullptr;
   p.drop = drop;
   p.trace = g_bwd_trace;
   {
@@ -769,7 +667,7 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   else fa_bwd_kernel<D, OutT, false><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (!kF32 && !fused_cvt) {
+  if (!kF32) {
     fa_bwd_dq_convert_kernel<<<148 * 8, 256, 0, st>>>(dq_acc, static_cast<__nv_bfloat16*>(dq), n, accumulate_dq ? 1 : 0);
     e = cudaGetLastError();
   }
@@ -779,16 +677,15 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
 }  // namespace
 
 bool tc_bwd_supported(int d) { return d == 64 || d == 128; }
-// kernels one tc_bwd call launches: prep + main (+ the dQ conversion pass when it is not fused into the main kernel)
+// kernels one tc_bwd call launches: prep + main (+ the fp32 -> bf16 dQ conversion pass for bf16 gradients)
 int tc_bwd_num_launches(bool grads_f32) {
-  return (grads_f32 || (bwd_fused_convert_enabled() && !bwd_dq_red_enabled())) ? 2 : 3;
+  return grads_f32 ? 2 : 3;
 }
 void tc_bwd_set_trace(long long* buf) { g_bwd_trace = buf; }
 
 size_t tc_bwd_workspace_bytes(int BH, int T, int d) {
-  // lse_pad + delta_pad + fp32 dQ accumulator (the latter only used for bf16 gradients) + per-Q-tile arrival counters
-  return 2 * align256((size_t)BH * pad_rows(T) * 4) + align256((size_t)BH * T * d * 4) +
-         align256((size_t)BH * (pad_rows(T) / kTile) * 4);
+  // lse_pad + delta_pad + fp32 dQ accumulator (the latter only used for bf16 gradients)
+  return 2 * align256((size_t)BH * pad_rows(T) * 4) + align256((size_t)BH * T * d * 4);
 }
 
 cudaError_t tc_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* o,

@@ -299,28 +299,6 @@ def test_full_size_sampled_heads_vs_c_oracle(cuda_device, cfg3):
             assert rel_inf(f(got), r[key].astype(np.float64)) <= BF16_REL, key
 
 
-def test_full_size_fused_dq_conversion_equals_separate_pass(cuda_device, cfg3, monkeypatch):
-    """Opt-in alternative (FA_B200_BWD_CVT=fused): the CTA that delivers the last partial sum of a Q tile converts it
-    to bf16 inside the main kernel.  A lost or double-counted partial would move elements by percent; the default
-    separate conversion pass is the check: both sum the same fp32 partials (in arbitrary order), so dQ agrees to bf16
-    rounding; dK / dV are bit-identical.  Repeated three times because arrival order differs from launch to launch."""
-    import torch
-    q, k, v, g = cfg3["q"], cfg3["k"], cfg3["v"], cfg3["g"]
-    o, lse = device.flash_attn_fwd(q, k, v, True)
-    before = _lib.launch_count()
-    dq0, dk0, dv0 = device.flash_attn_bwd(q, k, v, o, g, lse, True)
-    assert _lib.launch_count() - before == 3  # prep + main + conversion
-    monkeypatch.setenv("FA_B200_BWD_CVT", "fused")
-    scale = float(dq0.float().abs().max())
-    for _ in range(3):
-        before = _lib.launch_count()
-        dq1, dk1, dv1 = device.flash_attn_bwd(q, k, v, o, g, lse, True)
-        assert _lib.launch_count() - before == 2  # prep + main: no conversion kernel
-        assert torch.equal(dk0, dk1) and torch.equal(dv0, dv1)
-        assert float((dq1.float() - dq0.float()).abs().max()) <= 1e-2 * scale
-        assert float(((dq1.float() - dq0.float()).abs() > 4e-3 * scale).float().mean()) <= 1e-5
-
-
 def test_full_size_backward_identities(cuda_device, cfg3):
     """sum_j dV_j = sum_i dO_i (rows of P sum to one) and <dQ, Q> = <dK, K> (S is bilinear), per head; and
     backward is linear in dO."""

@@ -26,7 +26,7 @@ struct RateOut {
 };
 
 constexpr int kRateThreads = 512;
-constexpr int kRounds = 32;  // x 8 k-steps = 256 MMAs per measurement
+constexpr int kRounds = 128;  // x 8 k-steps = 1024 MMAs per measurement
 
 
 // elect-predicated forms: executed by the whole (converged) warp, one lane issues.  The operands are then warp-uniform
@@ -176,6 +176,87 @@ __global__ void __launch_bounds__(kRateThreads, 1) rate_kernel(RateOut* out, int
   tc_fence_before();
   __syncthreads();
   if (warp == 13) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Latency of one dependent step of the attention pipelines: issue 8 MMAs (one 128 x 128 x 128 product) + tcgen05.commit,
+// then wait on the mbarrier -- either in the issuing warp or in ANOTHER warp that answers through a second mbarrier
+// (the MMA -> consumer -> MMA round trip of the S -> softmax -> PV and dS -> dQ -> drain -> dP chains).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) latency_kernel(long long* out, int groups, int via_consumer, int consumer_ld) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_mma, bar_back;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 65536 / 16; i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_mma, 1);
+    mbar_init(&bar_back, 4);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(&tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sA = smem_u32(smem), sB = sA + 32768;
+  if (warp == 5) {
+    const uint64_t a0 = make_smem_desc(sA, 16, 1024), b0 = make_smem_desc(sB, 16, 1024);
+    const uint32_t id = make_idesc(kFmtBF16, 128, 128, 0, 0);
+    const long long t0 = clock64();
+    for (int g = 0; g < groups; ++g) {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        umma_ss_w(tmem, desc_advance(a0, (kk >> 2) * 16384 + (kk & 3) * 32), desc_advance(b0, (kk >> 2) * 16384 + (kk & 3) * 32), id, kk > 0);
+      umma_commit_w(&bar_mma);
+      if (via_consumer) mbar_wait_w(&bar_back, g & 1);
+      else mbar_wait_w(&bar_mma, g & 1);
+      tc_fence_after();
+    }
+    if (lane == 0) out[0] = clock64() - t0;
+  } else if (warp < 4 && via_consumer) {
+    const uint32_t t = tmem + (uint32_t(warp * 32) << 16);
+    uint32_t acc = 0;
+    for (int g = 0; g < groups; ++g) {
+      mbar_wait(&bar_mma, g & 1);
+      tc_fence_after();
+      if (consumer_ld) {
+        uint32_t rr[32];
+        tmem_ld_x32(t, rr);
+        tmem_wait_ld();
+        acc += rr[3];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_back);
+    }
+    if (acc == 0x1234567) out[1] = acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 512);
+}
+
+static void run_latency() {
+  long long* d;
+  cudaMalloc(&d, 16);
+  cudaFuncSetAttribute(latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  const char* names[3] = {"issuing warp waits on its own commit", "consumer warps wait, arrive back (no TMEM read)",
+                          "consumer warps wait, tcgen05.ld 32 columns, arrive back"};
+  for (int v = 0; v < 3; ++v) {
+    const int groups = 256;
+    latency_kernel<<<1, 256, 65536>>>(d, groups, v > 0, v > 1);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long c = 0;
+    cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+    printf("dependent step (8 MMAs 128x128x16 + commit + wait): %-58s %7.1f cycles per step (8 MMAs back to back: ~520)  %s\n", names[v],
+           double(c) / groups, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  }
+  cudaFree(d);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -372,7 +453,7 @@ int main(int argc, char** argv) {
   cudaMalloc(&d, sizeof(RateOut));
   const int smem_bytes = 196608;
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  const int only_pair = argc > 1 && !strcmp(argv[1], "pair");
+  const int only_pair = argc > 1 && (!strcmp(argv[1], "pair") || !strcmp(argv[1], "lat"));
   if (!only_pair) {
     printf("cycles per tcgen05.mma (M=128, K=16, bf16), 256 back-to-back MMAs on one SM; background = other warps of the CTA\n");
     printf("%-40s %4s | %8s %14s %14s %14s %14s\n", "form", "N", "alone", "+st.shared x8w", "+tc.ld x4w", "+tc.ld x12w", "+st x8w,ld x4w");
@@ -403,7 +484,13 @@ int main(int argc, char** argv) {
             snprintf(buf, sizeof buf, "%s%.0fB/clk", (mode & 1) && !(mode & 2) ? "st " : (mode & 1) ? "st+ld(ld) " : "ld ",
                      (mode & 1) && !(mode & 2) ? lsu : ld);
           } else {
-            snprintf(buf, sizeof buf, "%.1f", double(h.mma_cycles) / (kRounds * 8));
+            // MMA cycles, and what the background warps achieved next to the MMAs (st.shared B/clk | tcgen05.ld B/clk)
+            const double lsu = h.bg_cycles ? double(h.lsu_iters) * 8 * 4096 / h.bg_cycles : 0;
+            const double nld = (mode & 4) ? 12 : 4;
+            const double ld = h.bg_cycles ? double(h.ldtm_iters) * nld * 4096 / h.bg_cycles : 0;
+            if (mode == 0) snprintf(buf, sizeof buf, "%.1f", double(h.mma_cycles) / (kRounds * 8));
+            else if ((mode & 1) && !(mode & 2)) snprintf(buf, sizeof buf, "%.1f st%.0f", double(h.mma_cycles) / (kRounds * 8), lsu);
+            else snprintf(buf, sizeof buf, "%.1f ld%.0f", double(h.mma_cycles) / (kRounds * 8), ld);
           }
           printf(mode == 0 ? " %8s" : " %14s", buf);
         }
@@ -411,6 +498,7 @@ int main(int argc, char** argv) {
       }
     }
   }
+  run_latency();
   int fails = 0;
   for (int mode = 0; mode < 3; ++mode)
     for (int N : {128, 256})
