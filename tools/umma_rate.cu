@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "fa_ptx.cuh"
+#include "fa_tma_host.h"
 
 using namespace fa;
 
@@ -260,18 +261,108 @@ static void run_latency() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Chip-wide throughput of the backward's dQ path: every SM streams 128-row x 32-column fp32 slabs (16 KB, the staging
+// unit of fa_bwd_kernel) from shared memory into a [rows][128] fp32 tensor with cp.reduce.async.bulk.tensor (.add) or
+// plain TMA stores, two staging buffers and cp.async.bulk.wait_group.read as in the kernel.
+// ---------------------------------------------------------------------------------------------------------------
+template <int kInFlight>
+__global__ void __launch_bounds__(128, 1) reduce_kernel(const __grid_constant__ CUtensorMap map, int n_tiles, int iters, int do_reduce, int cols,
+                                                        long long* cycles, float* gbase) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  for (int i = threadIdx.x; i < 65536 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u);
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int slab_bytes = cols * 4 * 128;
+    const long long t0 = clock64();
+    uint32_t chunk = 0;
+    for (int it = 0; it < iters; ++it) {
+      const int tile = (blockIdx.x * 7 + it) % n_tiles;  // CTAs walk the tensor at different offsets, every tile is hit by many CTAs
+      for (int c = 0; c < 128 / cols; ++c, ++chunk) {
+        if (chunk >= kInFlight) tma_store_wait_read<kInFlight - 1>();
+        uint8_t* buf = smem + (chunk % kInFlight) * slab_bytes;
+        if (do_reduce == 3) {  // 1-D bulk reduce of 16 KB = 32 whole rows of the tile (contiguous in global memory)
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gbase + ((size_t)tile * 128 + c * 32) * 128),
+                       "r"(smem_u32(buf)), "r"(16384)
+                       : "memory");
+        } else if (do_reduce == 2) {  // tensor form, box {128 columns, 32 rows}: rows of 512 B
+          tma_reduce_add_3d(&map, buf, 0, tile * 128 + c * 32, 0);
+        } else if (do_reduce) tma_reduce_add_3d(&map, buf, c * cols, tile * 128, 0);
+        else tma_store_3d(&map, buf, c * cols, tile * 128, 0);
+        tma_store_commit();
+      }
+    }
+    tma_store_wait_all<0>();
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+}
+
+static void run_reduce() {
+  const int n_tiles = 8192;  // x 64 KB = 512 MB
+  float* buf;
+  long long* cyc;
+  cudaMalloc(&buf, (size_t)n_tiles * 128 * 128 * 4);
+  cudaMemset(buf, 0, (size_t)n_tiles * 128 * 128 * 4);
+  cudaMalloc(&cyc, 148 * 8);
+  auto launch = [&](int in_flight, const CUtensorMap& map, int grid, int iters, int do_reduce, int cols) {
+    if (in_flight == 2) reduce_kernel<2><<<grid, 128, 65536>>>(map, n_tiles, iters, do_reduce, cols, cyc, buf);
+    if (in_flight == 4) reduce_kernel<4><<<grid, 128, 65536>>>(map, n_tiles, iters, do_reduce, cols, cyc, buf);
+    if (in_flight == 8) reduce_kernel<8><<<grid, 128, 65536>>>(map, n_tiles, iters, do_reduce, cols, cyc, buf);
+  };
+  cudaFuncSetAttribute(reduce_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  cudaFuncSetAttribute(reduce_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  cudaFuncSetAttribute(reduce_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  printf("dQ path: 128-row fp32 slabs from shared memory into a [rows][128] fp32 tensor, one issuing thread per SM, 148 CTAs\n");
+  for (int do_reduce = 0; do_reduce < 2; ++do_reduce)
+    for (int cols : {32, 16, 8})
+      for (int in_flight : {2, 4, 8}) {
+        if (cols * 512 * in_flight > 65536) continue;
+        CUtensorMap map;
+        if (make_tmap_3d(&map, buf, 4, 128, (uint64_t)n_tiles * 128, 1, cols, 128, 0)) return;
+        const int iters = 1000, grid = 148;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        launch(in_flight, map, grid, 50, do_reduce, cols);
+        cudaEventRecord(e0);
+        launch(in_flight, map, grid, iters, do_reduce, cols);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        long long c0 = 0;
+        cudaMemcpy(&c0, cyc, 8, cudaMemcpyDeviceToHost);
+        const double bytes = double(grid) * iters * 65536.0;
+        printf("TMA %-10s slab %2d KB x %d in flight (%2d KB): %7.1f GB/s chip-wide, %6.1f B/clk per SM, %5.0f cycles per 64 KB tile  %s\n",
+               do_reduce ? "reduce-add" : "store", cols / 2, in_flight, cols / 2 * in_flight, bytes / ms * 1e-6, 65536.0 * iters / double(c0),
+               double(c0) / iters, e == cudaSuccess ? "" : cudaGetErrorString(e));
+      }
+  for (int mode : {2, 3}) {  // wide rows
+    CUtensorMap map;
+    if (make_tmap_3d(&map, buf, 4, 128, (uint64_t)n_tiles * 128, 1, 128, 32, 0)) return;
+    const int iters = 1000, grid = 148;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    launch(2, map, grid, 50, mode, 32);
+    cudaEventRecord(e0);
+    launch(2, map, grid, iters, mode, 32);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaDeviceSynchronize();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    long long c0 = 0;
+    cudaMemcpy(&c0, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("TMA reduce-add, 16 KB = 32 rows x 512 B, %-22s x 2 in flight: %7.1f GB/s chip-wide, %6.1f B/clk per SM, %5.0f cycles per 64 KB tile  %s\n",
+           mode == 2 ? "tensor box {128, 32}" : "1-D bulk (contiguous)", double(grid) * iters * 65536.0 / ms * 1e-6, 65536.0 * iters / double(c0),
+           double(c0) / iters, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  }
+  cudaFree(buf); cudaFree(cyc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // CTA pair: D[256 x N] = A[256 x K] B[N x K]^T with tcgen05.mma.cta_group::2.  CTA r holds rows [128 r, +128) of A and
 // rows [N/2 r, +N/2) of B (both K-major, 128-B swizzle, written by hand with st.shared) and receives rows [128 r, +128)
 // of D in its own TMEM (lanes 0-127, columns [0, N)).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
@@ -499,6 +590,7 @@ int main(int argc, char** argv) {
     }
   }
   run_latency();
+  run_reduce();
   int fails = 0;
   for (int mode = 0; mode < 3; ++mode)
     for (int N : {128, 256})
