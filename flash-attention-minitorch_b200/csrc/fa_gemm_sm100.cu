@@ -64,7 +64,9 @@ struct GemmBarriers {
 };
 
 // kAMn / kBMn: operand stored with its M / N dimension contiguous (MN-major) instead of K contiguous (K-major)
-template <bool kAMn, bool kBMn, int kStages>
+// kHeads: some operand is in head layout (a separate instantiation: the plain GEMM's producer loop must not carry the
+// head-coordinate branches -- measured 131 -> 185 us on the MN x MN weight-gradient GEMM when it did)
+template <bool kAMn, bool kBMn, int kStages, bool kHeads>
 __global__ void __launch_bounds__(kGemmThreads, kStages <= 2 ? 2 : 1)
 fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
@@ -112,7 +114,7 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint8_t* b = sB + st * kSlabBytes;
         if constexpr (kAMn) {  // global [K][M]: four boxes of (32 m) x (32 k rows)
           for (int x = 0; x < 4; ++x) {
-            if (p.a_heads) {  // [tokens][E] in head layout, tokens = the reduction dimension
+            if (kHeads && p.a_heads) {  // [tokens][E] in head layout, tokens = the reduction dimension
               const HeadCoord h = head_coord(p, m0 + 32 * x, k0);
               tma_load_3d(a + x * 4096, &map_a, &bars.full[st], h.c0, h.c1, h.c2, kEvictNormal);
             } else {
@@ -120,7 +122,7 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
           }
         } else {               // global [M][K]: one box of (32 k) x (128 m rows)
-          if (p.a_heads) {
+          if (kHeads && p.a_heads) {
             const HeadCoord h = head_coord(p, k0, m0);
             tma_load_3d(a, &map_a, &bars.full[st], h.c0, h.c1, h.c2, kEvictNormal);
           } else {
@@ -129,7 +131,7 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         if constexpr (kBMn) {
           for (int x = 0; x < 4; ++x) {
-            if (p.b_heads) {
+            if (kHeads && p.b_heads) {
               const HeadCoord h = head_coord(p, n0 + 32 * x, k0);
               tma_load_3d(b + x * 4096, &map_b, &bars.full[st], h.c0, h.c1, h.c2, kEvictNormal);
             } else {
@@ -202,7 +204,7 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       named_bar_sync(1, 128);
       if (leader) {
         HeadCoord h = {n0 + c * 32, m0, 0};
-        if (p.c_heads) h = head_coord(p, n0 + c * 32, m0);
+        if (kHeads && p.c_heads) h = head_coord(p, n0 + c * 32, m0);
         if (reduce) tma_reduce_add_3d(&map_c, buf, h.c0, h.c1, h.c2);
         else tma_store_3d(&map_c, buf, h.c0, h.c1, h.c2);
         tma_store_commit();
@@ -235,6 +237,7 @@ cudaError_t launch_gemm(const float* a, const float* b, float* c, const float* b
   cudaError_t e;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.c = c; p.bias = bias; p.accumulate = accumulate ? 1 : 0;
+  const bool heads = hl.a || hl.b || hl.c;
   p.a_heads = hl.a; p.b_heads = hl.b; p.c_heads = hl.c; p.T = hl.T > 0 ? hl.T : 1; p.H = hl.H; p.d = hl.d > 0 ? hl.d : 1;
   // split-K when the output has too few tiles to fill the 148 SMs (weight gradients: 256 x 256 outputs reduced over
   // thousands of tokens): each split keeps at least 8 k-blocks, partial tiles are red.added into a zeroed C
@@ -254,13 +257,15 @@ cudaError_t launch_gemm(const float* a, const float* b, float* c, const float* b
   }
   dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
   if (p.k_blocks_per_split <= 16) {
-    e = cudaFuncSetAttribute(fa_gemm_tf32_kernel<kAMn, kBMn, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(2));
+    auto kern = heads ? fa_gemm_tf32_kernel<kAMn, kBMn, 2, true> : fa_gemm_tf32_kernel<kAMn, kBMn, 2, false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(2));
     if (e != cudaSuccess) return e;
-    fa_gemm_tf32_kernel<kAMn, kBMn, 2><<<grid, kGemmThreads, gemm_smem(2), st>>>(ma, mb, mc, p);
+    kern<<<grid, kGemmThreads, gemm_smem(2), st>>>(ma, mb, mc, p);
   } else {
-    e = cudaFuncSetAttribute(fa_gemm_tf32_kernel<kAMn, kBMn, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(6));
+    auto kern = heads ? fa_gemm_tf32_kernel<kAMn, kBMn, 6, true> : fa_gemm_tf32_kernel<kAMn, kBMn, 6, false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(6));
     if (e != cudaSuccess) return e;
-    fa_gemm_tf32_kernel<kAMn, kBMn, 6><<<grid, kGemmThreads, gemm_smem(6), st>>>(ma, mb, mc, p);
+    kern<<<grid, kGemmThreads, gemm_smem(6), st>>>(ma, mb, mc, p);
   }
   return cudaGetLastError();
 }

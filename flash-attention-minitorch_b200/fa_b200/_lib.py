@@ -73,10 +73,11 @@ def load_library() -> ctypes.CDLL:
     lib.fa_b200_dropout_effective_p.restype = f32
     lib.fa_b200_gemm_tf32.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
     lib.fa_b200_gemm_tf32.restype = ci
-    lib.fa_b200_gemm_tf32_heads.argtypes = [vp, vp, vp, vp] + [ci] * 12 + [vp]
-    lib.fa_b200_gemm_tf32_heads.restype = ci
-    lib.fa_b200_colsum_heads_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
-    lib.fa_b200_colsum_heads_f32.restype = ci
+    if hasattr(lib, "fa_b200_gemm_tf32_heads"):  # (absent only in older builds loaded through FA_B200_LIB for A/B runs)
+        lib.fa_b200_gemm_tf32_heads.argtypes = [vp, vp, vp, vp] + [ci] * 12 + [vp]
+        lib.fa_b200_gemm_tf32_heads.restype = ci
+        lib.fa_b200_colsum_heads_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
+        lib.fa_b200_colsum_heads_f32.restype = ci
     lib.fa_b200_colsum_f32.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.fa_b200_colsum_f32.restype = ci
     for name, args in (("layernorm_fwd", [vp] * 6 + [ci, ci, f32, vp]), ("layernorm_bwd", [vp] * 8 + [ci, ci, vp]),

@@ -20,6 +20,8 @@ from __future__ import annotations
 
 import math
 
+import os
+
 import torch
 
 from .. import _lib, device
@@ -139,6 +141,8 @@ def _gemm_heads(a, b, c, bias, M, N, K, a_mn, b_mn, a_h, b_h, c_h, T, H, d):
 
 def heads_layout_ok(x, T: int, d: int) -> bool:
     """The TMA-permuting GEMM needs whole 32-column slabs per head and row tiles inside one batch."""
+    if os.environ.get("FA_MT_HEAD_LAYOUT", "1") == "0":  # A/B switch: projections as linear + permute + contiguous
+        return False
     return x.is_cuda and x.dtype == torch.float32 and T % 128 == 0 and d % 32 == 0
 
 
