@@ -28,6 +28,9 @@
 
 namespace fa {
 
+long long* g_fwd_trace = nullptr;  // developer timeline buffer (tc_fwd_set_trace)
+void tc_fwd_set_trace(long long* buf) { g_fwd_trace = buf; }
+
 namespace {
 
 constexpr int kBlockM = 128;  // rows per Q tile (= TMEM lanes)
@@ -46,6 +49,7 @@ struct FwdParams {
   float* m_out;
   float* l_out;
   Dropout drop;  // used by the kDrop instantiations only
+  long long* trace;  // developer timeline (tools/fa_check tracefwd): clock64 stamps of CTA (0, 0), 16 slots per K/V step
 };
 
 // kTF32 = false: bf16 storage, kind::f16 MMAs (UMMA_K = 16).  kTF32 = true: fp32 storage read directly by TMA,
@@ -114,6 +118,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   const int nkv = (T + kBlockN - 1) / kBlockN;
   const int n0 = p.causal ? min(2 * blk + 1, nkv) : nkv;
   const int n1 = p.causal ? min(2 * blk + 2, nkv) : nkv;
+  long long* const tr = (blockIdx.x == 0 && blockIdx.y == 0) ? p.trace : nullptr;
+#define FA_TRF(j_, e_) do { if (tr && (j_) < 16 && lane == 0) tr[(j_) * 16 + (e_)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
     mbar_init(&bars.q_full, 1);
@@ -215,6 +221,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         if (j < n0) {
           mbar_wait_w(&bars.p_full[0], j & 1);
           tc_fence_after();
+          FA_TRF(j, 8);
           issue_pv(0, st, j > 0);
           umma_commit_w(&bars.o_full[0]);
         }
@@ -224,8 +231,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           issue_qk(0, stn);
           umma_commit_w(&bars.s_full[0]);
         }
+        FA_TRF(j, 9);
         mbar_wait_w(&bars.p_full[1], j & 1);
         tc_fence_after();
+        FA_TRF(j, 10);
         issue_pv(1, st, j > 0);
         umma_commit_w(&bars.o_full[1]);
         umma_commit_w(&bars.v_empty[st]);
@@ -236,6 +245,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           umma_commit_w(&bars.s_full[1]);
           umma_commit_w(&bars.k_empty[stn]);
         }
+        FA_TRF(j, 11);
       }
     }
   }
@@ -264,6 +274,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     for (int j = 0; j < nt; ++j) {
       mbar_wait(&bars.s_full[t], j & 1);
       tc_fence_after();
+      if ((warp & 3) == 0) FA_TRF(j, 4 * t + 0);
       float s[128];
       {
         uint32_t* sr = reinterpret_cast<uint32_t*>(s);
@@ -273,6 +284,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         tmem_ld_x32(tS + 96, sr + 96);
         tmem_wait_ld();
       }
+      if ((warp & 3) == 0) FA_TRF(j, 4 * t + 1);
       const bool diag = p.causal && (j == qt);
       const bool tail = (j == nkv - 1) && (T - j * kBlockN < kBlockN);
       if (diag || tail) {
@@ -317,6 +329,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
       }
       const float nm = -m_ref * c2;
+      if ((warp & 3) == 0) FA_TRF(j, 4 * t + 2);
 #if FA_FWD_PACKED
       const float2 c2v = make_float2(c2, c2), nmv = make_float2(nm, nm);
       float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
@@ -394,6 +407,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.p_full[t]);
+      if ((warp & 3) == 0) FA_TRF(j, 4 * t + 3);
     }
 
     // epilogue: O_t / l -> global, statistics
@@ -447,6 +461,7 @@ cudaError_t launch_fwd_impl(const void* q, const void* k, const void* v, void* o
   p.m_out = m_out;
   p.l_out = l_out;
   p.drop = drop;
+  p.trace = g_fwd_trace;
   dim3 grid((T + 2 * kBlockM - 1) / (2 * kBlockM), BH);
   fa_fwd_kernel<D, OutT, kTF32, kDrop><<<grid, kFwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, p);
   return cudaGetLastError();

@@ -37,6 +37,7 @@ cudaError_t tc_fwd_tf32(const float* q, const float* k, const float* v, float* o
 
 bool tc_bwd_supported(int d);
 int tc_bwd_num_launches(bool grads_f32);
+void tc_fwd_set_trace(long long* dev_buf);  // same for the forward (CTA (0,0): the heaviest causal block)
 void tc_bwd_set_trace(long long* dev_buf);  // developer timeline buffer (256 int64), nullptr = off
 size_t tc_bwd_workspace_bytes(int BH, int T, int d);
 // dq/dk/dv are bf16 or fp32 (grads_f32).  workspace: tc_bwd_workspace_bytes() bytes of device memory.

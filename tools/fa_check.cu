@@ -404,6 +404,46 @@ static int time_tc(int BH, int T, int d, int causal, int iters, bool do_bwd, flo
   return 0;
 }
 
+extern "C" void fa_b200_debug_fwd_trace(void* dev_buf);
+
+// forward timeline of CTA (0,0) (the heaviest causal block): slots per K/V step j: 0-3 tile 0 {S ready, S loaded, row max done,
+// P stored}, 4-7 the same for tile 1, 8-11 MMA warp {P0 seen, PV0+QK0 issued, P1 seen, PV1+QK1 issued}
+static int trace_fwd(int BH, int T, int d, int causal) {
+  const size_t n = (size_t)BH * T * d, rows = (size_t)BH * T;
+  Dev dev;
+  __nv_bfloat16* t[4];
+  for (auto& p : t) p = dev.alloc<__nv_bfloat16>(n);
+  float* lse = dev.alloc<float>(rows);
+  std::vector<__nv_bfloat16> h(1 << 20);
+  for (auto& x : h) x = __float2bfloat16(urand());
+  for (int i = 0; i < 3; ++i)
+    for (size_t off = 0; off < n; off += h.size())
+      CK(cudaMemcpy(t[i] + off, h.data(), std::min(h.size(), n - off) * 2, cudaMemcpyHostToDevice));
+  long long* tr = dev.alloc<long long>(512);
+  FA(fa_b200_fwd(t[0], t[1], t[2], t[3], lse, nullptr, nullptr, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, nullptr));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemset(tr, 0, 512 * 8));
+  fa_b200_debug_fwd_trace(tr);
+  FA(fa_b200_fwd(t[0], t[1], t[2], t[3], lse, nullptr, nullptr, FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, nullptr));
+  CK(cudaDeviceSynchronize());
+  fa_b200_debug_fwd_trace(nullptr);
+  std::vector<long long> hh(512);
+  CK(cudaMemcpy(hh.data(), tr, 512 * 8, cudaMemcpyDeviceToHost));
+  const long long t0 = hh[0];
+  printf("fwd timeline of CTA(0,0), cycles relative to the first S0 ready\n");
+  printf("  j | T0: S_rdy  loaded  maxed  P_done | T1: S_rdy  loaded  maxed  P_done | MMA: P0_seen iss0  P1_seen   iss1\n");
+  for (int j = 0; j < 16; ++j) {
+    printf("%3d |", j);
+    for (int e = 0; e < 12; ++e) {
+      const long long v = hh[j * 16 + e];
+      printf(" %7lld", v ? v - t0 : -1);
+      if (e == 3 || e == 7) printf(" |");
+    }
+    printf("\n");
+  }
+  return 0;
+}
+
 extern "C" void fa_b200_debug_bwd_trace(void* dev_buf);
 
 static int trace_bwd(int BH, int T, int d, int causal) {
@@ -498,6 +538,9 @@ int main(int argc, char** argv) {
     int BH = argc > 2 ? atoi(argv[2]) : 512, T = argc > 3 ? atoi(argv[3]) : 1024, d = argc > 4 ? atoi(argv[4]) : 64;
     int causal = argc > 5 ? atoi(argv[5]) : 0, iters = argc > 6 ? atoi(argv[6]) : 20;
     return time_tf32(BH, T, d, causal, iters);
+  } else if (mode == "tracefwd") {
+    return trace_fwd(argc > 2 ? atoi(argv[2]) : 512, argc > 3 ? atoi(argv[3]) : 4096, argc > 4 ? atoi(argv[4]) : 128,
+                     argc > 5 ? atoi(argv[5]) : 1);
   } else if (mode == "trace") {
     return trace_bwd(argc > 2 ? atoi(argv[2]) : 512, argc > 3 ? atoi(argv[3]) : 4096, argc > 4 ? atoi(argv[4]) : 128,
                      argc > 5 ? atoi(argv[5]) : 1);
