@@ -1,0 +1,464 @@
+// fa_bwd_tf32_sm100.cu -- flash-attention backward on fp32 storage with tf32 tensor cores (head dim 32), sm_100a.
+//
+// The fp32 / TF32 path of the backward (north_star: max-abs 1e-3 against the reference): replaces the CUDA-core
+// kernels of fa_simt.cu for the head dimension of the reference's machine-translation model (n_embd 256, 8 heads),
+// where they were 42 % of a training step.  Same algorithm and pipeline as fa_bwd_sm100.cu (one CTA = one 128-row K/V
+// tile streaming the Q/dO tiles, scores kept transposed so that P^T / dS^T are TMEM A operands), with what tf32 changes:
+//   * kind::tf32, UMMA_K = 8; fp32 tiles are read by TMA as they are (no conversion pass);
+//   * a 32-bit operand can be K-major in the 128B swizzle but MN-major only in the 128B swizzle with 32-byte atoms,
+//     and a K-major operand faults in that layout (tools/umma_probe) -- so every tile that is used in both major-nesses
+//     (Q, dO, K) is loaded TWICE, once per layout; at d = 32 a tile is 16 KB and both copies fit;
+//   * dS^T goes to TMEM (tf32, A operand of dK) AND to shared memory in the MN-major 32-byte-atom layout (A operand of
+//     dQ = dS K, whose M dimension is the query index); TMEM has room for every matrix at d = 32
+//     (S | dP | dV | dK | dQ | dS^T = 480 columns), so nothing aliases and dP(i+1) / S(i+1) are issued early;
+//   * fp32 gradients: dK / dV straight from TMEM, dQ reduce-added by TMA into the caller's buffer -- no conversion pass.
+#include <cuda.h>
+#include <math.h>
+
+#include "fa_internal.h"
+#include "fa_ptx.cuh"
+#include "fa_tma_host.h"
+
+namespace fa {
+
+namespace {
+
+constexpr int kTile = 128;
+constexpr int kD = 32;
+constexpr int kThreads = 512;
+constexpr int kTileBytes = kTile * kD * 4;  // 16 KB: 128 rows x 128 B
+
+// shared-memory map (bytes); every tile 1024-B aligned
+constexpr int kOffKk = 0;                        // K, K-major   (A of S^T)
+constexpr int kOffKm = kOffKk + kTileBytes;      // K, MN-major  (B of dQ)
+constexpr int kOffVk = kOffKm + kTileBytes;      // V, K-major   (A of dP^T)
+constexpr int kOffQk = kOffVk + kTileBytes;      // Q, K-major   (B of S^T), 2 stages
+constexpr int kOffQm = kOffQk + 2 * kTileBytes;  // Q, MN-major  (B of dK), 2 stages
+constexpr int kOffDOk = kOffQm + 2 * kTileBytes; // dO, K-major  (B of dP^T)
+constexpr int kOffDOm = kOffDOk + kTileBytes;    // dO, MN-major (B of dV)
+constexpr int kOffDS = kOffDOm + kTileBytes;     // dS^T [128 keys][128 queries] tf32, MN-major A of dQ: 4 boxes of 32 queries
+constexpr int kOffStage = kOffDS + 4 * kTileBytes;  // dQ staging: 128 rows x 32 fp32
+constexpr int kOffStats = kOffStage + kTileBytes;   // [2 stages][L, -delta][128] fp32
+constexpr int kOffBars = kOffStats + 2 * 2 * 128 * 4;
+constexpr int kSmemBytes = kOffBars + 256;
+// TMEM columns
+constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 288, kColDQ = 320, kColDS = 352;
+
+struct Params {
+  int T, Tpad, causal;
+  float tau, scale_log2;
+  const float* lse_pad;    // [BH][Tpad]  lse * log2(e); +inf on padding rows (=> P = 0 there)
+  const float* delta_pad;  // [BH][Tpad]  -rowsum(dO o O); 0 on padding rows
+  float* dk;
+  float* dv;
+};
+
+struct Barriers {
+  uint64_t kv_full;
+  uint64_t q_full[2], q_empty[2], do_full, do_empty;
+  uint64_t s_full, p_full, dp_full, ds_full, ds_empty, dq_full, dq_drained, dkv_full;
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+fa_bwd_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qm,
+                   const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_km,
+                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
+                   const __grid_constant__ CUtensorMap map_dom, const __grid_constant__ CUtensorMap map_dq, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  float* sStats = reinterpret_cast<float*>(smem + kOffStats);
+  uint8_t* sDS = smem + kOffDS;
+  uint8_t* sStage = smem + kOffStage;
+  Barriers& bars = *reinterpret_cast<Barriers*>(smem + kOffBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBars + 192);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int T = p.T;
+  const int bh = blockIdx.y;
+  const int j = blockIdx.x;
+  const int nq = (T + kTile - 1) / kTile;
+  const int i0 = p.causal ? j : 0;
+  const int n = nq - i0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars.kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.q_full[s], 1);
+      mbar_init(&bars.q_empty[s], 1);
+    }
+    mbar_init(&bars.do_full, 1);
+    mbar_init(&bars.do_empty, 1);
+    mbar_init(&bars.s_full, 1);
+    mbar_init(&bars.p_full, 8);
+    mbar_init(&bars.dp_full, 1);
+    mbar_init(&bars.ds_full, 8);
+    mbar_init(&bars.ds_empty, 1);
+    mbar_init(&bars.dq_full, 1);
+    mbar_init(&bars.dq_drained, 4);
+    mbar_init(&bars.dkv_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= 12) reg_dealloc<88>();
+  if (warp == 12) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&map_q);
+      tma_prefetch_desc(&map_qm);
+      tma_prefetch_desc(&map_k);
+      tma_prefetch_desc(&map_km);
+      tma_prefetch_desc(&map_v);
+      tma_prefetch_desc(&map_do);
+      tma_prefetch_desc(&map_dom);
+      mbar_arrive_expect_tx(&bars.kv_full, 3 * kTileBytes);
+      tma_load_3d(smem + kOffKk, &map_k, &bars.kv_full, 0, j * kTile, bh, kEvictFirst);
+      tma_load_3d(smem + kOffKm, &map_km, &bars.kv_full, 0, j * kTile, bh, kEvictFirst);
+      tma_load_3d(smem + kOffVk, &map_v, &bars.kv_full, 0, j * kTile, bh, kEvictFirst);
+      for (int il = 0; il < n; ++il) {
+        const int i = i0 + il;
+        const int s = il & 1;
+        mbar_wait(&bars.q_empty[s], ((il >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars.q_full[s], 2 * kTileBytes + 1024);
+        tma_load_3d(smem + kOffQk + s * kTileBytes, &map_q, &bars.q_full[s], 0, i * kTile, bh, kEvictLast);
+        tma_load_3d(smem + kOffQm + s * kTileBytes, &map_qm, &bars.q_full[s], 0, i * kTile, bh, kEvictLast);
+        const size_t soff = (size_t)bh * p.Tpad + (size_t)i * kTile;
+        bulk_load_1d(sStats + s * 256, p.lse_pad + soff, 512, &bars.q_full[s]);
+        bulk_load_1d(sStats + s * 256 + 128, p.delta_pad + soff, 512, &bars.q_full[s]);
+        mbar_wait(&bars.do_empty, (il & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars.do_full, 2 * kTileBytes);
+        tma_load_3d(smem + kOffDOk, &map_do, &bars.do_full, 0, i * kTile, bh, kEvictLast);
+        tma_load_3d(smem + kOffDOm, &map_dom, &bars.do_full, 0, i * kTile, bh, kEvictLast);
+      }
+    }
+  } else if (warp == 13) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, `_w` forms)
+    constexpr uint32_t idesc_sT = make_idesc(kFmtTF32, 128, 128, 0, 0);  // K-major x K-major
+    constexpr uint32_t idesc_acc = make_idesc(kFmtTF32, 128, kD, 0, 1);  // TMEM x MN-major
+    constexpr uint32_t idesc_dq = make_idesc(kFmtTF32, 128, kD, 1, 1);   // MN-major x MN-major
+    const uint32_t base = smem_u32(smem);
+    // K-major [128 x 32 fp32]: a k-step (8 tf32) is 32 B inside the 128-B row.  MN-major (32-byte atoms): a k-step is
+    // 8 "K" rows = 1 KB, 4-row groups 512 B apart, 32-element MN atoms one 16 KB box apart.
+    auto kmaj0 = [](uint32_t a) { return make_smem_desc(a, 16, 1024); };
+    auto mnmaj0 = [](uint32_t a) { return make_smem_desc(a, kTileBytes, 512, kDescSw128Base32); };
+    const uint64_t dKk = kmaj0(base + kOffKk), dVk = kmaj0(base + kOffVk), dKm = mnmaj0(base + kOffKm), dDSm = mnmaj0(base + kOffDS);
+    auto issue_sT = [&](uint64_t a0, uint64_t b0, uint32_t col) {
+#pragma unroll
+      for (int kk = 0; kk < kD / 8; ++kk) umma_ss_w<true>(tmem + col, desc_advance(a0, kk * 32), desc_advance(b0, kk * 32), idesc_sT, kk > 0);
+    };
+    auto issue_ts = [&](uint32_t d_col, uint32_t a_col, uint64_t b0, bool acc) {  // dV / dK: A = P^T / dS^T in TMEM
+#pragma unroll
+      for (int kk = 0; kk < kTile / 8; ++kk)
+        umma_ts_w<true>(tmem + d_col, tmem + a_col + kk * 8, desc_advance(b0, kk * 1024), idesc_acc, (acc || kk > 0) ? 1u : 0u);
+    };
+    auto issue_dq = [&]() {
+#pragma unroll
+      for (int kk = 0; kk < kTile / 8; ++kk)
+        umma_ss_w<true>(tmem + kColDQ, desc_advance(dDSm, kk * 1024), desc_advance(dKm, kk * 1024), idesc_dq, kk > 0);
+    };
+    auto qk = [&](int il) { return kmaj0(base + kOffQk + (il & 1) * kTileBytes); };
+    auto qm = [&](int il) { return mnmaj0(base + kOffQm + (il & 1) * kTileBytes); };
+    const uint64_t dDOk = kmaj0(base + kOffDOk), dDOm = mnmaj0(base + kOffDOm);
+
+    mbar_wait_w(&bars.kv_full, 0);
+    mbar_wait_w(&bars.q_full[0], 0);
+    tc_fence_after();
+    issue_sT(dKk, qk(0), kColS);
+    umma_commit_w(&bars.s_full);
+    mbar_wait_w(&bars.do_full, 0);
+    tc_fence_after();
+    issue_sT(dVk, dDOk, kColDP);
+    umma_commit_w(&bars.dp_full);
+    for (int il = 0; il < n; ++il) {
+      mbar_wait_w(&bars.p_full, il & 1);
+      tc_fence_after();
+      issue_ts(kColDV, kColS, dDOm, il > 0);  // dV += P^T dO
+      umma_commit_w(&bars.do_empty);          // dV(il) and dP(il) (issued earlier) are the last readers of dO(il)
+      if (il + 1 < n) {
+        mbar_wait_w(&bars.q_full[(il + 1) & 1], ((il + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_sT(dKk, qk(il + 1), kColS);  // P(il) has been consumed by the MMAs just issued (in-order pipe)
+        umma_commit_w(&bars.s_full);
+      }
+      mbar_wait_w(&bars.ds_full, il & 1);  // all of dP(il) has been read, dS^T(il) is in TMEM and in shared memory
+      tc_fence_after();
+      if (il + 1 < n) {
+        mbar_wait_w(&bars.do_full, (il + 1) & 1);
+        tc_fence_after();
+        issue_sT(dVk, dDOk, kColDP);  // dP(il+1) first: it is what the compute warps wait for next
+        umma_commit_w(&bars.dp_full);
+      }
+      issue_ts(kColDK, kColDS, qm(il), il > 0);  // dK += dS^T Q
+      if (il > 0) mbar_wait_w(&bars.dq_drained, (il - 1) & 1);
+      tc_fence_after();
+      issue_dq();  // dQ(il) = dS K
+      umma_commit_w(&bars.dq_full);
+      umma_commit_w(&bars.ds_empty);
+      umma_commit_w(&bars.q_empty[il & 1]);
+    }
+    umma_commit_w(&bars.dkv_full);
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ compute warps
+    reg_alloc<168>();
+    const int g = warp >> 2;               // which half of the 128 query columns
+    const int r = (warp & 3) * 32 + lane;  // key row within the tile == TMEM lane
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + kColS + lane_base + g * 64;
+    const uint32_t tDP = tmem + kColDP + lane_base + g * 64;
+    const uint32_t tDS = tmem + kColDS + lane_base + g * 64;
+    const float c2 = p.scale_log2;
+    for (int il = 0; il < n; ++il) {
+      const int i = i0 + il;
+      const float* sL = sStats + (il & 1) * 256 + g * 64;
+      const float* sD = sL + 128;
+      // ---- P^T = exp2(c S^T - L)
+      mbar_wait(&bars.q_full[il & 1], (il >> 1) & 1);  // L / delta of this Q tile have landed
+      mbar_wait(&bars.s_full, il & 1);
+      tc_fence_after();
+      float pr[64];
+      {
+        uint32_t* u = reinterpret_cast<uint32_t*>(pr);
+        tmem_ld_x32(tS, u);
+        tmem_ld_x32(tS + 32, u + 32);
+        tmem_wait_ld();
+      }
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        const float4 L4 = *reinterpret_cast<const float4*>(sL + c);
+        pr[c + 0] = ex2_approx(fmaf(pr[c + 0], c2, -L4.x));
+        pr[c + 1] = ex2_approx(fmaf(pr[c + 1], c2, -L4.y));
+        pr[c + 2] = ex2_approx(fmaf(pr[c + 2], c2, -L4.z));
+        pr[c + 3] = ex2_approx(fmaf(pr[c + 3], c2, -L4.w));
+      }
+      if (p.causal && i == j) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (g * 64 + c < r) pr[c] = 0.f;  // key index > query index
+      }
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) pk[c] = to_tf32(pr[h * 32 + c]);
+          tmem_st_x32(tS + h * 32, pk);  // in place: this thread group has consumed these columns of S
+        }
+        // tau folded into the kept P values: dS^T = (tau P^T) o (dP^T - delta)
+        const float2 tau2 = make_float2(p.tau, p.tau);
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          const float2 t2 = fmul2(make_float2(pr[c], pr[c + 1]), tau2);
+          pr[c] = t2.x;
+          pr[c + 1] = t2.y;
+        }
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.p_full);
+      // ---- dS^T = (tau P^T) o (dP^T - delta)  -> TMEM (A of dK) and shared memory (MN-major A of dQ)
+      mbar_wait(&bars.dp_full, il & 1);
+      tc_fence_after();
+      if (il > 0) mbar_wait(&bars.ds_empty, (il - 1) & 1);  // dK(i-1) / dQ(i-1) have finished reading dS^T
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float dp[32];
+        tmem_ld_x32(tDP + hf * 32, reinterpret_cast<uint32_t*>(dp));
+        tmem_wait_ld();
+        uint32_t dsb[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 D4 = *reinterpret_cast<const float4*>(sD + hf * 32 + c);
+          const float2 a = fmul2(make_float2(pr[hf * 32 + c], pr[hf * 32 + c + 1]), fadd2(make_float2(dp[c], dp[c + 1]), make_float2(D4.x, D4.y)));
+          const float2 b = fmul2(make_float2(pr[hf * 32 + c + 2], pr[hf * 32 + c + 3]), fadd2(make_float2(dp[c + 2], dp[c + 3]), make_float2(D4.z, D4.w)));
+          dsb[c] = to_tf32(a.x);
+          dsb[c + 1] = to_tf32(a.y);
+          dsb[c + 2] = to_tf32(b.x);
+          dsb[c + 3] = to_tf32(b.y);
+        }
+        tmem_st_x32(tDS + hf * 32, dsb);
+        // box 2g + hf = query columns [64g + 32hf, +32): row r = 128 B, 32-byte chunks XORed with (r & 3)
+        uint8_t* row = sDS + (2 * g + hf) * kTileBytes + r * 128;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16)
+          *reinterpret_cast<uint4*>(row + ((((c16 >> 1) ^ (r & 3)) << 5) | ((c16 & 1) << 4))) =
+              make_uint4(dsb[c16 * 4], dsb[c16 * 4 + 1], dsb[c16 * 4 + 2], dsb[c16 * 4 + 3]);
+      }
+      tmem_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.ds_full);
+    }
+    // ---- epilogue: group 0 stores dV_j, group 1 stores dK_j (fp32, 32 columns = one 128-byte row per thread)
+    mbar_wait(&bars.dkv_full, 0);
+    tc_fence_after();
+    const int kv_row = j * kTile + r;
+    uint32_t rr[32];
+    tmem_ld_x32(tmem + (g == 0 ? kColDV : kColDK) + lane_base, rr);  // (warp-collective: every lane takes part)
+    tmem_wait_ld();
+    if (kv_row < T) {
+      float* out = (g == 0 ? p.dv : p.dk) + ((size_t)bh * T + kv_row) * kD;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) *reinterpret_cast<uint4*>(out + c) = make_uint4(rr[c], rr[c + 1], rr[c + 2], rr[c + 3]);
+    }
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ dQ drain warps
+    reg_dealloc<88>();
+    const int w = warp - 8;
+    const int r = w * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t tDQ = tmem + kColDQ + (uint32_t(w * 32) << 16);
+    const bool leader = (warp == 8 && lane == 0);
+    for (int il = 0; il < n; ++il) {
+      const int i = i0 + il;
+      mbar_wait(&bars.dq_full, il & 1);
+      tc_fence_after();
+      uint32_t rr[32];
+      tmem_ld_x32(tDQ, rr);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.dq_drained);
+      if (leader) tma_store_wait_read<0>();  // the staging slab is no longer being read
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        *reinterpret_cast<uint4*>(sStage + r * 128 + ((ch ^ (r & 7)) << 4)) =
+            make_uint4(rr[ch * 4], rr[ch * 4 + 1], rr[ch * 4 + 2], rr[ch * 4 + 3]);
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (leader) {
+        tma_reduce_add_3d(&map_dq, sStage, 0, i * kTile, bh);
+        tma_store_commit();
+      }
+    }
+    if (leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) tmem_dealloc(tmem, 512);
+}
+
+// -delta = -rowsum(dO o O), lse -> log2 domain, both padded to a multiple of 128 rows per head; optionally zero-fills dQ
+// (the main kernel reduce-adds into it).  The same pass writes copies of Q, K, V, dO ROUNDED to tf32 (cvt.rna): the tensor
+// core truncates fp32 operands (one-sided, up to 2^-10 relative), which biases sums of same-sign terms -- dV = P^T dO with
+// P >= 0 came out 5e-4 low relative, 1.5e-3 absolute at |dO| <= 1; rounding to nearest first halves the error and removes
+// the bias, at the price of one more memory-bound pass over the four tensors.  8 lanes own one 32-float row.
+__device__ __forceinline__ float4 round4_tf32(float4 x) {
+  return make_float4(__uint_as_float(to_tf32(x.x)), __uint_as_float(to_tf32(x.y)), __uint_as_float(to_tf32(x.z)),
+                     __uint_as_float(to_tf32(x.w)));
+}
+__global__ void __launch_bounds__(256)
+fa_bwd_tf32_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                        const float* __restrict__ o, const float* __restrict__ dO, const float* __restrict__ lse,
+                        float* __restrict__ qr, float* __restrict__ kr, float* __restrict__ vr, float* __restrict__ dor,
+                        float* __restrict__ lse_pad, float* __restrict__ delta_pad, float* __restrict__ dq_zero, int T, int Tpad,
+                        size_t total_rows_pad) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane >> 3, li = lane & 7;
+  const size_t warp_global = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t row = warp_global * 4 + sub; row < total_rows_pad; row += nwarps * 4) {
+    const size_t bh = row / Tpad;
+    const int t = (int)(row - bh * Tpad);
+    float acc = 0.f;
+    if (t < T) {
+      const size_t base = (bh * T + t) * kD + li * 4;
+      const float4 a = *reinterpret_cast<const float4*>(o + base);
+      const float4 b = *reinterpret_cast<const float4*>(dO + base);
+      acc = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+      *reinterpret_cast<float4*>(dor + base) = round4_tf32(b);
+      *reinterpret_cast<float4*>(qr + base) = round4_tf32(*reinterpret_cast<const float4*>(q + base));
+      *reinterpret_cast<float4*>(kr + base) = round4_tf32(*reinterpret_cast<const float4*>(k + base));
+      *reinterpret_cast<float4*>(vr + base) = round4_tf32(*reinterpret_cast<const float4*>(v + base));
+      if (dq_zero) *reinterpret_cast<float4*>(dq_zero + base) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int off = 4; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (li == 0) {
+      delta_pad[row] = t < T ? -acc : 0.f;
+      lse_pad[row] = t < T ? lse[bh * T + t] * 1.4426950408889634f : INFINITY;
+    }
+  }
+}
+
+size_t pad_rows(int T) { return (size_t)((T + kTile - 1) / kTile) * kTile; }
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+}  // namespace
+
+bool tc_bwd_tf32_supported(int d) { return d == kD; }
+
+// padded L and -delta + tf32-rounded copies of Q, K, V, dO
+size_t tc_bwd_tf32_workspace_bytes(int BH, int T) {
+  return 2 * align256((size_t)BH * pad_rows(T) * 4) + 4 * align256((size_t)BH * T * kD * 4);
+}
+
+cudaError_t tc_bwd_tf32(const float* q, const float* k, const float* v, const float* o, const float* dO, const float* lse,
+                        float* dq, float* dk, float* dv, bool accumulate_dq, void* workspace, int BH, int T, bool causal,
+                        cudaStream_t st) {
+  if (BH > 65535 || !workspace) return cudaErrorInvalidValue;
+  const size_t Tpad = pad_rows(T);
+  char* ws = static_cast<char*>(workspace);
+  float* lse_pad = reinterpret_cast<float*>(ws);
+  ws += align256((size_t)BH * Tpad * 4);
+  float* delta_pad = reinterpret_cast<float*>(ws);
+  ws += align256((size_t)BH * Tpad * 4);
+  float* rounded[4];  // q, k, v, dO
+  for (auto& r : rounded) {
+    r = reinterpret_cast<float*>(ws);
+    ws += align256((size_t)BH * T * kD * 4);
+  }
+  {
+    const size_t rows = (size_t)BH * Tpad;
+    size_t blocks = (rows + 31) / 32;  // 8 warps x 4 rows per block
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    fa_bwd_tf32_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(q, k, v, o, dO, lse, rounded[0], rounded[1], rounded[2], rounded[3],
+                                                            lse_pad, delta_pad, accumulate_dq ? nullptr : dq, T, (int)Tpad, rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  q = rounded[0];
+  k = rounded[1];
+  v = rounded[2];
+  dO = rounded[3];
+  CUtensorMap mq, mqm, mk, mkm, mv, mdo, mdom, mdq;
+  // K-major copies: 128B swizzle (mode 1); MN-major copies: 128B swizzle with 32-byte atoms (mode 2)
+  if (make_tmap_3d(&mq, q, 4, kD, T, BH, kD, kTile, 1) || make_tmap_3d(&mqm, q, 4, kD, T, BH, kD, kTile, 2) ||
+      make_tmap_3d(&mk, k, 4, kD, T, BH, kD, kTile, 1) || make_tmap_3d(&mkm, k, 4, kD, T, BH, kD, kTile, 2) ||
+      make_tmap_3d(&mv, v, 4, kD, T, BH, kD, kTile, 1) || make_tmap_3d(&mdo, dO, 4, kD, T, BH, kD, kTile, 1) ||
+      make_tmap_3d(&mdom, dO, 4, kD, T, BH, kD, kTile, 2) || make_tmap_3d(&mdq, dq, 4, kD, T, BH, kD, kTile, 1))
+    return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(fa_bwd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return e;
+  Params p;
+  p.T = T;
+  p.Tpad = (int)Tpad;
+  p.causal = causal ? 1 : 0;
+  p.tau = sqrtf(1.0f / (float)kD);
+  p.scale_log2 = p.tau * 1.4426950408889634f;
+  p.lse_pad = lse_pad;
+  p.delta_pad = delta_pad;
+  p.dk = dk;
+  p.dv = dv;
+  dim3 grid((unsigned)(Tpad / kTile), BH);
+  fa_bwd_tf32_kernel<<<grid, kThreads, kSmemBytes, st>>>(mq, mqm, mk, mkm, mv, mdo, mdom, mdq, p);
+  return cudaGetLastError();
+}
+
+}  // namespace fa

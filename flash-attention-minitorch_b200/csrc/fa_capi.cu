@@ -7,6 +7,8 @@
 // grow-only device arena instead of 6-10 cudaMalloc/cudaFree pairs per call.
 #include <stdarg.h>
 #include <stdio.h>
+
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 
@@ -156,9 +158,9 @@ int resolve_precision(int dtype, int precision, int d, bool backward) {
     return -1;
   }
   if (dtype == FA_DTYPE_F32) {
-    // tf32 tensor-core kernels exist for the forward (d in {32, 64}); everything else on fp32 storage runs the
-    // exact-fp32 CUDA-core kernels, which satisfy any tf32 tolerance
-    const bool tf32_ok = !backward && fa::tc_fwd_tf32_supported(d);
+    // tf32 tensor-core kernels exist for the forward (d in {32, 64}) and the backward (d = 32); everything else on fp32
+    // storage runs the exact-fp32 CUDA-core kernels, which satisfy any tf32 tolerance
+    const bool tf32_ok = backward ? fa::tc_bwd_tf32_supported(d) : fa::tc_fwd_tf32_supported(d);
     if (precision == FA_PREC_AUTO || precision == FA_PREC_TF32_TC) return tf32_ok ? FA_PREC_TF32_TC : FA_PREC_FP32_SIMT;
     if (precision == FA_PREC_FP32_SIMT) return FA_PREC_FP32_SIMT;
     if (precision == FA_PREC_BF16_TC) return tc_ok ? FA_PREC_BF16_TC : FA_PREC_FP32_SIMT;
@@ -246,6 +248,8 @@ size_t fa_b200_bwd_workspace_bytes(int dtype, int precision, int batch_heads, in
   if (prec == FA_PREC_BF16_TC && dtype == FA_DTYPE_BF16) return fa::tc_bwd_workspace_bytes(batch_heads, T, d);
   size_t bytes = align_up(rows * sizeof(float), 256);            // delta
   if (dtype == FA_DTYPE_BF16) bytes += 8 * align_up(n * sizeof(float), 256);  // fp32 images of 5 inputs + 3 grads
+  // the tf32 backward (padded L / delta) -- the larger of the two, so that the dropout fallback to the CUDA-core kernels fits
+  if (prec == FA_PREC_TF32_TC) bytes = std::max(bytes, fa::tc_bwd_tf32_workspace_bytes(batch_heads, T));
   return bytes;
 }
 
@@ -272,6 +276,11 @@ int bwd_impl(const void* q, const void* k, const void* v, const void* o, const v
     FA_CUDA(fa::tc_bwd((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
                        (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_out, lse, dq, dk, dv, false, accumulate_dq != 0,
                        workspace, batch_heads, T, d, causal != 0, st, drop), fa::tc_bwd_num_launches(false));
+    return FA_OK;
+  }
+  if (dtype == FA_DTYPE_F32 && prec == FA_PREC_TF32_TC && !drop.thr) {
+    FA_CUDA(fa::tc_bwd_tf32((const float*)q, (const float*)k, (const float*)v, (const float*)o, (const float*)d_out, lse,
+                            (float*)dq, (float*)dk, (float*)dv, accumulate_dq != 0, workspace, batch_heads, T, causal != 0, st), 2);
     return FA_OK;
   }
   float* delta = reinterpret_cast<float*>(ws);

@@ -176,13 +176,13 @@ def test_device_bf16_large_scores_exercise_lazy_rescale(cuda_device):
 
 @pytest.mark.parametrize("d", [32, 34, 100])
 def test_device_fp32_any_head_dim(cuda_device, d):
-    """Head dims outside the tensor-core set (the MT model's d=32, the reference test's d=34) on the exact fp32 path."""
+    """The exact fp32 CUDA-core path (FA_PREC_FP32_SIMT) at any head dim: the MT model's d=32, the reference test's d=34."""
     q, k, v, g = ao.make_inputs(2, 77, d, seed=d)
     dq_r, dk_r, dv_r, o_r, L_r = ao.attention_backward(q, k, v, g, True, np.float64)
     tq, tk, tv, tg = (_to_dev(x, cuda_device, bf16=False) for x in (q, k, v, g))
     o, lse = device.flash_attn_fwd(tq, tk, tv, True, precision=_lib.FA_PREC_FP32_SIMT)
     assert np.abs(o.cpu().numpy() - o_r).max() <= 1e-5
-    dq, dk, dv = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, True)
+    dq, dk, dv = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, True, precision=_lib.FA_PREC_FP32_SIMT)
     for got, ref in ((dq, dq_r), (dk, dk_r), (dv, dv_r)):
         assert np.abs(got.cpu().numpy() - ref).max() <= 1e-4
 
@@ -207,6 +207,42 @@ def test_device_tf32_forward_vs_oracle(cuda_device, BH, T, d, causal):
     dq, dk, dv = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, causal)
     for got, ref, name in ((dq, dq_r, "dq"), (dk, dk_r, "dk"), (dv, dv_r, "dv")):
         assert np.abs(got.cpu().numpy() - ref).max() <= FP32_ATOL, name
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("BH,T", [(3, 1), (2, 40), (3, 128), (2, 327), (4, 512), (1, 1000), (1, 2125)])
+def test_device_tf32_backward_vs_oracle(cuda_device, BH, T, causal):
+    """fp32 storage, head dim 32 (the reference MT model's): the backward runs on tcgen05 kind::tf32 (what FA_PREC_AUTO
+    selects) -- prep + main kernel = 2 launches -- and meets the north_star bar max-abs 1e-3 against the fp64 oracle for
+    dQ, dK, dV; with accumulate_dq it adds onto the caller's dq like the reference (src/flash_attn2_bw.cu:228); the
+    exact-fp32 CUDA-core backward stays available through FA_PREC_FP32_SIMT and agrees to 1e-3."""
+    import torch
+    d = 32
+    q, k, v, g = ao.make_inputs(BH, T, d, seed=900 + T)
+    dq_r, dk_r, dv_r, o_r, L_r = ao.attention_backward(q, k, v, g, causal, np.float64)
+    tq, tk, tv, tg = (_to_dev(x, cuda_device, bf16=False) for x in (q, k, v, g))
+    o, lse = device.flash_attn_fwd(tq, tk, tv, causal, precision=_lib.FA_PREC_FP32_SIMT)
+    before = _lib.launch_count()
+    dq, dk, dv = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, causal, precision=_lib.FA_PREC_TF32_TC)
+    assert _lib.launch_count() == before + 2
+    for got, ref, name in ((dq, dq_r, "dq"), (dk, dk_r, "dk"), (dv, dv_r, "dv")):
+        assert np.abs(got.cpu().numpy() - ref).max() <= FP32_ATOL, name
+    dq_a, dk_a, dv_a = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, causal)  # AUTO: the same kernel, bit-identical dK / dV
+    assert torch.equal(dk_a, dk) and torch.equal(dv_a, dv)
+    assert float((dq_a - dq).abs().max()) <= 1e-5  # (dQ: fp32 reduce-adds in L2 arrive in any order)
+    dq_s, dk_s, dv_s = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, causal, precision=_lib.FA_PREC_FP32_SIMT)
+    for a, b in ((dq, dq_s), (dk, dk_s), (dv, dv_s)):
+        assert float((a - b).abs().max()) <= FP32_ATOL
+    # accumulate_dq through the C ABI
+    lib = _lib.load_library()
+    ws = device.bwd_workspace(tq, _lib.FA_PREC_TF32_TC)
+    acc = torch.full_like(tq, 0.25)
+    dk2, dv2 = torch.empty_like(tq), torch.empty_like(tq)
+    _lib.check(lib.fa_b200_bwd(tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), o.data_ptr(), tg.data_ptr(), lse.data_ptr(),
+                               acc.data_ptr(), dk2.data_ptr(), dv2.data_ptr(), _lib.FA_DTYPE_F32, _lib.FA_PREC_TF32_TC, BH, T, d,
+                               1 if causal else 0, 1, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    assert np.abs(acc.cpu().numpy() - 0.25 - dq_r).max() <= FP32_ATOL
+    assert torch.equal(dk2, dk) and torch.equal(dv2, dv)
 
 
 def test_cfg2_full_size_tf32_forward(cuda_device):

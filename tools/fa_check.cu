@@ -324,6 +324,68 @@ static int check_tf32(int BH, int T, int d, int causal, float scale) {
   return !ok;
 }
 
+// tf32 tensor-core backward (fp32 storage, d = 32) against the exact-fp32 CUDA-core backward on the same inputs,
+// including accumulation into dq; times both.
+static int check_bwd_tf32(int BH, int T, int causal, bool timing) {
+  const int d = 32;
+  const size_t n = (size_t)BH * T * d, rows = (size_t)BH * T;
+  std::vector<float> h(n);
+  Dev dev;
+  float* t[5];  // q k v o dO
+  for (auto& p : t) p = dev.alloc<float>(n);
+  for (int i = 0; i < 5; ++i) {
+    for (auto& x : h) x = urand();
+    CK(cudaMemcpy(t[i], h.data(), n * 4, cudaMemcpyHostToDevice));
+  }
+  float *lse = dev.alloc<float>(rows), *g0[3], *g1[3];
+  for (auto& p : g0) p = dev.alloc<float>(n);
+  for (auto& p : g1) p = dev.alloc<float>(n);
+  FA(fa_b200_fwd(t[0], t[1], t[2], t[3], lse, nullptr, nullptr, FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, nullptr));
+  const size_t w0 = fa_b200_bwd_workspace_bytes(FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d);
+  const size_t w1 = fa_b200_bwd_workspace_bytes(FA_DTYPE_F32, FA_PREC_TF32_TC, BH, T, d);
+  char *ws0 = dev.alloc<char>(w0), *ws1 = dev.alloc<char>(w1);
+  // dq starts at 0.25 everywhere and is accumulated into (the reference's semantics)
+  for (auto& x : h) x = 0.25f;
+  CK(cudaMemcpy(g0[0], h.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(g1[0], h.data(), n * 4, cudaMemcpyHostToDevice));
+  FA(fa_b200_bwd(t[0], t[1], t[2], t[3], t[4], lse, g0[0], g0[1], g0[2], FA_DTYPE_F32, FA_PREC_FP32_SIMT, BH, T, d, causal, 1, ws0, w0, nullptr));
+  FA(fa_b200_bwd(t[0], t[1], t[2], t[3], t[4], lse, g1[0], g1[1], g1[2], FA_DTYPE_F32, FA_PREC_TF32_TC, BH, T, d, causal, 1, ws1, w1, nullptr));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("tf32 bwd BH=%d T=%d causal=%d: CUDA ERROR %s\n", BH, T, causal, cudaGetErrorString(e));
+    exit(3);
+  }
+  double ea[3], er[3];
+  for (int i = 0; i < 3; ++i) err_stats(d2h_f32(g1[i], n), d2h_f32(g0[i], n), ea[i], er[i]);
+  // inputs in (-1, 1): dQ, dK, dV are O(1); operands, P and dS rounded to tf32 keep max-abs below the north_star bar 1e-3
+  const bool ok = ea[0] < 1e-3 && ea[1] < 1e-3 && ea[2] < 1e-3;
+  printf("tf32 bwd BH=%d T=%5d d=32 causal=%d  dQ abs %.2e rel %.2e  dK abs %.2e rel %.2e  dV abs %.2e rel %.2e  %s\n", BH, T, causal,
+         ea[0], er[0], ea[1], er[1], ea[2], er[2], ok ? "OK" : "FAIL");
+  if (timing) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int v = 0; v < 2; ++v) {
+      const int prec = v ? FA_PREC_TF32_TC : FA_PREC_FP32_SIMT;
+      float** g = v ? g1 : g0;
+      char* ws = v ? ws1 : ws0;
+      const size_t wb = v ? w1 : w0;
+      const int iters = v ? 20 : 3;
+      cudaEventRecord(e0);
+      for (int it = 0; it < iters; ++it)
+        FA(fa_b200_bwd(t[0], t[1], t[2], t[3], t[4], lse, g[0], g[1], g[2], FA_DTYPE_F32, prec, BH, T, d, causal, 0, ws, wb, nullptr));
+      cudaEventRecord(e1);
+      CK(cudaDeviceSynchronize());
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      ms /= iters;
+      const double flops = 10.0 * BH * double(T) * T * d * (causal ? 0.5 : 1.0);
+      printf("time %s bwd BH=%d T=%d d=32 causal=%d: %.3f ms  %.1f TFLOP/s\n", v ? "tf32-tc  " : "fp32-simt", BH, T, causal, ms, flops / ms * 1e-9);
+    }
+  }
+  return !ok;
+}
+
 static int time_tf32(int BH, int T, int d, int causal, int iters) {
   const size_t n = (size_t)BH * T * d, rows = (size_t)BH * T;
   Dev dev;
@@ -533,6 +595,14 @@ int main(int argc, char** argv) {
           for (int T : {1, 40, 128, 256, 327, 1000, 1024, 2048 + 77}) bad += check_tf32(3, T, d, causal, 1.f);
       bad += check_tf32(2, 1024, 64, 1, 6.f);
       bad += check_tf32(2, 1024, 32, 0, 6.f);
+    }
+  } else if (mode == "bwd32") {
+    if (argc >= 5) {
+      bad = check_bwd_tf32(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), true);
+    } else {
+      for (int causal : {0, 1})
+        for (int T : {1, 40, 128, 256, 327, 512, 1000, 2048 + 77}) bad += check_bwd_tf32(3, T, causal, false);
+      bad += check_bwd_tf32(88, 512, 1, true);  // the MT model's attention: 11 sequences x 8 heads, L = 512
     }
   } else if (mode == "time32") {
     int BH = argc > 2 ? atoi(argv[2]) : 512, T = argc > 3 ? atoi(argv[3]) : 1024, d = argc > 4 ? atoi(argv[4]) : 64;

@@ -356,6 +356,12 @@ int main(int argc, char** argv) {
       fails += run_case<float, true>("tf32 A=smemMN B=smemK (32B atom)", A_SMEM_MN, B_SMEM_K, N, 64, v) != 0;
     }
   }
+  // forms of the tf32 backward at d = 32: N = 32 accumulators (dV, dK, dQ), A from TMEM or MN-major shared memory,
+  // B MN-major; and the score products with K = 32
+  fails += run_case<float, true>("tf32 A=smemMN B=smemMN (32B atom)", A_SMEM_MN, B_SMEM_MN, 128, 128, 2) != 0;
+  fails += run_case<float, true>("tf32 A=smemMN B=smemMN (32B atom)", A_SMEM_MN, B_SMEM_MN, 32, 128, 2) != 0;
+  fails += run_case<float, true>("tf32 A=tmem   B=smemMN(32B atom)", A_TMEM, B_SMEM_MN, 32, 128, 2) != 0;
+  fails += run_case<float, true>("tf32 A=smemK  B=smemK", A_SMEM_K, B_SMEM_K, 128, 32, 0) != 0;
   // K-major tf32 operands in the 32B-atom swizzle: measured on B200 -> "misaligned address" from the MMA (the 32-byte
   // k-step advance is not a legal start address in that layout), i.e. one fp32 tile cannot serve both as a K-major and
   // as an MN-major tf32 operand.  The launch faults the context, so it only runs on request: umma_probe full kmajor32
