@@ -256,7 +256,10 @@ cudaError_t launch_gemm(const float* a, const float* b, float* c, const float* b
     if (e != cudaSuccess) return e;
   }
   dim3 grid((N + kBN - 1) / kBN, (M + kBM - 1) / kBM, splits);
-  if (p.k_blocks_per_split <= 16) {
+  // Short reductions on a grid that oversubscribes the SMs: the 2-stage variant (two CTAs per SM hide each other's
+  // prologue / epilogue).  A grid of at most one CTA per SM gains nothing from that and needs the deep ring instead:
+  // with 2 stages every k-block waits a full TMA latency (the 5632 x 256 x 256 layers: ~10 us for 0.7 us of math).
+  if (p.k_blocks_per_split <= 16 && (long long)grid.x * grid.y * grid.z > 148) {
     auto kern = heads ? fa_gemm_tf32_kernel<kAMn, kBMn, 2, true> : fa_gemm_tf32_kernel<kAMn, kBMn, 2, false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(2));
     if (e != cudaSuccess) return e;
@@ -367,7 +370,9 @@ cudaError_t colsum_f32(const float* x, float* out, int M, int N, bool accumulate
   }
   const int col_blocks = (N / 4 + 31) / 32;
   int strips = (148 * 8 + col_blocks - 1) / col_blocks;
-  if (strips > (M + 7) / 8) strips = (M + 7) / 8;
+  // at least 8 rows per row lane: narrow matrices (N = 256: two column blocks) otherwise end up with one row per thread
+  // and ~600 atomics per column (18 us for 5.8 MB)
+  if (strips > (M + 63) / 64) strips = (M + 63) / 64;
   colsum_kernel<<<dim3(col_blocks, strips), 256, 0, st>>>(x, out, M, N);
   return cudaGetLastError();
 }

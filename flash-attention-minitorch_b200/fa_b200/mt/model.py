@@ -76,6 +76,7 @@ class Module:
             p.value.grad = gflat[off:off + n].view(p.value.shape)
             off += n
         self._flat = (flat, gflat)
+        ops.grad_sink.direct = True  # weight / bias gradient kernels accumulate straight into the flat gradient views
         return self._flat
 
 

@@ -89,11 +89,35 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _gemm(a, b, out_shape, M, N, K, a_mn, b_mn, bias=None):
-    c = torch.empty(out_shape, device=a.device, dtype=torch.float32)
+def _gemm(a, b, out_shape, M, N, K, a_mn, b_mn, bias=None, into=None):
+    """C = A B (+ bias) into a fresh tensor, or C += A B when `into` is given (a parameter's gradient buffer)."""
+    c = into if into is not None else torch.empty(out_shape, device=a.device, dtype=torch.float32)
     _lib.check(_lib.load_library().fa_b200_gemm_tf32(a.data_ptr(), b.data_ptr(), c.data_ptr(),
-                                                     bias.data_ptr() if bias is not None else None, M, N, K, a_mn, b_mn, 0, _st()))
+                                                     bias.data_ptr() if bias is not None else None, M, N, K, a_mn, b_mn,
+                                                     1 if into is not None else 0, _st()))
     return c
+
+
+class grad_sink:
+    """With flattened parameters (Module.flatten_parameters) every Parameter.value.grad is a view of ONE static flat
+    buffer that zero_grad() clears with a single memset.  The weight / bias gradient kernels then accumulate STRAIGHT into
+    those views (GEMM epilogue `C +=`, column sums with accumulate) and the autograd Functions return None for the
+    parameter inputs -- autograd's AccumulateGrad would otherwise launch one extra `grad += dW` kernel per parameter per
+    step (~70 of the ~280 launches of a step, 13 % of its device time) and allocate every dW / db twice."""
+    direct = False
+
+
+def _sink(p):
+    """The gradient buffer the kernels may accumulate into for parameter tensor `p`, or None (ordinary autograd)."""
+    if grad_sink.direct and p is not None and p.is_leaf and p.requires_grad and p.grad is not None and p.grad.is_contiguous():
+        return p.grad
+    return None
+
+
+def _colsum(dy2d, M, N, into=None):
+    db = into if into is not None else torch.empty(N, device=dy2d.device, dtype=torch.float32)
+    _lib.check(_lib.load_library().fa_b200_colsum_f32(dy2d.data_ptr(), db.data_ptr(), M, N, 1 if into is not None else 0, _st()))
+    return db
 
 
 class _Linear(torch.autograd.Function):
@@ -105,7 +129,7 @@ class _Linear(torch.autograd.Function):
         M, K = x.shape
         N = w.shape[1]
         ctx.save_for_backward(x, w)
-        ctx.has_bias = b is not None
+        ctx.bias = b
         return _gemm(x, w, (M, N), M, N, K, 0, 1, b.contiguous() if b is not None else None)
 
     @staticmethod
@@ -115,12 +139,15 @@ class _Linear(torch.autograd.Function):
         M, K = x.shape
         N = w.shape[1]
         dx = _gemm(dy, w, (M, K), M, K, N, 0, 0)      # dX = dY W^T : W rows are the K-major B operand
-        dw = _gemm(x, dy, (K, N), K, N, M, 1, 1)      # dW = X^T dY : both operands MN-major
+        gw = _sink(w)
+        dw = _gemm(x, dy, (K, N), K, N, M, 1, 1, into=gw)  # dW = X^T dY : both operands MN-major
         db = None
-        if ctx.has_bias:
-            db = torch.empty(N, device=dy.device, dtype=torch.float32)
-            _lib.check(_lib.load_library().fa_b200_colsum_f32(dy.data_ptr(), db.data_ptr(), M, N, 0, _st()))
-        return dx, dw, db
+        if ctx.bias is not None:
+            gb = _sink(ctx.bias)
+            db = _colsum(dy, M, N, into=gb)
+            if gb is not None:
+                db = None
+        return dx, (None if gw is not None else dw), db
 
 
 def linear(x, weight, bias=None):
@@ -132,10 +159,10 @@ def linear(x, weight, bias=None):
     return y if bias is None else y + bias
 
 
-def _gemm_heads(a, b, c, bias, M, N, K, a_mn, b_mn, a_h, b_h, c_h, T, H, d):
+def _gemm_heads(a, b, c, bias, M, N, K, a_mn, b_mn, a_h, b_h, c_h, T, H, d, accumulate=0):
     _lib.check(_lib.load_library().fa_b200_gemm_tf32_heads(a.data_ptr(), b.data_ptr(), c.data_ptr(),
-                                                           bias.data_ptr() if bias is not None else None, M, N, K, a_mn, b_mn, 0,
-                                                           a_h, b_h, c_h, T, H, d, _st()))
+                                                           bias.data_ptr() if bias is not None else None, M, N, K, a_mn, b_mn,
+                                                           accumulate, a_h, b_h, c_h, T, H, d, _st()))
     return c
 
 
@@ -158,7 +185,7 @@ class _LinearToHeads(torch.autograd.Function):
         y = torch.empty(B, H, T, d, device=x.device, dtype=torch.float32)
         _gemm_heads(x, w, y, b.contiguous() if b is not None else None, M, H * d, K, 0, 1, 0, 0, 1, T, H, d)
         ctx.save_for_backward(x, w)
-        ctx.dims, ctx.has_bias = (B, T, H, d), b is not None
+        ctx.dims, ctx.bias = (B, T, H, d), b
         return y
 
     @staticmethod
@@ -169,12 +196,18 @@ class _LinearToHeads(torch.autograd.Function):
         M, K = x.shape
         E = H * d
         dx = _gemm_heads(dy, w, torch.empty(M, K, device=x.device, dtype=torch.float32), None, M, K, E, 0, 0, 1, 0, 0, T, H, d)
-        dw = _gemm_heads(x, dy, torch.empty(K, E, device=x.device, dtype=torch.float32), None, K, E, M, 1, 1, 0, 1, 0, T, H, d)
+        gw = _sink(w)
+        dw = _gemm_heads(x, dy, gw if gw is not None else torch.empty(K, E, device=x.device, dtype=torch.float32), None, K, E, M,
+                         1, 1, 0, 1, 0, T, H, d, accumulate=1 if gw is not None else 0)
         db = None
-        if ctx.has_bias:
-            db = torch.empty(E, device=x.device, dtype=torch.float32)
-            _lib.check(_lib.load_library().fa_b200_colsum_heads_f32(dy.data_ptr(), db.data_ptr(), B, H, T, d, 0, _st()))
-        return dx, dw, db, None, None, None, None
+        if ctx.bias is not None:
+            gb = _sink(ctx.bias)
+            db = gb if gb is not None else torch.empty(E, device=x.device, dtype=torch.float32)
+            _lib.check(_lib.load_library().fa_b200_colsum_heads_f32(dy.data_ptr(), db.data_ptr(), B, H, T, d,
+                                                                    1 if gb is not None else 0, _st()))
+            if gb is not None:
+                db = None
+        return dx, (None if gw is not None else dw), db, None, None, None, None
 
 
 class _LinearFromHeads(torch.autograd.Function):
@@ -189,7 +222,7 @@ class _LinearFromHeads(torch.autograd.Function):
         y = torch.empty(M, N, device=o.device, dtype=torch.float32)
         _gemm_heads(o, w, y, b.contiguous() if b is not None else None, M, N, E, 0, 1, 1, 0, 0, T, H, d)
         ctx.save_for_backward(o, w)
-        ctx.has_bias = b is not None
+        ctx.bias = b
         return y
 
     @staticmethod
@@ -199,12 +232,16 @@ class _LinearFromHeads(torch.autograd.Function):
         M, E, N = B * T, H * d, w.shape[1]
         dy = dy.contiguous()
         do = _gemm_heads(dy, w, torch.empty_like(o), None, M, E, N, 0, 0, 0, 0, 1, T, H, d)
-        dw = _gemm_heads(o, dy, torch.empty(E, N, device=o.device, dtype=torch.float32), None, E, N, M, 1, 1, 1, 0, 0, T, H, d)
+        gw = _sink(w)
+        dw = _gemm_heads(o, dy, gw if gw is not None else torch.empty(E, N, device=o.device, dtype=torch.float32), None, E, N, M,
+                         1, 1, 1, 0, 0, T, H, d, accumulate=1 if gw is not None else 0)
         db = None
-        if ctx.has_bias:
-            db = torch.empty(N, device=o.device, dtype=torch.float32)
-            _lib.check(_lib.load_library().fa_b200_colsum_f32(dy.data_ptr(), db.data_ptr(), M, N, 0, _st()))
-        return do, dw, db
+        if ctx.bias is not None:
+            gb = _sink(ctx.bias)
+            db = _colsum(dy, M, N, into=gb)
+            if gb is not None:
+                db = None
+        return do, (None if gw is not None else dw), db
 
 
 def linear_to_heads(x, weight, bias, B: int, T: int, H: int, d: int):
