@@ -42,11 +42,11 @@ extern "C" {
 #define FA_DTYPE_BF16 1
 
 /* ---- arithmetic used for the two contractions ----
- * AUTO      : bf16 storage -> BF16_TC; fp32 storage -> TF32_TC when the shape is covered (forward, d in {32,64}),
- *             else FP32_SIMT.  In the host-pointer API AUTO means FP32_SIMT (the reference computes in fp32).
+ * AUTO      : bf16 storage -> BF16_TC; fp32 storage -> TF32_TC when the shape is covered (forward: d in {32,64};
+ *             backward: d = 32 without dropout), else FP32_SIMT.  In the host-pointer API AUTO means FP32_SIMT (the reference computes in fp32).
  * FP32_SIMT : fp32 FMA on CUDA cores (any d <= 128 -- the reference's own limit, src/flash_attn_fw.cu:43 -- and any T); exact-fp32 cross-check path
- * TF32_TC   : tcgen05.mma kind::tf32 on fp32 storage read directly by TMA (no conversion pass); shapes it does
- *             not cover run FP32_SIMT
+ * TF32_TC   : tcgen05.mma kind::tf32 on fp32 storage read directly by TMA (no conversion pass; the backward rounds its
+ *             operands to tf32 in its prep pass); shapes it does not cover run FP32_SIMT
  * BF16_TC   : tcgen05.mma kind::f16 (bf16 inputs, fp32 accumulate); fp32 storage is converted on device */
 #define FA_PREC_AUTO 0
 #define FA_PREC_FP32_SIMT 1
