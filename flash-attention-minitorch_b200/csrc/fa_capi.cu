@@ -378,6 +378,12 @@ int fa_b200_layernorm_bwd(const float* x, const float* w, const float* dy, const
   FA_CUDA(fa::layernorm_bwd(x, w, dy, mean, rstd, dx, dw, db, rows, dim, FA_ST), 2);
   return FA_OK;
 }
+int fa_b200_layernorm_bwd_accum(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
+                                float* dw, float* db, int rows, int dim, void* stream) {
+  if (!x || !w || !dy || !mean || !rstd || !dx || !dw || !db) return fail(FA_ERR_BAD_ARG, "fa_b200_layernorm_bwd_accum: null pointer");
+  FA_CUDA(fa::layernorm_bwd(x, w, dy, mean, rstd, dx, dw, db, rows, dim, FA_ST, true), 2);
+  return FA_OK;
+}
 int fa_b200_gelu_fwd(const float* x, float* y, size_t n, void* stream) {
   if (!x || !y) return fail(FA_ERR_BAD_ARG, "fa_b200_gelu_fwd: null pointer");
   FA_CUDA(fa::gelu(x, nullptr, y, n, false, FA_ST), 1);
@@ -403,6 +409,11 @@ int fa_b200_embedding_fwd(const long long* idx, const float* w, float* y, size_t
 int fa_b200_embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, void* stream) {
   if (!idx || !dy || !dw) return fail(FA_ERR_BAD_ARG, "fa_b200_embedding_bwd: null pointer");
   FA_CUDA(fa::embedding_bwd(idx, dy, dw, n_idx, dim, vocab, FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_embedding_bwd_accum(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, void* stream) {
+  if (!idx || !dy || !dw) return fail(FA_ERR_BAD_ARG, "fa_b200_embedding_bwd_accum: null pointer");
+  FA_CUDA(fa::embedding_bwd(idx, dy, dw, n_idx, dim, vocab, FA_ST, true), 1);
   return FA_OK;
 }
 int fa_b200_softmax_loss_fwd(const float* logits, const long long* target, float* loss, float* lse, int rows, int n_classes,

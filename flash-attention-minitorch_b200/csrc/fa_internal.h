@@ -78,12 +78,13 @@ cudaError_t colsum_f32(const float* x, float* out, int M, int N, bool accumulate
 cudaError_t layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, int rows,
                           int dim, float eps, cudaStream_t st);
 cudaError_t layernorm_bwd(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
-                          float* dw, float* db, int rows, int dim, cudaStream_t st);
+                          float* dw, float* db, int rows, int dim, cudaStream_t st, bool accumulate = false);
 cudaError_t gelu(const float* x, const float* dy, float* y, size_t n, bool backward, cudaStream_t st);
 cudaError_t dropout_apply(const float* x, float* y, size_t n, Dropout drop, const unsigned long long* seed_offset,
                           cudaStream_t st);
 cudaError_t embedding_fwd(const long long* idx, const float* w, float* y, size_t n_idx, int dim, cudaStream_t st);
-cudaError_t embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, cudaStream_t st);
+cudaError_t embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, cudaStream_t st,
+                          bool accumulate = false);
 cudaError_t softmax_loss_fwd(const float* logits, const long long* target, float* loss, float* lse, int rows, int C,
                              cudaStream_t st);
 cudaError_t softmax_loss_bwd(const float* logits, const long long* target, const float* lse, const float* gscale,

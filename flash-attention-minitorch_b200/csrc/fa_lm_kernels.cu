@@ -275,11 +275,13 @@ cudaError_t layernorm_fwd(const float* x, const float* w, const float* b, float*
   return cudaGetLastError();
 }
 cudaError_t layernorm_bwd(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
-                          float* dw, float* db, int rows, int dim, cudaStream_t st) {
+                          float* dw, float* db, int rows, int dim, cudaStream_t st, bool accumulate) {
   if (rows <= 0 || dim <= 0 || (dim & 3)) return cudaErrorInvalidValue;
   cudaError_t e;
-  if ((e = cudaMemsetAsync(dw, 0, (size_t)dim * 4, st)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(db, 0, (size_t)dim * 4, st)) != cudaSuccess) return e;
+  if (!accumulate) {  // (accumulate: dw / db are a parameter's gradient buffer, the strips atomically add onto it)
+    if ((e = cudaMemsetAsync(dw, 0, (size_t)dim * 4, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(db, 0, (size_t)dim * 4, st)) != cudaSuccess) return e;
+  }
   layernorm_bwd_dx_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, w, dy, mean, rstd, dx, rows, dim);
   const int col_blocks = (dim + 255) / 256;
   int strips = (kSMs * 2) / col_blocks;
@@ -306,9 +308,12 @@ cudaError_t embedding_fwd(const long long* idx, const float* w, float* y, size_t
   embedding_fwd_kernel<<<ew_grid(n_idx * (dim / 4), 256), 256, 0, st>>>(idx, w, y, n_idx, dim / 4);
   return cudaGetLastError();
 }
-cudaError_t embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(dw, 0, vocab * dim * 4, st);
-  if (e != cudaSuccess) return e;
+cudaError_t embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, cudaStream_t st,
+                          bool accumulate) {
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, vocab * dim * 4, st);
+    if (e != cudaSuccess) return e;
+  }
   embedding_bwd_kernel<<<ew_grid(n_idx * dim, 256), 256, 0, st>>>(idx, dy, dw, n_idx, dim);
   return cudaGetLastError();
 }

@@ -80,10 +80,10 @@ def load_library() -> ctypes.CDLL:
         lib.fa_b200_colsum_heads_f32.restype = ci
     lib.fa_b200_colsum_f32.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.fa_b200_colsum_f32.restype = ci
-    for name, args in (("layernorm_fwd", [vp] * 6 + [ci, ci, f32, vp]), ("layernorm_bwd", [vp] * 8 + [ci, ci, vp]),
+    for name, args in (("layernorm_fwd", [vp] * 6 + [ci, ci, f32, vp]), ("layernorm_bwd", [vp] * 8 + [ci, ci, vp]), ("layernorm_bwd_accum", [vp] * 8 + [ci, ci, vp]),
                        ("gelu_fwd", [vp, vp, sz, vp]), ("gelu_bwd", [vp, vp, vp, sz, vp]),
                        ("dropout_apply", [vp, vp, sz, f32, u64, vp, vp]), ("embedding_fwd", [vp, vp, vp, sz, ci, vp]),
-                       ("embedding_bwd", [vp, vp, vp, sz, ci, sz, vp]), ("softmax_loss_fwd", [vp] * 4 + [ci, ci, vp]),
+                       ("embedding_bwd", [vp, vp, vp, sz, ci, sz, vp]), ("embedding_bwd_accum", [vp, vp, vp, sz, ci, sz, vp]), ("softmax_loss_fwd", [vp] * 4 + [ci, ci, vp]),
                        ("softmax_loss_bwd", [vp] * 5 + [ci, ci, vp]),
                        ("adam_step", [vp] * 4 + [sz, f32, f32, f32, f32, f32, vp])):
         fn = getattr(lib, "fa_b200_" + name)

@@ -270,6 +270,7 @@ class _LayerNorm(torch.autograd.Function):
         _lib.check(_lib.load_library().fa_b200_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), mean.data_ptr(),
                                                              rstd.data_ptr(), rows, dim, float(eps), _st()))
         ctx.save_for_backward(x, w, mean, rstd)
+        ctx.bias = b
         return y
 
     @staticmethod
@@ -277,9 +278,16 @@ class _LayerNorm(torch.autograd.Function):
         x, w, mean, rstd = ctx.saved_tensors
         dy = dy.contiguous()
         rows, dim = x.shape
-        dx, dw, db = torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
-        _lib.check(_lib.load_library().fa_b200_layernorm_bwd(x.data_ptr(), w.data_ptr(), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                                             dx.data_ptr(), dw.data_ptr(), db.data_ptr(), rows, dim, _st()))
+        dx = torch.empty_like(x)
+        gw, gb = _sink(w), _sink(ctx.bias)
+        lib = _lib.load_library()
+        if gw is not None and gb is not None:  # straight into the flat gradient views (grad_sink)
+            _lib.check(lib.fa_b200_layernorm_bwd_accum(x.data_ptr(), w.data_ptr(), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                       dx.data_ptr(), gw.data_ptr(), gb.data_ptr(), rows, dim, _st()))
+            return dx, None, None, None
+        dw, db = torch.empty_like(w), torch.empty_like(w)
+        _lib.check(lib.fa_b200_layernorm_bwd(x.data_ptr(), w.data_ptr(), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                             dx.data_ptr(), dw.data_ptr(), db.data_ptr(), rows, dim, _st()))
         return dx, dw, db, None
 
 
@@ -376,7 +384,7 @@ class _Embedding(torch.autograd.Function):
         y = torch.empty(tuple(idx.shape) + (w.shape[1],), device=w.device, dtype=torch.float32)
         _lib.check(_lib.load_library().fa_b200_embedding_fwd(idx.data_ptr(), w.data_ptr(), y.data_ptr(), idx.numel(), w.shape[1], _st()))
         ctx.save_for_backward(idx)
-        ctx.vocab = w.shape[0]
+        ctx.vocab, ctx.weight = w.shape[0], w
         return y
 
     @staticmethod
@@ -384,6 +392,11 @@ class _Embedding(torch.autograd.Function):
         (idx,) = ctx.saved_tensors
         dy = dy.contiguous()
         dim = dy.shape[-1]
+        gw = _sink(ctx.weight)
+        if gw is not None:  # scatter-add straight into the (already zeroed) flat gradient view: no 10 MB memset + add
+            _lib.check(_lib.load_library().fa_b200_embedding_bwd_accum(idx.data_ptr(), dy.data_ptr(), gw.data_ptr(), idx.numel(), dim,
+                                                                       ctx.vocab, _st()))
+            return None, None
         dw = torch.empty(ctx.vocab, dim, device=dy.device, dtype=torch.float32)
         _lib.check(_lib.load_library().fa_b200_embedding_bwd(idx.data_ptr(), dy.data_ptr(), dw.data_ptr(), idx.numel(), dim, ctx.vocab, _st()))
         return None, dw

@@ -166,12 +166,16 @@ int fa_b200_layernorm_fwd(const float* x, const float* w, const float* b, float*
                           int dim, float eps, void* stream);
 int fa_b200_layernorm_bwd(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
                           float* dw, float* db, int rows, int dim, void* stream);
+/* the same with dw / db ACCUMULATED into (a parameter's gradient buffer) instead of overwritten */
+int fa_b200_layernorm_bwd_accum(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
+                                float* dw, float* db, int rows, int dim, void* stream);
 int fa_b200_gelu_fwd(const float* x, float* y, size_t n, void* stream);
 int fa_b200_gelu_bwd(const float* x, const float* dy, float* dx, size_t n, void* stream);
 int fa_b200_dropout_apply(const float* x, float* y, size_t n, float p_drop, unsigned long long seed,
                           const unsigned long long* seed_offset_dev, void* stream);
 int fa_b200_embedding_fwd(const long long* idx, const float* w, float* y, size_t n_idx, int dim, void* stream);
 int fa_b200_embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, void* stream);
+int fa_b200_embedding_bwd_accum(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, void* stream);
 int fa_b200_softmax_loss_fwd(const float* logits, const long long* target, float* loss, float* lse, int rows, int n_classes,
                              void* stream);
 int fa_b200_softmax_loss_bwd(const float* logits, const long long* target, const float* lse, const float* gscale,
