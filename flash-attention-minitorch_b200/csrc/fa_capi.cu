@@ -348,7 +348,7 @@ int fa_b200_gemm_tf32_heads(const float* a, const float* b, float* c, const floa
                                 static_cast<cudaStream_t>(stream), hl);
   if (e == cudaErrorInvalidValue)
     return fail(FA_ERR_BAD_ARG, "fa_b200_gemm_tf32_heads: unsupported shape M=%d N=%d K=%d T=%d H=%d d=%d (needs multiples of 4, "
-                "T %% 128 == 0, d %% 32 == 0, head-layout operand width H*d)", M, N, K, T, H, d);
+                "T %% 128 == 0, d %% 32 == 0, head-layout operand width a multiple of H*d)", M, N, K, T, H, d);
   FA_CUDA(e, 1);
   return FA_OK;
 }
@@ -356,6 +356,12 @@ int fa_b200_gemm_tf32_heads(const float* a, const float* b, float* c, const floa
 int fa_b200_colsum_heads_f32(const float* x, float* out, int B, int H, int T, int d, int accumulate, void* stream) {
   if (!x || !out) return fail(FA_ERR_BAD_ARG, "fa_b200_colsum_heads_f32: null pointer");
   FA_CUDA(fa::colsum_heads_f32(x, out, B, H, T, d, accumulate != 0, static_cast<cudaStream_t>(stream)), 1);
+  return FA_OK;
+}
+
+int fa_b200_colsum_heads_parts_f32(const float* x, float* out, int parts, int B, int H, int T, int d, int accumulate, void* stream) {
+  if (!x || !out) return fail(FA_ERR_BAD_ARG, "fa_b200_colsum_heads_parts_f32: null pointer");
+  FA_CUDA(fa::colsum_heads_f32(x, out, B, H, T, d, accumulate != 0, static_cast<cudaStream_t>(stream), parts), 1);
   return FA_OK;
 }
 

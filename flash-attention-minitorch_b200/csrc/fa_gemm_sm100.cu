@@ -47,8 +47,10 @@ struct GemmParams {
   // the attention kernels consume and produce.  Its tensor map is {d, T, B*H}; a 32-column slab is (part of) one head and a
   // row tile stays inside one batch (T % 128 == 0), so the TMA engine does the (B,T,H,d) <-> (B,H,T,d) permutation for free:
   // the projections write Q/K/V straight into attention layout and read O / dQ / dK / dV straight out of it.
+  // A head-layout operand may be `parts` such tensors back to back ((parts, B, H, T, d): q | k | v of one fused
+  // projection): its logical width is parts * H * d and part w of it starts B*H heads further.
   int a_heads, b_heads, c_heads;
-  int T, H, d;
+  int T, H, d, E, BH;  // E = H * d, BH = B * H
 };
 
 // coordinates of the 32-wide slab starting at column `e` / row `m` of a head-layout matrix in its {d, T, B*H} tensor map
@@ -56,7 +58,8 @@ struct HeadCoord {
   int c0, c1, c2;
 };
 __device__ __forceinline__ HeadCoord head_coord(const GemmParams& p, int e, int m) {
-  return {e % p.d, m % p.T, (m / p.T) * p.H + e / p.d};
+  const int part = e / p.E, el = e - part * p.E;
+  return {el % p.d, m % p.T, part * p.BH + (m / p.T) * p.H + el / p.d};
 }
 
 struct GemmBarriers {
@@ -223,22 +226,26 @@ cudaError_t launch_gemm(const float* a, const float* b, float* c, const float* b
   CUtensorMap ma, mb;
   // K-major operand [rows][K]: box (32 k, 128 rows), 128B swizzle.  MN-major operand [K][cols]: box (32 cols, 32 k rows),
   // 128B swizzle with 32-byte atoms.  Head-layout operands: {d, T, B*H} with the same boxes.
-  const uint64_t tokens = kAMn ? (uint64_t)K : (uint64_t)M;  // token count of a head-layout A (its other dim is H*d)
-  const uint64_t BH_a = hl.a ? tokens / hl.T * hl.H : 0;
-  if (hl.a ? make_tmap_3d(&ma, a, 4, hl.d, hl.T, BH_a, 32, kAMn ? 32 : 128, kAMn ? 2 : 1)
+  // token count and number of parts ((parts, B, H, T, d)) of each head-layout operand
+  const int E = hl.H * hl.d > 0 ? hl.H * hl.d : 1;
+  const uint64_t tokens = hl.a ? (kAMn ? (uint64_t)K : (uint64_t)M) : hl.b ? (uint64_t)K : (uint64_t)M;
+  const uint64_t BH = (hl.a || hl.b || hl.c) ? tokens / hl.T * hl.H : 0;
+  const uint64_t parts_a = (kAMn ? M : K) / E, parts_b = N / E, parts_c = N / E;
+  if (hl.a ? make_tmap_3d(&ma, a, 4, hl.d, hl.T, parts_a * BH, 32, kAMn ? 32 : 128, kAMn ? 2 : 1)
            : (kAMn ? make_tmap_3d(&ma, a, 4, M, K, 1, 32, 32, 2) : make_tmap_3d(&ma, a, 4, K, M, 1, 32, 128, 1)))
     return cudaErrorInvalidValue;
-  if (hl.b ? make_tmap_3d(&mb, b, 4, hl.d, hl.T, (uint64_t)K / hl.T * hl.H, 32, 32, 2)  // only the MN-major B (dW = X^T dY_heads)
+  if (hl.b ? make_tmap_3d(&mb, b, 4, hl.d, hl.T, parts_b * BH, 32, 32, 2)  // only the MN-major B (dW = X^T dY_heads)
            : (kBMn ? make_tmap_3d(&mb, b, 4, N, K, 1, 32, 32, 2) : make_tmap_3d(&mb, b, 4, K, N, 1, 32, 128, 1)))
     return cudaErrorInvalidValue;
   CUtensorMap mc;  // C [M][N]: slabs of (32 columns, 128 rows), 128B swizzle, clipped at the edges by the TMA engine
-  if (hl.c ? make_tmap_3d(&mc, c, 4, hl.d, hl.T, (uint64_t)M / hl.T * hl.H, 32, 128, 1) : make_tmap_3d(&mc, c, 4, N, M, 1, 32, 128, 1))
+  if (hl.c ? make_tmap_3d(&mc, c, 4, hl.d, hl.T, parts_c * BH, 32, 128, 1) : make_tmap_3d(&mc, c, 4, N, M, 1, 32, 128, 1))
     return cudaErrorInvalidValue;
   cudaError_t e;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.c = c; p.bias = bias; p.accumulate = accumulate ? 1 : 0;
   const bool heads = hl.a || hl.b || hl.c;
   p.a_heads = hl.a; p.b_heads = hl.b; p.c_heads = hl.c; p.T = hl.T > 0 ? hl.T : 1; p.H = hl.H; p.d = hl.d > 0 ? hl.d : 1;
+  p.E = E; p.BH = (int)BH;
   // split-K when the output has too few tiles to fill the 148 SMs (weight gradients: 256 x 256 outputs reduced over
   // thousands of tokens): each split keeps at least 8 k-blocks, partial tiles are red.added into a zeroed C
   const int tiles = ((N + kBN - 1) / kBN) * ((M + kBM - 1) / kBM);
@@ -309,23 +316,26 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   }
 }
 
-// out[h * d + dd] += sum over (b, t) of x[b][h][t][dd]   (bias gradient of a projection whose output is in head layout)
+// out[part * H * d + h * d + dd] += sum over (b, t) of x[part][b][h][t][dd]   (bias gradient of a projection whose output is in
+// head layout; parts = 3 for a fused q | k | v projection)
 __global__ void __launch_bounds__(256) colsum_heads_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H,
                                                           int T, int d) {
-  const int h = blockIdx.x, dd = threadIdx.x % d, lanes = blockDim.x / d, r = threadIdx.x / d;
-  __shared__ float part[256];
+  const int part = blockIdx.x / H, h = blockIdx.x - part * H;
+  const int dd = threadIdx.x % d, lanes = blockDim.x / d, r = threadIdx.x / d;
+  x += (size_t)part * B * H * T * d;
+  __shared__ float part_sum[256];
   float acc = 0.f;
   if (r < lanes)
     for (int row = blockIdx.y * lanes + r; row < B * T; row += lanes * gridDim.y) {
       const int b = row / T, t = row - b * T;
       acc += x[(((size_t)b * H + h) * T + t) * d + dd];
     }
-  part[threadIdx.x] = r < lanes ? acc : 0.f;
+  part_sum[threadIdx.x] = r < lanes ? acc : 0.f;
   __syncthreads();
   if (threadIdx.x < d) {
     float s = 0.f;
-    for (int i = 0; i < lanes; ++i) s += part[i * d + threadIdx.x];
-    atomicAdd(out + h * d + threadIdx.x, s);
+    for (int i = 0; i < lanes; ++i) s += part_sum[i * d + threadIdx.x];
+    atomicAdd(out + (size_t)part * H * d + h * d + threadIdx.x, s);
   }
 }
 
@@ -339,9 +349,10 @@ cudaError_t gemm_tf32(const float* a, const float* b, float* c, const float* bia
     if (hl.T <= 0 || hl.H <= 0 || hl.d <= 0 || hl.d % 32 || hl.T % 128) return cudaErrorInvalidValue;
     if (hl.b && !b_mn_major) return cudaErrorInvalidValue;
     const int E = hl.H * hl.d;
-    if (hl.a && (a_mn_major ? (M != E || K % hl.T) : (K != E || M % hl.T))) return cudaErrorInvalidValue;
-    if (hl.b && (N != E || K % hl.T)) return cudaErrorInvalidValue;
-    if (hl.c && (N != E || M % hl.T)) return cudaErrorInvalidValue;
+    // the head-layout dimension is one or several (q | k | v) full widths E
+    if (hl.a && (a_mn_major ? (M % E || K % hl.T) : (K % E || M % hl.T))) return cudaErrorInvalidValue;
+    if (hl.b && (N % E || K % hl.T)) return cudaErrorInvalidValue;
+    if (hl.c && (N % E || M % hl.T)) return cudaErrorInvalidValue;
   }
   if (a_mn_major) return b_mn_major ? launch_gemm<true, true>(a, b, c, bias, M, N, K, accumulate, hl, st)
                                     : launch_gemm<true, false>(a, b, c, bias, M, N, K, accumulate, hl, st);
@@ -349,16 +360,16 @@ cudaError_t gemm_tf32(const float* a, const float* b, float* c, const float* bia
                     : launch_gemm<false, false>(a, b, c, bias, M, N, K, accumulate, hl, st);
 }
 
-cudaError_t colsum_heads_f32(const float* x, float* out, int B, int H, int T, int d, bool accumulate, cudaStream_t st) {
-  if (B <= 0 || H <= 0 || T <= 0 || d <= 0 || d > 256) return cudaErrorInvalidValue;
+cudaError_t colsum_heads_f32(const float* x, float* out, int B, int H, int T, int d, bool accumulate, cudaStream_t st, int parts) {
+  if (B <= 0 || H <= 0 || T <= 0 || d <= 0 || d > 256 || parts <= 0) return cudaErrorInvalidValue;
   if (!accumulate) {
-    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)H * d * 4, st);
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)parts * H * d * 4, st);
     if (e != cudaSuccess) return e;
   }
-  int strips = (148 * 4 + H - 1) / H;
+  int strips = (148 * 4 + parts * H - 1) / (parts * H);
   const int lanes = 256 / d;
   if (strips > (B * T + lanes - 1) / lanes) strips = (B * T + lanes - 1) / lanes;
-  colsum_heads_kernel<<<dim3(H, strips), 256, 0, st>>>(x, out, B, H, T, d);
+  colsum_heads_kernel<<<dim3(parts * H, strips), 256, 0, st>>>(x, out, B, H, T, d);
   return cudaGetLastError();
 }
 

@@ -72,7 +72,8 @@ struct HeadLayout {
 constexpr HeadLayout kNoHeads = {0, 0, 0, 0, 0, 0};
 cudaError_t gemm_tf32(const float* a, const float* b, float* c, const float* bias, int M, int N, int K, bool a_mn_major,
                       bool b_mn_major, bool accumulate, cudaStream_t st, HeadLayout hl = kNoHeads);
-cudaError_t colsum_heads_f32(const float* x, float* out, int B, int H, int T, int d, bool accumulate, cudaStream_t st);
+cudaError_t colsum_heads_f32(const float* x, float* out, int B, int H, int T, int d, bool accumulate, cudaStream_t st,
+                             int parts = 1);  // x = (parts, B, H, T, d), out = [parts][H * d]
 cudaError_t colsum_f32(const float* x, float* out, int M, int N, bool accumulate, cudaStream_t st);
 // fa_lm_kernels.cu: one fused pass per operator (dims multiples of 4; dw/db/embedding-dw are zeroed inside)
 cudaError_t layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, int rows,

@@ -78,6 +78,9 @@ def load_library() -> ctypes.CDLL:
         lib.fa_b200_gemm_tf32_heads.restype = ci
         lib.fa_b200_colsum_heads_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
         lib.fa_b200_colsum_heads_f32.restype = ci
+    if hasattr(lib, "fa_b200_colsum_heads_parts_f32"):
+        lib.fa_b200_colsum_heads_parts_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp]
+        lib.fa_b200_colsum_heads_parts_f32.restype = ci
     lib.fa_b200_colsum_f32.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.fa_b200_colsum_f32.restype = ci
     for name, args in (("layernorm_fwd", [vp] * 6 + [ci, ci, f32, vp]), ("layernorm_bwd", [vp] * 8 + [ci, ci, vp]), ("layernorm_bwd_accum", [vp] * 8 + [ci, ci, vp]),

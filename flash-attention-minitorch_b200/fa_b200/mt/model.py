@@ -61,23 +61,54 @@ class Module:
 
     def flatten_parameters(self):
         """Move every parameter into ONE flat buffer (values) with a twin flat buffer for gradients; each
-        Parameter.value becomes a view of the first and its .grad a view of the second (autograd accumulates into it
-        in place).  One optimizer kernel and one all-reduce then cover the whole model.  Returns (values, grads)."""
+        Parameter.value becomes a view of the first and its .grad a view of the second (the gradient kernels accumulate
+        into it in place, ops.grad_sink).  One optimizer kernel and one all-reduce then cover the whole model.
+        Modules may ask for several parameters to be laid out together (Module.fuse_parameters): the q / k / v projection
+        weights of an attention layer are interleaved row by row into one (in, 3 E) matrix -- each stays addressable as a
+        strided view -- so that the layer runs ONE projection GEMM.  Returns (values, grads)."""
         params = self.parameters()
-        sizes = [p.value.numel() for p in params]
-        total = (sum(sizes) + 3) // 4 * 4  # the elementwise kernels move float4s
         ref = params[0].value
+        groups = [g for m in self.modules() for g in m.fuse_parameters() if all(p.value.is_cuda for p in g[0])]
+        in_group = {id(p) for g in groups for p in g[0]}
+        sizes = [p.value.numel() for p in params if id(p) not in in_group]
+        total = sum(sizes) + sum(sum(p.value.numel() for p in g[0]) for g in groups)
+        total = (total + 3) // 4 * 4  # the elementwise kernels move float4s
         flat = torch.zeros(total, device=ref.device, dtype=ref.dtype)
         gflat = torch.zeros_like(flat)
         off = 0
-        for p, n in zip(params, sizes):
-            flat[off:off + n].copy_(p.value.detach().reshape(-1))
-            p.value = flat[off:off + n].view(p.value.shape).requires_grad_(True)
-            p.value.grad = gflat[off:off + n].view(p.value.shape)
+
+        def attach(p, view, gview):
+            view.copy_(p.value.detach())
+            p.value = view.requires_grad_(True)
+            p.value.grad = gview
+
+        for p in params:
+            if id(p) in in_group:
+                continue
+            n = p.value.numel()
+            attach(p, flat[off:off + n].view(p.value.shape), gflat[off:off + n].view(p.value.shape))
+            off += n
+        for members, on_fused in groups:
+            rows = members[0].value.shape[0] if members[0].value.dim() == 2 else 1
+            widths = [p.value.numel() // rows for p in members]
+            n = rows * sum(widths)
+            block, gblock = flat[off:off + n].view(rows, sum(widths)), gflat[off:off + n].view(rows, sum(widths))
+            col = 0
+            for p, w in zip(members, widths):  # column slices: strided views for matrices, contiguous ones for vectors
+                attach(p, block[:, col:col + w].view(p.value.shape) if rows == 1 else block[:, col:col + w],
+                       gblock[:, col:col + w].view(p.value.shape) if rows == 1 else gblock[:, col:col + w])
+                col += w
+            fused = (block if rows > 1 else block.view(-1)).requires_grad_(True)
+            fused.grad = gblock if rows > 1 else gblock.view(-1)
+            on_fused(fused)
             off += n
         self._flat = (flat, gflat)
         ops.grad_sink.direct = True  # weight / bias gradient kernels accumulate straight into the flat gradient views
         return self._flat
+
+    def fuse_parameters(self):
+        """[(parameters to lay out side by side, callback receiving the fused leaf tensor)] -- see flatten_parameters."""
+        return []
 
 
 def _rparam(in_size: int, shape, device, dtype, gen) -> Parameter:
@@ -124,6 +155,14 @@ class MultiHeadAttention(Module):
         self.out_projection = Linear(n_embd, n_embd, bias, device, dtype, gen)
         self.attention_fn = attention_fn
 
+    def fuse_parameters(self):
+        """q | k | v weights interleaved into one (in, 3 E) matrix, their biases side by side (flatten_parameters)."""
+        projs = (self.q_projection, self.k_projection, self.v_projection)
+        groups = [([p.weights for p in projs], lambda t: setattr(self, "_wqkv", t))]
+        if all(p.has_bias for p in projs):
+            groups.append(([p.bias for p in projs], lambda t: setattr(self, "_bqkv", t)))
+        return groups
+
     def forward(self, x):
         B, T, E = x.shape
         H, d = self.n_head, self.attn_hidden_dim
@@ -132,9 +171,20 @@ class MultiHeadAttention(Module):
         # ops.linear_to_heads / linear_from_heads write / read that layout directly when T % 128 == 0 and d % 32 == 0
         # (the GEMM's tensor maps permute); otherwise they are linear + permute + contiguous as in the reference.
         bias = lambda lin: lin.bias.value if lin.has_bias else None  # noqa: E731
-        q = ops.linear_to_heads(x2, self.q_projection.weights.value, bias(self.q_projection), B, T, H, d)
-        k = ops.linear_to_heads(x2, self.k_projection.weights.value, bias(self.k_projection), B, T, H, d)
-        v = ops.linear_to_heads(x2, self.v_projection.weights.value, bias(self.v_projection), B, T, H, d)
+        wqkv = getattr(self, "_wqkv", None)
+        if wqkv is not None and ops.fused_qkv_enabled():
+            # flattened parameters: the three projections are ONE GEMM over the interleaved weight -- straight into a
+            # (3, B, H, T, d) tensor when the head-layout GEMM applies, else (B*T, 3E) followed by one permute copy
+            bqkv = getattr(self, "_bqkv", None)
+            if ops.heads_layout_ok(x2, T, d):
+                qkv = ops.qkv_to_heads(x2, wqkv, bqkv, B, T, H, d)
+            else:
+                qkv = ops.linear(x2, wqkv, bqkv).view(B, T, 3, H, d).permute(2, 0, 3, 1, 4).contiguous()
+            q, k, v = qkv.unbind(0)
+        else:
+            q = ops.linear_to_heads(x2, self.q_projection.weights.value, bias(self.q_projection), B, T, H, d)
+            k = ops.linear_to_heads(x2, self.k_projection.weights.value, bias(self.k_projection), B, T, H, d)
+            v = ops.linear_to_heads(x2, self.v_projection.weights.value, bias(self.v_projection), B, T, H, d)
         o = self.attention_fn(q, k, v, self.causal)
         return ops.linear_from_heads(o, self.out_projection.weights.value, bias(self.out_projection)).view(B, T, E)
 

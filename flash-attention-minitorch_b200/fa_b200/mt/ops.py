@@ -166,6 +166,10 @@ def _gemm_heads(a, b, c, bias, M, N, K, a_mn, b_mn, a_h, b_h, c_h, T, H, d, accu
     return c
 
 
+def fused_qkv_enabled() -> bool:
+    return os.environ.get("FA_MT_FUSED_QKV", "1") != "0"  # A/B switch
+
+
 def heads_layout_ok(x, T: int, d: int) -> bool:
     """The TMA-permuting GEMM needs whole 32-column slabs per head and row tiles inside one batch."""
     if os.environ.get("FA_MT_HEAD_LAYOUT", "1") == "0":  # A/B switch: projections as linear + permute + contiguous
@@ -242,6 +246,51 @@ class _LinearFromHeads(torch.autograd.Function):
             if gb is not None:
                 db = None
         return do, (None if gw is not None else dw), db
+
+
+class _QKVToHeads(torch.autograd.Function):
+    """The three projections of project_to_query_key_value (modules_transfomer.py:79-89) as ONE GEMM: x (B*T, in) times the
+    interleaved weight [in][Wq | Wk | Wv] (+ [bq | bk | bv]) written directly as (3, B, H, T, d) -- q, k, v are its three
+    slices, already in attention layout.  Backward: one input-gradient GEMM over K = 3 H d reading (dq | dk | dv) out of
+    head layout, one weight-gradient GEMM (N = 3 H d) and one bias reduction: 4 launches per layer instead of 12, and no
+    summation of three input gradients."""
+
+    @staticmethod
+    def forward(ctx, x, wqkv, bqkv, B, T, H, d):
+        x = x.contiguous()
+        M, K = x.shape
+        E3 = 3 * H * d
+        y = torch.empty(3, B, H, T, d, device=x.device, dtype=torch.float32)
+        _gemm_heads(x, wqkv, y, bqkv, M, E3, K, 0, 1, 0, 0, 1, T, H, d)
+        ctx.save_for_backward(x, wqkv)
+        ctx.dims, ctx.bias = (B, T, H, d), bqkv
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wqkv = ctx.saved_tensors
+        B, T, H, d = ctx.dims
+        dy = dy.contiguous()
+        M, K = x.shape
+        E3 = 3 * H * d
+        dx = _gemm_heads(dy, wqkv, torch.empty(M, K, device=x.device, dtype=torch.float32), None, M, K, E3, 0, 0, 1, 0, 0, T, H, d)
+        gw = _sink(wqkv)
+        dw = _gemm_heads(x, dy, gw if gw is not None else torch.empty(K, E3, device=x.device, dtype=torch.float32), None, K, E3, M,
+                         1, 1, 0, 1, 0, T, H, d, accumulate=1 if gw is not None else 0)
+        db = None
+        if ctx.bias is not None:
+            gb = _sink(ctx.bias)
+            db = gb if gb is not None else torch.empty(E3, device=x.device, dtype=torch.float32)
+            _lib.check(_lib.load_library().fa_b200_colsum_heads_parts_f32(dy.data_ptr(), db.data_ptr(), 3, B, H, T, d,
+                                                                          1 if gb is not None else 0, _st()))
+            if gb is not None:
+                db = None
+        return dx, (None if gw is not None else dw), db, None, None, None, None
+
+
+def qkv_to_heads(x, wqkv, bqkv, B: int, T: int, H: int, d: int):
+    """x (B*T, in), interleaved weight (in, 3 H d) -> (3, B, H, T, d); callers check heads_layout_ok first."""
+    return _QKVToHeads.apply(x, wqkv, bqkv, B, T, H, d)
 
 
 def linear_to_heads(x, weight, bias, B: int, T: int, H: int, d: int):

@@ -148,6 +148,10 @@ int fa_b200_gemm_tf32_heads(const float* a, const float* b, float* c, const floa
                             int b_mn_major, int accumulate, int a_heads, int b_heads, int c_heads, int T, int H, int d,
                             void* stream);
 int fa_b200_colsum_heads_f32(const float* x, float* out, int B, int H, int T, int d, int accumulate, void* stream);
+/* A head-layout operand of fa_b200_gemm_tf32_heads may also be `parts` such tensors back to back, (parts, B, H, T, d) --
+ * q | k | v of one fused projection: its logical width is then parts * H * d (N = 3 H d for the fused forward / weight
+ * gradient, K = 3 H d for the fused input gradient).  fa_b200_colsum_heads_parts_f32: out[part][h*d + dd] (+)= sum_{b,t}. */
+int fa_b200_colsum_heads_parts_f32(const float* x, float* out, int parts, int B, int H, int T, int d, int accumulate, void* stream);
 /* One fused, device-resident pass per operator of the model path (reference formulas in parentheses); fp32, row-major,
  * inner dimensions and element counts multiples of 4.
  *   layernorm : y = w (x - mean) / sqrt(var + eps) + b, biased variance (minitorch/modules_basic.py:166-175);

@@ -183,3 +183,37 @@ def test_head_layout_projections_equal_linear_plus_permute(cuda_device, B, T, H,
     # and against fp64 on the CPU within the tf32 bar
     ref = (x.double().cpu() @ w.double().cpu() + b.double().cpu()).view(B, T, H, d).permute(0, 2, 1, 3)
     assert float((fused[0].double().cpu() - ref).abs().max()) <= 3e-3 * K ** 0.5
+
+
+@pytest.mark.parametrize("B,T,H,d,K", [(2, 128, 2, 32, 64), (3, 256, 8, 32, 256), (1, 128, 2, 64, 128)])
+def test_fused_qkv_projection_equals_three_projections(cuda_device, B, T, H, d, K):
+    """ops.qkv_to_heads (one GEMM over the interleaved weight [in][Wq | Wk | Wv], output (3, B, H, T, d)) against three
+    ops.linear_to_heads on the same kernels: q, k, v and the input gradient agree to fp32 rounding (same products, the
+    input gradient is summed inside one K = 3 E reduction instead of by two adds), weight / bias gradients to 1e-5 relative."""
+    torch.manual_seed(7 * B + T + d)
+    E = H * d
+    x = torch.randn(B * T, K, device=cuda_device)
+    ws = [torch.randn(K, E, device=cuda_device) / K ** 0.5 for _ in range(3)]
+    bs = [torch.randn(E, device=cuda_device) for _ in range(3)]
+    gy = torch.randn(3, B, H, T, d, device=cuda_device)
+
+    xx = x.clone().requires_grad_(True)
+    wqkv = torch.cat(ws, dim=1).contiguous().requires_grad_(True)
+    bqkv = torch.cat(bs).contiguous().requires_grad_(True)
+    before = _lib.launch_count()
+    y = ops.qkv_to_heads(xx, wqkv, bqkv, B, T, H, d)
+    (y * gy).sum().backward()
+    assert _lib.launch_count() - before == 4  # forward GEMM, dX GEMM, dW GEMM, bias reduction
+
+    x3 = x.clone().requires_grad_(True)
+    w3 = [w.clone().requires_grad_(True) for w in ws]
+    b3 = [b.clone().requires_grad_(True) for b in bs]
+    ys = [ops.linear_to_heads(x3, w3[i], b3[i], B, T, H, d) for i in range(3)]
+    sum((ys[i] * gy[i]).sum() for i in range(3)).backward()
+
+    tol = lambda c: 1e-5 * max(1.0, float(c.abs().max()))  # noqa: E731
+    for i in range(3):
+        assert float((y[i] - ys[i]).abs().max()) <= tol(ys[i])
+        assert float((wqkv.grad[:, i * E:(i + 1) * E] - w3[i].grad).abs().max()) <= tol(w3[i].grad)
+        assert float((bqkv.grad[i * E:(i + 1) * E] - b3[i].grad).abs().max()) <= tol(b3[i].grad)
+    assert float((xx.grad - x3.grad).abs().max()) <= 1e-4 * max(1.0, float(x3.grad.abs().max()))
