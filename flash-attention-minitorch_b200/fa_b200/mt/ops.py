@@ -49,7 +49,8 @@ class _FlashAttn2(torch.autograd.Function):
 
 def flash_attention(q, k, v, causal: bool = True, p_drop: float = 0.0, seed: int = 0):
     """softmax(q k^T / sqrt(d) [+ causal mask]) v on the B200 kernels; q, k, v: (B, H, T, d) CUDA tensors.
-    fp32 tensors take the fp32 path (tf32 tensor-core forward where covered, exact-fp32 backward; 1e-3 bar)."""
+    fp32 tensors take the fp32 path (tf32 tensor-core forward and -- at d = 32 -- backward where covered, else the exact
+    fp32 CUDA-core kernels; 1e-3 bar)."""
     if not q.is_cuda:
         raise RuntimeError("flash_attention needs CUDA tensors: the product has no CPU attention path")
     return _FlashAttn2.apply(q, k, v, causal, p_drop, seed)

@@ -173,7 +173,7 @@ def main(argv=None) -> int:
     ap.add_argument("--p-dropout", type=float, default=0.1)
     ap.add_argument("--seed", type=int, default=11111)
     ap.add_argument("--attention-precision", choices=["fp32", "bf16"], default="fp32",
-                    help="fp32: tf32 tensor-core forward + exact-fp32 backward (1e-3 bar, default); bf16: forward and "
+                    help="fp32: tf32 tensor-core forward and backward on the fp32 tensors (1e-3 bar, default); bf16: forward and "
                          "backward on the bf16 tensor-core kernels (2e-2 bar)")
     ap.add_argument("--cuda-graph", type=lambda s: s.lower() in ("1", "true", "yes"), default=True,
                     help="capture forward+backward into a CUDA graph (default); False gives the reference's fw/bw split timers")
