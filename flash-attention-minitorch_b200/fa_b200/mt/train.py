@@ -47,8 +47,11 @@ class GradAllReducer:
         if self.world == 1:
             return
         if self.flat_grads is not None:
-            dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM)
-            self.flat_grads.div_(self.world)
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(self.flat_grads, op=dist.ReduceOp.AVG)  # averaged inside the collective: no extra pass
+            else:
+                dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM)
+                self.flat_grads.div_(self.world)
             return
         p0 = self.params[0].value
         if self.flat is None:
