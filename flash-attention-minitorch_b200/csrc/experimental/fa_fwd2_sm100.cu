@@ -1,0 +1,392 @@
+// EXPERIMENT (round 1, not built): measured SLOWER than fa_fwd_sm100.cu on B200 at config 3 shapes in every variant --
+//   (a) two full P tiles, K 1 stage, V 2 stages:            2.31-2.41 ms causal (shipped kernel 2.06): with only two V stages a
+//       V tile is requested when PV(j-2) retires and arrives too late; PVs lag, the softmax stalls on its P tile;
+//   (b) ONE P tile shared by the two Q tiles in turns, V 3 stages: 2.28-2.30 ms: store -> PV -> other tile's store is a new chain;
+//   (c) one 64-key HALF tile per Q tile, V 3 stages (this file): 2.29 ms; with MUFU ping-pong gates 2.77 ms: store A -> PV_A ->
+//       store B -> PV_B is again a chain (a half's exponentials take 512 cycles, a PV round trip ~1000).
+// What the idea needs is TWO full P tiles AND three V stages (256 KB with 128-key tiles): it does not fit in 227 KB.
+// All variants were parity-green (tools/fa_check fwd).  To build it again: add it to compile_cuda.sh, declare tc_fwd2 in
+// fa_internal.h and dispatch from tc_fwd (git history of this file's commit shows the three hunks).
+//
+// fa_fwd2_sm100.cu -- flash-attention forward, bf16, head dim 128: the "P through shared memory" pipeline.
+//
+// Same tiling as fa_fwd_sm100.cu (CTA = two 128-row Q tiles sharing each streamed K/V tile, one softmax thread per score
+// row, S and O in TMEM, lazy rescale), but P no longer overwrites S in TMEM: the softmax warps write P (bf16) into a
+// K-major shared-memory tile and PV runs smem x smem.  That breaks the dependency chain that bounds the first kernel
+// (profiles/fwd_timeline_r01f.txt):   S(j) -> softmax -> P(j) -> PV(j) -> QK(j+1) -> S(j+1)   -- QK(j+1) had to wait for
+// PV(j) because P(j) lived in the columns of S.  Here the S columns are free as soon as the softmax warps have LOADED
+// S(j) into registers (~60 cycles after it is ready), so QK(j+1) is issued then and S(j+1) is waiting when the softmax
+// of step j ends; the loop of a Q tile shrinks from  softmax + hand-off + PV + QK + latency  to  softmax + (PV off the
+// chain).  The MMA warp is an event loop over four kinds of ready work (QK / PV of either tile) instead of a fixed order.
+// Shared memory: Q0 Q1 | K (one stage: both QK(j) are issued early in a step) | V (three stages) | P (one 64-key half tile
+// per Q tile, 2 x 16 KB) = 7 x 32 KB.
+#include <cuda.h>
+#include <math.h>
+
+#include "fa_internal.h"
+#include "fa_ptx.cuh"
+#include "fa_tma_host.h"
+
+namespace fa {
+
+namespace {
+
+constexpr int kM = 128, kN = 128, kD2 = 128;
+constexpr int kThreads2 = 384;  // warps 0-7 softmax, 8 TMA, 9 MMA, 10-11 idle
+constexpr int kBox = 128 * 128;  // 128 rows x 128 B
+constexpr int kTile = 2 * kBox;  // 128 x 128 bf16
+constexpr int kVStages = 3;
+constexpr int kOffQ = 0, kOffK = 2 * kTile, kOffV = 3 * kTile, kOffP = (3 + kVStages) * kTile, kSmem2 = (4 + kVStages) * kTile + 1024;
+// P: one 64-key half tile (kBox bytes) per Q tile at kOffP + t * kBox, used alternately for keys [0,64) and [64,128)
+
+struct Fwd2Params {
+  int T, causal;
+  float tau, scale_log2;
+  void* o;
+  float* lse;
+  float* m_out;
+  float* l_out;
+  long long* trace;  // developer timeline (tools/fa_check tracefwd), CTA (0, 0)
+};
+
+struct Fwd2Barriers {
+  uint64_t q_full, k_full, k_empty, v_full[kVStages], v_empty[kVStages];
+  uint64_t s_full[2], s_free[2], p_full[2], o_full[2];  // p_full / o_full: one phase per HALF step (2 j + h)
+};
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// warp-uniform non-blocking test (the MMA warp stays converged)
+__device__ __forceinline__ bool mbar_test_w(uint64_t* bar, uint32_t parity) { return __all_sync(0xffffffffu, mbar_test(bar, parity)); }
+
+template <typename OutT>
+__device__ __forceinline__ void store32(OutT* dst, const float* x);
+template <>
+__device__ __forceinline__ void store32<float>(float* dst, const float* x) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+}
+template <>
+__device__ __forceinline__ void store32<__nv_bfloat16>(__nv_bfloat16* dst, const float* x) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8)
+    *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_bf16x2(x[i], x[i + 1]), pack_bf16x2(x[i + 2], x[i + 3]),
+                                                   pack_bf16x2(x[i + 4], x[i + 5]), pack_bf16x2(x[i + 6], x[i + 7]));
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads2, 1)
+fa_fwd2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+               const __grid_constant__ CUtensorMap map_v, const Fwd2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ Fwd2Barriers bars;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = p.T, bh = blockIdx.y;
+  const int blk = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;  // heavy causal blocks first
+  const int nkv = (T + kN - 1) / kN;
+  const int n0 = p.causal ? min(2 * blk + 1, nkv) : nkv;  // K/V tiles of Q tile 0 / 1 of this CTA (n1 >= n0)
+  const int n1 = p.causal ? min(2 * blk + 2, nkv) : nkv;
+  long long* const tr = (blockIdx.x == 0 && blockIdx.y == 0) ? p.trace : nullptr;
+#define FA_TR2F(j_, e_) do { if (tr && (j_) < 16 && lane == 0) tr[(j_) * 16 + (e_)] = clock64(); } while (0)
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars.q_full, 1);
+    mbar_init(&bars.k_full, 1);
+    mbar_init(&bars.k_empty, 1);
+    for (int s = 0; s < kVStages; ++s) {
+      mbar_init(&bars.v_full[s], 1);
+      mbar_init(&bars.v_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.s_full[s], 1);
+      mbar_init(&bars.s_free[s], 4);  // one arrival per softmax warp of the tile
+      mbar_init(&bars.p_full[s], 4);
+      mbar_init(&bars.o_full[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(&tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;  // S0 | S1 | O0 | O1
+
+  if (warp >= 8) {
+    reg_dealloc<80>();
+    if (warp == 8) {
+      // ------------------------------------------------------------------ TMA producer
+      if (lane == 0) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_k);
+        tma_prefetch_desc(&map_v);
+        mbar_arrive_expect_tx(&bars.q_full, 2 * kTile);
+        for (int t = 0; t < 2; ++t)
+          for (int b = 0; b < 2; ++b)
+            tma_load_3d(smem + kOffQ + t * kTile + b * kBox, &map_q, &bars.q_full, b * 64, (2 * blk + t) * kM, bh, kEvictFirst);
+        for (int j = 0; j < n1; ++j) {  // lane 0: Q and the K ring (one stage)
+          mbar_wait(&bars.k_empty, (j & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars.k_full, kTile);
+          for (int b = 0; b < 2; ++b) tma_load_3d(smem + kOffK + b * kBox, &map_k, &bars.k_full, b * 64, j * kN, bh, kEvictLast);
+        }
+      } else if (lane == 1) {
+        // lane 1: the V ring (two stages) -- its own thread, so that a V stage still held by a late PV never delays a K load
+        for (int j = 0; j < n1; ++j) {
+          const int st = j % kVStages;
+          mbar_wait(&bars.v_empty[st], ((j / kVStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars.v_full[st], kTile);
+          for (int b = 0; b < 2; ++b)
+            tma_load_3d(smem + kOffV + st * kTile + b * kBox, &map_v, &bars.v_full[st], b * 64, j * kN, bh, kEvictLast);
+        }
+      }
+    } else if (warp == 9) {
+      // ------------------------------------------------------------------ MMA issuer: an event loop (whole warp, `_w` forms)
+      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kM, kN, 0, 0);   // K-major x K-major
+      constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kM, kD2, 0, 1);  // K-major (P) x MN-major (V)
+      const uint32_t base = smem_u32(smem);
+      const uint64_t dQ0 = make_smem_desc(base + kOffQ, 16, 1024), dK0 = make_smem_desc(base + kOffK, 16, 1024),
+                     dP0 = make_smem_desc(base + kOffP, 16, 1024), dV0 = make_smem_desc(base + kOffV, kBox, 1024);
+      int qk_next[2] = {0, 0};
+      int pv_next[2] = {0, 0};  // in HALF steps: hs = 2 j + h, h = which 64 keys of K/V tile j
+      int k_rel = 0, v_rel = 0;  // K / V tiles already handed back to the producer
+      const int nn[2] = {n0, n1};
+      mbar_wait_w(&bars.q_full, 0);
+      while (pv_next[0] < 2 * n0 || pv_next[1] < 2 * n1) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          // ---- O_t += P_t(j, h) V_j[64 h .. 64 h + 64) : P half tile from shared memory (first: it is what the softmax waits for)
+          const int hs = pv_next[t];
+          const int pj = hs >> 1, h = hs & 1;
+          if (hs < 2 * nn[t] && mbar_test_w(&bars.p_full[t], hs & 1) && mbar_test_w(&bars.v_full[pj % kVStages], (pj / kVStages) & 1)) {
+            tc_fence_after();
+            const uint64_t p0 = desc_advance(dP0, t * kBox), v0 = desc_advance(dV0, (pj % kVStages) * kTile + h * 4 * 2048);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ss_w(tmem + 256 + t * 128, desc_advance(p0, kk * 32), desc_advance(v0, kk * 2048), idesc_pv, (hs > 0 || kk > 0) ? 1u : 0u);
+            umma_commit_w(&bars.o_full[t]);
+            FA_TR2F(pj, 9 + 2 * t);
+            pv_next[t] = hs + 1;
+            // V_j goes back to the producer once every tile that uses it has issued both halves
+            const int done = min(n0 > v_rel ? (pv_next[0] >> 1) : 0x7fffffff, pv_next[1] >> 1);
+            while (v_rel < done) {
+              umma_commit_w(&bars.v_empty[v_rel % kVStages]);
+              ++v_rel;
+            }
+          }
+          // ---- S_t(j) = Q_t K_j^T : as soon as the softmax warps have loaded S_t(j-1) and K_j has landed
+          const int j = qk_next[t];
+          if (j < nn[t] && (j == 0 || mbar_test_w(&bars.s_free[t], (j - 1) & 1)) && mbar_test_w(&bars.k_full, j & 1)) {
+            tc_fence_after();
+            const uint64_t q0 = desc_advance(dQ0, t * kTile);
+#pragma unroll
+            for (int kk = 0; kk < kD2 / 16; ++kk) {
+              const uint32_t off = (kk >> 2) * kBox + (kk & 3) * 32;
+              umma_ss_w(tmem + t * 128, desc_advance(q0, off), desc_advance(dK0, off), idesc_qk, kk > 0);
+            }
+            umma_commit_w(&bars.s_full[t]);
+            FA_TR2F(j, 8 + 2 * t);
+            qk_next[t] = j + 1;
+            // K_j goes back to the producer once every tile that uses it has issued its QK (tile 0 only has n0 steps)
+            const int done = min(n0 > k_rel ? qk_next[0] : 0x7fffffff, qk_next[1]);
+            if (k_rel < done) {  // (at most one tile per call: the ring has one stage)
+              umma_commit_w(&bars.k_empty);
+              ++k_rel;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax groups
+    reg_alloc<208>();
+    const int t = warp >> 2;
+    const int r = threadIdx.x & 127;
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + t * 128 + lane_base;
+    const uint32_t tO = tmem + 256 + t * 128 + lane_base;
+    uint8_t* sP = smem + kOffP + t * kBox + r * 128;  // this row of the tile's P half tile (64 keys = 128 B)
+    const int qt = 2 * blk + t;
+    const int nt = t == 0 ? n0 : n1;
+    const int row_g = qt * kM + r;
+    const float c2 = p.scale_log2;
+    float m_ref = -INFINITY, m_true = -INFINITY, l = 0.f;
+
+    // The exponentials of the two Q tiles take turns on the MUFU pipe (named barriers 2 / 3 = "tile 0 / tile 1 may go"): with
+    // the S -> P -> PV -> QK chain gone, one tile's S load + row max + P stores now overlap the other's exponentials.
+    // Tile 1 has n1 >= n0 steps; its steps beyond n0 run ungated.
+    if (t == 1) named_bar_arrive(2, 256);  // tile 0 goes first
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&bars.s_full[t], j & 1);
+      tc_fence_after();
+      if ((warp & 3) == 0) FA_TR2F(j, 4 * t + 0);
+      float s[128];
+      {
+        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+        tmem_ld_x32(tS + 0, sr + 0);
+        tmem_ld_x32(tS + 32, sr + 32);
+        tmem_ld_x32(tS + 64, sr + 64);
+        tmem_ld_x32(tS + 96, sr + 96);
+        tmem_wait_ld();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.s_free[t]);  // the S columns may be overwritten by QK_t(j+1)
+      if ((warp & 3) == 0) FA_TR2F(j, 4 * t + 1);
+      const bool diag = p.causal && (j == qt);
+      const bool tail = (j == nkv - 1) && (T - j * kN < kN);
+      if (diag || tail) {
+        int limit = 127;
+        if (diag) limit = r;
+        if (tail) limit = min(limit, T - 1 - j * kN);
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (c > limit) s[c] = -INFINITY;
+      }
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int c = 4; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, s[c]);
+        mx1 = fmaxf(mx1, s[c + 1]);
+        mx2 = fmaxf(mx2, s[c + 2]);
+        mx3 = fmaxf(mx3, s[c + 3]);
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      m_true = fmaxf(m_true, mx);
+      if (j == 0) {
+        m_ref = mx;
+      } else {
+        const bool need = (mx - m_ref) * c2 > 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          // O_t must be quiescent: PV(t, j-1) retired, PV(t, j) not yet issued (it waits for our P)
+          mbar_wait(&bars.o_full[t], 1);  // phase 2 (j-1) + 1: both halves of PV(t, j-1)
+          tc_fence_after();
+          const float m_new = fmaxf(m_ref, mx);
+          const float f = ex2_approx((m_ref - m_new) * c2);
+          l *= f;
+          m_ref = m_new;
+#pragma unroll
+          for (int c0 = 0; c0 < kD2; c0 += 32) {
+            uint32_t orr[32];
+            tmem_ld_x32(tO + c0, orr);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
+            tmem_st_x32(tO + c0, orr);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+        }
+      }
+      if ((warp & 3) == 0) FA_TR2F(j, 4 * t + 2);
+      const float nm = -m_ref * c2;
+      const float2 c2v = make_float2(c2, c2), nmv = make_float2(nm, nm);
+      float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+      if (j < n0) named_bar_sync(2 + t, 256);  // my turn on the MUFU pipe
+      // P goes to the MMA warp in two halves of 64 keys through ONE 16 KB half tile: the PV of the first half runs under
+      // the exponentials of the second, and only 4 MMAs remain after the softmax of a step.
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+          const int cc = h * 64 + c;
+          const float2 x0 = ffma2(make_float2(s[cc], s[cc + 1]), c2v, nmv);
+          const float2 x1 = ffma2(make_float2(s[cc + 2], s[cc + 3]), c2v, nmv);
+          const float2 p0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+          const float2 p1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+          la = fadd2(la, p0);
+          lb = fadd2(lb, p1);
+          pk[c >> 1] = pack_bf16x2(p0.x, p0.y);
+          pk[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+        }
+        // the half tile is free once the PV of the previous half step has read it: phase 2 j + h - 1 of o_full
+        if (j > 0 || h > 0) mbar_wait(&bars.o_full[t], (h ^ 1) & 1);
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16)  // 16-byte chunk c16 = keys [8 c16, +8) of this half, swizzled inside the 128-byte row
+          *reinterpret_cast<uint4*>(sP + ((c16 ^ (r & 7)) << 4)) = make_uint4(pk[c16 * 4], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.p_full[t]);
+      }
+      if (t == 0) named_bar_arrive(3, 256);            // tile 1's turn for step j
+      else if (j + 1 < n0) named_bar_arrive(2, 256);   // tile 0's turn for step j + 1
+      l += (la.x + la.y) + (lb.x + lb.y);
+      if ((warp & 3) == 0) FA_TR2F(j, 4 * t + 3);
+    }
+
+    // epilogue: O_t / l -> global, statistics
+    mbar_wait(&bars.o_full[t], 1);  // phase 2 (nt-1) + 1
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const bool row_ok = row_g < T;
+    OutT* orow = reinterpret_cast<OutT*>(p.o) + ((size_t)bh * T + (row_ok ? row_g : 0)) * kD2;
+#pragma unroll
+    for (int c0 = 0; c0 < kD2; c0 += 32) {
+      uint32_t orr[32];
+      tmem_ld_x32(tO + c0, orr);
+      tmem_wait_ld();
+      float x[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(orr[i]) * inv_l;
+      if (row_ok) store32<OutT>(orow + c0, x);
+    }
+    if (row_ok) {
+      const size_t idx = (size_t)bh * T + row_g;
+      if (p.lse) p.lse[idx] = m_ref * p.tau + logf(l);
+      if (p.m_out) p.m_out[idx] = m_true * p.tau;
+      if (p.l_out) p.l_out[idx] = l * expf((m_ref - m_true) * p.tau);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+template <typename OutT>
+cudaError_t launch_fwd2(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, float* lse, float* m_out,
+                        float* l_out, int BH, int T, bool causal, cudaStream_t st) {
+  CUtensorMap mq, mk, mv;
+  if (make_tmap_3d(&mq, q, 2, kD2, T, BH, 64, kM) || make_tmap_3d(&mk, k, 2, kD2, T, BH, 64, kN) ||
+      make_tmap_3d(&mv, v, 2, kD2, T, BH, 64, kN))
+    return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(fa_fwd2_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+  if (e != cudaSuccess) return e;
+  Fwd2Params p;
+  p.T = T;
+  p.causal = causal ? 1 : 0;
+  p.tau = sqrtf(1.0f / (float)kD2);
+  p.scale_log2 = p.tau * 1.4426950408889634f;
+  p.o = o;
+  p.lse = lse;
+  p.m_out = m_out;
+  p.l_out = l_out;
+  p.trace = nullptr;  // (tc_fwd_get_trace() when wired into the library)
+  dim3 grid((T + 2 * kM - 1) / (2 * kM), BH);
+  fa_fwd2_kernel<OutT><<<grid, kThreads2, kSmem2, st>>>(mq, mk, mv, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// bf16, d = 128, no dropout
+cudaError_t tc_fwd2(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, bool o_is_f32, float* lse,
+                    float* m_out, float* l_out, int BH, int T, bool causal, cudaStream_t st) {
+  if (BH > 65535) return cudaErrorInvalidValue;
+  return o_is_f32 ? launch_fwd2<float>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st)
+                  : launch_fwd2<__nv_bfloat16>(q, k, v, o, lse, m_out, l_out, BH, T, causal, st);
+}
+
+}  // namespace fa

@@ -20,6 +20,7 @@
 // and the saved logsumexp use the same m_ref), so the usual per-step O correction disappears
 // after the first tiles.
 #include <cuda.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include "fa_internal.h"
