@@ -4,6 +4,8 @@
 //   (b) ONE P tile shared by the two Q tiles in turns, V 3 stages: 2.28-2.30 ms: store -> PV -> other tile's store is a new chain;
 //   (c) one 64-key HALF tile per Q tile, V 3 stages (this file): 2.29 ms; with MUFU ping-pong gates 2.77 ms: store A -> PV_A ->
 //       store B -> PV_B is again a chain (a half's exponentials take 512 cycles, a PV round trip ~1000).
+//   (d) two half buffers per Q tile (= a full P tile each), K 1 stage, V 2 stages, separate completion barriers per half:
+//       hung at T = 256 (watchdog trap) and was not debugged further -- K with one stage leaves ~700 cycles for its TMA load.
 // What the idea needs is TWO full P tiles AND three V stages (256 KB with 128-key tiles): it does not fit in 227 KB.
 // All variants were parity-green (tools/fa_check fwd).  To build it again: add it to compile_cuda.sh, declare tc_fwd2 in
 // fa_internal.h and dispatch from tc_fwd (git history of this file's commit shows the three hunks).
