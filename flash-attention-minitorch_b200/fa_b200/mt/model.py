@@ -59,16 +59,18 @@ class Module:
     def __call__(self, *a, **kw):
         return self.forward(*a, **kw)
 
-    def flatten_parameters(self):
+    def flatten_parameters(self, fuse: Optional[bool] = None):
         """Move every parameter into ONE flat buffer (values) with a twin flat buffer for gradients; each
         Parameter.value becomes a view of the first and its .grad a view of the second (the gradient kernels accumulate
         into it in place, ops.grad_sink).  One optimizer kernel and one all-reduce then cover the whole model.
         Modules may ask for several parameters to be laid out together (Module.fuse_parameters): the q / k / v projection
         weights of an attention layer are interleaved row by row into one (in, 3 E) matrix -- each stays addressable as a
-        strided view -- so that the layer runs ONE projection GEMM.  Returns (values, grads)."""
+        strided view -- so that the layer runs ONE projection GEMM.  `fuse`: None = fuse on CUDA tensors only (default),
+        True / False = always / never (the CPU tests exercise the fused layout with True).  Returns (values, grads)."""
         params = self.parameters()
         ref = params[0].value
-        groups = [g for m in self.modules() for g in m.fuse_parameters() if all(p.value.is_cuda for p in g[0])]
+        groups = [] if fuse is False else [g for m in self.modules() for g in m.fuse_parameters()
+                                           if fuse or all(p.value.is_cuda for p in g[0])]
         in_group = {id(p) for g in groups for p in g[0]}
         sizes = [p.value.numel() for p in params if id(p) not in in_group]
         total = sum(sizes) + sum(sum(p.value.numel() for p in g[0]) for g in groups)

@@ -192,3 +192,30 @@ def test_flat_parameter_adam_equals_per_parameter_adam():
     fb = torch.cat([p.value.detach().reshape(-1) for p in b.parameters()])
     assert torch.equal(fa, fb)
     assert b.parameters()[0].value.grad.data_ptr() == ob.flat[1].data_ptr()  # gradients live in the flat bucket
+
+
+def test_fused_qkv_layout_of_flatten_parameters_equals_the_plain_model():
+    """flatten_parameters(fuse=True) interleaves the q | k | v projection weights of every attention layer into one
+    (in, 3E) matrix and puts their biases side by side (each parameter stays a view of it); the layer then runs ONE
+    projection.  Same values, same loss and same gradients as the unflattened model, and an Adam step through the flat
+    buffers moves the strided views."""
+    a, b = small_model(), small_model()
+    flat, gflat = b.flatten_parameters(fuse=True)
+    att = b.t_layer_1.attention
+    E = att.n_embd
+    assert att._wqkv.shape == (E, 3 * E) and att._bqkv.shape == (3 * E,)
+    assert not att.k_projection.weights.value.is_contiguous()  # a column slice of the fused matrix
+    assert torch.equal(att._wqkv[:, E:2 * E], att.k_projection.weights.value)
+    for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert na == nb and torch.equal(pa.value.detach(), pb.value.detach()), na
+    batch = synthetic_batch(2, 8, 40, "cpu", torch.Generator().manual_seed(4))
+    la, lb = loss_fn(batch, a), loss_fn(batch, b)
+    la.backward()
+    lb.backward()
+    assert abs(float(la) - float(lb)) <= 1e-12 * abs(float(la))
+    for (name, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.allclose(pa.value.grad, pb.value.grad, rtol=1e-9, atol=1e-12), name
+    assert torch.allclose(att._wqkv.grad[:, :E], att.q_projection.weights.value.grad)  # the fused gradient IS the per-projection one
+    before = att.v_projection.weights.value.detach().clone()
+    Adam(b.parameters(), lr=0.02, flat=(flat, gflat)).step()
+    assert not torch.equal(before, att.v_projection.weights.value.detach())  # the flat step moved the strided view
