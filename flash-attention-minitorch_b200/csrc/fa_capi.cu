@@ -381,15 +381,30 @@ int fa_b200_layernorm_fwd(const float* x, const float* w, const float* b, float*
 int fa_b200_layernorm_bwd(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
                           float* dw, float* db, int rows, int dim, void* stream) {
   if (!x || !w || !dy || !mean || !rstd || !dx || !dw || !db) return fail(FA_ERR_BAD_ARG, "fa_b200_layernorm_bwd: null pointer");
-  FA_CUDA(fa::layernorm_bwd(x, w, dy, mean, rstd, dx, dw, db, rows, dim, FA_ST), 2);
+  FA_CUDA(fa::layernorm_bwd(x, w, dy, mean, rstd, dx, dw, db, rows, dim, FA_ST), fa::layernorm_fused_width(dim) ? 1 : 2);
   return FA_OK;
 }
 int fa_b200_layernorm_bwd_accum(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
                                 float* dw, float* db, int rows, int dim, void* stream) {
   if (!x || !w || !dy || !mean || !rstd || !dx || !dw || !db) return fail(FA_ERR_BAD_ARG, "fa_b200_layernorm_bwd_accum: null pointer");
-  FA_CUDA(fa::layernorm_bwd(x, w, dy, mean, rstd, dx, dw, db, rows, dim, FA_ST, true), 2);
+  FA_CUDA(fa::layernorm_bwd(x, w, dy, mean, rstd, dx, dw, db, rows, dim, FA_ST, true), fa::layernorm_fused_width(dim) ? 1 : 2);
   return FA_OK;
 }
+int fa_b200_add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, float* sum, float* y,
+                              float* mean, float* rstd, int rows, int dim, float eps, void* stream) {
+  if (!a || !w || !bias || !y || !mean || !rstd || (b && !sum)) return fail(FA_ERR_BAD_ARG, "fa_b200_add_layernorm_fwd: null pointer");
+  if (b && !fa::layernorm_fused_width(dim)) return fail(FA_ERR_UNSUPPORTED, "fa_b200_add_layernorm_fwd: the fused add needs dim in {128, 256, 512}");
+  FA_CUDA(fa::add_layernorm_fwd(a, b, w, bias, sum, y, mean, rstd, rows, dim, eps, FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_layernorm_bwd_res(const float* x, const float* w, const float* dy, const float* mean, const float* rstd,
+                              const float* res, float* dx, float* dw, float* db, int rows, int dim, int accumulate, void* stream) {
+  if (!x || !w || !dy || !mean || !rstd || !dx || !dw || !db) return fail(FA_ERR_BAD_ARG, "fa_b200_layernorm_bwd_res: null pointer");
+  if (res && !fa::layernorm_fused_width(dim)) return fail(FA_ERR_UNSUPPORTED, "fa_b200_layernorm_bwd_res: the fused residual needs dim in {128, 256, 512}");
+  FA_CUDA(fa::layernorm_bwd(x, w, dy, mean, rstd, dx, dw, db, rows, dim, FA_ST, accumulate != 0, res), fa::layernorm_fused_width(dim) ? 1 : 2);
+  return FA_OK;
+}
+int fa_b200_layernorm_fused_width(int dim) { return fa::layernorm_fused_width(dim) ? 1 : 0; }
 int fa_b200_gelu_fwd(const float* x, float* y, size_t n, void* stream) {
   if (!x || !y) return fail(FA_ERR_BAD_ARG, "fa_b200_gelu_fwd: null pointer");
   FA_CUDA(fa::gelu(x, nullptr, y, n, false, FA_ST), 1);

@@ -320,22 +320,40 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 // head layout; parts = 3 for a fused q | k | v projection)
 __global__ void __launch_bounds__(256) colsum_heads_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H,
                                                           int T, int d) {
+  // thread = (row lane r, column quad q): float4 loads, four independent rows in flight per thread
   const int part = blockIdx.x / H, h = blockIdx.x - part * H;
-  const int dd = threadIdx.x % d, lanes = blockDim.x / d, r = threadIdx.x / d;
-  x += (size_t)part * B * H * T * d;
-  __shared__ float part_sum[256];
-  float acc = 0.f;
-  if (r < lanes)
-    for (int row = blockIdx.y * lanes + r; row < B * T; row += lanes * gridDim.y) {
-      const int b = row / T, t = row - b * T;
-      acc += x[(((size_t)b * H + h) * T + t) * d + dd];
+  const int dq = d >> 2, lanes = blockDim.x / dq;
+  const int q = threadIdx.x % dq, r = threadIdx.x / dq;
+  x += (size_t)part * B * H * T * d + (size_t)h * T * d + q * 4;
+  __shared__ float4 part_sum[256];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int BT = B * T, step = lanes * gridDim.y;
+  auto at = [&](int row) {
+    const int b = row / T, t = row - b * T;
+    return *reinterpret_cast<const float4*>(x + ((size_t)b * H * T + t) * d);
+  };
+  if (r < lanes) {
+    int row = blockIdx.y * lanes + r;
+    for (; row + 3 * step < BT; row += 4 * step) {
+      const float4 v0 = at(row), v1 = at(row + step), v2 = at(row + 2 * step), v3 = at(row + 3 * step);
+      acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+      acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
     }
-  part_sum[threadIdx.x] = r < lanes ? acc : 0.f;
+    for (; row < BT; row += step) {
+      const float4 v = at(row);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  part_sum[threadIdx.x] = acc;  // (threads past lanes * dq hold zeros)
   __syncthreads();
-  if (threadIdx.x < d) {
-    float s = 0.f;
-    for (int i = 0; i < lanes; ++i) s += part_sum[i * d + threadIdx.x];
-    atomicAdd(out + (size_t)part * H * d + h * d + threadIdx.x, s);
+  if (threadIdx.x < dq) {
+    float4 s = part_sum[threadIdx.x];
+    for (int i = 1; i < lanes; ++i) {
+      const float4 v = part_sum[i * dq + threadIdx.x];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* o = out + (size_t)part * H * d + h * d + threadIdx.x * 4;
+    atomicAdd(o, s.x); atomicAdd(o + 1, s.y); atomicAdd(o + 2, s.z); atomicAdd(o + 3, s.w);
   }
 }
 
@@ -361,14 +379,15 @@ cudaError_t gemm_tf32(const float* a, const float* b, float* c, const float* bia
 }
 
 cudaError_t colsum_heads_f32(const float* x, float* out, int B, int H, int T, int d, bool accumulate, cudaStream_t st, int parts) {
-  if (B <= 0 || H <= 0 || T <= 0 || d <= 0 || d > 256 || parts <= 0) return cudaErrorInvalidValue;
+  if (B <= 0 || H <= 0 || T <= 0 || d <= 0 || d > 256 || (d & 3) || parts <= 0) return cudaErrorInvalidValue;
   if (!accumulate) {
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)parts * H * d * 4, st);
     if (e != cudaSuccess) return e;
   }
   int strips = (148 * 4 + parts * H - 1) / (parts * H);
-  const int lanes = 256 / d;
-  if (strips > (B * T + lanes - 1) / lanes) strips = (B * T + lanes - 1) / lanes;
+  const int lanes = 256 / (d / 4);
+  // at least four rows per thread (the unrolled loop), else the strips only add atomics
+  if (strips > (B * T + 4 * lanes - 1) / (4 * lanes)) strips = (B * T + 4 * lanes - 1) / (4 * lanes);
   colsum_heads_kernel<<<dim3(parts * H, strips), 256, 0, st>>>(x, out, B, H, T, d);
   return cudaGetLastError();
 }

@@ -78,8 +78,14 @@ cudaError_t colsum_f32(const float* x, float* out, int M, int N, bool accumulate
 // fa_lm_kernels.cu: one fused pass per operator (dims multiples of 4; dw/db/embedding-dw are zeroed inside)
 cudaError_t layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, int rows,
                           int dim, float eps, cudaStream_t st);
+// a (+ b -> sum, the residual sum) then LayerNorm; b / sum may be null.  b needs dim in {128, 256, 512}
+cudaError_t add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, float* sum, float* y,
+                              float* mean, float* rstd, int rows, int dim, float eps, cudaStream_t st);
+bool layernorm_fused_width(int dim);
+// res (optional, fused widths only): dx = LN'(dy) + res
 cudaError_t layernorm_bwd(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
-                          float* dw, float* db, int rows, int dim, cudaStream_t st, bool accumulate = false);
+                          float* dw, float* db, int rows, int dim, cudaStream_t st, bool accumulate = false,
+                          const float* res = nullptr);
 cudaError_t gelu(const float* x, const float* dy, float* y, size_t n, bool backward, cudaStream_t st);
 cudaError_t dropout_apply(const float* x, float* y, size_t n, Dropout drop, const unsigned long long* seed_offset,
                           cudaStream_t st);

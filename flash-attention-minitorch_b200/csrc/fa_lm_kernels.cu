@@ -120,6 +120,122 @@ __global__ void layernorm_bwd_dwdb_kernel(const float* __restrict__ x, const flo
   }
 }
 
+// Register-resident variants for dim = 128 * kVec (the model's 256): every lane keeps its kVec float4s of the row in
+// registers, so the row is read once.
+//   forward : s = a (+ b) -- the residual sum of the layer before, written out when b is given -- and y = LN(s)
+//   backward: dx = LN'(dy) (+ res, the gradient that reaches the same tensor along the residual branch), and the CTA's
+//             share of dw / db reduced through shared memory, one atomic per column per CTA: ONE launch instead of
+//             dx kernel + dw/db kernel (+ autograd's add of the two branch gradients)
+template <int kVec>
+__global__ void __launch_bounds__(256) add_layernorm_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                const float* __restrict__ w, const float* __restrict__ bias,
+                                                                float* __restrict__ sum_out, float* __restrict__ y,
+                                                                float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                int rows, float eps) {
+  constexpr int dim = 128 * kVec;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const size_t base = (size_t)row * dim + lane * 4;
+  float4 v[kVec];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kVec; ++j) {
+    v[j] = *reinterpret_cast<const float4*>(a + base + j * 128);
+    if (b != nullptr) {
+      const float4 u = *reinterpret_cast<const float4*>(b + base + j * 128);
+      v[j] = make_float4(v[j].x + u.x, v[j].y + u.y, v[j].z + u.z, v[j].w + u.w);
+      *reinterpret_cast<float4*>(sum_out + base + j * 128) = v[j];
+    }
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  const float mean = warp_sum(s) / dim;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < kVec; ++j) {
+    const float c0 = v[j].x - mean, c1 = v[j].y - mean, c2 = v[j].z - mean, c3 = v[j].w - mean;
+    q += (c0 * c0 + c1 * c1) + (c2 * c2 + c3 * c3);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / dim + eps);
+#pragma unroll
+  for (int j = 0; j < kVec; ++j) {
+    const float4 ww = *reinterpret_cast<const float4*>(w + lane * 4 + j * 128);
+    const float4 bv = *reinterpret_cast<const float4*>(bias + lane * 4 + j * 128);
+    *reinterpret_cast<float4*>(y + base + j * 128) =
+        make_float4(ww.x * (v[j].x - mean) * rstd + bv.x, ww.y * (v[j].y - mean) * rstd + bv.y,
+                    ww.z * (v[j].z - mean) * rstd + bv.z, ww.w * (v[j].w - mean) * rstd + bv.w);
+  }
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+template <int kVec>
+__global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                  const float* __restrict__ dy, const float* __restrict__ mean_in,
+                                                                  const float* __restrict__ rstd_in, const float* __restrict__ res,
+                                                                  float* __restrict__ dx, float* __restrict__ dw,
+                                                                  float* __restrict__ db, int rows) {
+  constexpr int dim = 128 * kVec;
+  __shared__ float4 red[2][8][32 * kVec];  // [dw | db][warp][lane's float4s]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stride = gridDim.x * 8;
+  float4 ww[kVec], aw[kVec], ab[kVec];
+#pragma unroll
+  for (int j = 0; j < kVec; ++j) {
+    ww[j] = *reinterpret_cast<const float4*>(w + lane * 4 + j * 128);
+    aw[j] = ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += stride) {
+    const size_t base = (size_t)row * dim + lane * 4;
+    float4 xv[kVec], gv[kVec], rv[kVec];
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      xv[j] = *reinterpret_cast<const float4*>(x + base + j * 128);
+      gv[j] = *reinterpret_cast<const float4*>(dy + base + j * 128);
+      if (res != nullptr) rv[j] = *reinterpret_cast<const float4*>(res + base + j * 128);
+    }
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      // xv <- xhat;  gw = dy * w kept implicit (recomputed below: 4 FMULs are cheaper than 4 more live registers)
+      xv[j] = make_float4((xv[j].x - mean) * rstd, (xv[j].y - mean) * rstd, (xv[j].z - mean) * rstd, (xv[j].w - mean) * rstd);
+      const float g0 = gv[j].x * ww[j].x, g1 = gv[j].y * ww[j].y, g2 = gv[j].z * ww[j].z, g3 = gv[j].w * ww[j].w;
+      s1 += (g0 + g1) + (g2 + g3);
+      s2 += (g0 * xv[j].x + g1 * xv[j].y) + (g2 * xv[j].z + g3 * xv[j].w);
+      aw[j] = make_float4(aw[j].x + gv[j].x * xv[j].x, aw[j].y + gv[j].y * xv[j].y, aw[j].z + gv[j].z * xv[j].z,
+                          aw[j].w + gv[j].w * xv[j].w);
+      ab[j] = make_float4(ab[j].x + gv[j].x, ab[j].y + gv[j].y, ab[j].z + gv[j].z, ab[j].w + gv[j].w);
+    }
+    s1 = warp_sum(s1) / dim;
+    s2 = warp_sum(s2) / dim;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      float4 o = make_float4(rstd * (gv[j].x * ww[j].x - s1 - xv[j].x * s2), rstd * (gv[j].y * ww[j].y - s1 - xv[j].y * s2),
+                             rstd * (gv[j].z * ww[j].z - s1 - xv[j].z * s2), rstd * (gv[j].w * ww[j].w - s1 - xv[j].w * s2));
+      if (res != nullptr) o = make_float4(o.x + rv[j].x, o.y + rv[j].y, o.z + rv[j].z, o.w + rv[j].w);
+      *reinterpret_cast<float4*>(dx + base + j * 128) = o;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kVec; ++j) {
+    red[0][warp][j * 32 + lane] = aw[j];
+    red[1][warp][j * 32 + lane] = ab[j];
+  }
+  __syncthreads();
+  // 2 * dim column sums over the 8 warps: thread t takes scalar column t, t + 256, ...
+  const float* rf = reinterpret_cast<const float*>(red);
+  for (int i = threadIdx.x; i < 2 * dim; i += 256) {
+    const int which = i / dim, c = i % dim;  // c = (j * 32 + lane) * 4 + e  <->  column j * 128 + lane * 4 + e: the same index
+    float t = 0.f;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) t += rf[(which * 8 + wp) * dim + c];
+    atomicAdd((which ? db : dw) + c, t);
+  }
+}
+
 // ---------------------------------------------------------------- GELU (tanh approximation)
 __device__ __forceinline__ float gelu_f(float x) {
   const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
@@ -203,20 +319,21 @@ __global__ void softmax_loss_fwd_kernel(const float* __restrict__ logits, const 
                                         float* __restrict__ loss, float* __restrict__ lse_out, int C) {
   __shared__ float sh[32];
   const float* row = logits + (size_t)blockIdx.x * C;
-  float m = -INFINITY;
+  // one pass: every thread keeps a running (max, sum of exp relative to it); rescaled to the row maximum at the end
+  float m = -INFINITY, s = 0.f;
   for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
     const float4 v = *reinterpret_cast<const float4*>(row + c);
-    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-  }
-  m = block_reduce(m, sh, true);
-  float s = 0.f;
-  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    if (mx > m) {
+      s *= __expf(m - mx);  // (m = -inf on the first visit: s = 0 stays 0)
+      m = mx;
+    }
     s += (__expf(v.x - m) + __expf(v.y - m)) + (__expf(v.z - m) + __expf(v.w - m));
   }
-  s = block_reduce(s, sh, false);
+  const float mrow = block_reduce(m, sh, true);
+  s = block_reduce(m == -INFINITY ? 0.f : s * __expf(m - mrow), sh, false);
   if (threadIdx.x == 0) {
-    const float lse = m + logf(s);
+    const float lse = mrow + logf(s);
     lse_out[blockIdx.x] = lse;
     loss[blockIdx.x] = lse - row[target[blockIdx.x]];
   }
@@ -268,19 +385,44 @@ inline unsigned ew_grid(size_t items, int threads) {
 
 }  // namespace
 
-cudaError_t layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, int rows,
-                          int dim, float eps, cudaStream_t st) {
-  if (rows <= 0 || dim <= 0 || (dim & 3)) return cudaErrorInvalidValue;
-  layernorm_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, w, b, y, mean, rstd, rows, dim, eps);
+cudaError_t add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, float* sum, float* y,
+                              float* mean, float* rstd, int rows, int dim, float eps, cudaStream_t st) {
+  if (rows <= 0 || dim <= 0 || (dim & 3) || (b != nullptr && sum == nullptr)) return cudaErrorInvalidValue;
+  const unsigned grid = (rows + 7) / 8;
+  switch (dim) {
+    case 128: add_layernorm_fwd_kernel<1><<<grid, 256, 0, st>>>(a, b, w, bias, sum, y, mean, rstd, rows, eps); break;
+    case 256: add_layernorm_fwd_kernel<2><<<grid, 256, 0, st>>>(a, b, w, bias, sum, y, mean, rstd, rows, eps); break;
+    case 512: add_layernorm_fwd_kernel<4><<<grid, 256, 0, st>>>(a, b, w, bias, sum, y, mean, rstd, rows, eps); break;
+    default:
+      if (b != nullptr) return cudaErrorInvalidValue;  // (callers add separately for other widths)
+      layernorm_fwd_kernel<<<grid, 256, 0, st>>>(a, w, bias, y, mean, rstd, rows, dim, eps);
+  }
   return cudaGetLastError();
 }
+cudaError_t layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, int rows,
+                          int dim, float eps, cudaStream_t st) {
+  return add_layernorm_fwd(x, nullptr, w, b, nullptr, y, mean, rstd, rows, dim, eps, st);
+}
+bool layernorm_fused_width(int dim) { return dim == 128 || dim == 256 || dim == 512; }  // (1024: 64 KB of reduction smem)
 cudaError_t layernorm_bwd(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
-                          float* dw, float* db, int rows, int dim, cudaStream_t st, bool accumulate) {
+                          float* dw, float* db, int rows, int dim, cudaStream_t st, bool accumulate, const float* res) {
   if (rows <= 0 || dim <= 0 || (dim & 3)) return cudaErrorInvalidValue;
+  if (res != nullptr && !layernorm_fused_width(dim)) return cudaErrorInvalidValue;
   cudaError_t e;
   if (!accumulate) {  // (accumulate: dw / db are a parameter's gradient buffer, the strips atomically add onto it)
     if ((e = cudaMemsetAsync(dw, 0, (size_t)dim * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(db, 0, (size_t)dim * 4, st)) != cudaSuccess) return e;
+  }
+  if (layernorm_fused_width(dim)) {
+    // 4 CTAs (32 warps, one row each in flight) per SM cover the HBM latency; more rows than that loop
+    unsigned grid = (rows + 7) / 8;
+    if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
+    switch (dim) {
+      case 128: layernorm_bwd_fused_kernel<1><<<grid, 256, 0, st>>>(x, w, dy, mean, rstd, res, dx, dw, db, rows); break;
+      case 256: layernorm_bwd_fused_kernel<2><<<grid, 256, 0, st>>>(x, w, dy, mean, rstd, res, dx, dw, db, rows); break;
+      default: layernorm_bwd_fused_kernel<4><<<grid, 256, 0, st>>>(x, w, dy, mean, rstd, res, dx, dw, db, rows); break;
+    }
+    return cudaGetLastError();
   }
   layernorm_bwd_dx_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, w, dy, mean, rstd, dx, rows, dim);
   const int col_blocks = (dim + 255) / 256;

@@ -83,6 +83,12 @@ def load_library() -> ctypes.CDLL:
         lib.fa_b200_colsum_heads_parts_f32.restype = ci
     lib.fa_b200_colsum_f32.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.fa_b200_colsum_f32.restype = ci
+    lib.fa_b200_add_layernorm_fwd.argtypes = [vp] * 8 + [ci, ci, f32, vp]
+    lib.fa_b200_add_layernorm_fwd.restype = ci
+    lib.fa_b200_layernorm_bwd_res.argtypes = [vp] * 9 + [ci, ci, ci, vp]
+    lib.fa_b200_layernorm_bwd_res.restype = ci
+    lib.fa_b200_layernorm_fused_width.argtypes = [ci]
+    lib.fa_b200_layernorm_fused_width.restype = ci
     for name, args in (("layernorm_fwd", [vp] * 6 + [ci, ci, f32, vp]), ("layernorm_bwd", [vp] * 8 + [ci, ci, vp]), ("layernorm_bwd_accum", [vp] * 8 + [ci, ci, vp]),
                        ("gelu_fwd", [vp, vp, sz, vp]), ("gelu_bwd", [vp, vp, vp, sz, vp]),
                        ("dropout_apply", [vp, vp, sz, f32, u64, vp, vp]), ("embedding_fwd", [vp, vp, vp, sz, ci, vp]),

@@ -146,6 +146,10 @@ class LayerNorm1d(Module):
     def forward(self, x):
         return ops.layernorm(x, self.weights.value, self.bias.value, self.eps)
 
+    def add_forward(self, a, b=None):
+        """(a + b, LayerNorm(a + b)) in one pass -- the residual sum and the LayerNorm that follows it (b may be None)."""
+        return ops.add_layernorm(a, b, self.weights.value, self.bias.value, self.eps)
+
 
 class MultiHeadAttention(Module):
     def __init__(self, n_embd, n_head, causal, bias, device, dtype, gen, attention_fn):
@@ -182,6 +186,10 @@ class MultiHeadAttention(Module):
                 qkv = ops.qkv_to_heads(x2, wqkv, bqkv, B, T, H, d)
             else:
                 qkv = ops.linear(x2, wqkv, bqkv).view(B, T, 3, H, d).permute(2, 0, 3, 1, 4).contiguous()
+            packed = getattr(self.attention_fn, "packed", None)
+            if packed is not None:  # dq | dk | dv come back as one (3, B, H, T, d) gradient: no unbind / stack copies
+                o = packed(qkv, self.causal)
+                return ops.linear_from_heads(o, self.out_projection.weights.value, bias(self.out_projection)).view(B, T, E)
             q, k, v = qkv.unbind(0)
         else:
             q = ops.linear_to_heads(x2, self.q_projection.weights.value, bias(self.q_projection), B, T, H, d)
@@ -212,9 +220,19 @@ class TransformerLayer(Module):
         self.ff = FeedForward(n_embd, 256, p_dropout, bias, device, dtype, gen)
 
     def forward(self, x):
+        s, f = self.forward_pending(x, None)
+        return s + f
+
+    def forward_pending(self, x, delta):
+        """The layer applied to x + delta (delta may be None), returned as (s, f) with output = s + f: every residual
+        addition is left to the LayerNorm that follows it (ops.add_layernorm: one pass forward, one backward), the last
+        one to the next layer's ln_1 or the model's final ln.
+        (x + attn(ln_1(x)), then + ff(ln_2(.)): modules_transfomer.py TransformerLayer.forward.)"""
         B, T, E = x.shape
-        out = x + self.attention(self.ln_1(x.reshape(B * T, E)).view(B, T, E))
-        return out + self.ff(self.ln_2(out.reshape(B * T, E)).view(B, T, E))
+        s1, h = self.ln_1.add_forward(x.reshape(B * T, E), None if delta is None else delta.reshape(B * T, E))
+        a = self.attention(h.view(B, T, E))
+        s2, h2 = self.ln_2.add_forward(s1, a.reshape(B * T, E))
+        return s2.view(B, T, E), self.ff(h2.view(B, T, E))
 
 
 class DecoderLM(Module):
@@ -237,9 +255,10 @@ class DecoderLM(Module):
         B, T = idx.shape
         pos = torch.arange(T, device=idx.device).view(1, T)
         x = ops.dropout(self.token_embeddings(idx) + self.position_embeddings(pos), self.p_dropout, self.training)
+        delta = None  # the residual stream is x + delta; each addition happens inside the next LayerNorm's kernel
         for layer in (self.t_layer_1, self.t_layer_2, self.t_layer_3, self.t_layer_4):
-            x = layer(x)
-        x = self.ln(x.reshape(B * T, self.n_embd))
+            x, delta = layer.forward_pending(x, delta)
+        _, x = self.ln.add_forward(x.reshape(B * T, self.n_embd), delta.reshape(B * T, self.n_embd))
         return self.lm_head(x).view(B, T, self.n_vocab)
 
     def state_dict(self) -> Dict[str, torch.Tensor]:

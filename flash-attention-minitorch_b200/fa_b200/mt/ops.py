@@ -47,6 +47,34 @@ class _FlashAttn2(torch.autograd.Function):
         return dq, dk, dv, None, None, None
 
 
+class _FlashAttn2Packed(torch.autograd.Function):
+    """The same on a packed (3, B, H, T, d) tensor -- the output of the fused q | k | v projection: the backward kernels
+    write dq, dk, dv straight into the three slices of ONE (3, B, H, T, d) gradient, which the projection's backward
+    GEMMs read as it is (no unbind / stack copy in between)."""
+
+    @staticmethod
+    def forward(ctx, qkv, causal):
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        o, lse = device.flash_attn_fwd(q, k, v, bool(causal))
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.causal = bool(causal)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, o, lse = ctx.saved_tensors
+        dqkv = torch.empty_like(qkv)
+        device.flash_attn_bwd(qkv[0], qkv[1], qkv[2], o, d_out.contiguous(), lse, ctx.causal, out=(dqkv[0], dqkv[1], dqkv[2]))
+        return dqkv, None
+
+
+def flash_attention_packed(qkv, causal: bool = True):
+    """flash_attention(qkv[0], qkv[1], qkv[2]) for a contiguous (3, B, H, T, d) CUDA tensor."""
+    if not qkv.is_cuda:
+        raise RuntimeError("flash_attention needs CUDA tensors: the product has no CPU attention path")
+    return _FlashAttn2Packed.apply(qkv.contiguous(), causal)
+
+
 def flash_attention(q, k, v, causal: bool = True, p_drop: float = 0.0, seed: int = 0):
     """softmax(q k^T / sqrt(d) [+ causal mask]) v on the B200 kernels; q, k, v: (B, H, T, d) CUDA tensors.
     fp32 tensors take the fp32 path (tf32 tensor-core forward and -- at d = 32 -- backward where covered, else the exact
@@ -54,6 +82,9 @@ def flash_attention(q, k, v, causal: bool = True, p_drop: float = 0.0, seed: int
     if not q.is_cuda:
         raise RuntimeError("flash_attention needs CUDA tensors: the product has no CPU attention path")
     return _FlashAttn2.apply(q, k, v, causal, p_drop, seed)
+
+
+flash_attention.packed = flash_attention_packed
 
 
 def flash_attention_bf16(q, k, v, causal: bool = True, p_drop: float = 0.0, seed: int = 0):
@@ -339,6 +370,54 @@ class _LayerNorm(torch.autograd.Function):
         _lib.check(lib.fa_b200_layernorm_bwd(x.data_ptr(), w.data_ptr(), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                              dx.data_ptr(), dw.data_ptr(), db.data_ptr(), rows, dim, _st()))
         return dx, dw, db, None
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    """(a, b) -> (s, y) with s = a + b, y = LayerNorm(s): the residual sum of the layer before and the LayerNorm that
+    consumes it, one pass forward (b None: s is a itself).  Backward: ds = LN'(dy) + d_s, where d_s is the gradient that
+    reaches s along the residual branch -- one launch including the dw / db reduction, and no separate addition of the two
+    branch gradients."""
+
+    @staticmethod
+    def forward(ctx, a, b, w, bias, eps):
+        a = a.contiguous()
+        rows, dim = a.shape
+        y = torch.empty_like(a)
+        s = torch.empty_like(a) if b is not None else a
+        mean = torch.empty(rows, device=a.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        _lib.check(_lib.load_library().fa_b200_add_layernorm_fwd(a.data_ptr(), b.contiguous().data_ptr() if b is not None else None,
+                                                                 w.data_ptr(), bias.data_ptr(), s.data_ptr() if b is not None else None,
+                                                                 y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, dim, float(eps), _st()))
+        ctx.save_for_backward(s, w, mean, rstd)
+        ctx.bias, ctx.has_b = bias, b is not None
+        ctx.set_materialize_grads(False)  # an unused sum (the model's final ln) must not cost a zero tensor
+        return s, y
+
+    @staticmethod
+    def backward(ctx, d_s, dy):
+        s, w, mean, rstd = ctx.saved_tensors
+        rows, dim = s.shape
+        if dy is None:  # only the sum was used
+            return d_s, (d_s if ctx.has_b else None), None, None, None
+        dy = dy.contiguous()
+        ds = torch.empty_like(s)
+        gw, gb = _sink(w), _sink(ctx.bias)
+        sink = gw is not None and gb is not None
+        dw, db = (gw, gb) if sink else (torch.empty_like(w), torch.empty_like(w))
+        _lib.check(_lib.load_library().fa_b200_layernorm_bwd_res(s.data_ptr(), w.data_ptr(), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                                 d_s.contiguous().data_ptr() if d_s is not None else None, ds.data_ptr(),
+                                                                 dw.data_ptr(), db.data_ptr(), rows, dim, 1 if sink else 0, _st()))
+        return ds, (ds if ctx.has_b else None), (None if sink else dw), (None if sink else db), None
+
+
+def add_layernorm(a, b, weight, bias, eps: float):
+    """(a + b, LayerNorm(a + b)) for (rows, dim) tensors; b may be None (then the first result is a).  The pair the
+    transformer layers are built from: the sum is the residual stream, the LayerNorm output feeds the next sub-block."""
+    if _on_kernels(a, weight, bias) and (b is None or _on_kernels(b)) and _lib.load_library().fa_b200_layernorm_fused_width(a.shape[1]):
+        return _AddLayerNorm.apply(a, b, weight, bias, eps)
+    s = a if b is None else a + b
+    return s, layernorm(s, weight, bias, eps)
 
 
 def layernorm(x, weight, bias, eps: float):

@@ -173,6 +173,16 @@ int fa_b200_layernorm_bwd(const float* x, const float* w, const float* dy, const
 /* the same with dw / db ACCUMULATED into (a parameter's gradient buffer) instead of overwritten */
 int fa_b200_layernorm_bwd_accum(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
                                 float* dw, float* db, int rows, int dim, void* stream);
+/* The residual stream fused into LayerNorm (TransformerLayer.forward, minitorch/modules_transfomer.py: x + attn(ln_1(x)),
+ * x + ff(ln_2(x))): forward sum = a + b (b, sum optional) and y = LN(sum) in one pass; backward dx = LN'(dy) + res
+ * (res optional: the gradient arriving at the same tensor along the residual branch), dw / db overwritten or
+ * accumulated.  b / res need dim in {128, 256, 512} (fa_b200_layernorm_fused_width), where the row stays in
+ * registers and the backward is a single launch. */
+int fa_b200_add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, float* sum, float* y,
+                              float* mean, float* rstd, int rows, int dim, float eps, void* stream);
+int fa_b200_layernorm_bwd_res(const float* x, const float* w, const float* dy, const float* mean, const float* rstd,
+                              const float* res, float* dx, float* dw, float* db, int rows, int dim, int accumulate, void* stream);
+int fa_b200_layernorm_fused_width(int dim);
 int fa_b200_gelu_fwd(const float* x, float* y, size_t n, void* stream);
 int fa_b200_gelu_bwd(const float* x, const float* dy, float* dx, size_t n, void* stream);
 int fa_b200_dropout_apply(const float* x, float* y, size_t n, float p_drop, unsigned long long seed,

@@ -217,3 +217,67 @@ def test_fused_qkv_projection_equals_three_projections(cuda_device, B, T, H, d, 
         assert float((wqkv.grad[:, i * E:(i + 1) * E] - w3[i].grad).abs().max()) <= tol(w3[i].grad)
         assert float((bqkv.grad[i * E:(i + 1) * E] - b3[i].grad).abs().max()) <= tol(b3[i].grad)
     assert float((xx.grad - x3.grad).abs().max()) <= 1e-4 * max(1.0, float(x3.grad.abs().max()))
+
+
+@pytest.mark.parametrize("rows,dim", [(5632, 256), (77, 128), (9, 512), (1, 256)])
+@pytest.mark.parametrize("with_b", [True, False])
+def test_add_layernorm_fused_residual(cuda_device, rows, dim, with_b):
+    """ops.add_layernorm: (a + b, LN(a + b)) in one pass; its backward adds the gradient arriving at the sum along the
+    residual branch inside the LayerNorm-backward kernel (one launch, dw / db included).  Against the torch formula in
+    float64, with BOTH outputs used downstream (the transformer layer's pattern)."""
+    torch.manual_seed(rows + dim)
+    a, b = torch.randn(rows, dim) * 2 + 0.5, torch.randn(rows, dim)
+    w, bias = torch.rand(dim) + 0.5, torch.rand(dim) - 0.5
+    gs, gy = torch.rand(rows, dim) * 2 - 1, torch.rand(rows, dim) * 2 - 1
+
+    def run(dev, dt):
+        ins = [t.to(device=dev, dtype=dt).requires_grad_(True) for t in ((a, b, w, bias) if with_b else (a, w, bias))]
+        s, y = ops.add_layernorm(ins[0], ins[1] if with_b else None, ins[-2], ins[-1], 1e-5)
+        ((s * gs.to(device=dev, dtype=dt)).sum() + (y * gy.to(device=dev, dtype=dt)).sum()).backward()
+        return s, y, [t.grad for t in ins]
+
+    s_ref, y_ref, g_ref = run("cpu", torch.float64)
+    before = _lib.launch_count()
+    s, y, g = run(cuda_device, torch.float32)
+    assert _lib.launch_count() - before == 2  # one forward, one backward
+    assert float((s.double().cpu() - s_ref).abs().max()) <= 1e-6 * max(1.0, float(s_ref.abs().max()))
+    assert float((y.double().cpu() - y_ref).abs().max()) <= 1e-5
+    for got, ref in zip(g, g_ref):
+        assert float((got.double().cpu() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    # an unused sum costs nothing (no zero tensor is materialised for it) and gives the plain LayerNorm gradient
+    x1 = a.to(cuda_device).requires_grad_(True)
+    _, y1 = ops.add_layernorm(x1, None, w.to(cuda_device), bias.to(cuda_device), 1e-5)
+    (y1 * gy.to(cuda_device)).sum().backward()
+    x2 = a.to(cuda_device).requires_grad_(True)
+    (ops.layernorm(x2, w.to(cuda_device), bias.to(cuda_device), 1e-5) * gy.to(cuda_device)).sum().backward()
+    assert torch.equal(x1.grad, x2.grad)
+
+
+@pytest.mark.parametrize("parts,B,H,T,d", [(3, 11, 8, 512, 32), (1, 2, 2, 128, 64), (3, 1, 3, 40, 24), (2, 3, 1, 7, 128)])
+def test_colsum_heads_parts(cuda_device, parts, B, H, T, d):
+    """Bias gradient of a projection whose output is in head layout: out[part][h*d + dd] = sum over (b, t)."""
+    torch.manual_seed(parts + B + T)
+    x = torch.randn(parts, B, H, T, d, device=cuda_device)
+    out = torch.full((parts, H * d), 3.0, device=cuda_device)
+    ref = x.double().sum(dim=(1, 3)).reshape(parts, H * d)
+    lib = _lib.load_library()
+    _lib.check(lib.fa_b200_colsum_heads_parts_f32(x.data_ptr(), out.data_ptr(), parts, B, H, T, d, 0, None))
+    torch.cuda.synchronize()
+    assert float((out.double() - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+    _lib.check(lib.fa_b200_colsum_heads_parts_f32(x.data_ptr(), out.data_ptr(), parts, B, H, T, d, 1, None))
+    torch.cuda.synchronize()
+    assert float((out.double() - 2 * ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_packed_attention_equals_unpacked(cuda_device):
+    """ops.flash_attention.packed((3, B, H, T, d)) is flash_attention(q, k, v) with dq | dk | dv written into one tensor."""
+    torch.manual_seed(3)
+    qkv = torch.randn(3, 2, 4, 256, 32, device=cuda_device)
+    go = torch.randn(2, 4, 256, 32, device=cuda_device)
+    p = qkv.clone().requires_grad_(True)
+    o1 = ops.flash_attention.packed(p, True)
+    (o1 * go).sum().backward()
+    u = qkv.clone().requires_grad_(True)
+    o2 = ops.flash_attention(u[0], u[1], u[2], True)
+    (o2 * go).sum().backward()
+    assert torch.equal(o1, o2) and torch.equal(p.grad, u.grad) and p.grad.is_contiguous()
