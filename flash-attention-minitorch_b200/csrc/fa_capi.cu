@@ -398,10 +398,25 @@ int fa_b200_add_layernorm_fwd(const float* a, const float* b, const float* w, co
   return FA_OK;
 }
 int fa_b200_layernorm_bwd_res(const float* x, const float* w, const float* dy, const float* mean, const float* rstd,
-                              const float* res, float* dx, float* dw, float* db, int rows, int dim, int accumulate, void* stream) {
+                              const float* res, float* dx, float* dw, float* db, float* dcol, int rows, int dim, int accumulate,
+                              void* stream) {
   if (!x || !w || !dy || !mean || !rstd || !dx || !dw || !db) return fail(FA_ERR_BAD_ARG, "fa_b200_layernorm_bwd_res: null pointer");
-  if (res && !fa::layernorm_fused_width(dim)) return fail(FA_ERR_UNSUPPORTED, "fa_b200_layernorm_bwd_res: the fused residual needs dim in {128, 256, 512}");
-  FA_CUDA(fa::layernorm_bwd(x, w, dy, mean, rstd, dx, dw, db, rows, dim, FA_ST, accumulate != 0, res), fa::layernorm_fused_width(dim) ? 1 : 2);
+  if ((res || dcol) && !fa::layernorm_fused_width(dim)) return fail(FA_ERR_UNSUPPORTED, "fa_b200_layernorm_bwd_res: res / dcol need dim in {128, 256, 512}");
+  FA_CUDA(fa::layernorm_bwd(x, w, dy, mean, rstd, dx, dw, db, rows, dim, FA_ST, accumulate != 0, res, dcol), fa::layernorm_fused_width(dim) ? 1 : 2);
+  return FA_OK;
+}
+int fa_b200_gelu_dropout_fwd(const float* x, float* y, size_t n, float p_drop, unsigned long long seed,
+                             const unsigned long long* seed_offset_dev, void* stream) {
+  if (!x || !y) return fail(FA_ERR_BAD_ARG, "fa_b200_gelu_dropout_fwd: null pointer");
+  if (int rc = check_p_drop(p_drop, "fa_b200_gelu_dropout_fwd")) return rc;
+  FA_CUDA(fa::gelu_dropout(x, nullptr, y, n, false, fa::make_dropout(p_drop, seed), seed_offset_dev, FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_gelu_dropout_bwd(const float* x, const float* dy, float* dx, size_t n, float p_drop, unsigned long long seed,
+                             const unsigned long long* seed_offset_dev, void* stream) {
+  if (!x || !dy || !dx) return fail(FA_ERR_BAD_ARG, "fa_b200_gelu_dropout_bwd: null pointer");
+  if (int rc = check_p_drop(p_drop, "fa_b200_gelu_dropout_bwd")) return rc;
+  FA_CUDA(fa::gelu_dropout(x, dy, dx, n, true, fa::make_dropout(p_drop, seed), seed_offset_dev, FA_ST), 1);
   return FA_OK;
 }
 int fa_b200_layernorm_fused_width(int dim) { return fa::layernorm_fused_width(dim) ? 1 : 0; }
@@ -449,6 +464,14 @@ int fa_b200_softmax_loss_bwd(const float* logits, const long long* target, const
   FA_CUDA(fa::softmax_loss_bwd(logits, target, lse, gscale, dlogits, rows, n_classes, FA_ST), 1);
   return FA_OK;
 }
+int fa_b200_softmax_loss_bwd_colsum(const float* logits, const long long* target, const float* lse, const float* gscale,
+                                    float* dlogits, float* dcol, int rows, int n_classes, int accumulate, void* stream) {
+  if (!logits || !target || !lse || !gscale || !dlogits || !dcol) return fail(FA_ERR_BAD_ARG, "fa_b200_softmax_loss_bwd_colsum: null pointer");
+  if (!fa::softmax_loss_colsum_width(n_classes)) return fail(FA_ERR_UNSUPPORTED, "fa_b200_softmax_loss_bwd_colsum: n_classes must be a multiple of 4, at most 12288");
+  FA_CUDA(fa::softmax_loss_bwd_colsum(logits, target, lse, gscale, dlogits, dcol, rows, n_classes, accumulate != 0, FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_softmax_loss_colsum_width(int n_classes) { return fa::softmax_loss_colsum_width(n_classes) ? 1 : 0; }
 int fa_b200_adam_step(float* p, const float* g, float* m, float* v, size_t n, float step_size, float beta1, float beta2,
                       float v_coef, float eps, void* stream) {
   if (!p || !g || !m || !v) return fail(FA_ERR_BAD_ARG, "fa_b200_adam_step: null pointer");

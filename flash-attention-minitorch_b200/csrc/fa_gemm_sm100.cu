@@ -246,15 +246,23 @@ cudaError_t launch_gemm(const float* a, const float* b, float* c, const float* b
   const bool heads = hl.a || hl.b || hl.c;
   p.a_heads = hl.a; p.b_heads = hl.b; p.c_heads = hl.c; p.T = hl.T > 0 ? hl.T : 1; p.H = hl.H; p.d = hl.d > 0 ? hl.d : 1;
   p.E = E; p.BH = (int)BH;
-  // split-K when the output has too few tiles to fill the 148 SMs (weight gradients: 256 x 256 outputs reduced over
-  // thousands of tokens): each split keeps at least 8 k-blocks, partial tiles are red.added into a zeroed C
+  // split-K when the tiles do not fill whole waves of the 148 SMs -- weight gradients (256 x 256 outputs reduced over
+  // thousands of tokens: 4 tiles), but also 88 tiles (60 % of the SMs) or 158 (a second wave for 10 tiles).  Cost model:
+  // waves x (k-blocks per split + ~6 k-blocks of prologue / epilogue per CTA); each split keeps at least 8 k-blocks;
+  // partial tiles are red.added into a zeroed (or the accumulated-into) C.
   const int tiles = ((N + kBN - 1) / kBN) * ((M + kBM - 1) / kBM);
   const int nk_total = (K + kBK - 1) / kBK;
   int splits = 1;
-  if (tiles < 74) {
-    splits = 148 / tiles;
-    if (splits > nk_total / 8) splits = nk_total / 8;
-    if (splits < 1) splits = 1;
+  if (tiles <= 2 * 148) {
+    long long best = -1;
+    for (int sp = 1; sp <= 40 && (sp == 1 || nk_total / sp >= 8); ++sp) {
+      const long long waves = ((long long)tiles * sp + 147) / 148;
+      const long long cost = waves * ((nk_total + sp - 1) / sp + 6);
+      if (best < 0 || cost < best) {
+        best = cost;
+        splits = sp;
+      }
+    }
   }
   p.k_blocks_per_split = (nk_total + splits - 1) / splits;
   splits = (nk_total + p.k_blocks_per_split - 1) / p.k_blocks_per_split;  // no empty split

@@ -82,10 +82,12 @@ cudaError_t layernorm_fwd(const float* x, const float* w, const float* b, float*
 cudaError_t add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, float* sum, float* y,
                               float* mean, float* rstd, int rows, int dim, float eps, cudaStream_t st);
 bool layernorm_fused_width(int dim);
-// res (optional, fused widths only): dx = LN'(dy) + res
+// res, dcol (optional, fused widths only): dx = LN'(dy) + res;  dcol (+)= column sums of dx
 cudaError_t layernorm_bwd(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
                           float* dw, float* db, int rows, int dim, cudaStream_t st, bool accumulate = false,
-                          const float* res = nullptr);
+                          const float* res = nullptr, float* dcol = nullptr);
+cudaError_t gelu_dropout(const float* x, const float* dy, float* y, size_t n, bool backward, Dropout drop,
+                         const unsigned long long* seed_offset, cudaStream_t st);
 cudaError_t gelu(const float* x, const float* dy, float* y, size_t n, bool backward, cudaStream_t st);
 cudaError_t dropout_apply(const float* x, float* y, size_t n, Dropout drop, const unsigned long long* seed_offset,
                           cudaStream_t st);
@@ -96,6 +98,10 @@ cudaError_t softmax_loss_fwd(const float* logits, const long long* target, float
                              cudaStream_t st);
 cudaError_t softmax_loss_bwd(const float* logits, const long long* target, const float* lse, const float* gscale,
                              float* dlogits, int rows, int C, cudaStream_t st);
+// + dcol (+)= column sums of dlogits (the logits layer's bias gradient); C <= 12288
+bool softmax_loss_colsum_width(int C);
+cudaError_t softmax_loss_bwd_colsum(const float* logits, const long long* target, const float* lse, const float* gscale,
+                                    float* dlogits, float* dcol, int rows, int C, bool accumulate, cudaStream_t st);
 cudaError_t adam_step(float* p, const float* g, float* m, float* v, size_t n, float step_size, float b1, float b2,
                       float v_coef, float eps, cudaStream_t st);
 

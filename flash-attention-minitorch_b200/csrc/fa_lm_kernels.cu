@@ -176,16 +176,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const float* _
                                                                   const float* __restrict__ dy, const float* __restrict__ mean_in,
                                                                   const float* __restrict__ rstd_in, const float* __restrict__ res,
                                                                   float* __restrict__ dx, float* __restrict__ dw,
-                                                                  float* __restrict__ db, int rows) {
+                                                                  float* __restrict__ db, float* __restrict__ dcol, int rows) {
+  // dcol (optional): += column sums of dx -- the bias gradient of the linear layer whose output was the `b` of the
+  // forward sum (its dy IS this dx), saving that layer's separate bias reduction pass over the same tensor
   constexpr int dim = 128 * kVec;
-  __shared__ float4 red[2][8][32 * kVec];  // [dw | db][warp][lane's float4s]
+  __shared__ float4 red[3][8][32 * kVec];  // [dw | db | dcol][warp][lane's float4s]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stride = gridDim.x * 8;
-  float4 ww[kVec], aw[kVec], ab[kVec];
+  float4 ww[kVec], aw[kVec], ab[kVec], ac[kVec];
 #pragma unroll
   for (int j = 0; j < kVec; ++j) {
     ww[j] = *reinterpret_cast<const float4*>(w + lane * 4 + j * 128);
-    aw[j] = ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    aw[j] = ab[j] = ac[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int row = blockIdx.x * 8 + warp; row < rows; row += stride) {
     const size_t base = (size_t)row * dim + lane * 4;
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const float* _
       float4 o = make_float4(rstd * (gv[j].x * ww[j].x - s1 - xv[j].x * s2), rstd * (gv[j].y * ww[j].y - s1 - xv[j].y * s2),
                              rstd * (gv[j].z * ww[j].z - s1 - xv[j].z * s2), rstd * (gv[j].w * ww[j].w - s1 - xv[j].w * s2));
       if (res != nullptr) o = make_float4(o.x + rv[j].x, o.y + rv[j].y, o.z + rv[j].z, o.w + rv[j].w);
+      ac[j] = make_float4(ac[j].x + o.x, ac[j].y + o.y, ac[j].z + o.z, ac[j].w + o.w);
       *reinterpret_cast<float4*>(dx + base + j * 128) = o;
     }
   }
@@ -223,16 +226,17 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const float* _
   for (int j = 0; j < kVec; ++j) {
     red[0][warp][j * 32 + lane] = aw[j];
     red[1][warp][j * 32 + lane] = ab[j];
+    red[2][warp][j * 32 + lane] = ac[j];
   }
   __syncthreads();
-  // 2 * dim column sums over the 8 warps: thread t takes scalar column t, t + 256, ...
+  // 2 (3) * dim column sums over the 8 warps: thread t takes scalar column t, t + 256, ...
   const float* rf = reinterpret_cast<const float*>(red);
-  for (int i = threadIdx.x; i < 2 * dim; i += 256) {
+  for (int i = threadIdx.x; i < (dcol != nullptr ? 3 : 2) * dim; i += 256) {
     const int which = i / dim, c = i % dim;  // c = (j * 32 + lane) * 4 + e  <->  column j * 128 + lane * 4 + e: the same index
     float t = 0.f;
 #pragma unroll
     for (int wp = 0; wp < 8; ++wp) t += rf[(which * 8 + wp) * dim + c];
-    atomicAdd((which ? db : dw) + c, t);
+    atomicAdd((which == 0 ? dw : which == 1 ? db : dcol) + c, t);
   }
 }
 
@@ -246,9 +250,15 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   const float t = tanhf(u);
   return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * 0.7978845608028654f * (1.f + 3.f * 0.044715f * x * x);
 }
-// mode 0: y = gelu(x);  mode 1: y = dy * gelu'(x)
+// mode 0: y = drop(gelu(x));  mode 1: y = drop(dy) * gelu'(x).  drop = the dropout_kernel mask below (same key, same
+// element index), or the identity when kDrop is false: FeedForward's gelu -> dropout pair as one pass each way.
+template <bool kDrop>
 __global__ void gelu_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ y, size_t n4,
-                            int mode) {
+                            int mode, uint32_t key, uint32_t thr, float scale, const unsigned long long* __restrict__ seed_offset) {
+  if (kDrop && seed_offset) {
+    const unsigned long long o = *seed_offset;
+    key = drop_mix(key ^ drop_mix((uint32_t)o + 0x9E3779B9u * (uint32_t)(o >> 32)));
+  }
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -258,6 +268,11 @@ __global__ void gelu_kernel(const float* __restrict__ x, const float* __restrict
     } else {
       const float4 g = reinterpret_cast<const float4*>(dy)[i];
       o = make_float4(g.x * gelu_grad_f(v.x), g.y * gelu_grad_f(v.y), g.z * gelu_grad_f(v.z), g.w * gelu_grad_f(v.w));
+    }
+    if (kDrop) {
+      const uint32_t w = drop_keep_word(drop_mix(key ^ ((uint32_t)i * kDropRowMul) ^ ((uint32_t)(i >> 32) * kDropColMul)), thr);
+      o = make_float4((w & 0x80u) ? o.x * scale : 0.f, (w & 0x8000u) ? o.y * scale : 0.f, (w & 0x800000u) ? o.z * scale : 0.f,
+                      (w & 0x80000000u) ? o.w * scale : 0.f);
     }
     reinterpret_cast<float4*>(y)[i] = o;
   }
@@ -354,6 +369,50 @@ __global__ void softmax_loss_bwd_kernel(const float* __restrict__ logits, const 
   }
 }
 
+// The same plus dcol[j] += sum_i dlogits[i][j] -- the bias gradient of the linear layer that produced the logits -- in
+// the same pass: a CTA takes a strip of rows, thread t owns column quads t, t + 256, ... (C <= 4 * 256 * kLossQuads), keeps
+// their sums in registers and issues one atomic per column at the end.
+constexpr int kLossQuads = 12;
+__global__ void __launch_bounds__(256) softmax_loss_bwd_colsum_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                                                      const float* __restrict__ lse, const float* __restrict__ gscale,
+                                                                      float* __restrict__ dlogits, float* __restrict__ dcol, int rows,
+                                                                      int C, int rows_per_block) {
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float4 acc[kLossQuads];
+#pragma unroll
+  for (int k = 0; k < kLossQuads; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0; r < r1; ++r) {
+    const float* row = logits + (size_t)r * C;
+    float* out = dlogits + (size_t)r * C;
+    const float L = lse[r], g = gscale[r];
+    const int t = (int)target[r];
+    float4 v[kLossQuads];  // the whole row slice first: kLossQuads independent 16-byte loads in flight per thread
+#pragma unroll
+    for (int k = 0; k < kLossQuads; ++k) {
+      const int c = (k * 256 + threadIdx.x) * 4;
+      if (c < C) v[k] = __ldcs(reinterpret_cast<const float4*>(row + c));
+    }
+#pragma unroll
+    for (int k = 0; k < kLossQuads; ++k) {
+      const int c = (k * 256 + threadIdx.x) * 4;
+      if (c < C) {
+        float4 o = make_float4(g * __expf(v[k].x - L), g * __expf(v[k].y - L), g * __expf(v[k].z - L), g * __expf(v[k].w - L));
+        if (t >= c && t < c + 4) (&o.x)[t - c] -= g;
+        *reinterpret_cast<float4*>(out + c) = o;
+        acc[k] = make_float4(acc[k].x + o.x, acc[k].y + o.y, acc[k].z + o.z, acc[k].w + o.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kLossQuads; ++k) {
+    const int c = (k * 256 + threadIdx.x) * 4;
+    if (c < C) {
+      atomicAdd(dcol + c, acc[k].x); atomicAdd(dcol + c + 1, acc[k].y);
+      atomicAdd(dcol + c + 2, acc[k].z); atomicAdd(dcol + c + 3, acc[k].w);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- Adam over one flat parameter buffer
 // m = b1 m + (1-b1) g;  v = b2 v + (1-b1) g^2  (sic: the reference uses 1-beta1 here, minitorch/optim.py:68);
 // p -= step_size * m / (sqrt(v) + eps),  step_size = lr sqrt(1-b2^t) / (1-b1^t) computed by the host.
@@ -405,22 +464,24 @@ cudaError_t layernorm_fwd(const float* x, const float* w, const float* b, float*
 }
 bool layernorm_fused_width(int dim) { return dim == 128 || dim == 256 || dim == 512; }  // (1024: 64 KB of reduction smem)
 cudaError_t layernorm_bwd(const float* x, const float* w, const float* dy, const float* mean, const float* rstd, float* dx,
-                          float* dw, float* db, int rows, int dim, cudaStream_t st, bool accumulate, const float* res) {
+                          float* dw, float* db, int rows, int dim, cudaStream_t st, bool accumulate, const float* res, float* dcol) {
   if (rows <= 0 || dim <= 0 || (dim & 3)) return cudaErrorInvalidValue;
-  if (res != nullptr && !layernorm_fused_width(dim)) return cudaErrorInvalidValue;
+  if ((res != nullptr || dcol != nullptr) && !layernorm_fused_width(dim)) return cudaErrorInvalidValue;
   cudaError_t e;
   if (!accumulate) {  // (accumulate: dw / db are a parameter's gradient buffer, the strips atomically add onto it)
     if ((e = cudaMemsetAsync(dw, 0, (size_t)dim * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(db, 0, (size_t)dim * 4, st)) != cudaSuccess) return e;
+    if (dcol != nullptr && (e = cudaMemsetAsync(dcol, 0, (size_t)dim * 4, st)) != cudaSuccess) return e;
   }
   if (layernorm_fused_width(dim)) {
-    // 4 CTAs (32 warps, one row each in flight) per SM cover the HBM latency; more rows than that loop
-    unsigned grid = (rows + 7) / 8;
-    if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
+    // two rows per warp (5632 rows: 352 CTAs, all resident at 3 CTAs of 80 registers x 256 threads per SM, so no
+    // second wave and half the atomics of one row per warp); more rows than 3 CTAs per SM can take loop
+    unsigned grid = (rows + 15) / 16;
+    if (grid > (unsigned)kSMs * 3) grid = kSMs * 3;
     switch (dim) {
-      case 128: layernorm_bwd_fused_kernel<1><<<grid, 256, 0, st>>>(x, w, dy, mean, rstd, res, dx, dw, db, rows); break;
-      case 256: layernorm_bwd_fused_kernel<2><<<grid, 256, 0, st>>>(x, w, dy, mean, rstd, res, dx, dw, db, rows); break;
-      default: layernorm_bwd_fused_kernel<4><<<grid, 256, 0, st>>>(x, w, dy, mean, rstd, res, dx, dw, db, rows); break;
+      case 128: layernorm_bwd_fused_kernel<1><<<grid, 256, 0, st>>>(x, w, dy, mean, rstd, res, dx, dw, db, dcol, rows); break;
+      case 256: layernorm_bwd_fused_kernel<2><<<grid, 256, 0, st>>>(x, w, dy, mean, rstd, res, dx, dw, db, dcol, rows); break;
+      default: layernorm_bwd_fused_kernel<4><<<grid, 256, 0, st>>>(x, w, dy, mean, rstd, res, dx, dw, db, dcol, rows); break;
     }
     return cudaGetLastError();
   }
@@ -435,7 +496,14 @@ cudaError_t layernorm_bwd(const float* x, const float* w, const float* dy, const
 }
 cudaError_t gelu(const float* x, const float* dy, float* y, size_t n, bool backward, cudaStream_t st) {
   if (n & 3) return cudaErrorInvalidValue;
-  gelu_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(x, dy, y, n / 4, backward ? 1 : 0);
+  gelu_kernel<false><<<ew_grid(n / 4, 256), 256, 0, st>>>(x, dy, y, n / 4, backward ? 1 : 0, 0u, 0u, 1.f, nullptr);
+  return cudaGetLastError();
+}
+cudaError_t gelu_dropout(const float* x, const float* dy, float* y, size_t n, bool backward, Dropout drop,
+                         const unsigned long long* seed_offset, cudaStream_t st) {
+  if (n & 3) return cudaErrorInvalidValue;
+  const uint32_t key = drop_head_key(drop.seed_lo, drop.seed_hi, 0xE1E7u);  // the key of dropout_apply: same mask
+  gelu_kernel<true><<<ew_grid(n / 4, 256), 256, 0, st>>>(x, dy, y, n / 4, backward ? 1 : 0, key, drop.thr, drop.keep_scale, seed_offset);
   return cudaGetLastError();
 }
 cudaError_t dropout_apply(const float* x, float* y, size_t n, Dropout drop, const unsigned long long* seed_offset,
@@ -469,6 +537,20 @@ cudaError_t softmax_loss_bwd(const float* logits, const long long* target, const
                              float* dlogits, int rows, int C, cudaStream_t st) {
   if (rows <= 0 || C <= 0 || (C & 3)) return cudaErrorInvalidValue;
   softmax_loss_bwd_kernel<<<rows, 256, 0, st>>>(logits, target, lse, gscale, dlogits, C);
+  return cudaGetLastError();
+}
+bool softmax_loss_colsum_width(int C) { return C > 0 && !(C & 3) && C <= 4 * 256 * kLossQuads; }
+cudaError_t softmax_loss_bwd_colsum(const float* logits, const long long* target, const float* lse, const float* gscale,
+                                    float* dlogits, float* dcol, int rows, int C, bool accumulate, cudaStream_t st) {
+  if (rows <= 0 || !softmax_loss_colsum_width(C)) return cudaErrorInvalidValue;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dcol, 0, (size_t)C * 4, st);
+    if (e != cudaSuccess) return e;
+  }
+  int strips = kSMs * 2;  // two CTAs per SM (<= 128 registers), each thread with up to kLossQuads 16-byte loads in flight
+  if (strips > rows) strips = rows;
+  const int rpb = (rows + strips - 1) / strips;
+  softmax_loss_bwd_colsum_kernel<<<(rows + rpb - 1) / rpb, 256, 0, st>>>(logits, target, lse, gscale, dlogits, dcol, rows, C, rpb);
   return cudaGetLastError();
 }
 cudaError_t adam_step(float* p, const float* g, float* m, float* v, size_t n, float step_size, float b1, float b2,

@@ -85,8 +85,16 @@ def load_library() -> ctypes.CDLL:
     lib.fa_b200_colsum_f32.restype = ci
     lib.fa_b200_add_layernorm_fwd.argtypes = [vp] * 8 + [ci, ci, f32, vp]
     lib.fa_b200_add_layernorm_fwd.restype = ci
-    lib.fa_b200_layernorm_bwd_res.argtypes = [vp] * 9 + [ci, ci, ci, vp]
+    lib.fa_b200_layernorm_bwd_res.argtypes = [vp] * 10 + [ci, ci, ci, vp]
+    for name in ("fa_b200_gelu_dropout_fwd", "fa_b200_gelu_dropout_bwd"):
+        fn = getattr(lib, name)
+        fn.argtypes = ([vp, vp] if name.endswith("fwd") else [vp, vp, vp]) + [sz, f32, u64, vp, vp]
+        fn.restype = ci
     lib.fa_b200_layernorm_bwd_res.restype = ci
+    lib.fa_b200_softmax_loss_bwd_colsum.argtypes = [vp] * 6 + [ci, ci, ci, vp]
+    lib.fa_b200_softmax_loss_bwd_colsum.restype = ci
+    lib.fa_b200_softmax_loss_colsum_width.argtypes = [ci]
+    lib.fa_b200_softmax_loss_colsum_width.restype = ci
     lib.fa_b200_layernorm_fused_width.argtypes = [ci]
     lib.fa_b200_layernorm_fused_width.restype = ci
     for name, args in (("layernorm_fwd", [vp] * 6 + [ci, ci, f32, vp]), ("layernorm_bwd", [vp] * 8 + [ci, ci, vp]), ("layernorm_bwd_accum", [vp] * 8 + [ci, ci, vp]),

@@ -133,8 +133,13 @@ class Linear(Module):
             self.bias = _rparam(in_size, (out_size,), device, dtype, gen)
         self.has_bias = bool(bias)
 
-    def forward(self, x):
-        return ops.linear(x, self.weights.value, self.bias.value if self.has_bias else None)
+    def forward(self, x, bias_grad: bool = True):
+        return ops.linear(x, self.weights.value, self.bias.value if self.has_bias else None, bias_grad)
+
+    def fused_bias_grad_ok(self, like, M: int) -> bool:
+        """The LayerNorm that consumes this layer's (M, out) output may take over its bias gradient (ops.add_layernorm
+        b_bias); `like`: any tensor on the device / of the dtype of the input."""
+        return self.has_bias and ops.fused_bias_grad_ok(like, M, self.weights.value, self.bias.value)
 
 
 class LayerNorm1d(Module):
@@ -146,9 +151,10 @@ class LayerNorm1d(Module):
     def forward(self, x):
         return ops.layernorm(x, self.weights.value, self.bias.value, self.eps)
 
-    def add_forward(self, a, b=None):
-        """(a + b, LayerNorm(a + b)) in one pass -- the residual sum and the LayerNorm that follows it (b may be None)."""
-        return ops.add_layernorm(a, b, self.weights.value, self.bias.value, self.eps)
+    def add_forward(self, a, b=None, b_bias=None):
+        """(a + b, LayerNorm(a + b)) in one pass -- the residual sum and the LayerNorm that follows it (b may be None).
+        b_bias: see ops.add_layernorm."""
+        return ops.add_layernorm(a, b, self.weights.value, self.bias.value, self.eps, b_bias)
 
 
 class MultiHeadAttention(Module):
@@ -169,7 +175,8 @@ class MultiHeadAttention(Module):
             groups.append(([p.bias for p in projs], lambda t: setattr(self, "_bqkv", t)))
         return groups
 
-    def forward(self, x):
+    def forward(self, x, bias_grad: bool = True):
+        """bias_grad=False: the caller hands out_projection's bias to the add_layernorm that consumes the output."""
         B, T, E = x.shape
         H, d = self.n_head, self.attn_hidden_dim
         x2 = x.reshape(B * T, E)
@@ -189,14 +196,14 @@ class MultiHeadAttention(Module):
             packed = getattr(self.attention_fn, "packed", None)
             if packed is not None:  # dq | dk | dv come back as one (3, B, H, T, d) gradient: no unbind / stack copies
                 o = packed(qkv, self.causal)
-                return ops.linear_from_heads(o, self.out_projection.weights.value, bias(self.out_projection)).view(B, T, E)
+                return ops.linear_from_heads(o, self.out_projection.weights.value, bias(self.out_projection), bias_grad).view(B, T, E)
             q, k, v = qkv.unbind(0)
         else:
             q = ops.linear_to_heads(x2, self.q_projection.weights.value, bias(self.q_projection), B, T, H, d)
             k = ops.linear_to_heads(x2, self.k_projection.weights.value, bias(self.k_projection), B, T, H, d)
             v = ops.linear_to_heads(x2, self.v_projection.weights.value, bias(self.v_projection), B, T, H, d)
         o = self.attention_fn(q, k, v, self.causal)
-        return ops.linear_from_heads(o, self.out_projection.weights.value, bias(self.out_projection)).view(B, T, E)
+        return ops.linear_from_heads(o, self.out_projection.weights.value, bias(self.out_projection), bias_grad).view(B, T, E)
 
 
 class FeedForward(Module):
@@ -205,11 +212,11 @@ class FeedForward(Module):
         self.linear_out = Linear(middle_dim, n_embd, bias, device, dtype, gen)
         self.p_dropout = p_dropout
 
-    def forward(self, x):
+    def forward(self, x, bias_grad: bool = True):
+        """bias_grad=False: the caller hands linear_out's bias to the add_layernorm that consumes the output."""
         B, T, E = x.shape
-        h = ops.gelu(self.linear_in(x.reshape(B * T, E)))
-        h = ops.dropout(h, self.p_dropout, self.training)
-        return self.linear_out(h).view(B, T, E)
+        h = ops.gelu_dropout(self.linear_in(x.reshape(B * T, E)), self.p_dropout, self.training)
+        return self.linear_out(h, bias_grad).view(B, T, E)
 
 
 class TransformerLayer(Module):
@@ -220,19 +227,26 @@ class TransformerLayer(Module):
         self.ff = FeedForward(n_embd, 256, p_dropout, bias, device, dtype, gen)
 
     def forward(self, x):
-        s, f = self.forward_pending(x, None)
+        s, f, _ = self.forward_pending(x, None, None, fuse_tail=False)
         return s + f
 
-    def forward_pending(self, x, delta):
-        """The layer applied to x + delta (delta may be None), returned as (s, f) with output = s + f: every residual
-        addition is left to the LayerNorm that follows it (ops.add_layernorm: one pass forward, one backward), the last
-        one to the next layer's ln_1 or the model's final ln.
+    def forward_pending(self, x, delta, delta_bias=None, fuse_tail: bool = True):
+        """The layer applied to x + delta (delta may be None), returned as (s, f, f_bias) with output = s + f: every
+        residual addition is left to the LayerNorm that follows it (ops.add_layernorm: one pass forward, one backward),
+        the last one to the next layer's ln_1 or the model's final ln -- the caller passes (s, f, f_bias) on as
+        (x, delta, delta_bias).  f_bias / delta_bias: the bias of the linear layer that produced f / delta when its
+        gradient is left to that LayerNorm's backward kernel (only with fuse_tail), else None.
         (x + attn(ln_1(x)), then + ff(ln_2(.)): modules_transfomer.py TransformerLayer.forward.)"""
         B, T, E = x.shape
-        s1, h = self.ln_1.add_forward(x.reshape(B * T, E), None if delta is None else delta.reshape(B * T, E))
-        a = self.attention(h.view(B, T, E))
-        s2, h2 = self.ln_2.add_forward(s1, a.reshape(B * T, E))
-        return s2.view(B, T, E), self.ff(h2.view(B, T, E))
+        M = B * T
+        s1, h = self.ln_1.add_forward(x.reshape(M, E), None if delta is None else delta.reshape(M, E), delta_bias)
+        outp = self.attention.out_projection
+        fuse_a = outp.fused_bias_grad_ok(h, M)
+        a = self.attention(h.view(B, T, E), bias_grad=not fuse_a)
+        s2, h2 = self.ln_2.add_forward(s1, a.reshape(M, E), outp.bias.value if fuse_a else None)
+        fuse_f = fuse_tail and self.ff.linear_out.fused_bias_grad_ok(h2, M)
+        f = self.ff(h2.view(B, T, E), bias_grad=not fuse_f)
+        return s2.view(B, T, E), f, (self.ff.linear_out.bias.value if fuse_f else None)
 
 
 class DecoderLM(Module):
@@ -251,15 +265,17 @@ class DecoderLM(Module):
         self.ln = LayerNorm1d(n_embd, ln_eps, device, dtype)
         self.lm_head = Linear(n_embd, n_vocab, bias, device, dtype, gen)
 
-    def forward(self, idx):
+    def forward(self, idx, head_bias_grad: bool = True):
+        """Logits (B, T, n_vocab).  head_bias_grad=False: the caller (loss_fn) hands lm_head's bias to ops.softmax_loss,
+        whose backward kernel reduces its gradient."""
         B, T = idx.shape
         pos = torch.arange(T, device=idx.device).view(1, T)
         x = ops.dropout(self.token_embeddings(idx) + self.position_embeddings(pos), self.p_dropout, self.training)
-        delta = None  # the residual stream is x + delta; each addition happens inside the next LayerNorm's kernel
+        delta = delta_bias = None  # the residual stream is x + delta; each addition happens inside the next LayerNorm's kernel
         for layer in (self.t_layer_1, self.t_layer_2, self.t_layer_3, self.t_layer_4):
-            x, delta = layer.forward_pending(x, delta)
-        _, x = self.ln.add_forward(x.reshape(B * T, self.n_embd), delta.reshape(B * T, self.n_embd))
-        return self.lm_head(x).view(B, T, self.n_vocab)
+            x, delta, delta_bias = layer.forward_pending(x, delta, delta_bias)
+        _, x = self.ln.add_forward(x.reshape(B * T, self.n_embd), delta.reshape(B * T, self.n_embd), delta_bias)
+        return self.lm_head(x, head_bias_grad).view(B, T, self.n_vocab)
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {n: p.value.detach() for n, p in self.named_parameters()}
@@ -267,7 +283,10 @@ class DecoderLM(Module):
 
 def loss_fn(batch, model: DecoderLM):
     """MLE loss averaged over all positions (project/run_machine_translation.py:158-177)."""
-    logits = model(batch["input_ids"])
+    ids, labels = batch["input_ids"], batch["labels"]
+    head = model.lm_head
+    fuse = head.has_bias and ops.fused_logits_bias_grad_ok(head.weights.value, ids.numel(), head.weights.value, head.bias.value, labels)
+    logits = model(ids, head_bias_grad=not fuse)
     B, T, V = logits.shape
-    loss = ops.softmax_loss(logits.view(B * T, V), batch["labels"].view(B * T))
+    loss = ops.softmax_loss(logits.view(B * T, V), labels.view(B * T), head.bias.value if fuse else None)
     return (loss * batch["label_token_weights"].view(B * T)).mean()

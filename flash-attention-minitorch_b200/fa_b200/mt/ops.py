@@ -156,12 +156,12 @@ class _Linear(torch.autograd.Function):
     """y = x @ W + b with W (in, out): forward and both backward products on the tf32 tensor-core GEMM, no transposes."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, bias_grad=True):
         x, w = x.contiguous(), w.contiguous()
         M, K = x.shape
         N = w.shape[1]
         ctx.save_for_backward(x, w)
-        ctx.bias = b
+        ctx.bias = b if bias_grad else None  # bias_grad False: add_layernorm(..., b_bias=) reduces it (see there)
         return _gemm(x, w, (M, N), M, N, K, 0, 1, b.contiguous() if b is not None else None)
 
     @staticmethod
@@ -179,16 +179,28 @@ class _Linear(torch.autograd.Function):
             db = _colsum(dy, M, N, into=gb)
             if gb is not None:
                 db = None
-        return dx, (None if gw is not None else dw), db
+        return dx, (None if gw is not None else dw), db, None
 
 
-def linear(x, weight, bias=None):
+def linear(x, weight, bias=None, bias_grad: bool = True):
+    """x @ W + b.  bias_grad=False (kernel path only): this call leaves the bias gradient to the add_layernorm that
+    consumes its output (pass the bias there as b_bias) -- check fused_bias_grad_ok first."""
     M, K = x.shape
     N = weight.shape[1]
     if _on_kernels(x, weight) and M % 4 == 0 and N % 4 == 0 and K % 4 == 0:
-        return _Linear.apply(x, weight, bias)
+        return _Linear.apply(x, weight, bias, bias_grad)
+    assert bias_grad, "bias_grad=False needs the kernel path"
     y = x @ weight
     return y if bias is None else y + bias
+
+
+def fused_bias_grad_ok(like, M: int, weight, bias) -> bool:
+    """True when linear / linear_from_heads of an (M, in) input on the device / dtype of `like` run on the kernels AND an
+    add_layernorm of their output width can take over the bias reduction (FA_MT_FUSED_BIAS_GRAD=0 turns it off)."""
+    import os
+    K, N = weight.shape
+    return (bias is not None and os.environ.get("FA_MT_FUSED_BIAS_GRAD", "1") != "0" and _on_kernels(like, weight, bias)
+            and M % 4 == 0 and K % 4 == 0 and bool(_lib.load_library().fa_b200_layernorm_fused_width(N)))
 
 
 def _gemm_heads(a, b, c, bias, M, N, K, a_mn, b_mn, a_h, b_h, c_h, T, H, d, accumulate=0):
@@ -251,14 +263,14 @@ class _LinearFromHeads(torch.autograd.Function):
     (modules_transfomer.py:154-157) folded into the A-operand tensor map; backward writes dO straight into head layout."""
 
     @staticmethod
-    def forward(ctx, o, w, b):
+    def forward(ctx, o, w, b, bias_grad=True):
         o, w = o.contiguous(), w.contiguous()
         B, H, T, d = o.shape
         M, E, N = B * T, H * d, w.shape[1]
         y = torch.empty(M, N, device=o.device, dtype=torch.float32)
         _gemm_heads(o, w, y, b.contiguous() if b is not None else None, M, N, E, 0, 1, 1, 0, 0, T, H, d)
         ctx.save_for_backward(o, w)
-        ctx.bias = b
+        ctx.bias = b if bias_grad else None
         return y
 
     @staticmethod
@@ -277,7 +289,7 @@ class _LinearFromHeads(torch.autograd.Function):
             db = _colsum(dy, M, N, into=gb)
             if gb is not None:
                 db = None
-        return do, (None if gw is not None else dw), db
+        return do, (None if gw is not None else dw), db, None
 
 
 class _QKVToHeads(torch.autograd.Function):
@@ -332,12 +344,12 @@ def linear_to_heads(x, weight, bias, B: int, T: int, H: int, d: int):
     return linear(x, weight, bias).view(B, T, H, d).permute(0, 2, 1, 3).contiguous()
 
 
-def linear_from_heads(o, weight, bias):
-    """o (B, H, T, d) -> (B*T, out) = merge_heads(o) @ W + b."""
+def linear_from_heads(o, weight, bias, bias_grad: bool = True):
+    """o (B, H, T, d) -> (B*T, out) = merge_heads(o) @ W + b.  (bias_grad: see linear.)"""
     B, H, T, d = o.shape
     if heads_layout_ok(o, T, d) and _on_kernels(o, weight) and weight.shape[1] % 4 == 0:
-        return _LinearFromHeads.apply(o, weight, bias)
-    return linear(o.permute(0, 2, 1, 3).contiguous().view(B * T, H * d), weight, bias)
+        return _LinearFromHeads.apply(o, weight, bias, bias_grad)
+    return linear(o.permute(0, 2, 1, 3).contiguous().view(B * T, H * d), weight, bias, bias_grad)
 
 
 class _LayerNorm(torch.autograd.Function):
@@ -379,7 +391,7 @@ class _AddLayerNorm(torch.autograd.Function):
     branch gradients."""
 
     @staticmethod
-    def forward(ctx, a, b, w, bias, eps):
+    def forward(ctx, a, b, w, bias, eps, b_bias=None):
         a = a.contiguous()
         rows, dim = a.shape
         y = torch.empty_like(a)
@@ -390,7 +402,7 @@ class _AddLayerNorm(torch.autograd.Function):
                                                                  w.data_ptr(), bias.data_ptr(), s.data_ptr() if b is not None else None,
                                                                  y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, dim, float(eps), _st()))
         ctx.save_for_backward(s, w, mean, rstd)
-        ctx.bias, ctx.has_b = bias, b is not None
+        ctx.bias, ctx.has_b, ctx.b_bias = bias, b is not None, (b_bias if b is not None else None)
         ctx.set_materialize_grads(False)  # an unused sum (the model's final ln) must not cost a zero tensor
         return s, y
 
@@ -398,24 +410,30 @@ class _AddLayerNorm(torch.autograd.Function):
     def backward(ctx, d_s, dy):
         s, w, mean, rstd = ctx.saved_tensors
         rows, dim = s.shape
+        bb = ctx.b_bias
         if dy is None:  # only the sum was used
-            return d_s, (d_s if ctx.has_b else None), None, None, None
+            return d_s, (d_s if ctx.has_b else None), None, None, None, (d_s.sum(0) if bb is not None and d_s is not None else None)
         dy = dy.contiguous()
         ds = torch.empty_like(s)
-        gw, gb = _sink(w), _sink(ctx.bias)
-        sink = gw is not None and gb is not None
+        gw, gb, gc = _sink(w), _sink(ctx.bias), _sink(bb)
+        sink = gw is not None and gb is not None and (bb is None or gc is not None)
         dw, db = (gw, gb) if sink else (torch.empty_like(w), torch.empty_like(w))
+        dc = None if bb is None else (gc if sink else torch.empty_like(w))
         _lib.check(_lib.load_library().fa_b200_layernorm_bwd_res(s.data_ptr(), w.data_ptr(), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                                                  d_s.contiguous().data_ptr() if d_s is not None else None, ds.data_ptr(),
-                                                                 dw.data_ptr(), db.data_ptr(), rows, dim, 1 if sink else 0, _st()))
-        return ds, (ds if ctx.has_b else None), (None if sink else dw), (None if sink else db), None
+                                                                 dw.data_ptr(), db.data_ptr(), dc.data_ptr() if dc is not None else None,
+                                                                 rows, dim, 1 if sink else 0, _st()))
+        return ds, (ds if ctx.has_b else None), (None if sink else dw), (None if sink else db), None, (None if sink else dc)
 
 
-def add_layernorm(a, b, weight, bias, eps: float):
+def add_layernorm(a, b, weight, bias, eps: float, b_bias=None):
     """(a + b, LayerNorm(a + b)) for (rows, dim) tensors; b may be None (then the first result is a).  The pair the
-    transformer layers are built from: the sum is the residual stream, the LayerNorm output feeds the next sub-block."""
+    transformer layers are built from: the sum is the residual stream, the LayerNorm output feeds the next sub-block.
+    b_bias: the bias of the linear layer that produced b with bias_grad=False -- the gradient of b is also that layer's dy,
+    so its bias gradient (the column sums) comes out of this backward kernel for free."""
     if _on_kernels(a, weight, bias) and (b is None or _on_kernels(b)) and _lib.load_library().fa_b200_layernorm_fused_width(a.shape[1]):
-        return _AddLayerNorm.apply(a, b, weight, bias, eps)
+        return _AddLayerNorm.apply(a, b, weight, bias, eps, b_bias)
+    assert b_bias is None, "b_bias needs the kernel path (fused_bias_grad_ok)"
     s = a if b is None else a + b
     return s, layernorm(s, weight, bias, eps)
 
@@ -473,6 +491,29 @@ class _Dropout(torch.autograd.Function):
         return dx, None, None, None
 
 
+class _GeluDropout(torch.autograd.Function):
+    """dropout(gelu(x)) as one pass each way; the mask is the one `dropout` would draw at this call site."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, step):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        _lib.check(_lib.load_library().fa_b200_gelu_dropout_fwd(x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed),
+                                                                step.data_ptr() if step is not None else None, _st()))
+        ctx.save_for_backward(x)
+        ctx.p, ctx.seed, ctx.step = float(p), int(seed), step
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        _lib.check(_lib.load_library().fa_b200_gelu_dropout_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), ctx.p, ctx.seed,
+                                                                ctx.step.data_ptr() if ctx.step is not None else None, _st()))
+        return dx, None, None, None
+
+
 class DropoutState:
     """Seeds of the fused dropout.  Every call site gets its own (base seed, call index) pair; `step` is a device-side
     counter mixed in by the kernel, so a captured CUDA graph (fixed call indices) still draws fresh masks per replay:
@@ -492,15 +533,28 @@ class DropoutState:
 dropout_state = DropoutState()
 
 
+def _next_dropout_seed(x):
+    st = dropout_state
+    st.calls += 1
+    if st.step is None:
+        st.step = torch.zeros(1, dtype=torch.int64, device=x.device)
+    return (st.base_seed << 32) ^ st.calls, st.step
+
+
+def gelu_dropout(x, p: float, training: bool, generator=None):
+    """dropout(gelu(x), p): one kernel each way on the kernel path, the two reference operators otherwise."""
+    if training and p > 0.0 and _on_kernels(x) and x.numel() % 4 == 0:
+        seed, step = _next_dropout_seed(x)
+        return _GeluDropout.apply(x, p, seed, step)
+    return dropout(gelu(x), p, training, generator)
+
+
 def dropout(x, p: float, training: bool, generator=None):
     if not training or p <= 0.0:
         return x
     if _on_kernels(x) and x.numel() % 4 == 0:
-        st = dropout_state
-        st.calls += 1
-        if st.step is None:
-            st.step = torch.zeros(1, dtype=torch.int64, device=x.device)
-        return _Dropout.apply(x, p, (st.base_seed << 32) ^ st.calls, st.step)
+        seed, step = _next_dropout_seed(x)
+        return _Dropout.apply(x, p, seed, step)
     mask = (torch.rand(x.shape, device=x.device, generator=generator) < (1.0 - p)).to(x.dtype)
     return (x * mask) * (1.0 / (1.0 - p))
 
@@ -539,13 +593,14 @@ def embedding(idx, weight):
 
 class _SoftmaxLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, target):
+    def forward(ctx, logits, target, logits_bias=None):
         logits, target = logits.contiguous(), target.contiguous().long()
         rows, C = logits.shape
         loss = torch.empty(rows, device=logits.device, dtype=torch.float32)
         lse = torch.empty_like(loss)
         _lib.check(_lib.load_library().fa_b200_softmax_loss_fwd(logits.data_ptr(), target.data_ptr(), loss.data_ptr(), lse.data_ptr(), rows, C, _st()))
         ctx.save_for_backward(logits, target, lse)
+        ctx.logits_bias = logits_bias
         return loss
 
     @staticmethod
@@ -553,16 +608,35 @@ class _SoftmaxLoss(torch.autograd.Function):
         logits, target, lse = ctx.saved_tensors
         rows, C = logits.shape
         dlogits = torch.empty_like(logits)
-        _lib.check(_lib.load_library().fa_b200_softmax_loss_bwd(logits.data_ptr(), target.data_ptr(), lse.data_ptr(),
-                                                                dloss.contiguous().data_ptr(), dlogits.data_ptr(), rows, C, _st()))
-        return dlogits, None
+        lib = _lib.load_library()
+        bb = ctx.logits_bias
+        if bb is None:
+            _lib.check(lib.fa_b200_softmax_loss_bwd(logits.data_ptr(), target.data_ptr(), lse.data_ptr(), dloss.contiguous().data_ptr(),
+                                                    dlogits.data_ptr(), rows, C, _st()))
+            return dlogits, None, None
+        gc = _sink(bb)  # the logits layer's bias gradient = column sums of dlogits, reduced in the same pass
+        dc = gc if gc is not None else torch.empty(C, device=logits.device, dtype=torch.float32)
+        _lib.check(lib.fa_b200_softmax_loss_bwd_colsum(logits.data_ptr(), target.data_ptr(), lse.data_ptr(), dloss.contiguous().data_ptr(),
+                                                       dlogits.data_ptr(), dc.data_ptr(), rows, C, 1 if gc is not None else 0, _st()))
+        return dlogits, None, (None if gc is not None else dc)
 
 
-def softmax_loss(logits, target):
-    """(minibatch, C) logits, (minibatch,) integer targets -> (minibatch,) losses."""
+def softmax_loss(logits, target, logits_bias=None):
+    """(minibatch, C) logits, (minibatch,) integer targets -> (minibatch,) losses.
+    logits_bias: the bias of the linear layer that produced `logits` with bias_grad=False (fused_logits_bias_grad_ok):
+    its gradient is reduced inside the loss-backward kernel."""
     if _on_kernels(logits) and target.is_cuda and logits.shape[1] % 4 == 0:
-        return _SoftmaxLoss.apply(logits, target)
+        return _SoftmaxLoss.apply(logits, target, logits_bias)
+    assert logits_bias is None, "logits_bias needs the kernel path"
     return torch.logsumexp(logits, dim=1) - logits.gather(1, target.view(-1, 1).long()).view(-1)
+
+
+def fused_logits_bias_grad_ok(like, M: int, weight, bias, target) -> bool:
+    """The loss backward may take over the bias gradient of linear(like-shaped (M, in) input, weight, bias)."""
+    import os
+    K, N = weight.shape
+    return (bias is not None and os.environ.get("FA_MT_FUSED_LOGITS_BIAS_GRAD", "1") != "0" and _on_kernels(like, weight, bias)
+            and target.is_cuda and M % 4 == 0 and K % 4 == 0 and bool(_lib.load_library().fa_b200_softmax_loss_colsum_width(N)))
 
 
 def launch_count() -> int:

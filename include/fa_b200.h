@@ -176,12 +176,20 @@ int fa_b200_layernorm_bwd_accum(const float* x, const float* w, const float* dy,
 /* The residual stream fused into LayerNorm (TransformerLayer.forward, minitorch/modules_transfomer.py: x + attn(ln_1(x)),
  * x + ff(ln_2(x))): forward sum = a + b (b, sum optional) and y = LN(sum) in one pass; backward dx = LN'(dy) + res
  * (res optional: the gradient arriving at the same tensor along the residual branch), dw / db overwritten or
- * accumulated.  b / res need dim in {128, 256, 512} (fa_b200_layernorm_fused_width), where the row stays in
- * registers and the backward is a single launch. */
+ * accumulated.  dcol (optional) (+)= the column sums of dx -- the bias gradient of the linear layer that produced b
+ * (out_projection / ff.linear_out), whose dy is this dx.  b / res / dcol need dim in {128, 256, 512}
+ * (fa_b200_layernorm_fused_width), where the row stays in registers and the backward is a single launch. */
 int fa_b200_add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, float* sum, float* y,
                               float* mean, float* rstd, int rows, int dim, float eps, void* stream);
 int fa_b200_layernorm_bwd_res(const float* x, const float* w, const float* dy, const float* mean, const float* rstd,
-                              const float* res, float* dx, float* dw, float* db, int rows, int dim, int accumulate, void* stream);
+                              const float* res, float* dx, float* dw, float* db, float* dcol, int rows, int dim, int accumulate,
+                              void* stream);
+/* FeedForward's gelu -> dropout pair (minitorch/modules_transfomer.py FeedForward.forward) as one pass each way:
+ * y = drop(gelu(x));  dx = drop(dy) gelu'(x), with exactly the mask of fa_b200_dropout_apply(p_drop, seed, seed_offset_dev). */
+int fa_b200_gelu_dropout_fwd(const float* x, float* y, size_t n, float p_drop, unsigned long long seed,
+                             const unsigned long long* seed_offset_dev, void* stream);
+int fa_b200_gelu_dropout_bwd(const float* x, const float* dy, float* dx, size_t n, float p_drop, unsigned long long seed,
+                             const unsigned long long* seed_offset_dev, void* stream);
 int fa_b200_layernorm_fused_width(int dim);
 int fa_b200_gelu_fwd(const float* x, float* y, size_t n, void* stream);
 int fa_b200_gelu_bwd(const float* x, const float* dy, float* dx, size_t n, void* stream);
@@ -194,6 +202,11 @@ int fa_b200_softmax_loss_fwd(const float* logits, const long long* target, float
                              void* stream);
 int fa_b200_softmax_loss_bwd(const float* logits, const long long* target, const float* lse, const float* gscale,
                              float* dlogits, int rows, int n_classes, void* stream);
+/* softmax_loss_bwd that also reduces dcol[j] (+)= sum_i dlogits[i][j] -- the bias gradient of the linear layer that
+ * produced the logits (lm_head), in the same pass; n_classes <= 12288 (fa_b200_softmax_loss_colsum_width). */
+int fa_b200_softmax_loss_bwd_colsum(const float* logits, const long long* target, const float* lse, const float* gscale,
+                                    float* dlogits, float* dcol, int rows, int n_classes, int accumulate, void* stream);
+int fa_b200_softmax_loss_colsum_width(int n_classes);
 int fa_b200_adam_step(float* p, const float* g, float* m, float* v, size_t n, float step_size, float beta1, float beta2,
                       float v_coef, float eps, void* stream);
 

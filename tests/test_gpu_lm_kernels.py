@@ -281,3 +281,74 @@ def test_packed_attention_equals_unpacked(cuda_device):
     o2 = ops.flash_attention(u[0], u[1], u[2], True)
     (o2 * go).sum().backward()
     assert torch.equal(o1, o2) and torch.equal(p.grad, u.grad) and p.grad.is_contiguous()
+
+
+def test_layernorm_backward_also_reduces_the_producer_bias_gradient(cuda_device):
+    """linear(..., bias_grad=False) followed by add_layernorm(..., b_bias=bias): the bias gradient (column sums of the
+    gradient of b) comes out of the LayerNorm-backward kernel; same numbers as the linear layer's own reduction."""
+    torch.manual_seed(12)
+    rows, K, dim = 640, 64, 256
+    x, a = torch.randn(rows, K, device=cuda_device), torch.randn(rows, dim, device=cuda_device)
+    W, bl = torch.randn(K, dim, device=cuda_device) / 8, torch.randn(dim, device=cuda_device)
+    w, bias = torch.rand(dim, device=cuda_device) + 0.5, torch.rand(dim, device=cuda_device) - 0.5
+    gs, gy = torch.randn(rows, dim, device=cuda_device), torch.randn(rows, dim, device=cuda_device)
+
+    def run(fused):
+        ins = [t.clone().requires_grad_(True) for t in (x, a, W, bl, w, bias)]
+        xx, aa, WW, bb, ww, bi = ins
+        assert ops.fused_bias_grad_ok(xx, rows, WW, bb)
+        before = _lib.launch_count()
+        b = ops.linear(xx, WW, bb, bias_grad=not fused)
+        s, y = ops.add_layernorm(aa, b, ww, bi, 1e-5, bb if fused else None)
+        ((s * gs).sum() + (y * gy).sum()).backward()
+        return _lib.launch_count() - before, [t.grad for t in ins]
+
+    n_plain, g_plain = run(False)
+    n_fused, g_fused = run(True)
+    assert n_plain - n_fused == 1  # the separate bias reduction is gone
+    for gp, gf in zip(g_plain, g_fused):
+        assert float((gp - gf).abs().max()) <= 1e-5 * max(1.0, float(gp.abs().max()))
+    ref = g_plain[1].double().sum(0)  # gradient of b == gradient of a: its column sums
+    assert float((g_fused[3].double() - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_gelu_dropout_equals_gelu_then_dropout(cuda_device):
+    torch.manual_seed(13)
+    x, gy = torch.randn(512, 256, device=cuda_device) * 2, torch.randn(512, 256, device=cuda_device)
+    st = ops.dropout_state
+    calls, step = st.calls, st.step
+    a = x.clone().requires_grad_(True)
+    y1 = ops.gelu_dropout(a, 0.1, True)
+    (y1 * gy).sum().backward()
+    st.calls = calls  # replay the same call site: same mask
+    b = x.clone().requires_grad_(True)
+    y2 = ops.dropout(ops.gelu(b), 0.1, True)
+    (y2 * gy).sum().backward()
+    assert torch.equal(y1, y2) and float((y1 == 0).float().mean()) > 0.05
+    assert float((a.grad - b.grad).abs().max()) <= 1e-6 * max(1.0, float(b.grad.abs().max()))
+    assert torch.equal(ops.gelu_dropout(a, 0.1, False), ops.gelu(a))  # eval mode: plain gelu
+
+
+@pytest.mark.parametrize("rows,C", [(5632, 10000), (12, 36), (300, 12288)])
+def test_softmax_loss_backward_also_reduces_the_logits_bias_gradient(cuda_device, rows, C):
+    torch.manual_seed(rows)
+    K = 32
+    x = torch.randn(rows, K, device=cuda_device)
+    W, b = torch.randn(K, C, device=cuda_device) / 4, torch.randn(C, device=cuda_device)
+    target = torch.randint(0, C, (rows,), device=cuda_device)
+    wts = torch.rand(rows, device=cuda_device)
+
+    def run(fused):
+        ins = [t.clone().requires_grad_(True) for t in (x, W, b)]
+        assert ops.fused_logits_bias_grad_ok(ins[0], rows, ins[1], ins[2], target)
+        before = _lib.launch_count()
+        logits = ops.linear(ins[0], ins[1], ins[2], bias_grad=not fused)
+        loss = ops.softmax_loss(logits, target, ins[2] if fused else None)
+        (loss * wts).mean().backward()
+        return _lib.launch_count() - before, loss, [t.grad for t in ins]
+
+    n_plain, l_plain, g_plain = run(False)
+    n_fused, l_fused, g_fused = run(True)
+    assert n_plain - n_fused == 1 and torch.equal(l_plain, l_fused)
+    for gp, gf in zip(g_plain, g_fused):
+        assert float((gp - gf).abs().max()) <= 1e-5 * max(1e-3, float(gp.abs().max()))
