@@ -467,7 +467,7 @@ int fa_b200_softmax_loss_bwd(const float* logits, const long long* target, const
 int fa_b200_softmax_loss_bwd_colsum(const float* logits, const long long* target, const float* lse, const float* gscale,
                                     float* dlogits, float* dcol, int rows, int n_classes, int accumulate, void* stream) {
   if (!logits || !target || !lse || !gscale || !dlogits || !dcol) return fail(FA_ERR_BAD_ARG, "fa_b200_softmax_loss_bwd_colsum: null pointer");
-  if (!fa::softmax_loss_colsum_width(n_classes)) return fail(FA_ERR_UNSUPPORTED, "fa_b200_softmax_loss_bwd_colsum: n_classes must be a multiple of 4, at most 12288");
+  if (!fa::softmax_loss_colsum_width(n_classes)) return fail(FA_ERR_UNSUPPORTED, "fa_b200_softmax_loss_bwd_colsum: n_classes must be a multiple of 4, at most 49152");
   FA_CUDA(fa::softmax_loss_bwd_colsum(logits, target, lse, gscale, dlogits, dcol, rows, n_classes, accumulate != 0, FA_ST), 1);
   return FA_OK;
 }

@@ -98,7 +98,7 @@ cudaError_t softmax_loss_fwd(const float* logits, const long long* target, float
                              cudaStream_t st);
 cudaError_t softmax_loss_bwd(const float* logits, const long long* target, const float* lse, const float* gscale,
                              float* dlogits, int rows, int C, cudaStream_t st);
-// + dcol (+)= column sums of dlogits (the logits layer's bias gradient); C <= 12288
+// + dcol (+)= column sums of dlogits (the logits layer's bias gradient); C <= 49152
 bool softmax_loss_colsum_width(int C);
 cudaError_t softmax_loss_bwd_colsum(const float* logits, const long long* target, const float* lse, const float* gscale,
                                     float* dlogits, float* dcol, int rows, int C, bool accumulate, cudaStream_t st);

@@ -370,10 +370,11 @@ __global__ void softmax_loss_bwd_kernel(const float* __restrict__ logits, const 
 }
 
 // The same plus dcol[j] += sum_i dlogits[i][j] -- the bias gradient of the linear layer that produced the logits -- in
-// the same pass: a CTA takes a strip of rows, thread t owns column quads t, t + 256, ... (C <= 4 * 256 * kLossQuads), keeps
-// their sums in registers and issues one atomic per column at the end.
-constexpr int kLossQuads = 12;
-__global__ void __launch_bounds__(256) softmax_loss_bwd_colsum_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+// the same pass: a CTA takes a strip of rows and a chunk of 4 * 256 * kLossQuads columns (blockIdx.y), thread t owns
+// column quads t, t + 256, ... of the chunk, keeps their sums in registers and issues one atomic per column at the end.
+// (6 quads per thread: ~70 registers, three CTAs per SM -- 12 quads / two CTAs left the loads idle during the exps.)
+constexpr int kLossQuads = 6;
+__global__ void __launch_bounds__(256, 3) softmax_loss_bwd_colsum_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                                                                       const float* __restrict__ lse, const float* __restrict__ gscale,
                                                                       float* __restrict__ dlogits, float* __restrict__ dcol, int rows,
                                                                       int C, int rows_per_block) {
@@ -389,12 +390,12 @@ __global__ void __launch_bounds__(256) softmax_loss_bwd_colsum_kernel(const floa
     float4 v[kLossQuads];  // the whole row slice first: kLossQuads independent 16-byte loads in flight per thread
 #pragma unroll
     for (int k = 0; k < kLossQuads; ++k) {
-      const int c = (k * 256 + threadIdx.x) * 4;
+      const int c = ((blockIdx.y * kLossQuads + k) * 256 + threadIdx.x) * 4;
       if (c < C) v[k] = __ldcs(reinterpret_cast<const float4*>(row + c));
     }
 #pragma unroll
     for (int k = 0; k < kLossQuads; ++k) {
-      const int c = (k * 256 + threadIdx.x) * 4;
+      const int c = ((blockIdx.y * kLossQuads + k) * 256 + threadIdx.x) * 4;
       if (c < C) {
         float4 o = make_float4(g * __expf(v[k].x - L), g * __expf(v[k].y - L), g * __expf(v[k].z - L), g * __expf(v[k].w - L));
         if (t >= c && t < c + 4) (&o.x)[t - c] -= g;
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(256) softmax_loss_bwd_colsum_kernel(const floa
   }
 #pragma unroll
   for (int k = 0; k < kLossQuads; ++k) {
-    const int c = (k * 256 + threadIdx.x) * 4;
+    const int c = ((blockIdx.y * kLossQuads + k) * 256 + threadIdx.x) * 4;
     if (c < C) {
       atomicAdd(dcol + c, acc[k].x); atomicAdd(dcol + c + 1, acc[k].y);
       atomicAdd(dcol + c + 2, acc[k].z); atomicAdd(dcol + c + 3, acc[k].w);
@@ -539,7 +540,7 @@ cudaError_t softmax_loss_bwd(const float* logits, const long long* target, const
   softmax_loss_bwd_kernel<<<rows, 256, 0, st>>>(logits, target, lse, gscale, dlogits, C);
   return cudaGetLastError();
 }
-bool softmax_loss_colsum_width(int C) { return C > 0 && !(C & 3) && C <= 4 * 256 * kLossQuads; }
+bool softmax_loss_colsum_width(int C) { return C > 0 && !(C & 3) && C <= 4 * 256 * kLossQuads * 8; }
 cudaError_t softmax_loss_bwd_colsum(const float* logits, const long long* target, const float* lse, const float* gscale,
                                     float* dlogits, float* dcol, int rows, int C, bool accumulate, cudaStream_t st) {
   if (rows <= 0 || !softmax_loss_colsum_width(C)) return cudaErrorInvalidValue;
@@ -547,10 +548,11 @@ cudaError_t softmax_loss_bwd_colsum(const float* logits, const long long* target
     cudaError_t e = cudaMemsetAsync(dcol, 0, (size_t)C * 4, st);
     if (e != cudaSuccess) return e;
   }
-  int strips = kSMs * 2;  // two CTAs per SM (<= 128 registers), each thread with up to kLossQuads 16-byte loads in flight
+  const int chunks = (C + 4 * 256 * kLossQuads - 1) / (4 * 256 * kLossQuads);
+  int strips = (kSMs * 3 + chunks - 1) / chunks;  // three CTAs per SM, each thread with up to kLossQuads 16-byte loads in flight
   if (strips > rows) strips = rows;
   const int rpb = (rows + strips - 1) / strips;
-  softmax_loss_bwd_colsum_kernel<<<(rows + rpb - 1) / rpb, 256, 0, st>>>(logits, target, lse, gscale, dlogits, dcol, rows, C, rpb);
+  softmax_loss_bwd_colsum_kernel<<<dim3((rows + rpb - 1) / rpb, chunks), 256, 0, st>>>(logits, target, lse, gscale, dlogits, dcol, rows, C, rpb);
   return cudaGetLastError();
 }
 cudaError_t adam_step(float* p, const float* g, float* m, float* v, size_t n, float step_size, float b1, float b2,

@@ -203,7 +203,7 @@ int fa_b200_softmax_loss_fwd(const float* logits, const long long* target, float
 int fa_b200_softmax_loss_bwd(const float* logits, const long long* target, const float* lse, const float* gscale,
                              float* dlogits, int rows, int n_classes, void* stream);
 /* softmax_loss_bwd that also reduces dcol[j] (+)= sum_i dlogits[i][j] -- the bias gradient of the linear layer that
- * produced the logits (lm_head), in the same pass; n_classes <= 12288 (fa_b200_softmax_loss_colsum_width). */
+ * produced the logits (lm_head), in the same pass; n_classes <= 49152 (fa_b200_softmax_loss_colsum_width). */
 int fa_b200_softmax_loss_bwd_colsum(const float* logits, const long long* target, const float* lse, const float* gscale,
                                     float* dlogits, float* dcol, int rows, int n_classes, int accumulate, void* stream);
 int fa_b200_softmax_loss_colsum_width(int n_classes);

@@ -329,7 +329,7 @@ def test_gelu_dropout_equals_gelu_then_dropout(cuda_device):
     assert torch.equal(ops.gelu_dropout(a, 0.1, False), ops.gelu(a))  # eval mode: plain gelu
 
 
-@pytest.mark.parametrize("rows,C", [(5632, 10000), (12, 36), (300, 12288)])
+@pytest.mark.parametrize("rows,C", [(5632, 10000), (12, 36), (300, 12288), (40, 20000)])
 def test_softmax_loss_backward_also_reduces_the_logits_bias_gradient(cuda_device, rows, C):
     torch.manual_seed(rows)
     K = 32

@@ -90,6 +90,14 @@ report("layernorm fwd 5632x256", timeit(lambda: _lib.check(lib.fa_b200_layernorm
        nbytes=2.0 * 4 * M * E)
 report("layernorm bwd 5632x256", timeit(lambda: _lib.check(lib.fa_b200_layernorm_bwd(P(x), P(lw), P(dy), P(mean), P(rstd), P(dx), P(dlw), P(dlb), M, E, st()))),
        nbytes=5.0 * 4 * M * E)
+x2, ssum, dcol = torch.randn(M, E, **f32), torch.empty(M, E, **f32), torch.zeros(E, **f32)
+report("residual add + layernorm fwd 5632x256", timeit(lambda: _lib.check(lib.fa_b200_add_layernorm_fwd(P(x), P(x2), P(lw), P(lb), P(ssum), P(y), P(mean), P(rstd), M, E, 1e-5, st()))),
+       nbytes=4.0 * 4 * M * E)
+report("layernorm bwd + branch grad + dw/db + producer bias grad (accumulating) 5632x256",
+       timeit(lambda: _lib.check(lib.fa_b200_layernorm_bwd_res(P(x), P(lw), P(dy), P(mean), P(rstd), P(x2), P(dx), P(dlw), P(dlb), P(dcol), M, E, 1, st()))),
+       nbytes=4.0 * 4 * M * E)
+report("gelu+dropout fwd 5632x256", timeit(lambda: _lib.check(lib.fa_b200_gelu_dropout_fwd(P(x), P(y), M * MID, 0.1, 7, None, st()))), nbytes=2.0 * 4 * M * MID)
+report("gelu+dropout bwd 5632x256", timeit(lambda: _lib.check(lib.fa_b200_gelu_dropout_bwd(P(x), P(dy), P(dx), M * MID, 0.1, 7, None, st()))), nbytes=3.0 * 4 * M * MID)
 report("gelu fwd 5632x256", timeit(lambda: _lib.check(lib.fa_b200_gelu_fwd(P(x), P(y), M * MID, st()))), nbytes=2.0 * 4 * M * MID)
 report("gelu bwd 5632x256", timeit(lambda: _lib.check(lib.fa_b200_gelu_bwd(P(x), P(dy), P(dx), M * MID, st()))), nbytes=3.0 * 4 * M * MID)
 report("dropout 5632x256", timeit(lambda: _lib.check(lib.fa_b200_dropout_apply(P(x), P(y), M * MID, 0.1, 7, None, st()))), nbytes=2.0 * 4 * M * MID)
@@ -99,6 +107,13 @@ report("softmax_loss fwd 5632x10000", timeit(lambda: _lib.check(lib.fa_b200_soft
        nbytes=4.0 * M * V)
 report("softmax_loss bwd 5632x10000", timeit(lambda: _lib.check(lib.fa_b200_softmax_loss_bwd(P(yv), P(target), P(lse), P(gs), P(dyv), M, V, st()))),
        nbytes=2.0 * 4 * M * V)
+dbv = torch.zeros(V, **f32)
+report("softmax_loss bwd + lm_head bias grad 5632x10000", timeit(lambda: _lib.check(lib.fa_b200_softmax_loss_bwd_colsum(P(yv), P(target), P(lse), P(gs), P(dyv), P(dbv), M, V, 1, st()))),
+       nbytes=2.0 * 4 * M * V)
+qkv = torch.randn(3, 11, 8, 512, 32, **f32)
+dbq = torch.zeros(3 * E, **f32)
+report("bias grad of the fused q|k|v projection (3,11,8,512,32)", timeit(lambda: _lib.check(lib.fa_b200_colsum_heads_parts_f32(P(qkv), P(dbq), 3, 11, 8, 512, 32, 1, st()))),
+       nbytes=4.0 * 3 * M * E)
 n = 9273616
 p_, g_, m_, v_ = (torch.randn(n, **f32) for _ in range(4))
 v_.abs_()
