@@ -452,6 +452,22 @@ int fa_b200_embedding_bwd_accum(const long long* idx, const float* dy, float* dw
   FA_CUDA(fa::embedding_bwd(idx, dy, dw, n_idx, dim, vocab, FA_ST, true), 1);
   return FA_OK;
 }
+int fa_b200_embed_pos_dropout_fwd(const long long* idx, const float* tok_w, const float* pos_w, float* y, size_t n_idx, int T, int dim,
+                                  float p_drop, unsigned long long seed, const unsigned long long* seed_offset_dev, void* stream) {
+  if (!idx || !tok_w || !pos_w || !y) return fail(FA_ERR_BAD_ARG, "fa_b200_embed_pos_dropout_fwd: null pointer");
+  if (int rc = check_p_drop(p_drop, "fa_b200_embed_pos_dropout_fwd")) return rc;
+  FA_CUDA(fa::embed_pos_dropout_fwd(idx, tok_w, pos_w, y, n_idx, T, dim, fa::make_dropout(p_drop, seed), seed_offset_dev, FA_ST), 1);
+  return FA_OK;
+}
+int fa_b200_embed_pos_dropout_bwd(const long long* idx, const float* dy, float* dtok, float* dpos, size_t n_idx, int T, int dim,
+                                  size_t tok_rows, size_t pos_rows, float p_drop, unsigned long long seed,
+                                  const unsigned long long* seed_offset_dev, int accumulate, void* stream) {
+  if (!idx || !dy || !dtok || !dpos) return fail(FA_ERR_BAD_ARG, "fa_b200_embed_pos_dropout_bwd: null pointer");
+  if (int rc = check_p_drop(p_drop, "fa_b200_embed_pos_dropout_bwd")) return rc;
+  FA_CUDA(fa::embed_pos_dropout_bwd(idx, dy, dtok, dpos, n_idx, T, dim, tok_rows, pos_rows, fa::make_dropout(p_drop, seed),
+                                    seed_offset_dev, accumulate != 0, FA_ST), 1);
+  return FA_OK;
+}
 int fa_b200_softmax_loss_fwd(const float* logits, const long long* target, float* loss, float* lse, int rows, int n_classes,
                              void* stream) {
   if (!logits || !target || !loss || !lse) return fail(FA_ERR_BAD_ARG, "fa_b200_softmax_loss_fwd: null pointer");

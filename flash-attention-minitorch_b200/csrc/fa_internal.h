@@ -94,6 +94,12 @@ cudaError_t dropout_apply(const float* x, float* y, size_t n, Dropout drop, cons
 cudaError_t embedding_fwd(const long long* idx, const float* w, float* y, size_t n_idx, int dim, cudaStream_t st);
 cudaError_t embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, cudaStream_t st,
                           bool accumulate = false);
+// y[r] = drop(tok[idx[r]] + pos[r % T]) and its backward (scatter-add onto both tables; zeroed first unless accumulate)
+cudaError_t embed_pos_dropout_fwd(const long long* idx, const float* tok, const float* pos, float* y, size_t n_idx, int T, int dim,
+                                  Dropout drop, const unsigned long long* seed_offset, cudaStream_t st);
+cudaError_t embed_pos_dropout_bwd(const long long* idx, const float* dy, float* dtok, float* dpos, size_t n_idx, int T, int dim,
+                                  size_t tok_rows, size_t pos_rows, Dropout drop, const unsigned long long* seed_offset,
+                                  bool accumulate, cudaStream_t st);
 cudaError_t softmax_loss_fwd(const float* logits, const long long* target, float* loss, float* lse, int rows, int C,
                              cudaStream_t st);
 cudaError_t softmax_loss_bwd(const float* logits, const long long* target, const float* lse, const float* gscale,

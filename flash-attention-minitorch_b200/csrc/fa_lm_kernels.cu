@@ -318,6 +318,50 @@ __global__ void embedding_bwd_kernel(const long long* __restrict__ idx, const fl
   }
 }
 
+// The model's input stage as one pass each way (DecoderLM.forward, minitorch/modules_transfomer.py: token embedding +
+// position embedding, then dropout): y[r] = drop(tok[idx[r]] + pos[r % T]);  backward: g = drop(dy[r]) scattered onto
+// dtok[idx[r]] and dpos[r % T].  Same mask as dropout_kernel on the flattened (rows, dim) tensor (thr = 0: identity).
+__global__ void embed_pos_dropout_fwd_kernel(const long long* __restrict__ idx, const float* __restrict__ tok,
+                                             const float* __restrict__ pos, float* __restrict__ y, size_t n_idx, int T, int dim4,
+                                             uint32_t key, uint32_t thr, float scale, const unsigned long long* __restrict__ seed_offset) {
+  if (seed_offset) {
+    const unsigned long long o = *seed_offset;
+    key = drop_mix(key ^ drop_mix((uint32_t)o + 0x9E3779B9u * (uint32_t)(o >> 32)));
+  }
+  const size_t total = n_idx * dim4, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / dim4;
+    const int c = (int)(i - r * dim4);
+    const float4 a = reinterpret_cast<const float4*>(tok)[(size_t)idx[r] * dim4 + c];
+    const float4 b = reinterpret_cast<const float4*>(pos)[(size_t)(r % T) * dim4 + c];
+    const uint32_t w = drop_keep_word(drop_mix(key ^ ((uint32_t)i * kDropRowMul) ^ ((uint32_t)(i >> 32) * kDropColMul)), thr);
+    reinterpret_cast<float4*>(y)[i] =
+        make_float4((w & 0x80u) ? (a.x + b.x) * scale : 0.f, (w & 0x8000u) ? (a.y + b.y) * scale : 0.f,
+                    (w & 0x800000u) ? (a.z + b.z) * scale : 0.f, (w & 0x80000000u) ? (a.w + b.w) * scale : 0.f);
+  }
+}
+__global__ void embed_pos_dropout_bwd_kernel(const long long* __restrict__ idx, const float* __restrict__ dy, float* __restrict__ dtok,
+                                             float* __restrict__ dpos, size_t n_idx, int T, int dim4, uint32_t key, uint32_t thr,
+                                             float scale, const unsigned long long* __restrict__ seed_offset) {
+  if (seed_offset) {
+    const unsigned long long o = *seed_offset;
+    key = drop_mix(key ^ drop_mix((uint32_t)o + 0x9E3779B9u * (uint32_t)(o >> 32)));
+  }
+  const size_t total = n_idx * dim4, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / dim4;
+    const int c = (int)(i - r * dim4);
+    const float4 g = reinterpret_cast<const float4*>(dy)[i];
+    const uint32_t w = drop_keep_word(drop_mix(key ^ ((uint32_t)i * kDropRowMul) ^ ((uint32_t)(i >> 32) * kDropColMul)), thr);
+    const float g0 = (w & 0x80u) ? g.x * scale : 0.f, g1 = (w & 0x8000u) ? g.y * scale : 0.f;
+    const float g2 = (w & 0x800000u) ? g.z * scale : 0.f, g3 = (w & 0x80000000u) ? g.w * scale : 0.f;
+    float* a = dtok + ((size_t)idx[r] * dim4 + c) * 4;
+    float* b = dpos + ((size_t)(r % T) * dim4 + c) * 4;
+    atomicAdd(a, g0); atomicAdd(a + 1, g1); atomicAdd(a + 2, g2); atomicAdd(a + 3, g3);
+    atomicAdd(b, g0); atomicAdd(b + 1, g1); atomicAdd(b + 2, g2); atomicAdd(b + 3, g3);
+  }
+}
+
 // ---------------------------------------------------------------- softmax cross-entropy (one CTA per row)
 __device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
   v = is_max ? warp_max(v) : warp_sum(v);
@@ -526,6 +570,28 @@ cudaError_t embedding_bwd(const long long* idx, const float* dy, float* dw, size
     if (e != cudaSuccess) return e;
   }
   embedding_bwd_kernel<<<ew_grid(n_idx * dim, 256), 256, 0, st>>>(idx, dy, dw, n_idx, dim);
+  return cudaGetLastError();
+}
+cudaError_t embed_pos_dropout_fwd(const long long* idx, const float* tok, const float* pos, float* y, size_t n_idx, int T, int dim,
+                                  Dropout drop, const unsigned long long* seed_offset, cudaStream_t st) {
+  if (dim <= 0 || (dim & 3) || T <= 0) return cudaErrorInvalidValue;
+  const uint32_t key = drop_head_key(drop.seed_lo, drop.seed_hi, 0xE1E7u);
+  embed_pos_dropout_fwd_kernel<<<ew_grid(n_idx * (dim / 4), 256), 256, 0, st>>>(idx, tok, pos, y, n_idx, T, dim / 4, key, drop.thr,
+                                                                                 drop.keep_scale, seed_offset);
+  return cudaGetLastError();
+}
+cudaError_t embed_pos_dropout_bwd(const long long* idx, const float* dy, float* dtok, float* dpos, size_t n_idx, int T, int dim,
+                                  size_t tok_rows, size_t pos_rows, Dropout drop, const unsigned long long* seed_offset,
+                                  bool accumulate, cudaStream_t st) {
+  if (dim <= 0 || (dim & 3) || T <= 0 || pos_rows < (size_t)T) return cudaErrorInvalidValue;
+  if (!accumulate) {
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(dtok, 0, tok_rows * dim * 4, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(dpos, 0, pos_rows * dim * 4, st)) != cudaSuccess) return e;
+  }
+  const uint32_t key = drop_head_key(drop.seed_lo, drop.seed_hi, 0xE1E7u);
+  embed_pos_dropout_bwd_kernel<<<ew_grid(n_idx * (dim / 4), 256), 256, 0, st>>>(idx, dy, dtok, dpos, n_idx, T, dim / 4, key, drop.thr,
+                                                                                 drop.keep_scale, seed_offset);
   return cudaGetLastError();
 }
 cudaError_t softmax_loss_fwd(const float* logits, const long long* target, float* loss, float* lse, int rows, int C,

@@ -269,8 +269,9 @@ class DecoderLM(Module):
         """Logits (B, T, n_vocab).  head_bias_grad=False: the caller (loss_fn) hands lm_head's bias to ops.softmax_loss,
         whose backward kernel reduces its gradient."""
         B, T = idx.shape
-        pos = torch.arange(T, device=idx.device).view(1, T)
-        x = ops.dropout(self.token_embeddings(idx) + self.position_embeddings(pos), self.p_dropout, self.training)
+        # dropout(token_embeddings(idx) + position_embeddings(arange(T))): one gather pass, one scatter pass back
+        x = ops.embed_pos_dropout(idx, self.token_embeddings.weights.value, self.position_embeddings.weights.value,
+                                  self.p_dropout, self.training)
         delta = delta_bias = None  # the residual stream is x + delta; each addition happens inside the next LayerNorm's kernel
         for layer in (self.t_layer_1, self.t_layer_2, self.t_layer_3, self.t_layer_4):
             x, delta, delta_bias = layer.forward_pending(x, delta, delta_bias)

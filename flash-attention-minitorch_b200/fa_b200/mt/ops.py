@@ -585,6 +585,51 @@ class _Embedding(torch.autograd.Function):
         return None, dw
 
 
+class _EmbedPosDropout(torch.autograd.Function):
+    """dropout(tok_w[idx] + pos_w[arange(T)]) for idx (B, T): one gather pass forward, one scatter pass backward."""
+
+    @staticmethod
+    def forward(ctx, idx, tok_w, pos_w, p, seed, step):
+        idx = idx.contiguous().long()
+        B, T = idx.shape
+        dim = tok_w.shape[1]
+        y = torch.empty(B, T, dim, device=tok_w.device, dtype=torch.float32)
+        _lib.check(_lib.load_library().fa_b200_embed_pos_dropout_fwd(idx.data_ptr(), tok_w.contiguous().data_ptr(), pos_w.contiguous().data_ptr(),
+                                                                     y.data_ptr(), idx.numel(), T, dim, float(p), int(seed),
+                                                                     step.data_ptr() if step is not None else None, _st()))
+        ctx.save_for_backward(idx)
+        ctx.tables, ctx.p, ctx.seed, ctx.step = (tok_w, pos_w), float(p), int(seed), step
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        tok_w, pos_w = ctx.tables
+        B, T = idx.shape
+        dim = tok_w.shape[1]
+        gt, gp = _sink(tok_w), _sink(pos_w)
+        sink = gt is not None and gp is not None
+        dt, dp = (gt, gp) if sink else (torch.empty_like(tok_w), torch.empty_like(pos_w))
+        _lib.check(_lib.load_library().fa_b200_embed_pos_dropout_bwd(idx.data_ptr(), dy.contiguous().data_ptr(), dt.data_ptr(), dp.data_ptr(),
+                                                                     idx.numel(), T, dim, tok_w.shape[0], pos_w.shape[0], ctx.p, ctx.seed,
+                                                                     ctx.step.data_ptr() if ctx.step is not None else None,
+                                                                     1 if sink else 0, _st()))
+        return None, (None if sink else dt), (None if sink else dp), None, None, None
+
+
+def embed_pos_dropout(idx, tok_weight, pos_weight, p: float, training: bool, generator=None):
+    """dropout(tok_weight[idx] + pos_weight[arange(T)], p) for idx (B, T) -- the model's input stage; one kernel each way on
+    the kernel path, the reference operators otherwise."""
+    B, T = idx.shape
+    if (_on_kernels(tok_weight, pos_weight) and idx.is_cuda and tok_weight.shape[1] % 4 == 0 and tok_weight.shape[1] == pos_weight.shape[1]
+            and pos_weight.shape[0] >= T and tok_weight.is_contiguous() and pos_weight.is_contiguous()):
+        drop = training and p > 0.0
+        seed, step = _next_dropout_seed(tok_weight) if drop else (0, None)
+        return _EmbedPosDropout.apply(idx, tok_weight, pos_weight, p if drop else 0.0, seed, step)
+    pos = torch.arange(T, device=idx.device).view(1, T)
+    return dropout(embedding(idx, tok_weight) + embedding(pos, pos_weight), p, training, generator)
+
+
 def embedding(idx, weight):
     if _on_kernels(weight) and idx.is_cuda and weight.shape[1] % 4 == 0:
         return _Embedding.apply(idx, weight)

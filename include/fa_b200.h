@@ -198,6 +198,15 @@ int fa_b200_dropout_apply(const float* x, float* y, size_t n, float p_drop, unsi
 int fa_b200_embedding_fwd(const long long* idx, const float* w, float* y, size_t n_idx, int dim, void* stream);
 int fa_b200_embedding_bwd(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, void* stream);
 int fa_b200_embedding_bwd_accum(const long long* idx, const float* dy, float* dw, size_t n_idx, int dim, size_t vocab, void* stream);
+/* The model's input stage (DecoderLM.forward, minitorch/modules_transfomer.py: token_embeddings(idx) +
+ * position_embeddings(arange(T)), then dropout) as one pass each way: y[r] = drop(tok_w[idx[r]] + pos_w[r % T]) for the
+ * n_idx = B*T row-major indices; bwd scatter-adds drop(dy[r]) onto dtok[idx[r]] and dpos[r % T] (both tables zeroed first
+ * unless accumulate).  Mask = fa_b200_dropout_apply's on the flattened (n_idx, dim) tensor; p_drop = 0: no dropout. */
+int fa_b200_embed_pos_dropout_fwd(const long long* idx, const float* tok_w, const float* pos_w, float* y, size_t n_idx, int T, int dim,
+                                  float p_drop, unsigned long long seed, const unsigned long long* seed_offset_dev, void* stream);
+int fa_b200_embed_pos_dropout_bwd(const long long* idx, const float* dy, float* dtok, float* dpos, size_t n_idx, int T, int dim,
+                                  size_t tok_rows, size_t pos_rows, float p_drop, unsigned long long seed,
+                                  const unsigned long long* seed_offset_dev, int accumulate, void* stream);
 int fa_b200_softmax_loss_fwd(const float* logits, const long long* target, float* loss, float* lse, int rows, int n_classes,
                              void* stream);
 int fa_b200_softmax_loss_bwd(const float* logits, const long long* target, const float* lse, const float* gscale,

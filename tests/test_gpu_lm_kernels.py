@@ -352,3 +352,31 @@ def test_softmax_loss_backward_also_reduces_the_logits_bias_gradient(cuda_device
     assert n_plain - n_fused == 1 and torch.equal(l_plain, l_fused)
     for gp, gf in zip(g_plain, g_fused):
         assert float((gp - gf).abs().max()) <= 1e-5 * max(1e-3, float(gp.abs().max()))
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_embed_pos_dropout_equals_the_three_operators(cuda_device, training):
+    """ops.embed_pos_dropout = dropout(embedding(idx, tok) + embedding(arange(T), pos)): same values (same mask at the
+    same call site), same table gradients; rows of the position table beyond T get no gradient."""
+    torch.manual_seed(21)
+    B, T, V, dim = 5, 64, 300, 128
+    idx = torch.randint(0, V, (B, T), device=cuda_device)
+    tok, pos = torch.randn(V, dim, device=cuda_device), torch.randn(V, dim, device=cuda_device)
+    gy = torch.randn(B, T, dim, device=cuda_device)
+    st = ops.dropout_state
+    calls = st.calls
+    t1, p1 = tok.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    before = _lib.launch_count()
+    y1 = ops.embed_pos_dropout(idx, t1, p1, 0.1, training)
+    (y1 * gy).sum().backward()
+    assert _lib.launch_count() - before == 2
+    st.calls = calls
+    t2, p2 = tok.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    ar = torch.arange(T, device=cuda_device).view(1, T)
+    y2 = ops.dropout(ops.embedding(idx, t2) + ops.embedding(ar, p2), 0.1, training)
+    (y2 * gy).sum().backward()
+    assert torch.equal(y1, y2)
+    assert training == bool((y1 == 0).any())
+    for a, b in ((t1.grad, t2.grad), (p1.grad, p2.grad)):
+        assert float((a - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max()))
+    assert float(p1.grad[T:].abs().max()) == 0.0
