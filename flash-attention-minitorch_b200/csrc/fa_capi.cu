@@ -430,6 +430,14 @@ int fa_b200_gelu_bwd(const float* x, const float* dy, float* dx, size_t n, void*
   FA_CUDA(fa::gelu(x, dy, dx, n, true, FA_ST), 1);
   return FA_OK;
 }
+int fa_b200_gelu_dropout_bwd_colsum(const float* x, const float* dy, float* dx, float* dcol, int rows, int dim, float p_drop,
+                                    unsigned long long seed, const unsigned long long* seed_offset_dev, int accumulate, void* stream) {
+  if (!x || !dy || !dx || !dcol) return fail(FA_ERR_BAD_ARG, "fa_b200_gelu_dropout_bwd_colsum: null pointer");
+  if (!fa::layernorm_fused_width(dim)) return fail(FA_ERR_UNSUPPORTED, "fa_b200_gelu_dropout_bwd_colsum: dim must be 128, 256 or 512");
+  if (int rc = check_p_drop(p_drop, "fa_b200_gelu_dropout_bwd_colsum")) return rc;
+  FA_CUDA(fa::gelu_dropout_bwd_colsum(x, dy, dx, dcol, rows, dim, fa::make_dropout(p_drop, seed), seed_offset_dev, accumulate != 0, FA_ST), 1);
+  return FA_OK;
+}
 int fa_b200_dropout_apply(const float* x, float* y, size_t n, float p_drop, unsigned long long seed,
                           const unsigned long long* seed_offset_dev, void* stream) {
   if (!x || !y) return fail(FA_ERR_BAD_ARG, "fa_b200_dropout_apply: null pointer");

@@ -89,6 +89,9 @@ cudaError_t layernorm_bwd(const float* x, const float* w, const float* dy, const
 cudaError_t gelu_dropout(const float* x, const float* dy, float* y, size_t n, bool backward, Dropout drop,
                          const unsigned long long* seed_offset, cudaStream_t st);
 cudaError_t gelu(const float* x, const float* dy, float* y, size_t n, bool backward, cudaStream_t st);
+// backward of drop(gelu(x)), x (rows, dim in {128, 256, 512}), plus dcol (+)= column sums of dx
+cudaError_t gelu_dropout_bwd_colsum(const float* x, const float* dy, float* dx, float* dcol, int rows, int dim, Dropout drop,
+                                    const unsigned long long* seed_offset, bool accumulate, cudaStream_t st);
 cudaError_t dropout_apply(const float* x, float* y, size_t n, Dropout drop, const unsigned long long* seed_offset,
                           cudaStream_t st);
 cudaError_t embedding_fwd(const long long* idx, const float* w, float* y, size_t n_idx, int dim, cudaStream_t st);

@@ -278,6 +278,55 @@ __global__ void gelu_kernel(const float* __restrict__ x, const float* __restrict
   }
 }
 
+// The backward of drop(gelu(x)) for x = (rows, 128 * kVec) that also reduces dcol[c] += sum_rows dx[.][c] -- the bias
+// gradient of the linear layer that produced x (ff.linear_in).  One warp per row, lanes own columns (as the LayerNorm
+// backward above): sums in registers, CTA reduction in shared memory, one atomic per column per CTA.
+template <int kVec>
+__global__ void __launch_bounds__(256) gelu_dropout_bwd_colsum_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                      float* __restrict__ dx, float* __restrict__ dcol, int rows,
+                                                                      uint32_t key, uint32_t thr, float scale,
+                                                                      const unsigned long long* __restrict__ seed_offset) {
+  constexpr int dim = 128 * kVec;
+  __shared__ float4 red[8][32 * kVec];
+  if (seed_offset) {
+    const unsigned long long o = *seed_offset;
+    key = drop_mix(key ^ drop_mix((uint32_t)o + 0x9E3779B9u * (uint32_t)(o >> 32)));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 ac[kVec];
+#pragma unroll
+  for (int j = 0; j < kVec; ++j) ac[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    float4 v[kVec], g[kVec];
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const size_t i = (size_t)row * (dim / 4) + j * 32 + lane;
+      v[j] = reinterpret_cast<const float4*>(x)[i];
+      g[j] = reinterpret_cast<const float4*>(dy)[i];
+    }
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const size_t i = (size_t)row * (dim / 4) + j * 32 + lane;  // the float4 index dropout_kernel hashes
+      const uint32_t w = drop_keep_word(drop_mix(key ^ ((uint32_t)i * kDropRowMul) ^ ((uint32_t)(i >> 32) * kDropColMul)), thr);
+      const float4 o = make_float4((w & 0x80u) ? g[j].x * gelu_grad_f(v[j].x) * scale : 0.f, (w & 0x8000u) ? g[j].y * gelu_grad_f(v[j].y) * scale : 0.f,
+                                   (w & 0x800000u) ? g[j].z * gelu_grad_f(v[j].z) * scale : 0.f,
+                                   (w & 0x80000000u) ? g[j].w * gelu_grad_f(v[j].w) * scale : 0.f);
+      reinterpret_cast<float4*>(dx)[i] = o;
+      ac[j] = make_float4(ac[j].x + o.x, ac[j].y + o.y, ac[j].z + o.z, ac[j].w + o.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kVec; ++j) red[warp][j * 32 + lane] = ac[j];
+  __syncthreads();
+  const float* rf = reinterpret_cast<const float*>(red);
+  for (int c = threadIdx.x; c < dim; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) t += rf[wp * dim + c];
+    atomicAdd(dcol + c, t);
+  }
+}
+
 // ---------------------------------------------------------------- dropout: y = x * keep / (1 - p), keep = f(seed, index)
 // The same call serves forward and backward (the op is linear in x): nothing is stored between them.
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n4, uint32_t key, uint32_t thr,
@@ -549,6 +598,23 @@ cudaError_t gelu_dropout(const float* x, const float* dy, float* y, size_t n, bo
   if (n & 3) return cudaErrorInvalidValue;
   const uint32_t key = drop_head_key(drop.seed_lo, drop.seed_hi, 0xE1E7u);  // the key of dropout_apply: same mask
   gelu_kernel<true><<<ew_grid(n / 4, 256), 256, 0, st>>>(x, dy, y, n / 4, backward ? 1 : 0, key, drop.thr, drop.keep_scale, seed_offset);
+  return cudaGetLastError();
+}
+cudaError_t gelu_dropout_bwd_colsum(const float* x, const float* dy, float* dx, float* dcol, int rows, int dim, Dropout drop,
+                                    const unsigned long long* seed_offset, bool accumulate, cudaStream_t st) {
+  if (rows <= 0 || !layernorm_fused_width(dim)) return cudaErrorInvalidValue;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dcol, 0, (size_t)dim * 4, st);
+    if (e != cudaSuccess) return e;
+  }
+  const uint32_t key = drop_head_key(drop.seed_lo, drop.seed_hi, 0xE1E7u);
+  unsigned grid = (rows + 15) / 16;  // two rows per warp
+  if (grid > (unsigned)kSMs * 4) grid = kSMs * 4;
+  switch (dim) {
+    case 128: gelu_dropout_bwd_colsum_kernel<1><<<grid, 256, 0, st>>>(x, dy, dx, dcol, rows, key, drop.thr, drop.keep_scale, seed_offset); break;
+    case 256: gelu_dropout_bwd_colsum_kernel<2><<<grid, 256, 0, st>>>(x, dy, dx, dcol, rows, key, drop.thr, drop.keep_scale, seed_offset); break;
+    default: gelu_dropout_bwd_colsum_kernel<4><<<grid, 256, 0, st>>>(x, dy, dx, dcol, rows, key, drop.thr, drop.keep_scale, seed_offset); break;
+  }
   return cudaGetLastError();
 }
 cudaError_t dropout_apply(const float* x, float* y, size_t n, Dropout drop, const unsigned long long* seed_offset,

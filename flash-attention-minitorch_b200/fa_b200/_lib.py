@@ -99,6 +99,8 @@ def load_library() -> ctypes.CDLL:
     lib.fa_b200_embed_pos_dropout_fwd.restype = ci
     lib.fa_b200_embed_pos_dropout_bwd.argtypes = [vp, vp, vp, vp, sz, ci, ci, sz, sz, f32, u64, vp, ci, vp]
     lib.fa_b200_embed_pos_dropout_bwd.restype = ci
+    lib.fa_b200_gelu_dropout_bwd_colsum.argtypes = [vp, vp, vp, vp, ci, ci, f32, u64, vp, ci, vp]
+    lib.fa_b200_gelu_dropout_bwd_colsum.restype = ci
     lib.fa_b200_layernorm_fused_width.argtypes = [ci]
     lib.fa_b200_layernorm_fused_width.restype = ci
     for name, args in (("layernorm_fwd", [vp] * 6 + [ci, ci, f32, vp]), ("layernorm_bwd", [vp] * 8 + [ci, ci, vp]), ("layernorm_bwd_accum", [vp] * 8 + [ci, ci, vp]),

@@ -215,7 +215,10 @@ class FeedForward(Module):
     def forward(self, x, bias_grad: bool = True):
         """bias_grad=False: the caller hands linear_out's bias to the add_layernorm that consumes the output."""
         B, T, E = x.shape
-        h = ops.gelu_dropout(self.linear_in(x.reshape(B * T, E)), self.p_dropout, self.training)
+        x2 = x.reshape(B * T, E)
+        fuse = self.linear_in.fused_bias_grad_ok(x2, B * T)  # linear_in's bias gradient comes out of the gelu backward pass
+        h = ops.gelu_dropout(self.linear_in(x2, bias_grad=not fuse), self.p_dropout, self.training,
+                             x_bias=self.linear_in.bias.value if fuse else None)
         return self.linear_out(h, bias_grad).view(B, T, E)
 
 

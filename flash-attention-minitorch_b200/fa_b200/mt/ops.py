@@ -492,16 +492,18 @@ class _Dropout(torch.autograd.Function):
 
 
 class _GeluDropout(torch.autograd.Function):
-    """dropout(gelu(x)) as one pass each way; the mask is the one `dropout` would draw at this call site."""
+    """dropout(gelu(x)) as one pass each way; the mask is the one `dropout` would draw at this call site (p = 0: none).
+    x_bias (optional): the bias of the linear layer that produced x with bias_grad=False -- its gradient, the column sums
+    of dx, is reduced in the backward pass."""
 
     @staticmethod
-    def forward(ctx, x, p, seed, step):
+    def forward(ctx, x, p, seed, step, x_bias=None):
         x = x.contiguous()
         y = torch.empty_like(x)
         _lib.check(_lib.load_library().fa_b200_gelu_dropout_fwd(x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed),
                                                                 step.data_ptr() if step is not None else None, _st()))
         ctx.save_for_backward(x)
-        ctx.p, ctx.seed, ctx.step = float(p), int(seed), step
+        ctx.p, ctx.seed, ctx.step, ctx.x_bias = float(p), int(seed), step, x_bias
         return y
 
     @staticmethod
@@ -509,9 +511,18 @@ class _GeluDropout(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        _lib.check(_lib.load_library().fa_b200_gelu_dropout_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), ctx.p, ctx.seed,
-                                                                ctx.step.data_ptr() if ctx.step is not None else None, _st()))
-        return dx, None, None, None
+        lib = _lib.load_library()
+        step = ctx.step.data_ptr() if ctx.step is not None else None
+        bb = ctx.x_bias
+        if bb is None:
+            _lib.check(lib.fa_b200_gelu_dropout_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), ctx.p, ctx.seed, step, _st()))
+            return dx, None, None, None, None
+        gc = _sink(bb)
+        dc = gc if gc is not None else torch.empty_like(bb)
+        rows, dim = x.shape
+        _lib.check(lib.fa_b200_gelu_dropout_bwd_colsum(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), dc.data_ptr(), rows, dim, ctx.p, ctx.seed,
+                                                       step, 1 if gc is not None else 0, _st()))
+        return dx, None, None, None, (None if gc is not None else dc)
 
 
 class DropoutState:
@@ -541,11 +552,14 @@ def _next_dropout_seed(x):
     return (st.base_seed << 32) ^ st.calls, st.step
 
 
-def gelu_dropout(x, p: float, training: bool, generator=None):
-    """dropout(gelu(x), p): one kernel each way on the kernel path, the two reference operators otherwise."""
-    if training and p > 0.0 and _on_kernels(x) and x.numel() % 4 == 0:
-        seed, step = _next_dropout_seed(x)
-        return _GeluDropout.apply(x, p, seed, step)
+def gelu_dropout(x, p: float, training: bool, generator=None, x_bias=None):
+    """dropout(gelu(x), p): one kernel each way on the kernel path, the two reference operators otherwise.
+    x_bias: see _GeluDropout (x 2-D, width accepted by fused_bias_grad_ok)."""
+    drop = training and p > 0.0
+    if (drop or x_bias is not None) and _on_kernels(x) and x.numel() % 4 == 0:
+        seed, step = _next_dropout_seed(x) if drop else (0, None)
+        return _GeluDropout.apply(x, p if drop else 0.0, seed, step, x_bias)
+    assert x_bias is None, "x_bias needs the kernel path (fused_bias_grad_ok)"
     return dropout(gelu(x), p, training, generator)
 
 

@@ -190,6 +190,10 @@ int fa_b200_gelu_dropout_fwd(const float* x, float* y, size_t n, float p_drop, u
                              const unsigned long long* seed_offset_dev, void* stream);
 int fa_b200_gelu_dropout_bwd(const float* x, const float* dy, float* dx, size_t n, float p_drop, unsigned long long seed,
                              const unsigned long long* seed_offset_dev, void* stream);
+/* gelu_dropout_bwd for x (rows, dim), dim in {128, 256, 512}, that also reduces dcol[c] (+)= sum_rows dx[.][c]: the bias
+ * gradient of the linear layer that produced x (ff.linear_in).  p_drop = 0: plain gelu backward. */
+int fa_b200_gelu_dropout_bwd_colsum(const float* x, const float* dy, float* dx, float* dcol, int rows, int dim, float p_drop,
+                                    unsigned long long seed, const unsigned long long* seed_offset_dev, int accumulate, void* stream);
 int fa_b200_layernorm_fused_width(int dim);
 int fa_b200_gelu_fwd(const float* x, float* y, size_t n, void* stream);
 int fa_b200_gelu_bwd(const float* x, const float* dy, float* dx, size_t n, void* stream);

@@ -380,3 +380,28 @@ def test_embed_pos_dropout_equals_the_three_operators(cuda_device, training):
     for a, b in ((t1.grad, t2.grad), (p1.grad, p2.grad)):
         assert float((a - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max()))
     assert float(p1.grad[T:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_gelu_dropout_backward_also_reduces_the_producer_bias_gradient(cuda_device, training):
+    torch.manual_seed(31)
+    rows, K, dim = 648, 64, 256
+    x, W, b = torch.randn(rows, K, device=cuda_device), torch.randn(K, dim, device=cuda_device) / 8, torch.randn(dim, device=cuda_device)
+    gy = torch.randn(rows, dim, device=cuda_device)
+    st = ops.dropout_state
+
+    def run(fused):
+        ins = [t.clone().requires_grad_(True) for t in (x, W, b)]
+        calls = st.calls
+        before = _lib.launch_count()
+        h = ops.linear(ins[0], ins[1], ins[2], bias_grad=not fused)
+        y = ops.gelu_dropout(h, 0.1, training, x_bias=ins[2] if fused else None)
+        (y * gy).sum().backward()
+        st.calls = calls  # the same call site for both runs: same mask
+        return _lib.launch_count() - before, y, [t.grad for t in ins]
+
+    n_plain, y_plain, g_plain = run(False)
+    n_fused, y_fused, g_fused = run(True)
+    assert n_plain - n_fused == 1 and torch.equal(y_plain, y_fused)
+    for gp, gf in zip(g_plain, g_fused):
+        assert float((gp - gf).abs().max()) <= 1e-5 * max(1.0, float(gp.abs().max()))
