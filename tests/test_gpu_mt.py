@@ -85,12 +85,15 @@ def test_kernel_backed_model_matches_fp64_torch_model(cuda_device):
         assert float((ga - gb).abs().max()) <= 2e-2 * float(gb.abs().max()) + 1e-5, name
 
 
-def test_flattened_fast_path_matches_fp64_torch_model(cuda_device):
+@pytest.mark.parametrize("n_embd,n_head", [(64, 2), (128, 4), (256, 8)])  # 128 / 256: the register-resident LayerNorm kernels
+def test_flattened_fast_path_matches_fp64_torch_model(cuda_device, n_embd, n_head):
     """The configuration the training script runs: flattened parameters (q | k | v weights interleaved, ONE head-layout
     projection GEMM), sequence length a multiple of 128 (head-layout GEMMs), head dim 32 (tf32 tensor-core attention
     forward AND backward), weight / bias / LayerNorm / embedding gradients accumulated by the kernels straight into the
-    flat gradient views -- against the same model in fp64 torch on the CPU, parameter by parameter."""
-    n_embd, n_head, T = 64, 2, 128  # d = 32
+    flat gradient views; at n_embd 128 / 256 also the residual sums and branch gradients inside the LayerNorm kernels and
+    the out_projection / linear_out / linear_in / lm_head bias gradients inside the LayerNorm, GELU and loss backward
+    passes -- against the same model in fp64 torch on the CPU, parameter by parameter."""
+    T = 128  # d = 32
     dev_model = DecoderLM(n_vocab=300, n_embd=n_embd, n_head=n_head, n_positions=T, p_dropout=0.0, device=cuda_device,
                           dtype=torch.float32, seed=5, attention_fn=ops.flash_attention)
     ref_model = DecoderLM(n_vocab=300, n_embd=n_embd, n_head=n_head, n_positions=T, p_dropout=0.0, device="cpu",
@@ -111,7 +114,7 @@ def test_flattened_fast_path_matches_fp64_torch_model(cuda_device):
     ld, lr = loss_fn(dev_batch, dev_model), loss_fn(batch, ref_model)
     ld.backward()
     lr.backward()
-    assert _lib.launch_count() - before > 100  # this repo's kernels ran (GEMMs, attention, LayerNorm, loss, ...)
+    assert _lib.launch_count() - before > 80  # this repo's kernels ran (GEMMs, attention, LayerNorm, loss, ...; 97 with every fusion on)
     assert abs(float(ld) - float(lr)) <= 1e-3 * abs(float(lr))
     for (name, a), (_, b) in zip(dev_model.named_parameters(), ref_model.named_parameters()):
         ga, gb = a.value.grad.double().cpu(), b.value.grad

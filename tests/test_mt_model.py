@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN, ROOT
-from _mt_helpers import vanilla_attention
+from _mt_helpers import reference_forward, vanilla_attention
 from fa_b200.mt import ops
 from fa_b200.mt.model import DecoderLM, FeedForward, LayerNorm1d, Linear, loss_fn
 from fa_b200.mt.optim import Adam
@@ -129,6 +129,27 @@ def test_model_is_causal_and_loss_matches_manual_cross_entropy():
     assert torch.equal(m(ids2)[:, :5], logits[:, :5])
     want = torch.nn.functional.cross_entropy(logits.view(-1, 40), batch["labels"].view(-1))
     assert abs(float(loss_fn(batch, m)) - float(want)) < 1e-12
+
+
+@pytest.mark.parametrize("flatten", [None, False, True])
+def test_model_forward_equals_an_operator_by_operator_restatement_of_the_reference(flatten):
+    """DecoderLM.forward (residual sums handed to the next LayerNorm, optional fused q | k | v layout) against
+    _mt_helpers.reference_forward, which is written straight from the reference's module formulas."""
+    m = small_model()
+    if flatten is not None:
+        m.flatten_parameters(fuse=flatten)
+    m.eval()
+    idx = synthetic_batch(3, 8, 40, "cpu", torch.Generator().manual_seed(9))["input_ids"]
+    got, want = m(idx), reference_forward(m, idx)
+    assert float((got - want).abs().max()) <= 1e-11 * max(1.0, float(want.abs().max()))
+    # a single layer through its public forward (the sum is formed here, not by a following LayerNorm)
+    layer = m.t_layer_2
+    x = torch.randn(2, 8, 16, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    s, f, f_bias = layer.forward_pending(x, None)
+    assert f_bias is None  # CPU tensors: no bias gradient is handed on
+    assert torch.allclose(layer(x), s + f, rtol=0, atol=1e-13)
+    s2, f2, _ = layer.forward_pending(x * 0.25, x * 0.75)  # the layer applied to a pending sum
+    assert torch.allclose(s2 + f2, layer(x), rtol=0, atol=1e-12)
 
 
 def test_training_reduces_loss_on_a_fixed_batch():
