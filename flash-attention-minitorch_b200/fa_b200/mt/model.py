@@ -278,6 +278,11 @@ class DecoderLM(Module):
         delta = delta_bias = None  # the residual stream is x + delta; each addition happens inside the next LayerNorm's kernel
         for layer in (self.t_layer_1, self.t_layer_2, self.t_layer_3, self.t_layer_4):
             x, delta, delta_bias = layer.forward_pending(x, delta, delta_bias)
+        hook = getattr(self, "grad_ready_hook", None)
+        if hook is not None and x.requires_grad:
+            # fires when the gradient of the last layer's output exists, i.e. the final LayerNorm and lm_head are done:
+            # the trainer starts the all-reduce of their gradients while the four layers' backward still runs
+            x.register_hook(lambda g: hook())
         _, x = self.ln.add_forward(x.reshape(B * T, self.n_embd), delta.reshape(B * T, self.n_embd), delta_bias)
         return self.lm_head(x, head_bias_grad).view(B, T, self.n_vocab)
 

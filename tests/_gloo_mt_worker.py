@@ -26,6 +26,14 @@ def main():
     model = build()
     opt = Adam(model.parameters(), lr=0.02)
     res = train(model, opt, n_iters=3, batch_size=3, seq_len=8, rank=rank, world=world, sync=lambda: None, seed=5)
+    # the same with flattened parameters (fused q | k | v layout) and the final-LayerNorm + lm_head gradients all-reduced
+    # from a backward hook while the rest of the backward runs (train(overlap_allreduce=True))
+    m2 = build()
+    flat2 = m2.flatten_parameters(fuse=True)
+    train(m2, Adam(m2.parameters(), lr=0.02, flat=flat2), n_iters=3, batch_size=3, seq_len=8, rank=rank, world=world,
+          sync=lambda: None, seed=5, overlap_allreduce=True)
+    assert m2.grad_ready_hook is not None  # the early range was found and used
+    overlap_flat = torch.cat([p.value.detach().reshape(-1) for p in m2.parameters()])
     # every rank must hold identical weights after synchronised steps
     flat = torch.cat([p.value.detach().reshape(-1) for p in model.parameters()])
     ref = flat.clone()
@@ -43,6 +51,7 @@ def main():
             sopt.step()
         sflat = torch.cat([p.value.detach().reshape(-1) for p in single.parameters()])
         print("dp==single", bool(torch.allclose(flat, sflat, rtol=1e-9, atol=1e-11)), "ranks_equal", same,
+              "overlap==single", bool(torch.allclose(overlap_flat, sflat, rtol=1e-9, atol=1e-11)),
               "loss", res["loss_first"], res["loss_last"])
     else:
         assert same

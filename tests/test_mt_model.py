@@ -196,7 +196,7 @@ def test_two_rank_gloo_data_parallel_equals_single_process_on_the_union_batch():
         procs.append(subprocess.Popen([sys.executable, worker], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
-    assert "dp==single True ranks_equal True" in outs[0], outs
+    assert "dp==single True ranks_equal True overlap==single True" in outs[0], outs
 
 
 def test_flat_parameter_adam_equals_per_parameter_adam():
