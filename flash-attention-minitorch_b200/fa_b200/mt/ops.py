@@ -8,18 +8,21 @@ reference stages every op through host numpy storage, minitorch/cuda_kernel_ops.
     gelu          tanh approximation             minitorch/nn.py:208-214
     dropout       x * Bernoulli(1-p) / (1-p)     minitorch/modules_basic.py:77-80
     embedding     one_hot(idx) @ W  == W[idx]    minitorch/modules_basic.py:46-53
+    add_layernorm     (a + b, layernorm(a + b)): a residual addition of TransformerLayer.forward and the LayerNorm after it
+    gelu_dropout      dropout(gelu(x))           FeedForward.forward, minitorch/modules_transfomer.py
+    embed_pos_dropout dropout(tok[idx] + pos[arange(T)])   DecoderLM.forward, minitorch/modules_transfomer.py
     softmax_loss  logsumexp(logits) - logits[target], no reduction           minitorch/nn.py:256-274
     flash_attention  q.flash_attn2(k, v, causal) minitorch/modules_transfomer.py:109-120 -> this repo's kernels
 
 On CUDA fp32 tensors every operator runs a hand-written kernel of libfa_b200.so: attention on the flash kernels, the
 linear layers (forward, dX, dW) on the tf32 tcgen05 GEMM, LayerNorm / GELU / dropout / embedding / loss as one fused pass
-each (rows N1-N4 of SURVEY.md §8f).  torch owns device memory, streams and the autograd tape only; the residual adds
-and reshapes between operators are the remaining ATen calls.
+each (rows N1-N4 of SURVEY.md §8f), with the residual additions, the gradient sums at the residual branch points and the
+bias gradients of the linear layers folded into the LayerNorm / GELU / loss kernels that touch the same tensors.  torch
+owns device memory, streams and the autograd tape only; the loss weighting / mean and reshapes are the remaining ATen calls.
 """
 from __future__ import annotations
 
 import math
-
 import os
 
 import torch
@@ -197,7 +200,6 @@ def linear(x, weight, bias=None, bias_grad: bool = True):
 def fused_bias_grad_ok(like, M: int, weight, bias) -> bool:
     """True when linear / linear_from_heads of an (M, in) input on the device / dtype of `like` run on the kernels AND an
     add_layernorm of their output width can take over the bias reduction (FA_MT_FUSED_BIAS_GRAD=0 turns it off)."""
-    import os
     K, N = weight.shape
     return (bias is not None and os.environ.get("FA_MT_FUSED_BIAS_GRAD", "1") != "0" and _on_kernels(like, weight, bias)
             and M % 4 == 0 and K % 4 == 0 and bool(_lib.load_library().fa_b200_layernorm_fused_width(N)))
@@ -692,7 +694,6 @@ def softmax_loss(logits, target, logits_bias=None):
 
 def fused_logits_bias_grad_ok(like, M: int, weight, bias, target) -> bool:
     """The loss backward may take over the bias gradient of linear(like-shaped (M, in) input, weight, bias)."""
-    import os
     K, N = weight.shape
     return (bias is not None and os.environ.get("FA_MT_FUSED_LOGITS_BIAS_GRAD", "1") != "0" and _on_kernels(like, weight, bias)
             and target.is_cuda and M % 4 == 0 and K % 4 == 0 and bool(_lib.load_library().fa_b200_softmax_loss_colsum_width(N)))
