@@ -57,9 +57,20 @@ struct GemmParams {
 struct HeadCoord {
   int c0, c1, c2;
 };
-__device__ __forceinline__ HeadCoord head_coord(const GemmParams& p, int e, int m) {
+// the coordinate splits into a part that depends on the feature index e only and one that depends on the token index m
+// only: the producer loop hoists whichever is fixed for the CTA (five runtime-divisor divisions per box otherwise --
+// 40 per k-block with two MN-major head operands, against ~260 cycles of MMA work per k-block)
+struct HeadPart {
+  int c, head;
+};
+__device__ __forceinline__ HeadPart head_e(const GemmParams& p, int e) {
   const int part = e / p.E, el = e - part * p.E;
-  return {el % p.d, m % p.T, part * p.BH + (m / p.T) * p.H + el / p.d};
+  return {el % p.d, part * p.BH + el / p.d};
+}
+__device__ __forceinline__ HeadPart head_m(const GemmParams& p, int m) { return {m % p.T, (m / p.T) * p.H}; }
+__device__ __forceinline__ HeadCoord head_coord(const GemmParams& p, int e, int m) {
+  const HeadPart pe = head_e(p, e), pm = head_m(p, m);
+  return {pe.c, pm.c, pe.head + pm.head};
 }
 
 struct GemmBarriers {
@@ -108,35 +119,47 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (lane == 0) {
       tma_prefetch_desc(&map_a);
       tma_prefetch_desc(&map_b);
+      // head-layout operands: the parts of the box coordinates that are fixed for this CTA
+      HeadPart ae[4] = {}, be[4] = {}, am = {};
+      if constexpr (kHeads) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          if (kAMn && p.a_heads) ae[x] = head_e(p, m0 + 32 * x);
+          if (kBMn && p.b_heads) be[x] = head_e(p, n0 + 32 * x);
+        }
+        if (!kAMn && p.a_heads) am = head_m(p, m0);
+      }
       for (int kb = 0; kb < nk; ++kb) {
         const int st = kb % kStages;
         const int k0 = (kb_begin + kb) * kBK;
+        HeadPart km = {};  // token part of the MN-major head operands' coordinates (tokens = the reduction dimension)
+        if (kHeads && ((kAMn && p.a_heads) || (kBMn && p.b_heads))) km = head_m(p, k0);
         mbar_wait(&bars.empty[st], ((kb / kStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&bars.full[st], 2 * kSlabBytes);
         uint8_t* a = sA + st * kSlabBytes;
         uint8_t* b = sB + st * kSlabBytes;
         if constexpr (kAMn) {  // global [K][M]: four boxes of (32 m) x (32 k rows)
+#pragma unroll
           for (int x = 0; x < 4; ++x) {
             if (kHeads && p.a_heads) {  // [tokens][E] in head layout, tokens = the reduction dimension
-              const HeadCoord h = head_coord(p, m0 + 32 * x, k0);
-              tma_load_3d(a + x * 4096, &map_a, &bars.full[st], h.c0, h.c1, h.c2, kEvictNormal);
+              tma_load_3d(a + x * 4096, &map_a, &bars.full[st], ae[x].c, km.c, ae[x].head + km.head, kEvictNormal);
             } else {
               tma_load_3d(a + x * 4096, &map_a, &bars.full[st], m0 + 32 * x, k0, 0, kEvictNormal);
             }
           }
         } else {               // global [M][K]: one box of (32 k) x (128 m rows)
           if (kHeads && p.a_heads) {
-            const HeadCoord h = head_coord(p, k0, m0);
-            tma_load_3d(a, &map_a, &bars.full[st], h.c0, h.c1, h.c2, kEvictNormal);
+            const HeadPart ke = head_e(p, k0);
+            tma_load_3d(a, &map_a, &bars.full[st], ke.c, am.c, ke.head + am.head, kEvictNormal);
           } else {
             tma_load_3d(a, &map_a, &bars.full[st], k0, m0, 0, kEvictNormal);
           }
         }
         if constexpr (kBMn) {
+#pragma unroll
           for (int x = 0; x < 4; ++x) {
             if (kHeads && p.b_heads) {
-              const HeadCoord h = head_coord(p, n0 + 32 * x, k0);
-              tma_load_3d(b + x * 4096, &map_b, &bars.full[st], h.c0, h.c1, h.c2, kEvictNormal);
+              tma_load_3d(b + x * 4096, &map_b, &bars.full[st], be[x].c, km.c, be[x].head + km.head, kEvictNormal);
             } else {
               tma_load_3d(b + x * 4096, &map_b, &bars.full[st], n0 + 32 * x, k0, 0, kEvictNormal);
             }
