@@ -17,9 +17,14 @@
 //
 // Warp roles (512 threads): warps 0-7 compute (thread = one key row x 64 query columns), warps 8-11 drain
 // dQ (TMEM -> swizzled smem -> cp.reduce.async.bulk), warp 12 TMA producer, warp 13 MMA issuer.
-// MMA issue order per step  dQ(i) dK(i) dP(i+1) dV(i+1) S(i+2)  keeps the pipe busy while the compute warps
-// turn S(i+1) into P and dP(i+1) into dS.  TMEM (512 columns): S | dP | dV | dK, with dQ aliasing dP when
-// d = 128 (dP(i+1) is only issued after dQ(i) has been drained) and a separate region when d = 64.
+// TMEM (512 columns at d = 128): R0 | R1 | dV | dK.  The two 128-column regions R0 / R1 are time-shared by FOUR tenants so
+// that no product ever waits for the drain of another (round 1 kept dQ in the dP columns, which put the chain
+// dS(i) -> dQ(i) -> drain -> dP(i+1) -> dS(i+1) on the critical path, ~4100 cycles per tile pair):
+//     R0:  S(i)  -> [compute warps pull it into registers at the start of the P phase] -> dP(i) -> [pulled into registers
+//          at the start of the dS phase] -> S(i+1)
+//     R1:  dQ(i-1) -> [drain warps pull it out] -> P(i) (bf16, stored at the END of the P phase) -> [dV(i) reads it] -> dQ(i)
+// MMA issue order per step  dQ(i-1) dP(i) dK(i-1) dV(i) S(i+1):  every wait of the issuing warp is for an event that lies
+// early in the compute warps' phase structure, so the tensor pipe runs ahead of them.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -30,11 +35,9 @@
 #include "fa_ptx.cuh"
 #include "fa_tma_host.h"
 
-// A/B switch for same-box experiments (tools/build_variant.sh + tools/ab.sh).  Fetching -delta into registers before the
-// wait for dP (to take the shared-memory load latency off the dS phase) measured 2.5 % SLOWER than loading it chunk by
-// chunk (6.64 vs 6.48 ms at config 3): the 32 extra live registers cost more than the latency they hide.
-#ifndef FA_BWD_DELTA_PREFETCH
-#define FA_BWD_DELTA_PREFETCH 0
+// A/B switches for same-box experiments (tools/build_variant.sh + tools/ab.sh).
+#ifndef FA_BWD_ORDER
+#define FA_BWD_ORDER 2  // MMA issue order inside a step: 0 = dQ(i-1) dK(i-1) dP(i) | 1 = dQ(i-1) dP(i) dK(i-1) | 2 = dK(i-1) dQ(i-1) dP(i), then dV(i) S(i+1)
 #endif
 
 namespace fa {
@@ -49,8 +52,8 @@ constexpr int kBoxBytes = 128 * 128;  // 128 rows x 128 B
 struct BwdParams {
   int T, Tpad, causal;
   float tau, scale_log2;
-  const float* lse_pad;    // [BH][Tpad]  lse * log2(e); +inf on padding rows (=> P = 0 there)
-  const float* delta_pad;  // [BH][Tpad]  -rowsum(dO o O) (negated: the main loop adds it with one packed FADD2); 0 on padding rows
+  const float* lse_pad;    // [BH][Tpad]  -lse * log2(e); -inf on padding rows (=> P = 0 there)
+  const float* delta_pad;  // [BH][Tpad]  -tau * rowsum(dO o O) (one packed FFMA2 gives tau (dP - delta)); 0 on padding rows
   void* dk;
   void* dv;
   float* dq_acc;  // fp32 dQ accumulator [BH][T][D] (workspace, or the caller's fp32 q_grad)
@@ -70,7 +73,6 @@ struct BwdCfg {
   static constexpr int kRegComputeDrop = 160, kRegDrainDrop = 104;              // 8*160 + 4*104 + 4*88 <= 16*128
   static constexpr int kQStages = 2;
   static constexpr int kDoStages = D >= 128 ? 1 : 2;
-  static constexpr bool kAliasDq = D >= 128;
   // shared-memory map (bytes)
   static constexpr int kOffK = 0;
   static constexpr int kOffV = kOffK + kTileBytes;
@@ -81,15 +83,14 @@ struct BwdCfg {
   static constexpr int kOffStats = kOffStage + 2 * kBoxBytes;     // [2 stages][L, delta][128] fp32
   static constexpr int kOffBars = kOffStats + 2 * 2 * 128 * 4;
   static constexpr int kSmemBytes = kOffBars + 256;
-  // TMEM columns
-  static constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 256 + D;
-  static constexpr uint32_t kColDQ = kAliasDq ? kColDP : 256 + 2 * D;
+  // TMEM columns: R0 = S(i) then dP(i); R1 = dQ(i-1) then P(i)
+  static constexpr uint32_t kColR0 = 0, kColR1 = 128, kColDV = 256, kColDK = 256 + D;
 };
 
 struct BwdBarriers {
   uint64_t kv_full;
   uint64_t q_full[2], q_empty[2], do_full[2], do_empty[2];
-  uint64_t s_full, p_full, dp_full, ds_full, ds_empty, dq_full, dq_drained, dkv_full;
+  uint64_t s_full, s_loaded, p_full, dp_full, dp_loaded, ds_full, ds_empty, dq_full, dq_drained, dkv_full;
 };
 
 template <typename OutT>
@@ -152,8 +153,10 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       mbar_init(&bars.do_empty[s], 1);
     }
     mbar_init(&bars.s_full, 1);
+    mbar_init(&bars.s_loaded, 8);
     mbar_init(&bars.p_full, 8);
     mbar_init(&bars.dp_full, 1);
+    mbar_init(&bars.dp_loaded, 8);
     mbar_init(&bars.ds_full, 8);
     mbar_init(&bars.ds_empty, 1);
     mbar_init(&bars.dq_full, 1);
@@ -189,6 +192,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const int i = i0 + il;
         const int s = il & 1;
         mbar_wait(&bars.q_empty[s], ((il >> 1) & 1) ^ 1);
+        if (tr && il < 16) tr[256 + il * 16 + 12] = clock64();
         mbar_arrive_expect_tx(&bars.q_full[s], Cfg::kTileBytes + 1024);
         for (int b = 0; b < Cfg::kBoxes; ++b)
           tma_load_3d(sQ + s * Cfg::kTileBytes + b * kBoxBytes, &map_q, &bars.q_full[s], b * 64, i * kTile, bh,
@@ -198,6 +202,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         bulk_load_1d(sStats + s * 256 + 128, p.delta_pad + soff, 512, &bars.q_full[s]);
         const int sd = il % Cfg::kDoStages;
         mbar_wait(&bars.do_empty[sd], ((il / Cfg::kDoStages) & 1) ^ 1);
+        if (tr && il < 16) tr[256 + il * 16 + 11] = clock64();
         mbar_arrive_expect_tx(&bars.do_full[sd], Cfg::kTileBytes);
         for (int b = 0; b < Cfg::kBoxes; ++b)
           tma_load_3d(sDO + sd * Cfg::kTileBytes + b * kBoxBytes, &map_do, &bars.do_full[sd], b * 64, i * kTile, bh,
@@ -224,10 +229,10 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) umma_ss_w(tmem + col, kstep(a0, kk), kstep(b0, kk), idesc_sT, kk > 0);
       };
-      auto issue_dv = [&](uint64_t do_mn, bool acc) {
+      auto issue_dv = [&](uint64_t do_mn, bool acc) {  // A = P^T (bf16, two per column) in R1
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_ts_w(tmem + Cfg::kColDV, tmem + Cfg::kColS + (kk >> 2) * 64 + (kk & 3) * 8, mnstep(do_mn, kk), idesc_acc,
+          umma_ts_w(tmem + Cfg::kColDV, tmem + Cfg::kColR1 + (kk >> 2) * 64 + (kk & 3) * 8, mnstep(do_mn, kk), idesc_acc,
                     (acc || kk > 0) ? 1u : 0u);
       };
       auto issue_dk = [&](uint64_t q_mn, bool acc) {
@@ -237,7 +242,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       };
       auto issue_dq = [&]() {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_ss_w(tmem + Cfg::kColDQ, mnstep(dDS_mn, kk), mnstep(dK_mn, kk), idesc_dq, kk > 0);
+        for (int kk = 0; kk < 8; ++kk) umma_ss_w(tmem + Cfg::kColR1, mnstep(dDS_mn, kk), mnstep(dK_mn, kk), idesc_dq, kk > 0);
       };
       auto q_tile = [&](int il) { return aQ + (il & 1) * Cfg::kTileBytes; };
       auto do_tile = [&](int il) { return aDO + (il % Cfg::kDoStages) * Cfg::kTileBytes; };
@@ -245,58 +250,66 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       mbar_wait_w(&bars.kv_full, 0);
       mbar_wait_w(&bars.q_full[0], 0);
       tc_fence_after();
-      issue_sT(dK_k, kmaj0(q_tile(0)), Cfg::kColS);
+      issue_sT(dK_k, kmaj0(q_tile(0)), Cfg::kColR0);
       umma_commit_w(&bars.s_full);
-      mbar_wait_w(&bars.do_full[0], 0);
-      tc_fence_after();
-      issue_sT(dV_k, kmaj0(do_tile(0)), Cfg::kColDP);
-      umma_commit_w(&bars.dp_full);
-      mbar_wait_w(&bars.p_full, 0);
-      tc_fence_after();
-      issue_dv(mnmaj0(do_tile(0)), false);
-      umma_commit_w(&bars.do_empty[0]);
-      if (n > 1) {
-        mbar_wait_w(&bars.q_full[1], 0);
-        tc_fence_after();
-        issue_sT(dK_k, kmaj0(q_tile(1)), Cfg::kColS);
-        umma_commit_w(&bars.s_full);
-      }
       for (int il = 0; il < n; ++il) {
-        mbar_wait_w(&bars.ds_full, il & 1);
-        if (!Cfg::kAliasDq && il > 0) mbar_wait_w(&bars.dq_drained, (il - 1) & 1);
-        tc_fence_after();
-        FA_TR(il, 8);
-        issue_dq();
-        umma_commit_w(&bars.dq_full);
-        issue_dk(mnmaj0(q_tile(il)), il > 0);
-        umma_commit_w(&bars.ds_empty);
-        umma_commit_w(&bars.q_empty[il & 1]);
-        FA_TR(il, 9);
-        if (il + 1 < n) {
-          const int nx = il + 1;
-          if (Cfg::kAliasDq) mbar_wait_w(&bars.dq_drained, il & 1);
-          mbar_wait_w(&bars.do_full[nx % Cfg::kDoStages], (nx / Cfg::kDoStages) & 1);
+        auto step_dq = [&]() {
+          if (il > 0) {
+            // dQ(il-1) -> R1 (P(il-1) was consumed by dV(il-1), issued before: the tensor pipe executes in order)
+            issue_dq();
+            umma_commit_w(&bars.dq_full);
+            if (FA_BWD_ORDER == 2) umma_commit_w(&bars.ds_empty);  // dK(il-1) went first: both readers of dS are done
+          }
+        };
+        if (il > 0) {
+          mbar_wait_w(&bars.ds_full, (il - 1) & 1);
+          tc_fence_after();
+          FA_TR(il, 8);
+        }
+        // dK(il-1) next (FA_BWD_ORDER 0): it releases the Q stage that Q(il+1) -- needed by S(il+1) below -- loads into, and
+        // the dS buffer; dP(il) -> R0 follows (needs S(il) in the compute warps' registers).  FA_BWD_ORDER 1 swaps the two.
+        auto step_dk = [&]() {
+          if (il > 0) {
+            issue_dk(mnmaj0(q_tile(il - 1)), il > 1);
+            if (FA_BWD_ORDER != 2) umma_commit_w(&bars.ds_empty);
+            umma_commit_w(&bars.q_empty[(il - 1) & 1]);
+            FA_TR(il, 9);
+          }
+        };
+        auto step_dp = [&]() {
+          mbar_wait_w(&bars.s_loaded, il & 1);
+          mbar_wait_w(&bars.do_full[il % Cfg::kDoStages], (il / Cfg::kDoStages) & 1);
           tc_fence_after();
           FA_TR(il, 10);
-          issue_sT(dV_k, kmaj0(do_tile(nx)), Cfg::kColDP);
+          issue_sT(dV_k, kmaj0(do_tile(il)), Cfg::kColR0);
           umma_commit_w(&bars.dp_full);
           FA_TR(il, 11);
-          mbar_wait_w(&bars.p_full, nx & 1);
+        };
+        if (FA_BWD_ORDER == 0) { step_dq(); step_dk(); step_dp(); }
+        else if (FA_BWD_ORDER == 1) { step_dq(); step_dp(); step_dk(); }
+        else { step_dk(); step_dq(); step_dp(); }
+        // dV(il) <- P(il) in R1 (the compute warps stored it after the drain of dQ(il-1))
+        mbar_wait_w(&bars.p_full, il & 1);
+        tc_fence_after();
+        FA_TR(il, 12);
+        issue_dv(mnmaj0(do_tile(il)), il > 0);
+        umma_commit_w(&bars.do_empty[il % Cfg::kDoStages]);
+        FA_TR(il, 13);
+        if (il + 1 < n) {
+          // S(il+1) -> R0, once the compute warps hold dP(il) in registers
+          mbar_wait_w(&bars.dp_loaded, il & 1);
+          mbar_wait_w(&bars.q_full[(il + 1) & 1], ((il + 1) >> 1) & 1);
           tc_fence_after();
-          FA_TR(il, 12);
-          issue_dv(mnmaj0(do_tile(nx)), true);
-          umma_commit_w(&bars.do_empty[nx % Cfg::kDoStages]);
-          FA_TR(il, 13);
-          if (il + 2 < n) {
-            const int n2 = il + 2;
-            mbar_wait_w(&bars.q_full[n2 & 1], (n2 >> 1) & 1);
-            tc_fence_after();
-            issue_sT(dK_k, kmaj0(q_tile(n2)), Cfg::kColS);
-            umma_commit_w(&bars.s_full);
-            FA_TR(il, 14);
-          }
+          issue_sT(dK_k, kmaj0(q_tile(il + 1)), Cfg::kColR0);
+          umma_commit_w(&bars.s_full);
+          FA_TR(il, 14);
         }
       }
+      mbar_wait_w(&bars.ds_full, (n - 1) & 1);
+      tc_fence_after();
+      issue_dq();
+      umma_commit_w(&bars.dq_full);
+      issue_dk(mnmaj0(q_tile(n - 1)), n > 1);
       umma_commit_w(&bars.dkv_full);
     }
   } else if (warp < 8) {
@@ -305,9 +318,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const int g = warp >> 2;                 // which half of the 128 query columns
     const int r = (warp & 3) * 32 + lane;    // key row within the tile == TMEM lane
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem + Cfg::kColS + lane_base;
-    const uint32_t tDP = tmem + Cfg::kColDP + lane_base;
-    const float c2 = p.scale_log2;
+    const uint32_t tR0 = tmem + Cfg::kColR0 + lane_base + g * 64;  // S^T(i), then dP^T(i): this thread's 64 query columns
+    const uint32_t tR1 = tmem + Cfg::kColR1 + lane_base + g * 64;  // P^T(i) (bf16, 32 columns) after dQ(i-1) has been drained
+    const float2 c2v = make_float2(p.scale_log2, p.scale_log2);
     uint8_t* ds_row = sDS + g * kBoxBytes + r * 128;
     // dropout: one 32-bit hash per 2 x 2 block of (query, key); this thread (one key row) uses the byte of its key
     // parity in the low half (even query) and in the high half (odd query) -- the same bits the forward drew
@@ -317,147 +330,123 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const uint32_t drop_sel2 = drop_sel_pair(drop_b0, drop_b0 + 2);
     const uint32_t drop_sh = 7 + 8 * drop_b0;
     const uint32_t drop_thr = p.drop.thr;
-    const float drop_scale = p.drop.keep_scale;
+    const float tau_keep = p.tau * p.drop.keep_scale;  // tau * Z for a kept element (dropout variant)
     for (int il = 0; il < n; ++il) {
       const int i = i0 + il;
-      const float* sL = sStats + (il & 1) * 256 + g * 64;
-      const float* sD = sL + 128;
+      const float* sL = sStats + (il & 1) * 256 + g * 64;  // -L log2(e) of the 64 query columns (-inf on padding rows)
+      const float* sD = sL + 128;                          // -tau * delta
       // ---- P^T = exp2(c * S^T - L)
       mbar_wait(&bars.q_full[il & 1], (il >> 1) & 1);  // L / delta of this Q tile have landed
       mbar_wait(&bars.s_full, il & 1);
       tc_fence_after();
       if (warp == 0) FA_TR(il, 0);
-      float pr[64];
+      // P is kept as packed bf16 pairs (32 registers instead of 64 fp32): exactly the values the dV product sees, and
+      // what leaves room to pull a whole dP row chunk (64 registers) out of TMEM in one go below
+      uint32_t pk[32];
       {
+        float pr[64];
         uint32_t* u = reinterpret_cast<uint32_t*>(pr);
-        tmem_ld_x32(tS + g * 64, u);
-        tmem_ld_x32(tS + g * 64 + 32, u + 32);
+        tmem_ld_x32(tR0, u);
+        tmem_ld_x32(tR0 + 32, u + 32);
         tmem_wait_ld();
-      }
-      FA_TR2(il, 0);
-      const bool diag = p.causal && (i == j);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.s_loaded);  // R0 may take dP(i)
+        FA_TR2(il, 0);
+        const bool diag = p.causal && (i == j);
 #pragma unroll
-      for (int c = 0; c < 64; c += 4) {
-        const float4 L4 = *reinterpret_cast<const float4*>(sL + c);
-        pr[c + 0] = ex2_approx(fmaf(pr[c + 0], c2, -L4.x));
-        pr[c + 1] = ex2_approx(fmaf(pr[c + 1], c2, -L4.y));
-        pr[c + 2] = ex2_approx(fmaf(pr[c + 2], c2, -L4.z));
-        pr[c + 3] = ex2_approx(fmaf(pr[c + 3], c2, -L4.w));
-      }
-      if (diag) {
+        for (int c = 0; c < 64; c += 4) {
+          const float4 L4 = *reinterpret_cast<const float4*>(sL + c);
+          const float2 x0 = ffma2(make_float2(pr[c], pr[c + 1]), c2v, make_float2(L4.x, L4.y));
+          const float2 x1 = ffma2(make_float2(pr[c + 2], pr[c + 3]), c2v, make_float2(L4.z, L4.w));
+          pr[c + 0] = ex2_approx(x0.x);
+          pr[c + 1] = ex2_approx(x0.y);
+          pr[c + 2] = ex2_approx(x1.x);
+          pr[c + 3] = ex2_approx(x1.y);
+        }
+        if (diag) {
 #pragma unroll
-        for (int c = 0; c < 64; ++c)
-          if (g * 64 + c < r) pr[c] = 0.f;  // key index > query index
+          for (int c = 0; c < 64; ++c)
+            if (g * 64 + c < r) pr[c] = 0.f;  // key index > query index
+        }
+        FA_TR2(il, 1);
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) pk[c >> 1] = pack_bf16x2(pr[c], pr[c + 1]);
       }
       // keep bits of this key row: query pair pi = c >> 1 of each 32-column half sits at bit (15 - pi % 16) for the
       // even query and bit (31 - pi % 16) for the odd one (shift-in order), halves 0 / 1 in keep_a / keep_b
-      FA_TR2(il, 1);
       uint32_t keep_a = 0u, keep_b = 0u;
       auto kept = [&](int c) {
         const int pos = 15 - ((c >> 1) & 15) + 16 * (c & 1);
         return (((c < 32 ? keep_a : keep_b) >> pos) & 1u) != 0u;
       };
-      {
-        uint32_t pk[32];
+      // R1 still holds dQ(i-1) until the drain warps have pulled it out
+      if (il > 0) mbar_wait(&bars.dq_drained, (il - 1) & 1);
+      FA_TR2(il, 2);
+      if constexpr (kDrop) {  // P^T o keep feeds dV; pk[] itself stays undropped for dS
+        uint32_t pd[32];
+        const uint32_t i2 = uint32_t(i * kTile + g * 64) >> 1;
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) pk[c >> 1] = pack_bf16x2(pr[c], pr[c + 1]);
-        if constexpr (kDrop) {  // P^T o keep feeds dV; pr[] itself stays undropped for dS
-          const uint32_t i2 = uint32_t(i * kTile + g * 64) >> 1;
-#pragma unroll
-          for (int c = 0; c < 64; c += 4) {
-            // the two lanes of a key pair need the same block words: each hashes one, a shuffle gives the other
-            const uint32_t mine = drop_keep_word(drop_mix(drop_colkey ^ ((i2 + (c >> 1) + (lane & 1)) * kDropRowMul)), drop_thr);
-            const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
-            const uint32_t w0 = (lane & 1) ? theirs : mine, w1 = (lane & 1) ? mine : theirs;  // queries c,c+1 | c+2,c+3
-            pk[c >> 1] &= drop_prmt(w0, drop_sel2);
-            pk[(c >> 1) + 1] &= drop_prmt(w1, drop_sel2);
-            uint32_t& acc = c < 32 ? keep_a : keep_b;
-            acc = (acc << 1) | ((w0 >> drop_sh) & 0x00010001u);
-            acc = (acc << 1) | ((w1 >> drop_sh) & 0x00010001u);
-          }
+        for (int c = 0; c < 64; c += 4) {
+          // the two lanes of a key pair need the same block words: each hashes one, a shuffle gives the other
+          const uint32_t mine = drop_keep_word(drop_mix(drop_colkey ^ ((i2 + (c >> 1) + (lane & 1)) * kDropRowMul)), drop_thr);
+          const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
+          const uint32_t w0 = (lane & 1) ? theirs : mine, w1 = (lane & 1) ? mine : theirs;  // queries c,c+1 | c+2,c+3
+          pd[c >> 1] = pk[c >> 1] & drop_prmt(w0, drop_sel2);
+          pd[(c >> 1) + 1] = pk[(c >> 1) + 1] & drop_prmt(w1, drop_sel2);
+          uint32_t& acc = c < 32 ? keep_a : keep_b;
+          acc = (acc << 1) | ((w0 >> drop_sh) & 0x00010001u);
+          acc = (acc << 1) | ((w1 >> drop_sh) & 0x00010001u);
         }
-        // P^T of query columns [64g, 64g+64) goes to TMEM columns [64g, 64g+32): inside the S columns this
-        // thread group has already consumed, so the two groups never touch each other's unread scores
-        FA_TR2(il, 2);
-        tmem_st_x32(tS + g * 64, pk);
-        // tau is folded into the kept P values here, where the MUFU pipe is the limiter and the FMA pipe has slack:
-        // dS^T = (tau P^T) o (dP^T - delta) then costs one FADD2 + one FMUL2 per pair on the critical dS phase
-        const float2 tau2 = make_float2(p.tau, p.tau);
-#pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          const float2 t2 = fmul2(make_float2(pr[c], pr[c + 1]), tau2);
-          pr[c] = t2.x;
-          pr[c + 1] = t2.y;
-        }
-        FA_TR2(il, 3);
-        tmem_wait_st();
+        tmem_st_x32(tR1, pd);
+      } else {
+        // P^T of query columns [64g, 64g+64) goes to R1 columns [64g, 64g+32)
+        tmem_st_x32(tR1, pk);
       }
+      tmem_wait_st();
       FA_TR2(il, 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.p_full);
       if (warp == 0) FA_TR(il, 1);
-      // ---- dS^T = (tau P^T) o (dP^T - delta)
-      // -delta of the first 32 query columns is fetched BEFORE waiting for dP: a shared-memory load takes ~150 cycles while
-      // the tensor pipe streams operands, and the compiler cannot hoist these loads over the dS stores below (both are
-      // shared memory) -- left in program order they cost one exposed load latency per 16-byte chunk of dS.  The second
-      // half's values are fetched into the same registers as soon as the first half's are consumed, ahead of that chunk's store.
-      float4 dl[8];
-#if FA_BWD_DELTA_PREFETCH
-#pragma unroll
-      for (int q = 0; q < 8; ++q) dl[q] = *reinterpret_cast<const float4*>(sD + q * 4);
-#endif
+      // ---- dS^T = P^T o (tau dP^T - tau delta)      (dropout: tau Z dP^T - tau delta)
       mbar_wait(&bars.dp_full, il & 1);
       tc_fence_after();
       if (warp == 0) FA_TR(il, 2);
-      // dP^T is consumed in two 32-column halves (32 live registers instead of 64: the drain warps need the registers to
-      // pull a whole dQ tile out of TMEM at once)
+      float dp[64];
+      tmem_ld_x32(tR0, reinterpret_cast<uint32_t*>(dp));
+      tmem_ld_x32(tR0 + 32, reinterpret_cast<uint32_t*>(dp) + 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.dp_loaded);  // R0 may take S(i+1)
+      FA_TR2(il, 5);
+      if (il > 0) mbar_wait(&bars.ds_empty, (il - 1) & 1);  // dK(i-1) / dQ(i-1) have finished reading dS
+      FA_TR2(il, 6);
+      const float2 tau2 = make_float2(p.tau, p.tau);
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        float dp[32];
-        tmem_ld_x32(tDP + g * 64 + hf * 32, reinterpret_cast<uint32_t*>(dp));
-        tmem_wait_ld();
-        FA_TR2(il, 5 + 3 * hf);
-        if (hf == 0 && il > 0) mbar_wait(&bars.ds_empty, (il - 1) & 1);  // dK(i-1) / dQ(i-1) have finished reading dS
-        FA_TR2(il, 6 + 3 * hf);
+      for (int ch = 0; ch < 8; ++ch) {  // 16-byte chunk of this thread's 128-byte dS^T row: 8 query columns
+        uint32_t out[4];
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          const int ch = hf * 4 + c8;  // 16-byte chunk of this thread's 128-byte dS^T row
-          float ds[8];
-#pragma unroll
-          for (int e = 0; e < 8; e += 4) {
-#if FA_BWD_DELTA_PREFETCH
-            const float4 D4 = dl[c8 * 2 + (e >> 2)];
-#else
-            const float4 D4 = *reinterpret_cast<const float4*>(sD + ch * 8 + e);
-#endif
-            const int c = ch * 8 + e, cl = c8 * 8 + e;
-            if constexpr (kDrop) {  // dP o Z with Z = keep / (1 - p); P itself stays undropped here
-              dp[cl + 0] *= kept(c + 0) ? drop_scale : 0.f;
-              dp[cl + 1] *= kept(c + 1) ? drop_scale : 0.f;
-              dp[cl + 2] *= kept(c + 2) ? drop_scale : 0.f;
-              dp[cl + 3] *= kept(c + 3) ? drop_scale : 0.f;
-            }
-            const float2 a = fmul2(make_float2(pr[c + 0], pr[c + 1]), fadd2(make_float2(dp[cl + 0], dp[cl + 1]), make_float2(D4.x, D4.y)));
-            const float2 b = fmul2(make_float2(pr[c + 2], pr[c + 3]), fadd2(make_float2(dp[cl + 2], dp[cl + 3]), make_float2(D4.z, D4.w)));
-            ds[e + 0] = a.x;
-            ds[e + 1] = a.y;
-            ds[e + 2] = b.x;
-            ds[e + 3] = b.y;
+        for (int e = 0; e < 8; e += 4) {
+          const float4 D4 = *reinterpret_cast<const float4*>(sD + ch * 8 + e);
+          const int c = ch * 8 + e;
+          float2 m0 = tau2, m1 = tau2;
+          if constexpr (kDrop) {
+            m0 = make_float2(kept(c + 0) ? tau_keep : 0.f, kept(c + 1) ? tau_keep : 0.f);
+            m1 = make_float2(kept(c + 2) ? tau_keep : 0.f, kept(c + 3) ? tau_keep : 0.f);
           }
-          if (FA_BWD_DELTA_PREFETCH && hf == 0) {  // refill with the second half's -delta before this chunk's store
-            dl[c8 * 2] = *reinterpret_cast<const float4*>(sD + 32 + c8 * 8);
-            dl[c8 * 2 + 1] = *reinterpret_cast<const float4*>(sD + 32 + c8 * 8 + 4);
-          }
-          uint4 v;
-          v.x = pack_bf16x2(ds[0], ds[1]);
-          v.y = pack_bf16x2(ds[2], ds[3]);
-          v.z = pack_bf16x2(ds[4], ds[5]);
-          v.w = pack_bf16x2(ds[6], ds[7]);
-          *reinterpret_cast<uint4*>(ds_row + ((ch ^ (r & 7)) << 4)) = v;
+          const float2 t0 = ffma2(make_float2(dp[c + 0], dp[c + 1]), m0, make_float2(D4.x, D4.y));
+          const float2 t1 = ffma2(make_float2(dp[c + 2], dp[c + 3]), m1, make_float2(D4.z, D4.w));
+          const uint32_t w0 = pk[c >> 1], w1 = pk[(c >> 1) + 1];
+          const float2 a = fmul2(make_float2(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u)), t0);
+          const float2 b = fmul2(make_float2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xffff0000u)), t1);
+          out[(e >> 1) + 0] = pack_bf16x2(a.x, a.y);
+          out[(e >> 1) + 1] = pack_bf16x2(b.x, b.y);
         }
-        FA_TR2(il, 7 + 3 * hf);
+        *reinterpret_cast<uint4*>(ds_row + ((ch ^ (r & 7)) << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
       }
+      FA_TR2(il, 7);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -480,7 +469,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       if constexpr (kDrop) {
         if (g == 0) {  // dV accumulated (P o keep)^T dO: apply the 1/(1-p) of Z once here
 #pragma unroll
-          for (int x = 0; x < 32; ++x) rr[x] = __float_as_uint(__uint_as_float(rr[x]) * drop_scale);
+          for (int x = 0; x < 32; ++x) rr[x] = __float_as_uint(__uint_as_float(rr[x]) * p.drop.keep_scale);
         }
       }
       if (row_ok) store_chunk32<OutT>(out + c0, rr);
@@ -491,7 +480,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     else reg_alloc<Cfg::kRegDrain>();
     const int w = warp - 8;
     const int r = w * 32 + lane;  // query row within the tile == TMEM lane
-    const uint32_t tDQ = tmem + Cfg::kColDQ + (uint32_t(w * 32) << 16);
+    const uint32_t tDQ = tmem + Cfg::kColR1 + (uint32_t(w * 32) << 16);
     const bool leader = (warp == 8 && lane == 0);
     uint32_t chunk_no = 0;
     for (int il = 0; il < n; ++il) {
@@ -537,6 +526,14 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       if (warp == 8) FA_TR(il, 7);
     }
     if (leader) tma_store_wait_all<0>();
+  } else if (warp == 14 && tr != nullptr && lane == 0) {
+    // developer timeline only: when do the Q / dO tiles land (slots 14 / 13 of the second table; 12 / 11 = load issued)
+    for (int il = 0; il < n && il < 16; ++il) {
+      mbar_wait(&bars.q_full[il & 1], (il >> 1) & 1);
+      tr[256 + il * 16 + 14] = clock64();
+      mbar_wait(&bars.do_full[il % Cfg::kDoStages], (il / Cfg::kDoStages) & 1);
+      tr[256 + il * 16 + 13] = clock64();
+    }
   }
 
   tc_fence_before();
@@ -551,7 +548,7 @@ template <int D>
 __global__ void __launch_bounds__(256)
 fa_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO,
                    const float* __restrict__ lse, float* __restrict__ lse_pad, float* __restrict__ delta_pad,
-                   float* __restrict__ dq_zero, int T, int Tpad, size_t total_rows_pad) {
+                   float* __restrict__ dq_zero, int T, int Tpad, size_t total_rows_pad, float tau) {
   constexpr int kLanesPerRow = D / 8;            // 16 (d = 128) or 8 (d = 64)
   constexpr int kRowsPerWarp = 32 / kLanesPerRow;
   const int lane = threadIdx.x & 31;
@@ -583,8 +580,8 @@ fa_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __r
 #pragma unroll
     for (int off = kLanesPerRow / 2; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (li == 0) {
-      delta_pad[row] = t < T ? -acc : 0.f;
-      lse_pad[row] = t < T ? lse[bh * T + t] * 1.4426950408889634f : INFINITY;
+      delta_pad[row] = t < T ? -tau * acc : 0.f;
+      lse_pad[row] = t < T ? -lse[bh * T + t] * 1.4426950408889634f : -INFINITY;
     }
   }
 }
@@ -631,7 +628,7 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
     size_t blocks = (rows + kRowsPerBlock - 1) / kRowsPerBlock;
     if (blocks > 148 * 32) blocks = 148 * 32;  // grid-stride beyond 32 blocks per SM
     fa_bwd_prep_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(o, dO, lse, lse_pad, delta_pad, zero ? dq_acc : nullptr, T,
-                                                          (int)Tpad, rows);
+                                                          (int)Tpad, rows, sqrtf(1.0f / (float)D));
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -658,10 +655,10 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   p.dq_acc = dq_acc;
   p.drop = drop;
   p.trace = g_bwd_trace;
-  {
-    const char* e = getenv("FA_B200_BWD_DEBUG_DQ");  // timing experiments only: results are wrong when set
-    p.dq_debug = !e ? 0 : e[0] == 's' && e[1] == 'k' ? 1 : e[0] == 's' && e[1] == 't' ? 2 : 0;
-  }
+  p.dq_debug = 0;
+#ifdef FA_B200_DEBUG_HOOKS  // developer builds only (tools/build_variant.sh <name> -DFA_B200_DEBUG_HOOKS): results are wrong when set
+  if (const char* e = getenv("FA_B200_BWD_DEBUG_DQ")) p.dq_debug = e[0] == 's' && e[1] == 'k' ? 1 : e[0] == 's' && e[1] == 't' ? 2 : 0;
+#endif
   dim3 grid((unsigned)(Tpad / kTile), BH);
   if (drop.thr) fa_bwd_kernel<D, OutT, true><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);
   else fa_bwd_kernel<D, OutT, false><<<grid, kBwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, mdo, mdq, p);

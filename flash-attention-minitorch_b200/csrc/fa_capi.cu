@@ -143,9 +143,23 @@ int host_precision() {
   }
   return g_host_precision;
 }
-// The reference ABI computes in plain fp32, so "auto" there means the exact-fp32 kernels; the tensor-core
-// precisions are opt-in (fa_b200_set_host_precision / FA_B200_HOST_PRECISION).
-int host_effective_precision() { return host_precision() == FA_PREC_AUTO ? FA_PREC_FP32_SIMT : host_precision(); }
+// "auto" on the reference ABI = tf32 tensor cores wherever a tcgen05 kernel covers the shape (resolve_precision falls
+// back to the exact-fp32 CUDA-core kernels for the rest): it meets the fp32-path bar of north_star (max-abs 1e-3
+// against the reference, |dO| <= 1: forward 4.9e-4, backward 7.4e-4 measured) and is what a user who only drops the
+// six .so files in gets.  FA_B200_HOST_PRECISION=fp32 (or fa_b200_set_host_precision) keeps exact fp32 arithmetic.
+int host_effective_precision() { return host_precision() == FA_PREC_AUTO ? FA_PREC_TF32_TC : host_precision(); }
+
+// FA_B200_HOST_ZERO_QGRAD=1: the caller promises that q_grad holds zeros on entry -- what every caller of the reference
+// passes (minitorch/cuda_kernel_ops.py:609-611) -- so the backward skips its upload (11 % of the H2D bytes) and
+// overwrites instead of accumulating.  Off by default: the reference kernels accumulate (src/flash_attn2_bw.cu:228).
+bool host_zero_qgrad() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("FA_B200_HOST_ZERO_QGRAD");
+    v = (s && s[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 bool valid_shape(int bh, int T, int d) { return bh > 0 && T > 0 && d > 0 && d <= 128; }
 
@@ -611,7 +625,9 @@ int fa_b200_host_bwd(const float* q, const float* k, const float* v, const float
   const int nchunks = (batch + hc - 1) / hc;
   const int nbuf = nchunks < kPipeBufs ? nchunks : kPipeBufs;
   const size_t cn = (size_t)hc * per_head, crows = (size_t)hc * N;
-  const size_t ws_bytes = tc ? fa::tc_bwd_workspace_bytes(hc, N, d) : 0;
+  const bool tf32 = prec == FA_PREC_TF32_TC;
+  const bool zero_qgrad = host_zero_qgrad();
+  const size_t ws_bytes = tc ? fa::tc_bwd_workspace_bytes(hc, N, d) : tf32 ? fa::tc_bwd_tf32_workspace_bytes(hc, N) : 0;
   const size_t buf_bytes = 8 * align_up(cn * 4, 256) + 4 * align_up(crows * 4, 256) + (tc ? 5 * align_up(cn * 2, 256) : 0) +
                            align_up(ws_bytes, 256) + 256;
   if (int rc = arena_reset(nbuf * buf_bytes + 4096)) return rc;
@@ -641,7 +657,7 @@ int fa_b200_host_bwd(const float* q, const float* k, const float* v, const float
     FA_CUDA(cudaMemcpyAsync(B.o, out + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
     FA_CUDA(cudaMemcpyAsync(B.g, out_grad + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
     // the reference accumulates into whatever the caller put in q_grad (src/flash_attn2_bw.cu:228)
-    FA_CUDA(cudaMemcpyAsync(B.gq, q_grad + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
+    if (!zero_qgrad) FA_CUDA(cudaMemcpyAsync(B.gq, q_grad + off, n * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
     FA_CUDA(cudaMemcpyAsync(B.l, l + roff, rows * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
     if (fa1) FA_CUDA(cudaMemcpyAsync(B.m, m + roff, rows * 4, cudaMemcpyHostToDevice, g_pipe.s_in), 0);
     FA_CUDA(cudaEventRecord(g_pipe.ev_in[b], g_pipe.s_in), 0);
@@ -654,11 +670,13 @@ int fa_b200_host_bwd(const float* q, const float* k, const float* v, const float
     if (tc) {
       const float* src[5] = {B.q, B.k, B.v, B.o, B.g};
       for (int j = 0; j < 5; ++j) FA_CUDA(fa::cvt_f32_to_bf16(src[j], B.b[j], n, st), 1);
-      FA_CUDA(fa::tc_bwd(B.b[0], B.b[1], B.b[2], B.b[3], B.b[4], lse, B.gq, B.gk, B.gv, true, true, B.ws, hn, N, d,
+      FA_CUDA(fa::tc_bwd(B.b[0], B.b[1], B.b[2], B.b[3], B.b[4], lse, B.gq, B.gk, B.gv, true, !zero_qgrad, B.ws, hn, N, d,
                          causal != 0, st), 2);
+    } else if (tf32) {
+      FA_CUDA(fa::tc_bwd_tf32(B.q, B.k, B.v, B.o, B.g, lse, B.gq, B.gk, B.gv, !zero_qgrad, B.ws, hn, N, causal != 0, st), 2);
     } else {
       FA_CUDA(fa::simt_bwd_prep(B.o, B.g, B.delta, nullptr, nullptr, nullptr, rows, d, st), 1);
-      FA_CUDA(fa::simt_bwd(B.q, B.k, B.v, B.g, lse, B.delta, B.gq, B.gk, B.gv, hn, N, d, causal != 0, true, st), 2);
+      FA_CUDA(fa::simt_bwd(B.q, B.k, B.v, B.g, lse, B.delta, B.gq, B.gk, B.gv, hn, N, d, causal != 0, !zero_qgrad, st), 2);
     }
     FA_CUDA(cudaEventRecord(g_pipe.ev_done[b], st), 0);
     FA_CUDA(cudaStreamWaitEvent(g_pipe.s_out, g_pipe.ev_done[b], 0), 0);

@@ -40,6 +40,20 @@ constexpr int kFwdThreads = 384;  // warps 0-7 softmax, 8 TMA, 9 MMA, 10-11 idle
 #ifndef FA_FWD_PACKED
 #define FA_FWD_PACKED 1  // FFMA2 / FADD2 in the softmax inner loop (measured: +2 % over scalar)
 #endif
+// Speculative exponent reference (FA_FWD_SPEC 1): the first 32 columns of a score tile are exponentiated against the
+// reference max of the PREVIOUS step while the row max of the new tile is still being reduced (the lazy rescale keeps that
+// reference valid unless the max grows by more than 2^8, in which case the chunk is recomputed).  It takes the 62-deep
+// FMNMX3 tree off the S -> P -> PV -> QK chain, but measured (same-box A/B, config 3): 2.05-2.09 ms against 2.00-2.03 ms
+// without it -- the interleaved max tree slows the first chunk by what it saves.  Off by default.
+#ifndef FA_FWD_SPEC
+#define FA_FWD_SPEC 0
+#endif
+// P is handed to the MMA warp in FA_FWD_PSIG pieces (1 or 2): with 2, the PV k-steps of the first 64 keys run under the
+// exponentials of the last 64 (measured: 2.00-2.03 ms against 2.05-2.06 ms with one piece; four pieces cost more in
+// tcgen05.wait::st + arrives than they hide, tools/experiments/fwd_quarter_pv_pingpong.patch).
+#ifndef FA_FWD_PSIG
+#define FA_FWD_PSIG 2
+#endif
 
 struct FwdParams {
   int T, BH, causal;
@@ -73,7 +87,7 @@ struct FwdCfg {
 struct FwdBarriers {
   uint64_t q_full;
   uint64_t k_full[4], k_empty[4], v_full[4], v_empty[4];
-  uint64_t s_full[2], p_full[2], o_full[2];
+  uint64_t s_full[2], p_full[2][FA_FWD_PSIG], o_full[2];
 };
 
 template <typename OutT>
@@ -132,7 +146,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bars.s_full[t], 1);
-      mbar_init(&bars.p_full[t], 4);  // one arrival per softmax warp
+      for (int h = 0; h < FA_FWD_PSIG; ++h) mbar_init(&bars.p_full[t][h], 4);  // one arrival per softmax warp
       mbar_init(&bars.o_full[t], 1);
     }
     fence_mbar_init();
@@ -194,16 +208,24 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           umma_ss_w<kTF32>(tmem + t * 128, desc_advance(q0, off), desc_advance(k0, off), idesc_qk, kk > 0);
         }
       };
-      auto issue_pv = [&](int t, int st, bool acc) {
+      auto issue_pv = [&](int t, int st, bool acc, int j) {
         const uint32_t va = sVa + st * Cfg::kTileBytes;
         // bf16: 16 key rows (2 KB) per k-step, 64-column atoms one box apart, 128B swizzle.
         // tf32: P is one tf32 per TMEM column, 8 columns per k-step; V: 8 key rows (1 KB) per k-step, 4-row groups
         // 512 B apart, 32-column atoms one box apart, 128B swizzle with 32-B atomicity.
         const uint64_t v0 = kTF32 ? make_smem_desc(va, Cfg::kBoxBytes, 512, kDescSw128Base32) : make_smem_desc(va, Cfg::kBoxBytes, 1024);
+        constexpr int kPerPiece = Cfg::kKStepsPV / FA_FWD_PSIG;
 #pragma unroll
-        for (int kk = 0; kk < Cfg::kKStepsPV; ++kk)
-          umma_ts_w<kTF32>(tmem + 256 + t * 128, tmem + t * 128 + kk * 8, desc_advance(v0, kk * (kTF32 ? 1024 : 2048)), idesc_pv,
-                           (acc || kk > 0) ? 1u : 0u);
+        for (int h = 0; h < FA_FWD_PSIG; ++h) {
+          mbar_wait_w(&bars.p_full[t][h], j & 1);  // piece h of P_t is in TMEM
+          tc_fence_after();
+#pragma unroll
+          for (int k2 = 0; k2 < kPerPiece; ++k2) {
+            const int kk = h * kPerPiece + k2;
+            umma_ts_w<kTF32>(tmem + 256 + t * 128, tmem + t * 128 + kk * 8, desc_advance(v0, kk * (kTF32 ? 1024 : 2048)), idesc_pv,
+                             (acc || kk > 0) ? 1u : 0u);
+          }
+        }
       };
       mbar_wait_w(&bars.q_full, 0);
       mbar_wait_w(&bars.k_full[0], 0);
@@ -220,10 +242,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const uint32_t phn = (jn / S) & 1;
         mbar_wait_w(&bars.v_full[st], ph);
         if (j < n0) {
-          mbar_wait_w(&bars.p_full[0], j & 1);
-          tc_fence_after();
           FA_TRF(j, 8);
-          issue_pv(0, st, j > 0);
+          issue_pv(0, st, j > 0, j);
           umma_commit_w(&bars.o_full[0]);
         }
         if (jn < n0) {
@@ -233,10 +253,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           umma_commit_w(&bars.s_full[0]);
         }
         FA_TRF(j, 9);
-        mbar_wait_w(&bars.p_full[1], j & 1);
-        tc_fence_after();
         FA_TRF(j, 10);
-        issue_pv(1, st, j > 0);
+        issue_pv(1, st, j > 0, j);
         umma_commit_w(&bars.o_full[1]);
         umma_commit_w(&bars.v_empty[st]);
         if (jn < n1) {
@@ -296,54 +314,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         for (int c = 0; c < 128; ++c)
           if (c > limit) s[c] = -INFINITY;
       }
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
-#pragma unroll
-      for (int c = 4; c < 128; c += 4) {
-        mx0 = fmaxf(mx0, s[c]);
-        mx1 = fmaxf(mx1, s[c + 1]);
-        mx2 = fmaxf(mx2, s[c + 2]);
-        mx3 = fmaxf(mx3, s[c + 3]);
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      m_true = fmaxf(m_true, mx);
-      if (j == 0) {
-        m_ref = mx;
-      } else {
-        const bool need = (mx - m_ref) * c2 > 8.f;
-        if (__any_sync(0xffffffffu, need)) {
-          // O_t must be quiescent: PV(t, j-1) retired, PV(t, j) not yet issued (it waits for our P).
-          mbar_wait(&bars.o_full[t], (j - 1) & 1);
-          tc_fence_after();
-          const float m_new = fmaxf(m_ref, mx);
-          const float f = ex2_approx((m_ref - m_new) * c2);
-          l *= f;
-          m_ref = m_new;
-#pragma unroll
-          for (int c0 = 0; c0 < D; c0 += 32) {
-            uint32_t orr[32];
-            tmem_ld_x32(tO + c0, orr);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
-            tmem_st_x32(tO + c0, orr);
-          }
-        }
-      }
-      const float nm = -m_ref * c2;
-      if ((warp & 3) == 0) FA_TRF(j, 4 * t + 2);
-#if FA_FWD_PACKED
-      const float2 c2v = make_float2(c2, c2), nmv = make_float2(nm, nm);
-      float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
-#else
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#endif
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {  // 32 score columns at a time
-        uint32_t pk[kTF32 ? 32 : 16];
+      // one chunk = 32 score columns: exponentials against the reference -nm / c2, row-sum partials, packed P words
+      constexpr int kPk = kTF32 ? 32 : 16;
+      const float2 c2v = make_float2(c2, c2);
+      auto exp_chunk = [&](const int q4, const float nm_, uint32_t* pk, float2& la, float2& lb) {
+        const float2 nmv = make_float2(nm_, nm_);
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           const int cc = q4 * 32 + c;
-#if FA_FWD_PACKED
           const float2 x0 = ffma2(make_float2(s[cc], s[cc + 1]), c2v, nmv);
           const float2 x1 = ffma2(make_float2(s[cc + 2], s[cc + 3]), c2v, nmv);
           float2 p0 = make_float2(ex2_mixed(x0.x, cc), ex2_mixed(x0.y, cc + 1));
@@ -356,30 +334,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           }
           la = fadd2(la, p0);
           lb = fadd2(lb, p1);
-          float q0 = p0.x, q1 = p0.y, q2 = p1.x, q3 = p1.y;
-#else
-          float q0 = ex2_mixed(fmaf(s[cc], c2, nm), cc);
-          float q1 = ex2_mixed(fmaf(s[cc + 1], c2, nm), cc + 1);
-          float q2 = ex2_mixed(fmaf(s[cc + 2], c2, nm), cc + 2);
-          float q3 = ex2_mixed(fmaf(s[cc + 3], c2, nm), cc + 3);
           if constexpr (kTF32) {
-            q0 = round_tf32(q0); q1 = round_tf32(q1); q2 = round_tf32(q2); q3 = round_tf32(q3);
-          }
-          l0 += q0;
-          l1 += q1;
-          l2 += q2;
-          l3 += q3;
-#endif
-          if constexpr (kTF32) {
-            pk[c] = __float_as_uint(q0);
-            pk[c + 1] = __float_as_uint(q1);
-            pk[c + 2] = __float_as_uint(q2);
-            pk[c + 3] = __float_as_uint(q3);
+            pk[c] = __float_as_uint(p0.x);
+            pk[c + 1] = __float_as_uint(p0.y);
+            pk[c + 2] = __float_as_uint(p1.x);
+            pk[c + 3] = __float_as_uint(p1.y);
           } else {
-            pk[c >> 1] = pack_bf16x2(q0, q1);
-            pk[(c >> 1) + 1] = pack_bf16x2(q2, q3);
+            pk[c >> 1] = pack_bf16x2(p0.x, p0.y);
+            pk[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
           }
-          if constexpr (kDrop) {  // l above is the undropped row sum; only P fed to the PV product is thinned
+          if constexpr (kDrop) {  // la / lb are the undropped row sum; only P fed to the PV product is thinned
             // the two lanes of a row pair need the same two block words: each hashes one, a shuffle gives the other
             const uint32_t j2 = (uint32_t(j * kBlockN + cc) >> 1) + (lane & 1);
             const uint32_t mine = drop_keep_word(drop_mix(drop_rowkey ^ (j2 * kDropColMul)), drop_thr);
@@ -396,18 +360,72 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             }
           }
         }
+      };
+      auto store_chunk = [&](const int q4, const uint32_t* pk) {
         if constexpr (kTF32) tmem_st_x32(tS + q4 * 32, pk);   // tf32: P fills all 128 columns of S
         else tmem_st_x16(tS + q4 * 16, pk);                    // bf16: two probabilities per column
+      };
+      auto signal_p = [&](const int h) {  // piece h of P_t is complete in TMEM
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.p_full[t][h]);
+      };
+
+      // Chunk 0 goes first, against the reference max of the previous step (speculation: independent of the max tree
+      // below, so ptxas interleaves the two).  j == 0 has no reference yet (m_ref = -inf gives inf / NaN here): it always
+      // takes the recompute branch, like any step whose row max outgrows the reference by more than 2^8.
+      uint32_t pk0[kPk];
+      float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+      float nm = -m_ref * c2;
+      if (FA_FWD_SPEC) exp_chunk(0, nm, pk0, la, lb);
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int c = 4; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, s[c]);
+        mx1 = fmaxf(mx1, s[c + 1]);
+        mx2 = fmaxf(mx2, s[c + 2]);
+        mx3 = fmaxf(mx3, s[c + 3]);
       }
-#if FA_FWD_PACKED
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      m_true = fmaxf(m_true, mx);
+      const bool need = (j == 0) || (mx - m_ref) * c2 > 8.f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = fmaxf(m_ref, mx);
+        if (j > 0) {
+          // O_t must be quiescent: PV(t, j-1) retired, PV(t, j) not yet issued (it waits for our P).
+          mbar_wait(&bars.o_full[t], (j - 1) & 1);
+          tc_fence_after();
+          const float f = ex2_approx((m_ref - m_new) * c2);
+          l *= f;
+#pragma unroll
+          for (int c0 = 0; c0 < D; c0 += 32) {
+            uint32_t orr[32];
+            tmem_ld_x32(tO + c0, orr);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
+            tmem_st_x32(tO + c0, orr);
+          }
+        }
+        m_ref = m_new;
+        nm = -m_ref * c2;
+        la = make_float2(0.f, 0.f);
+        lb = make_float2(0.f, 0.f);
+        if (FA_FWD_SPEC) exp_chunk(0, nm, pk0, la, lb);
+      }
+      if (!FA_FWD_SPEC) exp_chunk(0, nm, pk0, la, lb);
+      if ((warp & 3) == 0) FA_TRF(j, 4 * t + 2);
+      store_chunk(0, pk0);
+#pragma unroll
+      for (int q4 = 1; q4 < 4; ++q4) {
+        uint32_t pk[kPk];
+        exp_chunk(q4, nm, pk, la, lb);
+        store_chunk(q4, pk);
+        if (FA_FWD_PSIG == 2 && q4 == 1) signal_p(0);
+      }
+      signal_p(FA_FWD_PSIG - 1);
       l += (la.x + la.y) + (lb.x + lb.y);
-#else
-      l += (l0 + l1) + (l2 + l3);
-#endif
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.p_full[t]);
       if ((warp & 3) == 0) FA_TRF(j, 4 * t + 3);
     }
 

@@ -72,9 +72,12 @@ class Module:
         groups = [] if fuse is False else [g for m in self.modules() for g in m.fuse_parameters()
                                            if fuse or all(p.value.is_cuda for p in g[0])]
         in_group = {id(p) for g in groups for p in g[0]}
-        sizes = [p.value.numel() for p in params if id(p) not in in_group]
-        total = sum(sizes) + sum(sum(p.value.numel() for p in g[0]) for g in groups)
-        total = (total + 3) // 4 * 4  # the elementwise kernels move float4s
+        # Every parameter / fused group starts on a 32-element (128-byte) boundary: the kernels read weights and biases
+        # with float4 loads and as TMA tensors (16-byte aligned base), so one parameter whose size is not a multiple of
+        # four (say a 10002-entry vocabulary bias) must not misalign everything laid out after it.
+        align = lambda n: (n + 31) // 32 * 32  # noqa: E731
+        sizes = [align(p.value.numel()) for p in params if id(p) not in in_group]
+        total = sum(sizes) + sum(align(sum(p.value.numel() for p in g[0])) for g in groups)
         flat = torch.zeros(total, device=ref.device, dtype=ref.dtype)
         gflat = torch.zeros_like(flat)
         off = 0
@@ -89,7 +92,7 @@ class Module:
                 continue
             n = p.value.numel()
             attach(p, flat[off:off + n].view(p.value.shape), gflat[off:off + n].view(p.value.shape))
-            off += n
+            off += align(n)
         for members, on_fused in groups:
             rows = members[0].value.shape[0] if members[0].value.dim() == 2 else 1
             widths = [p.value.numel() // rows for p in members]
@@ -103,7 +106,7 @@ class Module:
             fused = (block if rows > 1 else block.view(-1)).requires_grad_(True)
             fused.grad = gblock if rows > 1 else gblock.view(-1)
             on_fused(fused)
-            off += n
+            off += align(n)
         self._flat = (flat, gflat)
         ops.grad_sink.direct = True  # weight / bias gradient kernels accumulate straight into the flat gradient views
         return self._flat

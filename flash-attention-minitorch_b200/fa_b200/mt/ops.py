@@ -117,7 +117,16 @@ def flash_attention_bf16(q, k, v, causal: bool = True, p_drop: float = 0.0, seed
 # the reference formula with torch, which is also what the GPU tests compare the kernels against.
 # ----------------------------------------------------------------------------------------------
 def _on_kernels(*tensors) -> bool:
-    return all(t.is_cuda and t.dtype == torch.float32 for t in tensors)
+    """True: every tensor is CUDA fp32 -> this repo's kernels.  False: every tensor lives on the CPU (unit tests).  A CUDA
+    tensor of any other dtype, or a CUDA / CPU mix, is an error: the product has no ATen / cuBLAS route on the GPU."""
+    on = [t.is_cuda for t in tensors]
+    if not any(on):
+        return False
+    if not all(on) or any(t.dtype != torch.float32 for t in tensors):
+        raise TypeError("fa_b200.mt.ops: CUDA operands must all be float32 CUDA tensors (got " +
+                        ", ".join(f"{t.device.type}/{str(t.dtype).replace('torch.', '')}" for t in tensors) +
+                        "); there is no library fallback on the GPU")
+    return True
 
 
 def _st():

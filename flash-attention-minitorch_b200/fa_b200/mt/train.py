@@ -112,7 +112,9 @@ def early_gradient_range(model: DecoderLM, flat_grads: torch.Tensor) -> Optional
     esz = flat_grads.element_size()
     offs = sorted(((p.value.grad.data_ptr() - flat_grads.data_ptr()) // esz, p.value.numel()) for p in ps)
     a, b = offs[0][0], offs[-1][0] + offs[-1][1]
-    if a < 0 or b > flat_grads.numel() or b - a != sum(n for _, n in offs) or any(not p.value.grad.is_contiguous() for p in ps):
+    # consecutive up to the alignment padding of Module.flatten_parameters (< 32 zero elements between two parameters)
+    gaps_ok = all(0 <= nxt[0] - (cur[0] + cur[1]) < 32 for cur, nxt in zip(offs, offs[1:]))
+    if a < 0 or b > flat_grads.numel() or not gaps_ok or any(not p.value.grad.is_contiguous() for p in ps):
         return None
     return a, b
 

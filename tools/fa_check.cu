@@ -538,7 +538,7 @@ static int trace_bwd(int BH, int T, int d, int causal) {
   const long long* hh = hst.data();
   const long long t0 = hh[0];
   printf("bwd timeline of CTA(0,0), cycles relative to first S ready\n");
-  printf(" il | CW: S_rdy  P_done  dP_rdy dS_w0   dS_w7 | DW: dQ_rdy drained  staged | MMA: dS_rdy iss_dQK drained  iss_dP   P_rdy  iss_dV   iss_S\n");
+  printf(" il | CW: S_rdy  P_done  dP_rdy dS_w0   dS_w7 | DW: dQ_rdy drained  staged | MMA: dS_rdy  iss_dK dO_seen  iss_dP  P_seen  iss_dV   iss_S\n");
   for (int il = 0; il < 16; ++il) {
     printf("%3d |", il);
     for (int e = 0; e < 15; ++e) {
@@ -549,11 +549,12 @@ static int trace_bwd(int BH, int T, int d, int causal) {
     printf("\n");
   }
   // second table: inside the compute warp 0 (slots 256 + il * 16 + e)
-  printf(" il | CW0: S_ld'd   exp'd  packed   tau'd   st'd | dP0ld'd ds_empty  half0 | dP1ld'd    -     half1   (relative to S_rdy of the same il)\n");
+  printf(" il | CW0: S_ld'd   exp'd drained     -    P_st'd | dP_ld'd ds_empty  dS_st'd | loads (relative to S_rdy of the same il): dO_issue  Q_issue  dO_landed  Q_landed\n");
   for (int il = 0; il < 16; ++il) {
     printf("%3d |", il);
     const long long base = hh[il * 16 + 0];
-    for (int e = 0; e < 11; ++e) {
+    for (int e = 0; e < 15; ++e) {
+      if (e >= 8 && e <= 10) continue;
       const long long v = hh[256 + il * 16 + e];
       printf(" %7lld", v ? v - base : -1);
       if (e == 4 || e == 7) printf(" |");
