@@ -5,14 +5,18 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (config.workload): BASELINE.json configs[2] -- FA-2 forward+backward, causal, B=32 H=16 T=4096 d=128,
-bf16 -- per GPU.  A "step" is one forward + one backward over one such batch.  With N GPUs every rank owns its
-own B*H = 512 independent heads (weak scaling; heads are sharded, the attention path has no collective).
-`value` is the whole-job TFLOP/s with inputs resident in HBM (algorithmic FLOPs 14*BH*T^2*d*0.5 per step, per
-GPU, summed over ranks / max-over-ranks CUDA-event time).  `e2e` is the same metric through the reference's
+bf16.  A "step" is one forward + one backward over that batch.  With N GPUs the B*H = 512 independent heads of
+the ONE batch are cut into N contiguous chunks (fa_b200.sharding.shard_bounds: 64 heads per GPU at N = 8; SURVEY.md
+section 8(e)) -- strong scaling, no collective on the attention path.  The weak-scaling figure (every rank its own 512
+heads) is reported beside it under "weak".  `value` is the whole-job TFLOP/s with inputs resident in HBM
+(algorithmic FLOPs 14*BH*T^2*d*0.5 of the whole batch per step / max-over-ranks CUDA-event time).  `e2e` is the same metric through the reference's
 host-pointer ABI (fa_b200_host_fwd / fa_b200_host_bwd behind launch_flash_attn_fw / _bw): fp32 HOST buffers
 (pinned), host<->device copies inside the timed region.  `cpu_baseline` / `--impl reference` time the CPU
 restatement of the reference's own attention path (oracle/attention_oracle.c, all host cores) on a bounded
-sample of the same workload.  torch is used for device memory, streams and torch.distributed only.
+sample of the same workload.  After the timed region two sampled heads of the very tensors that were timed are
+checked against the CPU oracle (`parity_check`), and the decoder-LM training run of BASELINE.json configs[4] is
+measured for ~1 s (`mt`: tokens/s and the reference's forward / backward / optimizer / all-reduce timers,
+project/run_machine_translation.py:196-221).  torch is used for device memory, streams and the timing barrier only.
 """
 from __future__ import annotations
 
@@ -159,7 +163,7 @@ def run_reference_arm(args):
     value = 3.5 * flops_fwd(heads, w["T"], w["d"], w["causal"]) * args.steps / total * 1e-12
     sample = f"{heads} of {w['B'] * w['H']} (b,h) problems per step (T={w['T']}, d={w['d']}, causal), fp32, fw+bw"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["name"], "sample": sample},
             "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
@@ -171,118 +175,229 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def parity_check(w, q, k, v, g, outs, grads, heads, p_drop, seed):
+    """Sampled heads of the tensors the timed region produced against the CPU oracle (the checker, never the product):
+    relative max-norm error per tensor for bf16 (bar 2e-2), max-abs for the fp32 / tf32 path (bar 1e-3)."""
+    import numpy as np
+    import torch
+    from fa_b200 import device
+    from oracle import c_oracle
+    c_oracle.use_all_cores()
+    T, causal, bf16 = w["T"], w["causal"], w["dtype"] == "bf16"
+    idx = torch.tensor(heads, device=q.device)
+    host = lambda t: t.index_select(0, idx).float().cpu().numpy()  # noqa: E731
+    keep, keep_scale = None, 1.0
+    if p_drop > 0:
+        keep = np.concatenate([device.dropout_mask(1, T, p_drop, seed, device=q.device, head_begin=h).cpu().numpy() for h in heads])
+        keep_scale = device.dropout_keep_scale(p_drop)
+    ref = c_oracle.attention(host(q), host(k), host(v), host(g) if grads is not None else None, causal, keep=keep, keep_scale=keep_scale)
+    got = {"o": host(outs[0])}
+    if grads is not None:
+        got.update(dq=host(grads[0]), dk=host(grads[1]), dv=host(grads[2]))
+    errs = {}
+    for name, x in got.items():
+        d = float(np.abs(x - ref[name]).max())
+        errs[name] = d / float(np.abs(ref[name]).max()) if bf16 else d
+    bar = 2e-2 if bf16 else 1e-3
+    return {"heads": list(heads), "of": int(q.shape[0]), "error": errs, "kind": "rel max-norm" if bf16 else "max-abs",
+            "bar": bar, "ok": bool(all(e <= bar and e == e for e in errs.values())),
+            "oracle": "oracle/attention_oracle.c (fp32, same inputs" + (", exported dropout mask)" if p_drop > 0 else ")")}
+
+
+def run_mt(dev, rank, world, iters=42):
+    """BASELINE.json configs[4]: decoder-LM training (n_vocab 10000, n_embd 256, 8 heads, 4 layers, L = 512, batch
+    int((5120+L)/L) per rank, dropout 0.1, Adam) on synthetic tokens, data-parallel over the ranks with the bucketed NCCL
+    gradient all-reduce of fa_b200_nccl_* (no torch.distributed in the loop).  Timers as the reference prints them
+    (project/run_machine_translation.py:196-221), summed over iterations >= 2."""
+    import torch
+    from fa_b200.mt import ops
+    from fa_b200.mt.model import DecoderLM
+    from fa_b200.mt.optim import Adam
+    from fa_b200.mt.train import job_min, train
+    L = 512
+    batch = int((128 * 40 + L) / L)
+    comm = None
+    if world > 1:
+        from fa_b200.mt.comm import NcclComm
+        comm = NcclComm().init(rank, world)
+    model = DecoderLM(n_vocab=10000, n_embd=256, n_head=8, n_positions=L, p_dropout=0.1, ln_eps=1e-5, bias=True, device=dev,
+                      seed=11111, attention_fn=ops.flash_attention)
+    opt = Adam(model.parameters(), lr=0.02, flat=model.flatten_parameters())
+    res = train(model, opt, iters, batch, L, rank, world, torch.cuda.synchronize, cuda_graph=True, overlap_allreduce=True, comm=comm)
+    slowest = job_min(res["tokens_per_s_per_rank"], rank, world, comm, dev)
+    if comm is not None:
+        comm.destroy()
+    n = max(res["timed_iters"], 1)
+    return {"metric": "decoder-LM training tokens/s (whole job)", "value": slowest * world, "unit": "tokens/s", "n_gpus": world,
+            "seq_len": L, "batch_per_rank": batch, "iters_timed": res["timed_iters"], "scaling": "weak (per-rank batch fixed, as the reference)",
+            "forward_plus_backward_s": res["forward_s"] + res["backward_s"], "allreduce_s": res["allreduce_s"], "opt_s": res["opt_s"],
+            "ms_per_iter": {"forward_backward_graph": (res["forward_s"] + res["backward_s"]) / n * 1e3,
+                            "allreduce_exposed": res["allreduce_s"] / n * 1e3, "opt": res["opt_s"] / n * 1e3},
+            "allreduce": "5 buckets from backward hooks inside the CUDA graph (fa_b200_nccl_allreduce_f32), last bucket after it"
+                         if world > 1 else "none (1 rank)",
+            "loss_first": res["loss_first"], "loss_last": res["loss_last"], "data": "synthetic uniform tokens",
+            "attention": "tf32 tcgen05 forward + backward (d = 32)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from fa_b200 import _lib, device
+    from fa_b200 import _lib, device, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpus_bound = 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        from fa_b200 import sharding
-        sharding.bind_to_gpu_numa(local)  # pinned e2e buffers land on the GPU's own NUMA node
+        # disjoint core slices per rank; the pinned e2e buffers allocated below are first-touched by them
+        cpus_bound = sharding.bind_to_gpu_numa(local, local, local_world)
     lib = _lib.load_library()
 
     w = WORKLOADS[args.workload]
-    BH, T, d, causal = w["B"] * w["H"], w["T"], w["d"], w["causal"]
+    BH_global, T, d, causal = w["B"] * w["H"], w["T"], w["d"], w["causal"]
     do_bwd, p_drop, seed = w["backward"], w["p_drop"], 4001
     tdt = torch.bfloat16 if w["dtype"] == "bf16" else torch.float32
-    torch.manual_seed(3001 + rank)
-    mk = lambda: (torch.rand(BH, T, d, device=dev) * 2 - 1).to(tdt)  # noqa: E731
-    q, k, v = mk(), mk(), mk()
-    outs = (torch.empty_like(q), torch.empty(BH, T, dtype=torch.float32, device=dev))
-    if do_bwd:
-        g = mk()
-        grads = (torch.empty_like(q), torch.empty_like(q), torch.empty_like(q))
-        ws = device.bwd_workspace(q)
+    strong = args.scaling == "strong"
+    h0, h1 = sharding.shard_bounds(BH_global, rank, world) if strong else (0, BH_global)
 
-    def fwd():
-        return device.flash_attn_fwd(q, k, v, causal, out=outs, p_drop=p_drop, seed=seed)
+    class Problem:
+        """Device-resident tensors of `BH` heads and the calls that make up one step on them."""
 
-    def bwd(o, lse):
-        device.flash_attn_bwd(q, k, v, o, g, lse, causal, workspace=ws, out=grads, p_drop=p_drop, seed=seed)
+        def __init__(self, BH, gen_seed):
+            torch.manual_seed(gen_seed)
+            mk = lambda: (torch.rand(BH, T, d, device=dev) * 2 - 1).to(tdt)  # noqa: E731
+            self.BH = BH
+            self.q, self.k, self.v = mk(), mk(), mk()
+            self.outs = (torch.empty_like(self.q), torch.empty(BH, T, dtype=torch.float32, device=dev))
+            self.g = self.grads = self.ws = None
+            if do_bwd:
+                self.g = mk()
+                self.grads = (torch.empty_like(self.q), torch.empty_like(self.q), torch.empty_like(self.q))
+                self.ws = device.bwd_workspace(self.q)
 
-    def step():
-        o, lse = fwd()
-        if do_bwd:
-            bwd(o, lse)
-        return o, lse
+        def fwd(self):
+            return device.flash_attn_fwd(self.q, self.k, self.v, causal, out=self.outs, p_drop=p_drop, seed=seed)
+
+        def bwd(self, o, lse):
+            device.flash_attn_bwd(self.q, self.k, self.v, o, self.g, lse, causal, workspace=self.ws, out=self.grads, p_drop=p_drop, seed=seed)
+
+        def step(self):
+            o, lse = self.fwd()
+            if do_bwd:
+                self.bwd(o, lse)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(prob, steps, warmup):
+        for _ in range(warmup):
+            prob.step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            prob.step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    prob = Problem(h1 - h0, 3001 + rank)
     sampler = ClockSampler(local)
     sampler.start()
     for _ in range(max(args.warmup, 3)):
-        step()
+        prob.step()
     barrier()
     sampler.wait_first_sample()
     launches0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_step = timed(prob, args.steps, 0)
     launches = _lib.launch_count() - launches0
 
     # per-kernel durations for the roofline object (same stream, same inputs, events around each call)
     # (back-to-back launches between events so that host launch latency is not on the timed path)
     reps = max(3, min(args.steps, 10))
-    o, lse = outs
+    o, lse = prob.outs
     a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     torch.cuda.synchronize()
     a.record()
     for _ in range(reps):
-        fwd()
+        prob.fwd()
     b.record()
     for _ in range(reps if do_bwd else 0):
-        bwd(o, lse)
+        prob.bwd(o, lse)
     c.record()
     torch.cuda.synchronize()
-    fw_ms, bw_ms = [a.elapsed_time(b) / reps], [b.elapsed_time(c) / reps if do_bwd else 0.0]
+    fw, bw = a.elapsed_time(b) / reps, (b.elapsed_time(c) / reps if do_bwd else 0.0)
     clocks = sampler.stop()
 
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    f_head = (3.5 if do_bwd else 1.0) * flops_fwd(1, T, d, causal)
+    heads_in_job = BH_global if strong else BH_global * world
+    value = f_head * heads_in_job / (ms_step * 1e-3) * 1e-12
+
+    # ---- parity of what was just timed: two sampled heads (first and last of this rank's chunk) against the CPU oracle
+    parity = None
+    if rank == 0:
+        heads = sorted({0, prob.BH - 1}) if T <= 4096 else [prob.BH - 1]
+        parity = parity_check(w, prob.q, prob.k, prob.v, prob.g, prob.outs, prob.grads, heads, p_drop, seed)
+
+    # ---- the other scaling mode beside it (N > 1): every rank a full batch of its own
+    other = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    f_step = (3.5 if do_bwd else 1.0) * flops_fwd(BH, T, d, causal)
-    value = f_step * world / (ms_step * 1e-3) * 1e-12
+        if strong:
+            del prob
+            torch.cuda.empty_cache()
+            prob = Problem(BH_global, 3001 + rank)
+            ms_w = timed(prob, min(args.steps, 5), 2)
+            other = {"scaling": "weak", "value": f_head * BH_global * world / (ms_w * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": ms_w,
+                     "batch_heads_per_gpu": BH_global, "steps": min(args.steps, 5)}
 
     # ---- e2e: reference-facing host-pointer ABI, pinned fp32 host buffers, copies inside the timed region
     if p_drop > 0:
         e2e = {"value": None, "unit": "TFLOP/s", "note": "the reference's host-pointer ABI has no dropout argument; "
                "dropout is a device-API feature (fa_b200_fwd_dropout / fa_b200_bwd_dropout)"}
     else:
-        e2e = run_e2e(lib, dev, BH, T, d, causal, steps=min(args.steps, 2), world=world, do_bwd=do_bwd,
+        del prob
+        torch.cuda.empty_cache()
+        e2e = run_e2e(lib, dev, h1 - h0, heads_in_job, T, d, causal, steps=max(5, min(args.steps, 10)), world=world, do_bwd=do_bwd,
                       prec=_lib.FA_PREC_BF16_TC if w["dtype"] == "bf16" else _lib.FA_PREC_TF32_TC)
+        e2e["cpus_bound_per_rank"] = cpus_bound
 
-    line = None
+    # ---- BASELINE.json configs[4]: the decoder-LM training run (about a second of GPU time)
+    mt = None
+    if args.workload == "cfg3" and not args.no_mt:
+        try:
+            mt = run_mt(dev, rank, world)
+        except Exception as exc:  # the headline line must not die with the side measurement
+            mt = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if rank == 0:
         peaks = measured_peaks()
+        spec = 2250.0
         if w["dtype"] != "bf16":  # kind::tf32 runs at half the bf16 rate; no separate measured tf32 peak exists
             peaks["tflops"] *= 0.5
+            peaks["burst"] *= 0.5
+            spec *= 0.5
             peaks["source"] += " / 2 for tf32"
-        fw, bw = statistics.mean(fw_ms), statistics.mean(bw_ms)
         dom_is_bw = bw >= fw
         dom_ms = bw if dom_is_bw else fw
-        dom_fl = (2.5 if dom_is_bw else 1.0) * flops_fwd(BH, T, d, causal)
+        BHr = h1 - h0
+        dom_fl = (2.5 if dom_is_bw else 1.0) * flops_fwd(BHr, T, d, causal)
         achieved = dom_fl / (dom_ms * 1e-3) * 1e-12
+        fwd_ach = flops_fwd(BHr, T, d, causal) / (fw * 1e-3) * 1e-12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and world == 1:
             try:
                 traffic = json.load(open(tpath)).get(args.workload, {}).get("bwd" if dom_is_bw else "fwd")
             except Exception:
@@ -290,27 +405,35 @@ def run_ours(args):
         # CPU baseline: rank 0 at N=1 only (the reference arm, --impl reference, covers N>1)
         cpu_heads = max(1, min(16, int(16 * (4096 / T) ** 2)))  # ~3 s of CPU work at any T
         cpu = cpu_reference_sample(cpu_heads, T, d, causal, backward=do_bwd) if world == 1 else None
+        per_gpu = value / world
         line = {"metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if strong else "weak",
                 "vs_baseline": None, "dtype": "bf16" if w["dtype"] == "bf16" else "tf32", "data": "synthetic",
-                "config": {"workload": w["name"], "batch_heads_per_gpu": BH, "global_batch_heads": BH * world, "seq_len": T,
+                "config": {"workload": w["name"], "batch_heads_per_gpu": BHr, "global_batch_heads": heads_in_job, "seq_len": T,
                            "head_dim": d, "causal": causal, "dropout": p_drop,
-                           "parallelism": f"batch*heads sharded x{world}, no collective",
-                           "l2": f"inputs ({q.numel() * q.element_size() / 1e6:.0f} MB per tensor per GPU) exceed the 126 MB L2; "
-                                 "no flush between iterations",
-                           "flops_per_step_per_gpu": f_step},
-                "per_gpu_tflops": value / world,
-                "frac_of_spec_bf16_2250": value / world / 2250.0,
+                           "parallelism": (f"the batch's {BH_global} (b, h) problems cut into {world} contiguous chunks" if strong
+                                           else f"{BH_global} (b, h) problems per GPU x{world}") + ", no collective",
+                           "l2": f"inputs ({BHr * T * d * (2 if tdt == torch.bfloat16 else 4) / 1e6:.0f} MB per tensor per GPU) "
+                                 + ("exceed" if BHr * T * d * 2 > 126e6 else "do not exceed") + " the 126 MB L2; no flush between iterations",
+                           "flops_per_step_whole_job": f_head * heads_in_job},
+                "per_gpu_tflops": per_gpu,
+                "frac_of_spec_bf16_2250": per_gpu / 2250.0,
                 "kernel_ms": {"forward": fw, "backward": bw},
                 "roofline": {"bound": "tensor", "kernel": "backward" if dom_is_bw else "forward", "achieved": achieved,
-                             "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
-                             "peak_source": peaks["source"],
-                             "forward": {"achieved": flops_fwd(BH, T, d, causal) / (fw * 1e-3) * 1e-12,
-                                         "frac": flops_fwd(BH, T, d, causal) / (fw * 1e-3) * 1e-12 / peaks["tflops"]}},
+                             "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                             "frac_burst": achieved / peaks["burst"], "frac_spec": achieved / spec, "traffic": traffic,
+                             "peak_source": peaks["source"] + "; frac_burst against bf16_tflops, frac_spec against the 2250 TFLOP/s datasheet figure",
+                             "forward": {"achieved": fwd_ach, "frac": fwd_ach / peaks["tflops"], "frac_burst": fwd_ach / peaks["burst"],
+                                         "frac_spec": fwd_ach / spec}},
                 "cpu_baseline": None if cpu is None else {
                     "value": cpu["tflops"], "unit": "TFLOP/s", "cores": cpu["cores"], "kind": "port",
-                    "sample": f"{cpu_heads} of {BH} (b,h) problems, {'fw+bw' if do_bwd else 'fw'}, fp32, {cpu['seconds']:.2f} s"},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                    "sample": f"{cpu_heads} of {BH_global} (b,h) problems, {'fw+bw' if do_bwd else 'fw'}, fp32, {cpu['seconds']:.2f} s"},
+                "e2e": e2e, "parity_check": parity, "gpu_launches": int(launches), "clocks": clocks}
+        if other is not None:
+            line["weak"] = other
+        if mt is not None:
+            line["mt"] = mt
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -318,9 +441,10 @@ def run_ours(args):
     return 0
 
 
-def run_e2e(lib, dev, BH, T, d, causal, steps, world, do_bwd=True, prec=None):
+def run_e2e(lib, dev, BH, heads_in_job, T, d, causal, steps, world, do_bwd=True, prec=None):
     """Same workload through fa_b200_host_fwd/bwd (what launch_flash_attn_fw/_bw forward to): pinned fp32 host
-    buffers in, fp32 host buffers out, bf16 tensor-core arithmetic on the device.  Returns the e2e object."""
+    buffers in, fp32 host buffers out, tensor-core arithmetic on the device.  This rank moves its BH heads; the job's
+    figure is the whole batch over the slowest rank.  Returns the e2e object."""
     import torch
     import torch.distributed as dist
     from fa_b200 import _lib
@@ -346,7 +470,7 @@ def run_e2e(lib, dev, BH, T, d, causal, steps, world, do_bwd=True, prec=None):
         if do_bwd:
             _lib.check(lib.fa_b200_host_bwd(P(hq), P(hk), P(hv), P(ho), P(hg), P(hgq), P(hgk), P(hgv), P(hl), P(hm), BH, T, d,
                                             int(causal), _lib.FA_CONV_FA2, stream))
-    try:
+    def measure():
         step()  # warm-up: arena allocation, first-touch
         if world > 1:
             dist.barrier()
@@ -357,19 +481,38 @@ def run_e2e(lib, dev, BH, T, d, causal, steps, world, do_bwd=True, prec=None):
             step()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        return e0.elapsed_time(e1) / steps
+
+    ms_zq = None
+    try:
+        ms = measure()  # strict reference semantics: q_grad is uploaded and accumulated into (src/flash_attn2_bw.cu:228)
+        if do_bwd and hasattr(lib, "fa_b200_set_host_zero_qgrad"):
+            # opt-in: the caller promises a zero q_grad -- what every caller of the reference passes
+            # (minitorch/cuda_kernel_ops.py:609-611) -- so its upload (11 % of the H2D bytes) is skipped
+            lib.fa_b200_set_host_zero_qgrad(1)
+            ms_zq = measure()
+            lib.fa_b200_set_host_zero_qgrad(0)
     finally:
         lib.fa_b200_set_host_precision(prev)
         lib.fa_b200_release_arena()
+    my_ms = ms
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    f_step = (3.5 if do_bwd else 1.0) * flops_fwd(BH, T, d, causal)
+    f_job = (3.5 if do_bwd else 1.0) * flops_fwd(heads_in_job, T, d, causal)
     h2d = (3 * n + (6 * n + rows if do_bwd else 0)) * 4   # fwd: q,k,v ; bwd: q,k,v,out,out_grad,q_grad + L
     d2h = (n + rows + (3 * n if do_bwd else 0)) * 4       # fwd: out, L ; bwd: q_grad,k_grad,v_grad
-    return {"value": f_step * world / (ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": ms, "steps": steps,
-            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+    zq = None
+    if ms_zq is not None:
+        tz = torch.tensor([ms_zq], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tz, op=dist.ReduceOp.MAX)
+        zq = {"value": f_job / (float(tz.item()) * 1e-3) * 1e-12, "ms_per_step": float(tz.item()), "h2d_bytes_per_step": h2d - n * 4,
+              "how": "fa_b200_set_host_zero_qgrad(1) / FA_B200_HOST_ZERO_QGRAD=1: q_grad assumed zero on entry, not uploaded"}
+    return {"value": f_job / (ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": ms, "steps": steps,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "bytes_are": "per rank", "zero_qgrad_opt_in": zq,
+            "h2d_GBps_this_rank": h2d / (my_ms * 1e-3) * 1e-9, "d2h_GBps_this_rank": d2h / (my_ms * 1e-3) * 1e-9,
             "api": "fa_b200_host_fwd" + (" + fa_b200_host_bwd" if do_bwd else "") + " (reference ABI launch_flash_attn_fw/_bw), pinned fp32 "
                    "host buffers streamed through a 3-buffer H2D/kernel/D2H pipeline, "
                    + ("bf16" if prec in (None, _lib.FA_PREC_BF16_TC) else "tf32") + " tensor-core arithmetic"}
@@ -383,6 +526,9 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg3",
                     help="cfg3 (default) is the headline configuration; cfg2 / cfg4 are recorded under profiles/ only")
+    ap.add_argument("--scaling", choices=["strong", "weak"], default="strong",
+                    help="N > 1: strong = the batch's 512 heads cut into N chunks (default, SURVEY.md 8e); weak = 512 heads per GPU")
+    ap.add_argument("--no-mt", action="store_true", help="skip the decoder-LM training measurement (`mt` object)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -28,8 +28,9 @@ fail=0
 for p in "${pids[@]:-}"; do [ -n "$p" ] && { wait "$p" || fail=1; }; done
 [ "$fail" = 0 ] || { echo "compile_cuda.sh: compilation failed" >&2; exit 1; }
 
-$NVCC $ARCH -shared -o "$LIB/libfa_b200.so" "$OBJ"/fa_simt.o "$OBJ"/fa_util.o "$OBJ"/fa_capi.o "$OBJ"/fa_fwd_sm100.o \
-  "$OBJ"/fa_bwd_sm100.o "$OBJ"/fa_bwd_tf32_sm100.o "$OBJ"/fa_gemm_sm100.o "$OBJ"/fa_lm_kernels.o -lcudart
+g++ -O2 -std=c++17 -fPIC -I/usr/local/cuda/include -c "$SRC/fa_nccl.cpp" -o "$OBJ/fa_nccl.o"
+$NVCC $ARCH -shared -o "$LIB/libfa_b200.so" "$OBJ"/fa_nccl.o "$OBJ"/fa_simt.o "$OBJ"/fa_util.o "$OBJ"/fa_capi.o "$OBJ"/fa_fwd_sm100.o \
+  "$OBJ"/fa_bwd_sm100.o "$OBJ"/fa_bwd_tf32_sm100.o "$OBJ"/fa_gemm_sm100.o "$OBJ"/fa_lm_kernels.o -lcudart -ldl
 
 shim() {  # name convention FW|BW
   g++ -O2 -fPIC -shared -DFA_SHIM_CONVENTION="$2" -DFA_SHIM_"$3" "$SRC/fa_legacy_shim.cpp" \

@@ -152,13 +152,13 @@ int host_effective_precision() { return host_precision() == FA_PREC_AUTO ? FA_PR
 // FA_B200_HOST_ZERO_QGRAD=1: the caller promises that q_grad holds zeros on entry -- what every caller of the reference
 // passes (minitorch/cuda_kernel_ops.py:609-611) -- so the backward skips its upload (11 % of the H2D bytes) and
 // overwrites instead of accumulating.  Off by default: the reference kernels accumulate (src/flash_attn2_bw.cu:228).
+int g_host_zero_qgrad = -1;  // -1: not yet initialised from the environment
 bool host_zero_qgrad() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_host_zero_qgrad < 0) {
     const char* s = getenv("FA_B200_HOST_ZERO_QGRAD");
-    v = (s && s[0] == '1') ? 1 : 0;
+    g_host_zero_qgrad = (s && s[0] == '1') ? 1 : 0;
   }
-  return v == 1;
+  return g_host_zero_qgrad == 1;
 }
 
 bool valid_shape(int bh, int T, int d) { return bh > 0 && T > 0 && d > 0 && d <= 128; }
@@ -523,6 +523,7 @@ void fa_b200_debug_bwd_trace(void* dev_buf) { fa::tc_bwd_set_trace(static_cast<l
 void fa_b200_debug_fwd_trace(void* dev_buf) { fa::tc_fwd_set_trace(static_cast<long long*>(dev_buf)); }
 
 void fa_b200_set_host_precision(int precision) { g_host_precision = precision; }
+void fa_b200_set_host_zero_qgrad(int on) { g_host_zero_qgrad = on ? 1 : 0; }
 int fa_b200_get_host_precision(void) { return host_precision(); }
 void fa_b200_release_arena(void) {
   std::lock_guard<std::mutex> lk(g_arena_mu);

@@ -118,6 +118,9 @@ def load_library() -> ctypes.CDLL:
     lib.fa_b200_set_host_precision.argtypes = [ci]
     lib.fa_b200_set_host_precision.restype = None
     lib.fa_b200_get_host_precision.restype = ci
+    if hasattr(lib, "fa_b200_set_host_zero_qgrad"):
+        lib.fa_b200_set_host_zero_qgrad.argtypes = [ci]
+        lib.fa_b200_set_host_zero_qgrad.restype = None
     lib.fa_b200_release_arena.restype = None
     _lib = lib
     return lib

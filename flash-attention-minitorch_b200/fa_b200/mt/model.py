@@ -69,31 +69,54 @@ class Module:
         True / False = always / never (the CPU tests exercise the fused layout with True).  Returns (values, grads)."""
         params = self.parameters()
         ref = params[0].value
-        groups = [] if fuse is False else [g for m in self.modules() for g in m.fuse_parameters()
-                                           if fuse or all(p.value.is_cuda for p in g[0])]
-        in_group = {id(p) for g in groups for p in g[0]}
         # Every parameter / fused group starts on a 32-element (128-byte) boundary: the kernels read weights and biases
         # with float4 loads and as TMA tensors (16-byte aligned base), so one parameter whose size is not a multiple of
         # four (say a 10002-entry vocabulary bias) must not misalign everything laid out after it.
         align = lambda n: (n + 31) // 32 * 32  # noqa: E731
-        sizes = [align(p.value.numel()) for p in params if id(p) not in in_group]
-        total = sum(sizes) + sum(align(sum(p.value.numel() for p in g[0])) for g in groups)
+
+        # Layout units, clustered per top-level child of this module (token_embeddings, ..., t_layer_1, ..., ln, lm_head):
+        # a child's own parameters first, then its fused groups -- so that every child is ONE contiguous range of the flat
+        # buffers (Module.flat_ranges), which is what lets the trainer all-reduce a layer's gradients as one bucket the
+        # moment its backward has finished.
+        units = []  # ("p", Parameter) | ("g", members, on_fused)
+        self._flat_children = []  # (attribute name, begin, end) in layout order
+        for name, child in vars(self).items():
+            if isinstance(child, Parameter):
+                subtree_params, subtree_groups = [child], []
+            elif isinstance(child, Module):
+                subtree_groups = [] if fuse is False else [g for m in child.modules() for g in m.fuse_parameters()
+                                                           if fuse or all(p.value.is_cuda for p in g[0])]
+                grouped = {id(p) for g in subtree_groups for p in g[0]}
+                subtree_params = [p for p in child.parameters() if id(p) not in grouped]
+            else:
+                continue
+            self._flat_children.append([name, len(units), None])
+            units += [("p", p) for p in subtree_params] + [("g", g[0], g[1]) for g in subtree_groups]
+            self._flat_children[-1][2] = len(units)
+
+        def unit_numel(u):
+            return u[1].value.numel() if u[0] == "p" else sum(p.value.numel() for p in u[1])
+
+        offsets, off = [], 0
+        for u in units:
+            offsets.append(off)
+            off += align(unit_numel(u))
+        total = off
         flat = torch.zeros(total, device=ref.device, dtype=ref.dtype)
         gflat = torch.zeros_like(flat)
-        off = 0
 
         def attach(p, view, gview):
             view.copy_(p.value.detach())
             p.value = view.requires_grad_(True)
             p.value.grad = gview
 
-        for p in params:
-            if id(p) in in_group:
+        for u, off in zip(units, offsets):
+            if u[0] == "p":
+                p = u[1]
+                n = p.value.numel()
+                attach(p, flat[off:off + n].view(p.value.shape), gflat[off:off + n].view(p.value.shape))
                 continue
-            n = p.value.numel()
-            attach(p, flat[off:off + n].view(p.value.shape), gflat[off:off + n].view(p.value.shape))
-            off += align(n)
-        for members, on_fused in groups:
+            members, on_fused = u[1], u[2]
             rows = members[0].value.shape[0] if members[0].value.dim() == 2 else 1
             widths = [p.value.numel() // rows for p in members]
             n = rows * sum(widths)
@@ -106,7 +129,9 @@ class Module:
             fused = (block if rows > 1 else block.view(-1)).requires_grad_(True)
             fused.grad = gblock if rows > 1 else gblock.view(-1)
             on_fused(fused)
-            off += align(n)
+        # element ranges of the flat buffers per top-level child (padding included)
+        self._flat_children = [(name, offsets[lo] if lo < len(offsets) else total, offsets[hi] if hi < len(offsets) else total)
+                               for name, lo, hi in self._flat_children if hi > lo]
         self._flat = (flat, gflat)
         ops.grad_sink.direct = True  # weight / bias gradient kernels accumulate straight into the flat gradient views
         return self._flat
@@ -114,6 +139,10 @@ class Module:
     def fuse_parameters(self):
         """[(parameters to lay out side by side, callback receiving the fused leaf tensor)] -- see flatten_parameters."""
         return []
+
+    def flat_ranges(self) -> Dict[str, Tuple[int, int]]:
+        """{top-level child name: [begin, end) of the flat parameter / gradient buffers} after flatten_parameters."""
+        return {name: (a, b) for name, a, b in getattr(self, "_flat_children", [])}
 
 
 def _rparam(in_size: int, shape, device, dtype, gen) -> Parameter:
@@ -279,13 +308,15 @@ class DecoderLM(Module):
         x = ops.embed_pos_dropout(idx, self.token_embeddings.weights.value, self.position_embeddings.weights.value,
                                   self.p_dropout, self.training)
         delta = delta_bias = None  # the residual stream is x + delta; each addition happens inside the next LayerNorm's kernel
-        for layer in (self.t_layer_1, self.t_layer_2, self.t_layer_3, self.t_layer_4):
-            x, delta, delta_bias = layer.forward_pending(x, delta, delta_bias)
         hook = getattr(self, "grad_ready_hook", None)
-        if hook is not None and x.requires_grad:
-            # fires when the gradient of the last layer's output exists, i.e. the final LayerNorm and lm_head are done:
-            # the trainer starts the all-reduce of their gradients while the four layers' backward still runs
-            x.register_hook(lambda g: hook())
+        layers = (self.t_layer_1, self.t_layer_2, self.t_layer_3, self.t_layer_4)
+        for k, layer in enumerate(layers):
+            x, delta, delta_bias = layer.forward_pending(x, delta, delta_bias)
+            if hook is not None and x.requires_grad:
+                # fires when the gradient of layer k's output exists, i.e. when everything downstream of it -- layers
+                # k+1.., the final LayerNorm and lm_head -- has finished its backward: the trainer starts the all-reduce of
+                # that part's gradients (bucket `len(layers) - 1 - k`, see train.gradient_buckets) while the rest runs
+                x.register_hook(lambda g, b=len(layers) - 1 - k: hook(b))
         _, x = self.ln.add_forward(x.reshape(B * T, self.n_embd), delta.reshape(B * T, self.n_embd), delta_bias)
         return self.lm_head(x, head_bias_grad).view(B, T, self.n_vocab)
 

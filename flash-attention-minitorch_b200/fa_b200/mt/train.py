@@ -5,9 +5,10 @@ int((128*40 + L) / L) (:385), loss_fn (:158-177) and the train() loop with its f
 timers accumulated over iterations 2..9 of 10 (:180-221).  The IWSLT corpus and the BPE tokenizer are not
 available offline, so batches are uniform random token ids of the same shape.
 
-Data parallelism: one process per GPU, identical initial weights (same seed), per-rank batches, and ONE
-collective per step -- an all-reduce(sum)/world of the flattened gradients over NCCL (NVLink 5 / NVSwitch).
-The attention path itself has no collective (heads are independent).
+Data parallelism: one process per GPU, identical initial weights (same seed), per-rank batches, and the gradient
+all-reduce (average) of the flat gradient buffer over NCCL (NVLink 5 / NVSwitch) through the thin C ABI
+fa_b200_nccl_* of libfa_b200.so (fa_b200/mt/comm.py; no torch.distributed on the GPU path) -- in five buckets that
+start from backward hooks as the layers' gradients complete.  The attention path itself has no collective.
 """
 from __future__ import annotations
 
@@ -33,55 +34,79 @@ def synthetic_batch(batch_size: int, seq_len: int, n_vocab: int, device, gen: to
 
 
 class GradAllReducer:
-    """One flat bucket for all gradients: a single all-reduce per step (payload ~36 MB at the reference config,
-    latency-bound on NVSwitch, so one launch beats per-parameter calls).  With flattened parameters
-    (Module.flatten_parameters) the bucket IS the gradient storage: no packing copies."""
+    """Gradient all-reduce of the data-parallel run.
+
+    With flattened parameters (Module.flatten_parameters) the flat gradient buffer IS the bucket storage -- no packing
+    copies.  Two modes:
+      * one all-reduce of the whole buffer after the backward (payload ~41 MB at the reference config);
+      * `buckets` = [(a, b), ...] in completion order (gradient_buckets): bucket i is all-reduced from a backward hook the
+        moment its gradients are complete (reduce_bucket, on a side stream), overlapping the rest of the backward;
+        __call__ joins and reduces what is left.  in_graph: hooks and join were captured into the step's CUDA graph.
+    Transport: `comm` (fa_b200.mt.comm.NcclComm, the thin C ABI fa_b200_nccl_* over NCCL / NVLink) for CUDA tensors;
+    torch.distributed (gloo) stands in on the CPU, where the unit tests run."""
 
     def __init__(self, params: List, world: int, flat_grads: Optional[torch.Tensor] = None,
-                 early: Optional[Tuple[int, int]] = None):
+                 buckets: Optional[List[Tuple[int, int]]] = None, comm=None):
         self.params, self.world = params, world
         self.numel = sum(p.value.numel() for p in params)
         self.flat: Optional[torch.Tensor] = None
         self.flat_grads = flat_grads
-        # Optional overlap (flat buffers only): the range `early` = [a, b) of the flat gradient buffer -- the final
-        # LayerNorm and lm_head, 10 of the 37 MB, complete after the first ~30 % of the backward -- is all-reduced from a
-        # backward hook (reduce_early, asynchronously on the collective's stream) while the rest of the backward runs;
-        # __call__ then reduces what is left.  in_graph: reduce_early / join_early were captured into the step's CUDA
-        # graph, so __call__ has nothing to wait for.
-        self.early = early if (early is not None and flat_grads is not None and world > 1) else None
+        self.comm = comm
+        self.buckets = list(buckets) if (buckets and flat_grads is not None and world > 1) else None
         self.in_graph = False
-        self._work = None
+        self._done: List[int] = []  # buckets reduced by hooks in the current step
+        self._works: List = []      # pending torch.distributed work handles (gloo path)
+        self._side = None           # side stream of the NCCL path
+        if self.buckets is not None and comm is not None:
+            self._side = torch.cuda.Stream()
 
     def _reduce(self, t: torch.Tensor, async_op: bool = False):
-        if dist.get_backend() == "nccl":
-            return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)  # averaged inside the collective: no extra pass
+        if self.comm is not None:
+            self.comm.all_reduce(t, average=True)  # averaged inside the collective: no extra pass
+            return None
         return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)  # (gloo: __call__ divides afterwards)
 
-    def reduce_early(self) -> None:
-        """Backward hook: the early range is complete -- start its all-reduce."""
-        if self.early is not None:
-            self._work = self._reduce(self.flat_grads[self.early[0]:self.early[1]], async_op=True)
+    def begin_step(self) -> None:
+        """Start of a training step: no bucket has been reduced yet."""
+        self._done = []
 
-    def join_early(self) -> None:
-        """Make the current stream (or the host, for gloo) wait for the early all-reduce."""
-        if self._work is not None:
-            self._work.wait()
-            self._work = None
+    def reduce_bucket(self, i: int) -> None:
+        """Backward hook: bucket i is complete -- start its all-reduce next to the rest of the backward."""
+        if self.buckets is None or i >= len(self.buckets) or i in self._done:
+            return
+        a, b = self.buckets[i]
+        self._done.append(i)
+        if self.comm is not None:
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                self.comm.all_reduce(self.flat_grads[a:b], average=True)
+        else:
+            self._works.append(self._reduce(self.flat_grads[a:b], async_op=True))
+
+    def join(self) -> None:
+        """Make the current stream (or the host, for gloo) wait for the bucket all-reduces started by the hooks."""
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+        for w in self._works:
+            w.wait()
+        self._works = []
 
     def __call__(self) -> None:
         if self.world == 1:
             return
         if self.flat_grads is not None:
-            if self.early is None:
+            if self.buckets is None:
                 self._reduce(self.flat_grads)
             else:
                 if not self.in_graph:
-                    self.join_early()
-                a, b = self.early
-                for lo, hi in ((0, a), (b, self.flat_grads.numel())):
-                    if hi > lo:
-                        self._reduce(self.flat_grads[lo:hi])
-            if dist.get_backend() != "nccl":
+                    self.join()
+                    rest = [i for i in range(len(self.buckets)) if i not in self._done]
+                else:
+                    rest = self._rest_in_graph
+                for i in rest:
+                    a, b = self.buckets[i]
+                    self._reduce(self.flat_grads[a:b])
+            if self.comm is None:
                 self.flat_grads.div_(self.world)
             return
         p0 = self.params[0].value
@@ -96,27 +121,41 @@ class GradAllReducer:
             else:
                 self.flat[off:off + n].copy_(g.reshape(-1))
             off += n
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.flat.div_(self.world)
+        if self.comm is not None:
+            self.comm.all_reduce(self.flat, average=True)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(self.world)
         off = 0
         for p in self.params:
             n = p.value.numel()
             p.value.grad = self.flat[off:off + n].view_as(p.value).clone()
             off += n
 
+    def mark_captured(self) -> None:
+        """The hooks ran during CUDA-graph capture: every replay re-runs their all-reduces, __call__ only adds the rest."""
+        self._rest_in_graph = [i for i in range(len(self.buckets or [])) if i not in self._done]
+        self._done = []
+        self.in_graph = True
 
-def early_gradient_range(model: DecoderLM, flat_grads: torch.Tensor) -> Optional[Tuple[int, int]]:
-    """[a, b) of the flat gradient buffer holding the final LayerNorm and lm_head gradients (None if they are not one
-    contiguous run of it): the part of the model whose gradients are complete first."""
-    ps = [p for m in (model.ln, model.lm_head) for p in m.parameters()]
-    esz = flat_grads.element_size()
-    offs = sorted(((p.value.grad.data_ptr() - flat_grads.data_ptr()) // esz, p.value.numel()) for p in ps)
-    a, b = offs[0][0], offs[-1][0] + offs[-1][1]
-    # consecutive up to the alignment padding of Module.flatten_parameters (< 32 zero elements between two parameters)
-    gaps_ok = all(0 <= nxt[0] - (cur[0] + cur[1]) < 32 for cur, nxt in zip(offs, offs[1:]))
-    if a < 0 or b > flat_grads.numel() or not gaps_ok or any(not p.value.grad.is_contiguous() for p in ps):
+
+def gradient_buckets(model: DecoderLM, flat_grads: torch.Tensor) -> Optional[List[Tuple[int, int]]]:
+    """Ranges of the flat gradient buffer in the order in which the backward completes them: [final LayerNorm + lm_head],
+    [layer 4], [layer 3], [layer 2], [embeddings + layer 1] -- the hook DecoderLM.forward registers on the output of layer k
+    fires when everything downstream of it is done (bucket index = 3 - k); the last bucket is complete only when the
+    backward ends.  None if the layout is not the clustered one of Module.flatten_parameters."""
+    r = model.flat_ranges()
+    need = ["token_embeddings", "position_embeddings", "t_layer_1", "t_layer_2", "t_layer_3", "t_layer_4", "ln", "lm_head"]
+    if any(k not in r for k in need):
         return None
-    return a, b
+    def span(names):
+        a, b = min(r[n][0] for n in names), max(r[n][1] for n in names)
+        return (a, b) if b - a == sum(r[n][1] - r[n][0] for n in names) else None
+    out = [span(["ln", "lm_head"]), span(["t_layer_4"]), span(["t_layer_3"]), span(["t_layer_2"]),
+           span(["token_embeddings", "position_embeddings", "t_layer_1"])]
+    if any(x is None for x in out) or sum(b - a for a, b in out) != flat_grads.numel():
+        return None
+    return out
 
 
 class GraphedStep:
@@ -135,14 +174,16 @@ class GraphedStep:
         assert optimizer.flat is not None, "graph capture needs flattened parameters"
         self.model, self.optimizer, self.ops = model, optimizer, ops
         self.static = {k: v.clone() for k, v in batch.items()}
-        early = reducer is not None and reducer.early is not None  # the early all-reduce (a backward hook) is captured too
+        early = reducer is not None and reducer.buckets is not None  # the bucket all-reduces (backward hooks) are captured too
 
         def fwd_bwd():
+            if reducer is not None:
+                reducer.begin_step()
             optimizer.zero_grad()
             loss = loss_fn(self.static, model)
             loss.backward()
             if early:
-                reducer.join_early()  # the collective's stream joins the capturing stream again
+                reducer.join()  # the collective's stream joins the capturing stream again
             return loss
 
         side = torch.cuda.Stream()
@@ -156,7 +197,7 @@ class GraphedStep:
         with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
             self.loss = fwd_bwd()
         if early:
-            reducer.in_graph = True
+            reducer.mark_captured()
 
     def __call__(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         for k, v in batch.items():
@@ -168,7 +209,7 @@ class GraphedStep:
 
 def train(model: DecoderLM, optimizer: Adam, n_iters: int, batch_size: int, seq_len: int, rank: int, world: int,
           sync: Callable[[], None], seed: int = 0, log: Optional[Callable[[str], None]] = None,
-          cuda_graph: bool = False, overlap_allreduce: bool = False) -> Dict[str, float]:
+          cuda_graph: bool = False, overlap_allreduce: bool = False, comm=None) -> Dict[str, float]:
     """Runs n_iters steps and returns the reference-style timers (iterations >= 2) plus tokens/s and losses.
     With cuda_graph the forward and backward are one graph replay, reported together as `backward_s` = 0."""
     from . import ops
@@ -176,9 +217,9 @@ def train(model: DecoderLM, optimizer: Adam, n_iters: int, batch_size: int, seq_
     device = next(iter(model.parameters())).value.device
     gen = torch.Generator().manual_seed(1000 * (rank + 1) + seed)
     ops.dropout_state.base_seed = 0x5EED + 7919 * rank  # different masks on different ranks
-    early = early_gradient_range(model, optimizer.flat[1]) if (overlap_allreduce and optimizer.flat is not None) else None
-    reducer = GradAllReducer(model.parameters(), world, optimizer.flat[1] if optimizer.flat is not None else None, early)
-    model.grad_ready_hook = reducer.reduce_early if reducer.early is not None else None
+    buckets = gradient_buckets(model, optimizer.flat[1]) if (overlap_allreduce and optimizer.flat is not None) else None
+    reducer = GradAllReducer(model.parameters(), world, optimizer.flat[1] if optimizer.flat is not None else None, buckets, comm)
+    model.grad_ready_hook = reducer.reduce_bucket if reducer.buckets is not None else None
     graphed = None
     fw = bw = comm = opt = 0.0
     timed_tokens, timed_s, losses = 0, 0.0, []
@@ -194,6 +235,7 @@ def train(model: DecoderLM, optimizer: Adam, n_iters: int, batch_size: int, seq_
             t1 = t2 = time.perf_counter()
         else:
             ops.dropout_state.begin_step()
+            reducer.begin_step()
             optimizer.zero_grad()
             loss = loss_fn(batch, model)
             sync()
@@ -221,6 +263,17 @@ def train(model: DecoderLM, optimizer: Adam, n_iters: int, batch_size: int, seq_
             "timed_iters": max(n_iters - 2, 0), "loss_first": losses[0], "loss_last": losses[-1], "losses": losses}
 
 
+def job_min(value: float, rank: int, world: int, comm, device) -> float:
+    """Minimum of a per-rank scalar over the job (one sum all-reduce of a one-hot vector through the C-ABI communicator)."""
+    if world == 1 or comm is None:
+        return float(value)
+    t = torch.zeros(world, device=device, dtype=torch.float32)
+    t[rank] = float(value)
+    comm.all_reduce(t, average=False)
+    torch.cuda.synchronize()
+    return float(t.min().item())
+
+
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(description="decoder-only LM training with B200 flash attention (synthetic tokens)")
     ap.add_argument("--model-max-length", type=int, default=512)
@@ -237,9 +290,10 @@ def main(argv=None) -> int:
                          "backward on the bf16 tensor-core kernels (2e-2 bar)")
     ap.add_argument("--cuda-graph", type=lambda s: s.lower() in ("1", "true", "yes"), default=True,
                     help="capture forward+backward into a CUDA graph (default); False gives the reference's fw/bw split timers")
-    ap.add_argument("--overlap-allreduce", type=lambda s: s.lower() in ("1", "true", "yes"), default=False,
-                    help="all-reduce the final LayerNorm + lm_head gradients from a backward hook, overlapped with the rest of "
-                         "the backward (inside the CUDA graph when --cuda-graph)")
+    ap.add_argument("--overlap-allreduce", type=lambda s: s.lower() in ("1", "true", "yes"), default=True,
+                    help="all-reduce the gradients bucket by bucket (final LayerNorm + lm_head, layer 4, 3, 2, then embeddings + "
+                         "layer 1) from backward hooks, overlapped with the rest of the backward (inside the CUDA graph when "
+                         "--cuda-graph); False: one all-reduce of the whole flat buffer after the backward")
     args = ap.parse_args(argv)
     if not args.use_flash_attention:
         raise SystemExit("only the flash-attention path exists here (the vanilla path is the reference's CPU oracle)")
@@ -248,8 +302,10 @@ def main(argv=None) -> int:
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    comm = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        from .comm import NcclComm
+        comm = NcclComm().init(rank, world)  # fa_b200_nccl_* (include/fa_b200.h): no torch.distributed in this loop
     L = args.model_max_length
     batch_size = int((128 * 40 + L) / L)  # run_machine_translation.py:385, per rank
     from . import ops
@@ -262,22 +318,20 @@ def main(argv=None) -> int:
         torch.cuda.synchronize()
 
     res = train(model, optimizer, args.iters, batch_size, L, rank, world, sync,
-                log=(lambda s: print(s, flush=True)) if rank == 0 else None, cuda_graph=args.cuda_graph, overlap_allreduce=args.overlap_allreduce)
-    t = torch.tensor([res["tokens_per_s_per_rank"]], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                log=(lambda s: print(s, flush=True)) if rank == 0 else None, cuda_graph=args.cuda_graph,
+                overlap_allreduce=args.overlap_allreduce, comm=comm)
+    slowest = job_min(res["tokens_per_s_per_rank"], rank, world, comm, device)
     if rank == 0:
         # same line the reference prints (run_machine_translation.py:221), plus the job-level throughput
         print("N: {}, Forward Time: {}, Backward Time: {}, Opt Time: {}".format(L, res["forward_s"], res["backward_s"], res["opt_s"]))
-        print(json.dumps({"metric": "decoder LM training tokens/s (whole job)", "value": float(t.item()) * world, "unit": "tokens/s",
+        print(json.dumps({"metric": "decoder LM training tokens/s (whole job)", "value": slowest * world, "unit": "tokens/s",
                           "n_gpus": world, "seq_len": L, "batch_per_rank": batch_size, "iters_timed": res["timed_iters"],
                           "cuda_graph": bool(args.cuda_graph), "overlap_allreduce": bool(args.overlap_allreduce), "attention_precision": args.attention_precision,
                           "forward_s": res["forward_s"], "backward_s": res["backward_s"], "allreduce_s": res["allreduce_s"],
                           "opt_s": res["opt_s"], "loss_first": res["loss_first"], "loss_last": res["loss_last"],
                           "data": "synthetic uniform tokens", "params": sum(p.value.numel() for p in model.parameters())}), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if comm is not None:
+        comm.destroy()
     return 0
 
 

@@ -43,7 +43,9 @@ extern "C" {
 
 /* ---- arithmetic used for the two contractions ----
  * AUTO      : bf16 storage -> BF16_TC; fp32 storage -> TF32_TC when the shape is covered (forward: d in {32,64};
- *             backward: d = 32 without dropout), else FP32_SIMT.  In the host-pointer API AUTO means FP32_SIMT (the reference computes in fp32).
+ *             backward: d = 32 without dropout), else FP32_SIMT.  The host-pointer API (fp32 storage) resolves AUTO the
+ *             same way: tf32 tensor cores wherever a tcgen05 kernel exists, which meets the 1e-3 max-abs bar of the
+ *             fp32 path; FA_B200_HOST_PRECISION=fp32 / fa_b200_set_host_precision(FA_PREC_FP32_SIMT) keeps exact fp32.
  * FP32_SIMT : fp32 FMA on CUDA cores (any d <= 128 -- the reference's own limit, src/flash_attn_fw.cu:43 -- and any T); exact-fp32 cross-check path
  * TF32_TC   : tcgen05.mma kind::tf32 on fp32 storage read directly by TMA (no conversion pass; the backward rounds its
  *             operands to tf32 in its prep pass); shapes it does not cover run FP32_SIMT
@@ -122,6 +124,10 @@ int fa_b200_host_bwd(const float* q, const float* k, const float* v, const float
  * environment variable FA_B200_HOST_PRECISION = auto | fp32 | tf32 | bf16 read at first use. */
 void fa_b200_set_host_precision(int precision);
 int fa_b200_get_host_precision(void);
+/* on = 1: fa_b200_host_bwd may assume that q_grad holds zeros on entry -- what every caller of the reference passes
+ * (minitorch/cuda_kernel_ops.py:609-611) -- and skips its upload (11 % of the H2D bytes); q_grad is then overwritten.
+ * Default 0 (the reference kernels accumulate, src/flash_attn2_bw.cu:228); environment: FA_B200_HOST_ZERO_QGRAD=1. */
+void fa_b200_set_host_zero_qgrad(int on);
 /* Release the device arena held by the host-pointer API. */
 void fa_b200_release_arena(void);
 
@@ -222,6 +228,25 @@ int fa_b200_softmax_loss_bwd_colsum(const float* logits, const long long* target
 int fa_b200_softmax_loss_colsum_width(int n_classes);
 int fa_b200_adam_step(float* p, const float* g, float* m, float* v, size_t n, float step_size, float beta1, float beta2,
                       float v_coef, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Gradient all-reduce of the data-parallel machine-translation run (BASELINE.json configs[4]; the reference itself has
+ * no distributed backend, its training loop is single-process: project/run_machine_translation.py:196-221).  One
+ * process per GPU; NCCL over NVLink 5 / NVSwitch, resolved with dlopen at first use (libfa_b200.so does not link it).
+ * Rank 0 calls fa_b200_nccl_unique_id and hands the 128 bytes to every rank (fa_b200/mt/comm.py: TCP rendezvous on
+ * MASTER_ADDR / MASTER_PORT); every rank then calls fa_b200_nccl_init on its CUDA device.  fa_b200_nccl_allreduce_f32
+ * sums (average = 0) or averages (average = 1) `count` floats in place on `stream`; it may be captured into a CUDA graph.
+ * All return FA_OK or an error code with the text in fa_b200_nccl_last_error().
+ * ------------------------------------------------------------------------------------------ */
+#define FA_B200_NCCL_UNIQUE_ID_BYTES 128
+int fa_b200_nccl_unique_id(void* id_out /* 128 bytes */);
+int fa_b200_nccl_init(const void* id /* 128 bytes */, int rank, int world);
+int fa_b200_nccl_allreduce_f32(float* buf, size_t count, int average, void* stream);
+int fa_b200_nccl_world(void);   /* 0 before init */
+int fa_b200_nccl_rank(void);    /* -1 before init */
+int fa_b200_nccl_version(void); /* NCCL_VERSION_CODE of the loaded library, -1 if libnccl cannot be loaded */
+int fa_b200_nccl_destroy(void);
+const char* fa_b200_nccl_last_error(void);
 
 /* ------------------------------------------------------------------------------------------
  * The reference entry points themselves.  Exported by the six shim libraries (not by libfa_b200.so,

@@ -54,27 +54,37 @@ def test_tensor_flash_attn_matches_reference_vanilla(cuda_device, name, method):
         assert np.abs(t.grad.to_numpy()[0] - g[key]).max() <= FP32_ATOL, key
 
 
+@pytest.mark.parametrize("precision", ["auto", "fp32"])
 @pytest.mark.parametrize("name", golden_files("fap_"))
-def test_saved_statistics_follow_each_family_convention(cuda_device, name):
+def test_saved_statistics_follow_each_family_convention(cuda_device, name, precision):
     """FA-1 libraries return l = sum exp(s - m), m = rowmax; FA-2 returns L in `l` and leaves `m` as passed
-    (-FLT_MAX) -- pinned by the authors' flash_attn_python.py outputs."""
-    g = np.load(os.path.join(GOLDEN, name))
-    be = mt.TensorBackend(mt.CudaKernelOps)
-    q, k, v = (_mt4(g[x].astype(np.float32), be) for x in ("q", "k", "v"))
-    o1, l1, m1 = mt.CudaKernelOps.flash_attn_fw(q, k, v, mt.tensor(False))
-    assert np.abs(o1.to_numpy()[0] - g["o_fa1"]).max() <= FP32_ATOL
-    assert np.abs(m1.to_numpy()[0] - g["m_fa1"]).max() <= 1e-5
-    assert rel_inf(l1.to_numpy()[0], g["l_fa1"]) <= 1e-5
-    o2, l2, m2 = mt.CudaKernelOps.flash_attn2_fw(q, k, v, mt.tensor(False))
-    assert np.abs(l2.to_numpy()[0] - g["L_fa2"]).max() <= 1e-4
-    assert np.all(m2.to_numpy() == -np.finfo(np.float32).max)
-    # each backward consumes its own convention
-    dO = _mt4(g["d_out"].astype(np.float32), be)
-    for fam, (o, l, m) in (("fa1", (o1, l1, m1)), ("fa2", (o2, l2, m2))):
-        bw = mt.CudaKernelOps.flash_attn_bw if fam == "fa1" else mt.CudaKernelOps.flash_attn2_bw
-        dq, dk, dv, _ = bw(q, k, v, o, dO, l, m, mt.tensor(False))
-        for got, key in ((dq, "dq_"), (dk, "dk_"), (dv, "dv_")):
-            assert np.abs(got.to_numpy()[0] - g[key + fam]).max() <= FP32_ATOL
+    (-FLT_MAX) -- pinned by the authors' flash_attn_python.py outputs.  `auto` is what a drop-in user gets (tf32 tensor
+    cores where a tcgen05 kernel covers the shape: everything within the 1e-3 bar of the fp32 path); `fp32` is the exact
+    CUDA-core arithmetic (statistics to 1e-5)."""
+    lib = _lib.load_library()
+    prev = lib.fa_b200_get_host_precision()
+    lib.fa_b200_set_host_precision(_lib.FA_PREC_AUTO if precision == "auto" else _lib.FA_PREC_FP32_SIMT)
+    stat_tol = 1e-3 if precision == "auto" else 1e-5
+    try:
+        g = np.load(os.path.join(GOLDEN, name))
+        be = mt.TensorBackend(mt.CudaKernelOps)
+        q, k, v = (_mt4(g[x].astype(np.float32), be) for x in ("q", "k", "v"))
+        o1, l1, m1 = mt.CudaKernelOps.flash_attn_fw(q, k, v, mt.tensor(False))
+        assert np.abs(o1.to_numpy()[0] - g["o_fa1"]).max() <= FP32_ATOL
+        assert np.abs(m1.to_numpy()[0] - g["m_fa1"]).max() <= stat_tol
+        assert rel_inf(l1.to_numpy()[0], g["l_fa1"]) <= 2 * stat_tol
+        o2, l2, m2 = mt.CudaKernelOps.flash_attn2_fw(q, k, v, mt.tensor(False))
+        assert np.abs(l2.to_numpy()[0] - g["L_fa2"]).max() <= 10 * stat_tol
+        assert np.all(m2.to_numpy() == -np.finfo(np.float32).max)
+        # each backward consumes its own convention
+        dO = _mt4(g["d_out"].astype(np.float32), be)
+        for fam, (o, l, m) in (("fa1", (o1, l1, m1)), ("fa2", (o2, l2, m2))):
+            bw = mt.CudaKernelOps.flash_attn_bw if fam == "fa1" else mt.CudaKernelOps.flash_attn2_bw
+            dq, dk, dv, _ = bw(q, k, v, o, dO, l, m, mt.tensor(False))
+            for got, key in ((dq, "dq_"), (dk, "dk_"), (dv, "dv_")):
+                assert np.abs(got.to_numpy()[0] - g[key + fam]).max() <= FP32_ATOL
+    finally:
+        lib.fa_b200_set_host_precision(prev)
 
 
 def test_backward_accumulates_into_q_grad_like_reference(cuda_device):

@@ -54,19 +54,30 @@ def _bw(lib, q, k, v, o, g, l, m, causal):
     return gq.reshape(q.shape), gk.reshape(q.shape), gv.reshape(q.shape)
 
 
+@pytest.mark.parametrize("precision", ["auto", "fp32"])
 @pytest.mark.parametrize("family", ["flash_attn", "flash_attn_causal", "flash_attn2"])
 @pytest.mark.parametrize("T,d,causal", [(128, 64, True), (327, 64, True), (200, 32, False), (77, 34, True)])
-def test_same_abi_same_results_as_reference_kernels(cuda_device, family, T, d, causal):
-    ref_fw, our_fw = _pair(family + "_fw")
-    ref_bw, our_bw = _pair(family + "_bw")
-    q, k, v, g = ao.make_inputs(8, T, d, seed=T * 3 + d)
-    ro, rl, rm = _fw(ref_fw, q, k, v, causal)
-    oo, ol, om = _fw(our_fw, q, k, v, causal)
-    assert np.abs(oo - ro).max() <= 1e-3
-    assert np.abs(ol - rl).max() <= 1e-3 * max(1.0, np.abs(rl).max())
-    assert np.abs(om - rm).max() <= 1e-3 * max(1.0, float(np.abs(rm).min()))  # FA-2: both leave -FLT_MAX
-    # each backward on the reference's own saved tensors
-    rdq, rdk, rdv = _bw(ref_bw, q, k, v, ro, g, rl, rm, causal)
-    odq, odk, odv = _bw(our_bw, q, k, v, ro, g, rl, rm, causal)
-    for a, b in ((odq, rdq), (odk, rdk), (odv, rdv)):
-        assert np.abs(a - b).max() <= 1e-3
+def test_same_abi_same_results_as_reference_kernels(cuda_device, family, T, d, causal, precision):
+    """`auto` = what the six dropped-in libraries do by default: tf32 tensor cores where a tcgen05 kernel covers the shape
+    (O, dQ, dK, dV within north_star's 1e-3; the saved row statistics, which only the matching backward consumes, within
+    2e-3 -- the tensor core truncates fp32 operands to tf32).  `fp32` = FA_B200_HOST_PRECISION=fp32: everything to 1e-3."""
+    lib = _lib.load_library()
+    prev = lib.fa_b200_get_host_precision()
+    lib.fa_b200_set_host_precision(_lib.FA_PREC_AUTO if precision == "auto" else _lib.FA_PREC_FP32_SIMT)
+    stat_tol = 2e-3 if precision == "auto" else 1e-3
+    try:
+        ref_fw, our_fw = _pair(family + "_fw")
+        ref_bw, our_bw = _pair(family + "_bw")
+        q, k, v, g = ao.make_inputs(8, T, d, seed=T * 3 + d)
+        ro, rl, rm = _fw(ref_fw, q, k, v, causal)
+        oo, ol, om = _fw(our_fw, q, k, v, causal)
+        assert np.abs(oo - ro).max() <= 1e-3
+        assert np.abs(ol - rl).max() <= stat_tol * max(1.0, np.abs(rl).max())
+        assert np.abs(om - rm).max() <= stat_tol * max(1.0, float(np.abs(rm).min()))  # FA-2: both leave -FLT_MAX
+        # each backward on the reference's own saved tensors
+        rdq, rdk, rdv = _bw(ref_bw, q, k, v, ro, g, rl, rm, causal)
+        odq, odk, odv = _bw(our_bw, q, k, v, ro, g, rl, rm, causal)
+        for a, b in ((odq, rdq), (odk, rdk), (odv, rdv)):
+            assert np.abs(a - b).max() <= 1e-3
+    finally:
+        lib.fa_b200_set_host_precision(prev)

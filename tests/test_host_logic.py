@@ -115,3 +115,67 @@ def test_two_rank_gloo_sharded_attention_matches_single_rank():
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "sharded==full True" in outs[0]
+
+
+# ---- thin NCCL C ABI (fa_b200_nccl_*) and its host side: what can be checked without a GPU ----
+def test_unique_id_rendezvous_over_tcp():
+    """Rank 0 serves the 128-byte id, the other ranks fetch it (fa_b200/mt/comm.py) -- three ranks as threads."""
+    import socket
+    import threading
+    from fa_b200.mt import comm
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    payload = bytes(range(128))
+    got = {}
+
+    def run(rank):
+        got[rank] = comm.exchange_unique_id(rank, 3, payload if rank == 0 else None, "127.0.0.1", port, timeout_s=30)
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in (1, 2, 0)]  # clients first: they retry until rank 0 listens
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    assert got == {0: payload, 1: payload, 2: payload}
+
+
+def test_nccl_abi_rejects_use_before_init():
+    import torch  # noqa: F401  (first: the process must not end up with two different libnccl.so.2)
+    from fa_b200.mt.comm import NcclComm
+    c = NcclComm()
+    lib = c._bind()
+    assert lib.fa_b200_nccl_world() == 0 and lib.fa_b200_nccl_rank() == -1
+    assert lib.fa_b200_nccl_allreduce_f32(None, 4, 1, None) != 0
+    assert b"not initialised" in lib.fa_b200_nccl_last_error()
+    assert lib.fa_b200_nccl_init(None, 0, 1) != 0
+    assert lib.fa_b200_nccl_destroy() == 0  # nothing to destroy: not an error
+
+
+def test_flat_layout_is_clustered_per_top_level_module_and_aligned():
+    """Module.flatten_parameters: every top-level child (embeddings, layers, final LayerNorm, lm_head) is one contiguous,
+    128-byte aligned range of the flat buffers -- what train.gradient_buckets cuts the gradient all-reduce along."""
+    import torch
+    from fa_b200.mt.model import DecoderLM
+    from fa_b200.mt.train import gradient_buckets
+    m = DecoderLM(n_vocab=50, n_embd=16, n_head=2, n_positions=8, p_dropout=0.0, device="cpu", dtype=torch.float64, seed=3,
+                  attention_fn=lambda q, k, v, causal: v)
+    before = {n: p.value.detach().clone() for n, p in m.named_parameters()}
+    flat, gflat = m.flatten_parameters(fuse=True)
+    r = m.flat_ranges()
+    assert list(r) == ["token_embeddings", "position_embeddings", "t_layer_1", "t_layer_2", "t_layer_3", "t_layer_4", "ln", "lm_head"]
+    ends = 0
+    for name, (a, b) in r.items():
+        assert a == ends and a % 32 == 0 and b > a
+        ends = b
+    assert ends == flat.numel()
+    esz = flat.element_size()
+    for n, p in m.named_parameters():
+        assert torch.equal(p.value.detach(), before[n])  # values survive the move
+        off = (p.value.data_ptr() - flat.data_ptr()) // esz
+        a, b = r[n.split(".")[0]]
+        assert a <= off < b and (p.value.grad.data_ptr() - gflat.data_ptr()) // esz == off
+    buckets = gradient_buckets(m, gflat)
+    assert buckets is not None and sum(b - a for a, b in buckets) == gflat.numel()
+    assert buckets[0] == (r["ln"][0], r["lm_head"][1]) and buckets[-1] == (0, r["t_layer_1"][1])
