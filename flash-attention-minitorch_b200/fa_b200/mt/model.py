@@ -310,6 +310,9 @@ class DecoderLM(Module):
         delta = delta_bias = None  # the residual stream is x + delta; each addition happens inside the next LayerNorm's kernel
         hook = getattr(self, "grad_ready_hook", None)
         layers = (self.t_layer_1, self.t_layer_2, self.t_layer_3, self.t_layer_4)
+        if hook is not None and x.requires_grad:
+            # gradient of the embedding stage's output: layer 1 is done, only the embedding scatter-add is left
+            x.register_hook(lambda g, b=len(layers): hook(b))
         for k, layer in enumerate(layers):
             x, delta, delta_bias = layer.forward_pending(x, delta, delta_bias)
             if hook is not None and x.requires_grad:

@@ -177,5 +177,8 @@ def test_flat_layout_is_clustered_per_top_level_module_and_aligned():
         a, b = r[n.split(".")[0]]
         assert a <= off < b and (p.value.grad.data_ptr() - gflat.data_ptr()) // esz == off
     buckets = gradient_buckets(m, gflat)
-    assert buckets is not None and sum(b - a for a, b in buckets) == gflat.numel()
-    assert buckets[0] == (r["ln"][0], r["lm_head"][1]) and buckets[-1] == (0, r["t_layer_1"][1])
+    assert buckets is not None and sum(b - a for a, b in buckets) == gflat.numel() and len(buckets) == 6
+    assert buckets[0] == (r["ln"][0], r["lm_head"][1]) and buckets[4] == r["t_layer_1"] and buckets[5] == (0, r["position_embeddings"][1])
+    # position rows >= seq_len never get a gradient: the embedding bucket stops after row seq_len of that table
+    trimmed = gradient_buckets(m, gflat, seq_len=8)
+    assert trimmed[:5] == buckets[:5] and trimmed[5] == (0, r["position_embeddings"][0] + 8 * 16)
