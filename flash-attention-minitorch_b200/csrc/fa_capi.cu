@@ -172,7 +172,7 @@ int resolve_precision(int dtype, int precision, int d, bool backward) {
     return -1;
   }
   if (dtype == FA_DTYPE_F32) {
-    // tf32 tensor-core kernels exist for the forward (d in {32, 64}) and the backward (d = 32); everything else on fp32
+    // tf32 tensor-core kernels exist for the forward and the backward at d in {32, 64}; everything else on fp32
     // storage runs the exact-fp32 CUDA-core kernels, which satisfy any tf32 tolerance
     const bool tf32_ok = backward ? fa::tc_bwd_tf32_supported(d) : fa::tc_fwd_tf32_supported(d);
     if (precision == FA_PREC_AUTO || precision == FA_PREC_TF32_TC) return tf32_ok ? FA_PREC_TF32_TC : FA_PREC_FP32_SIMT;
@@ -263,7 +263,7 @@ size_t fa_b200_bwd_workspace_bytes(int dtype, int precision, int batch_heads, in
   size_t bytes = align_up(rows * sizeof(float), 256);            // delta
   if (dtype == FA_DTYPE_BF16) bytes += 8 * align_up(n * sizeof(float), 256);  // fp32 images of 5 inputs + 3 grads
   // the tf32 backward (padded L / delta) -- the larger of the two, so that the dropout fallback to the CUDA-core kernels fits
-  if (prec == FA_PREC_TF32_TC) bytes = std::max(bytes, fa::tc_bwd_tf32_workspace_bytes(batch_heads, T));
+  if (prec == FA_PREC_TF32_TC) bytes = std::max(bytes, fa::tc_bwd_tf32_workspace_bytes(batch_heads, T, d));
   return bytes;
 }
 
@@ -294,7 +294,7 @@ int bwd_impl(const void* q, const void* k, const void* v, const void* o, const v
   }
   if (dtype == FA_DTYPE_F32 && prec == FA_PREC_TF32_TC && !drop.thr) {
     FA_CUDA(fa::tc_bwd_tf32((const float*)q, (const float*)k, (const float*)v, (const float*)o, (const float*)d_out, lse,
-                            (float*)dq, (float*)dk, (float*)dv, accumulate_dq != 0, workspace, batch_heads, T, causal != 0, st), 2);
+                            (float*)dq, (float*)dk, (float*)dv, accumulate_dq != 0, workspace, batch_heads, T, d, causal != 0, st), 2);
     return FA_OK;
   }
   float* delta = reinterpret_cast<float*>(ws);
@@ -628,7 +628,7 @@ int fa_b200_host_bwd(const float* q, const float* k, const float* v, const float
   const size_t cn = (size_t)hc * per_head, crows = (size_t)hc * N;
   const bool tf32 = prec == FA_PREC_TF32_TC;
   const bool zero_qgrad = host_zero_qgrad();
-  const size_t ws_bytes = tc ? fa::tc_bwd_workspace_bytes(hc, N, d) : tf32 ? fa::tc_bwd_tf32_workspace_bytes(hc, N) : 0;
+  const size_t ws_bytes = tc ? fa::tc_bwd_workspace_bytes(hc, N, d) : tf32 ? fa::tc_bwd_tf32_workspace_bytes(hc, N, d) : 0;
   const size_t buf_bytes = 8 * align_up(cn * 4, 256) + 4 * align_up(crows * 4, 256) + (tc ? 5 * align_up(cn * 2, 256) : 0) +
                            align_up(ws_bytes, 256) + 256;
   if (int rc = arena_reset(nbuf * buf_bytes + 4096)) return rc;
@@ -674,7 +674,7 @@ int fa_b200_host_bwd(const float* q, const float* k, const float* v, const float
       FA_CUDA(fa::tc_bwd(B.b[0], B.b[1], B.b[2], B.b[3], B.b[4], lse, B.gq, B.gk, B.gv, true, !zero_qgrad, B.ws, hn, N, d,
                          causal != 0, st), 2);
     } else if (tf32) {
-      FA_CUDA(fa::tc_bwd_tf32(B.q, B.k, B.v, B.o, B.g, lse, B.gq, B.gk, B.gv, !zero_qgrad, B.ws, hn, N, causal != 0, st), 2);
+      FA_CUDA(fa::tc_bwd_tf32(B.q, B.k, B.v, B.o, B.g, lse, B.gq, B.gk, B.gv, !zero_qgrad, B.ws, hn, N, d, causal != 0, st), 2);
     } else {
       FA_CUDA(fa::simt_bwd_prep(B.o, B.g, B.delta, nullptr, nullptr, nullptr, rows, d, st), 1);
       FA_CUDA(fa::simt_bwd(B.q, B.k, B.v, B.g, lse, B.delta, B.gq, B.gk, B.gv, hn, N, d, causal != 0, !zero_qgrad, st), 2);

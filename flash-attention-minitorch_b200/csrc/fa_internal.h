@@ -46,11 +46,11 @@ cudaError_t tc_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
                    bool accumulate_dq, void* workspace, int BH, int T, int d, bool causal, cudaStream_t st,
                    Dropout drop = kNoDropout);
 
-// fp32 storage, tf32 tensor cores, head dim 32 (fa_bwd_tf32_sm100.cu): fp32 gradients, dq accumulated into when asked
+// fp32 storage, tf32 tensor cores, head dim 32 or 64 (fa_bwd_tf32_sm100.cu): fp32 gradients, dq accumulated into when asked
 bool tc_bwd_tf32_supported(int d);
-size_t tc_bwd_tf32_workspace_bytes(int BH, int T);
+size_t tc_bwd_tf32_workspace_bytes(int BH, int T, int d);
 cudaError_t tc_bwd_tf32(const float* q, const float* k, const float* v, const float* o, const float* dO, const float* lse,
-                        float* dq, float* dk, float* dv, bool accumulate_dq, void* workspace, int BH, int T, bool causal,
+                        float* dq, float* dk, float* dv, bool accumulate_dq, void* workspace, int BH, int T, int d, bool causal,
                         cudaStream_t st);
 
 // ---- elementwise helpers (fa_util.cu) -------------------------------------------------------

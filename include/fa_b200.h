@@ -42,8 +42,8 @@ extern "C" {
 #define FA_DTYPE_BF16 1
 
 /* ---- arithmetic used for the two contractions ----
- * AUTO      : bf16 storage -> BF16_TC; fp32 storage -> TF32_TC when the shape is covered (forward: d in {32,64};
- *             backward: d = 32 without dropout), else FP32_SIMT.  The host-pointer API (fp32 storage) resolves AUTO the
+ * AUTO      : bf16 storage -> BF16_TC; fp32 storage -> TF32_TC when the shape is covered (forward and backward:
+ *             d in {32,64}; the backward without dropout), else FP32_SIMT.  The host-pointer API (fp32 storage) resolves AUTO the
  *             same way: tf32 tensor cores wherever a tcgen05 kernel exists, which meets the 1e-3 max-abs bar of the
  *             fp32 path; FA_B200_HOST_PRECISION=fp32 / fa_b200_set_host_precision(FA_PREC_FP32_SIMT) keeps exact fp32.
  * FP32_SIMT : fp32 FMA on CUDA cores (any d <= 128 -- the reference's own limit, src/flash_attn_fw.cu:43 -- and any T); exact-fp32 cross-check path

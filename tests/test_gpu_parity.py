@@ -220,14 +220,15 @@ def test_device_tf32_forward_vs_oracle(cuda_device, BH, T, d, causal):
 
 
 @pytest.mark.parametrize("causal", [False, True])
-@pytest.mark.parametrize("BH,T", [(3, 1), (2, 40), (3, 128), (2, 327), (4, 512), (1, 1000), (1, 2125)])
-def test_device_tf32_backward_vs_oracle(cuda_device, BH, T, causal):
-    """fp32 storage, head dim 32 (the reference MT model's): the backward runs on tcgen05 kind::tf32 (what FA_PREC_AUTO
-    selects) -- prep + main kernel = 2 launches -- and meets the north_star bar max-abs 1e-3 against the fp64 oracle for
-    dQ, dK, dV; with accumulate_dq it adds onto the caller's dq like the reference (src/flash_attn2_bw.cu:228); the
-    exact-fp32 CUDA-core backward stays available through FA_PREC_FP32_SIMT and agrees to 1e-3."""
+@pytest.mark.parametrize("d", [32, 64])
+@pytest.mark.parametrize("BH,T", [(3, 1), (2, 40), (2, 65), (3, 128), (2, 327), (4, 512), (1, 1000), (1, 2125)])
+def test_device_tf32_backward_vs_oracle(cuda_device, BH, T, causal, d):
+    """fp32 storage, head dim 32 (the reference MT model's) and 64 (the reference kernel tests',
+    kernel_tests/test_flashattn_bw.py:205-210): the backward runs on tcgen05 kind::tf32 (what FA_PREC_AUTO selects) -- prep +
+    main kernel = 2 launches -- and meets the north_star bar max-abs 1e-3 against the fp64 oracle for dQ, dK, dV; with
+    accumulate_dq it adds onto the caller's dq like the reference (src/flash_attn2_bw.cu:228); the exact-fp32 CUDA-core
+    backward stays available through FA_PREC_FP32_SIMT and agrees to 1e-3."""
     import torch
-    d = 32
     q, k, v, g = ao.make_inputs(BH, T, d, seed=900 + T)
     dq_r, dk_r, dv_r, o_r, L_r = ao.attention_backward(q, k, v, g, causal, np.float64)
     tq, tk, tv, tg = (_to_dev(x, cuda_device, bf16=False) for x in (q, k, v, g))

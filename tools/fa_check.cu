@@ -326,8 +326,7 @@ static int check_tf32(int BH, int T, int d, int causal, float scale) {
 
 // tf32 tensor-core backward (fp32 storage, d = 32) against the exact-fp32 CUDA-core backward on the same inputs,
 // including accumulation into dq; times both.
-static int check_bwd_tf32(int BH, int T, int causal, bool timing) {
-  const int d = 32;
+static int check_bwd_tf32(int BH, int T, int causal, bool timing, int d = 32) {
   const size_t n = (size_t)BH * T * d, rows = (size_t)BH * T;
   std::vector<float> h(n);
   Dev dev;
@@ -359,7 +358,7 @@ static int check_bwd_tf32(int BH, int T, int causal, bool timing) {
   for (int i = 0; i < 3; ++i) err_stats(d2h_f32(g1[i], n), d2h_f32(g0[i], n), ea[i], er[i]);
   // inputs in (-1, 1): dQ, dK, dV are O(1); operands, P and dS rounded to tf32 keep max-abs below the north_star bar 1e-3
   const bool ok = ea[0] < 1e-3 && ea[1] < 1e-3 && ea[2] < 1e-3;
-  printf("tf32 bwd BH=%d T=%5d d=32 causal=%d  dQ abs %.2e rel %.2e  dK abs %.2e rel %.2e  dV abs %.2e rel %.2e  %s\n", BH, T, causal,
+  printf("tf32 bwd BH=%d T=%5d d=%d causal=%d  dQ abs %.2e rel %.2e  dK abs %.2e rel %.2e  dV abs %.2e rel %.2e  %s\n", BH, T, d, causal,
          ea[0], er[0], ea[1], er[1], ea[2], er[2], ok ? "OK" : "FAIL");
   if (timing) {
     cudaEvent_t e0, e1;
@@ -380,7 +379,7 @@ static int check_bwd_tf32(int BH, int T, int causal, bool timing) {
       cudaEventElapsedTime(&ms, e0, e1);
       ms /= iters;
       const double flops = 10.0 * BH * double(T) * T * d * (causal ? 0.5 : 1.0);
-      printf("time %s bwd BH=%d T=%d d=32 causal=%d: %.3f ms  %.1f TFLOP/s\n", v ? "tf32-tc  " : "fp32-simt", BH, T, causal, ms, flops / ms * 1e-9);
+      printf("time %s bwd BH=%d T=%d d=%d causal=%d: %.3f ms  %.1f TFLOP/s\n", v ? "tf32-tc  " : "fp32-simt", BH, T, d, causal, ms, flops / ms * 1e-9);
     }
   }
   return !ok;
@@ -599,11 +598,13 @@ int main(int argc, char** argv) {
     }
   } else if (mode == "bwd32") {
     if (argc >= 5) {
-      bad = check_bwd_tf32(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), true);
+      bad = check_bwd_tf32(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), true, argc > 5 ? atoi(argv[5]) : 32);
     } else {
-      for (int causal : {0, 1})
-        for (int T : {1, 40, 128, 256, 327, 512, 1000, 2048 + 77}) bad += check_bwd_tf32(3, T, causal, false);
-      bad += check_bwd_tf32(88, 512, 1, true);  // the MT model's attention: 11 sequences x 8 heads, L = 512
+      for (int d : {32, 64})
+        for (int causal : {0, 1})
+          for (int T : {1, 40, 64, 65, 128, 256, 327, 512, 1000, 2048 + 77}) bad += check_bwd_tf32(3, T, causal, false, d);
+      bad += check_bwd_tf32(88, 512, 1, true);       // the MT model's attention: 11 sequences x 8 heads, L = 512
+      bad += check_bwd_tf32(8, 1024, 1, true, 64);   // the reference kernel tests' shape (B=1, H=8, d=64)
     }
   } else if (mode == "time32") {
     int BH = argc > 2 ? atoi(argv[2]) : 512, T = argc > 3 ? atoi(argv[3]) : 1024, d = argc > 4 ? atoi(argv[4]) : 64;
