@@ -109,6 +109,7 @@ class Module:
             view.copy_(p.value.detach())
             p.value = view.requires_grad_(True)
             p.value.grad = gview
+            ops.grad_sink.mark(p.value)  # the gradient kernels may accumulate straight into gview
 
         for u, off in zip(units, offsets):
             if u[0] == "p":
@@ -128,12 +129,12 @@ class Module:
                 col += w
             fused = (block if rows > 1 else block.view(-1)).requires_grad_(True)
             fused.grad = gblock if rows > 1 else gblock.view(-1)
+            ops.grad_sink.mark(fused)
             on_fused(fused)
         # element ranges of the flat buffers per top-level child (padding included)
         self._flat_children = [(name, offsets[lo] if lo < len(offsets) else total, offsets[hi] if hi < len(offsets) else total)
                                for name, lo, hi in self._flat_children if hi > lo]
         self._flat = (flat, gflat)
-        ops.grad_sink.direct = True  # weight / bias gradient kernels accumulate straight into the flat gradient views
         return self._flat
 
     def fuse_parameters(self):

@@ -147,13 +147,22 @@ class grad_sink:
     buffer that zero_grad() clears with a single memset.  The weight / bias gradient kernels then accumulate STRAIGHT into
     those views (GEMM epilogue `C +=`, column sums with accumulate) and the autograd Functions return None for the
     parameter inputs -- autograd's AccumulateGrad would otherwise launch one extra `grad += dW` kernel per parameter per
-    step (~70 of the ~280 launches of a step, 13 % of its device time) and allocate every dW / db twice."""
-    direct = False
+    step (~70 of the ~280 launches of a step, 13 % of its device time) and allocate every dW / db twice.
+
+    The switch is per tensor, not per process: flatten_parameters marks the views it creates (`mark`), every other tensor
+    -- another model in the same process, a parameter of a model that was never flattened -- keeps ordinary autograd
+    semantics (torch.autograd.grad, gradient hooks, retain_grad)."""
+    ATTR = "_fa_b200_flat_grad"
+
+    @staticmethod
+    def mark(t) -> None:
+        setattr(t, grad_sink.ATTR, True)
 
 
 def _sink(p):
     """The gradient buffer the kernels may accumulate into for parameter tensor `p`, or None (ordinary autograd)."""
-    if grad_sink.direct and p is not None and p.is_leaf and p.requires_grad and p.grad is not None and p.grad.is_contiguous():
+    if (p is not None and getattr(p, grad_sink.ATTR, False) and p.is_leaf and p.requires_grad and p.grad is not None
+            and p.grad.is_contiguous()):
         return p.grad
     return None
 
@@ -544,12 +553,23 @@ class DropoutState:
     def __init__(self):
         self.base_seed = 0x5EED
         self.calls = 0
-        self.step = None  # torch.int64 tensor of one element on the device, or None
+        self.steps = {}  # device -> torch.int64 tensor of one element living on that device
+
+    @property
+    def step(self):
+        """The counter of the current CUDA device (None before the first dropout call on it)."""
+        return self.steps.get(torch.device("cuda", torch.cuda.current_device())) if torch.cuda.is_available() else None
+
+    def counter(self, device):
+        dev = torch.device(device)
+        if dev not in self.steps:
+            self.steps[dev] = torch.zeros(1, dtype=torch.int64, device=dev)
+        return self.steps[dev]
 
     def begin_step(self):
         self.calls = 0
-        if self.step is not None:
-            self.step.add_(1)
+        for c in self.steps.values():
+            c.add_(1)
 
 
 dropout_state = DropoutState()
@@ -558,9 +578,7 @@ dropout_state = DropoutState()
 def _next_dropout_seed(x):
     st = dropout_state
     st.calls += 1
-    if st.step is None:
-        st.step = torch.zeros(1, dtype=torch.int64, device=x.device)
-    return (st.base_seed << 32) ^ st.calls, st.step
+    return (st.base_seed << 32) ^ st.calls, st.counter(x.device)
 
 
 def gelu_dropout(x, p: float, training: bool, generator=None, x_bias=None):
@@ -642,12 +660,28 @@ class _EmbedPosDropout(torch.autograd.Function):
         return None, (None if sink else dt), (None if sink else dp), None, None, None
 
 
+validate_ids = True  # range-check token ids / class labels on the kernel path (one reduction + host sync per call site)
+
+
+def check_ids(idx, n: int, what: str) -> None:
+    """The kernels index tables and logit rows with these integers unchecked (gather, scatter-add, row[target]): an id
+    outside [0, n) would read or atomically write out of bounds.  The reference raises IndexError for such ids (numpy
+    fancy indexing in nn.one_hot, minitorch/nn.py:244-246); so do we -- outside CUDA-graph capture, where a host sync is
+    allowed (GraphedStep runs its warm-up steps eagerly, so every training run is checked at least once)."""
+    if not validate_ids or idx.numel() == 0 or (idx.is_cuda and torch.cuda.is_current_stream_capturing()):
+        return
+    lo, hi = int(idx.min()), int(idx.max())
+    if lo < 0 or hi >= n:
+        raise IndexError(f"{what}: ids must lie in [0, {n}) (found min {lo}, max {hi})")
+
+
 def embed_pos_dropout(idx, tok_weight, pos_weight, p: float, training: bool, generator=None):
     """dropout(tok_weight[idx] + pos_weight[arange(T)], p) for idx (B, T) -- the model's input stage; one kernel each way on
     the kernel path, the reference operators otherwise."""
     B, T = idx.shape
     if (_on_kernels(tok_weight, pos_weight) and idx.is_cuda and tok_weight.shape[1] % 4 == 0 and tok_weight.shape[1] == pos_weight.shape[1]
             and pos_weight.shape[0] >= T and tok_weight.is_contiguous() and pos_weight.is_contiguous()):
+        check_ids(idx, tok_weight.shape[0], "embed_pos_dropout")
         drop = training and p > 0.0
         seed, step = _next_dropout_seed(tok_weight) if drop else (0, None)
         return _EmbedPosDropout.apply(idx, tok_weight, pos_weight, p if drop else 0.0, seed, step)
@@ -657,6 +691,7 @@ def embed_pos_dropout(idx, tok_weight, pos_weight, p: float, training: bool, gen
 
 def embedding(idx, weight):
     if _on_kernels(weight) and idx.is_cuda and weight.shape[1] % 4 == 0:
+        check_ids(idx, weight.shape[0], "embedding")
         return _Embedding.apply(idx, weight)
     return weight[idx]
 
@@ -696,6 +731,7 @@ def softmax_loss(logits, target, logits_bias=None):
     logits_bias: the bias of the linear layer that produced `logits` with bias_grad=False (fused_logits_bias_grad_ok):
     its gradient is reduced inside the loss-backward kernel."""
     if _on_kernels(logits) and target.is_cuda and logits.shape[1] % 4 == 0:
+        check_ids(target, logits.shape[1], "softmax_loss")
         return _SoftmaxLoss.apply(logits, target, logits_bias)
     assert logits_bias is None, "logits_bias needs the kernel path"
     return torch.logsumexp(logits, dim=1) - logits.gather(1, target.view(-1, 1).long()).view(-1)

@@ -1,15 +1,14 @@
+# tools/profile_round.sh <tag>   (run under gpurun, ONE GPU): the evidence set of a round.
+#   1. plain bench run, then the ncu launch list of the same command (shares of a step)
+#   2. ncu --set full of the two headline kernels (backward main kernel, forward) at the config-3 shapes, each after a plain run
+# Reports land in gpurun_out/; summarise them here (no GPU) with tools/profile_summarise.sh <tag>.
+tag=${1:-r02}
 set -x
 cd $GRAFT_REPO_ROOT
-python bench.py --steps 2 --warmup 1 > gpurun_out/plain_bench.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_r01b.csv python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_launch.log 2>&1
-build/fa_check time 512 4096 128 1 2 1 > gpurun_out/plain_time.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fa_bwd_kernel -s 1 -c 1 -o gpurun_out/prof_r01b_bwd build/fa_check time 512 4096 128 1 2 1 > gpurun_out/ncu_bwd.log 2>&1
-build/fa_check time 512 4096 128 1 2 1 > gpurun_out/plain_time.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fa_fwd_kernel -s 1 -c 1 -o gpurun_out/prof_r01b_fwd build/fa_check time 512 4096 128 1 2 1 > gpurun_out/ncu_fwd.log 2>&1
-build/fa_check time32 512 1024 64 0 2 > gpurun_out/plain_time32.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fa_fwd_kernel -s 1 -c 1 -o gpurun_out/prof_r01b_tf32 build/fa_check time32 512 1024 64 0 2 > gpurun_out/ncu_tf32.log 2>&1
-python bench.py --workload cfg2 --steps 20 --warmup 3 > gpurun_out/bench_cfg2.log 2>&1
-python bench.py --workload cfg4 --steps 5 --warmup 3 > gpurun_out/bench_cfg4.log 2>&1
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_cfg3.log 2>&1
-tail -c 600 gpurun_out/bench_cfg2.log gpurun_out/bench_cfg4.log gpurun_out/bench_cfg3.log
-ls -la gpurun_out | tail -20
+python bench.py --steps 2 --warmup 1 --no-mt > gpurun_out/plain_bench_$tag.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 1 --no-mt > gpurun_out/ncu_launch_$tag.log 2>&1
+build/fa_check time 512 4096 128 1 2 1 > gpurun_out/plain_time_$tag.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:fa_bwd_kernel -s 1 -c 1 -o gpurun_out/prof_${tag}_bwd build/fa_check time 512 4096 128 1 2 1 > gpurun_out/ncu_bwd_$tag.log 2>&1
+build/fa_check time 512 4096 128 1 2 1 > gpurun_out/plain_time_$tag.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:fa_fwd_kernel -s 1 -c 1 -o gpurun_out/prof_${tag}_fwd build/fa_check time 512 4096 128 1 2 1 > gpurun_out/ncu_fwd_$tag.log 2>&1
+ls -la gpurun_out | tail -8
