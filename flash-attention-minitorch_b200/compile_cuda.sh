@@ -18,7 +18,7 @@ NVFLAGS="$ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexp
 mkdir -p "$OBJ" "$LIB" "$SHIM"
 
 pids=()
-for f in fa_simt fa_util fa_capi fa_fwd_sm100 fa_bwd_sm100 fa_bwd_tf32_sm100 fa_gemm_sm100 fa_lm_kernels; do
+for f in fa_simt fa_util fa_capi fa_fwd_sm100 fa_fwd_pair_sm100 fa_bwd_sm100 fa_bwd_tf32_sm100 fa_gemm_sm100 fa_lm_kernels; do
   if [ ! -f "$OBJ/$f.o" ] || [ "$SRC/$f.cu" -nt "$OBJ/$f.o" ] || [ -n "$(find "$SRC" "$HERE/../include" -name '*.h' -newer "$OBJ/$f.o" -o -name '*.cuh' -newer "$OBJ/$f.o")" ]; then
     ( $NVCC $NVFLAGS -c "$SRC/$f.cu" -o "$OBJ/$f.o" > "$OBJ/$f.ptxas.log" 2>&1 || { cat "$OBJ/$f.ptxas.log"; exit 1; } ) &
     pids+=($!)
@@ -29,7 +29,7 @@ for p in "${pids[@]:-}"; do [ -n "$p" ] && { wait "$p" || fail=1; }; done
 [ "$fail" = 0 ] || { echo "compile_cuda.sh: compilation failed" >&2; exit 1; }
 
 g++ -O2 -std=c++17 -fPIC -I/usr/local/cuda/include -c "$SRC/fa_nccl.cpp" -o "$OBJ/fa_nccl.o"
-$NVCC $ARCH -shared -o "$LIB/libfa_b200.so" "$OBJ"/fa_nccl.o "$OBJ"/fa_simt.o "$OBJ"/fa_util.o "$OBJ"/fa_capi.o "$OBJ"/fa_fwd_sm100.o \
+$NVCC $ARCH -shared -o "$LIB/libfa_b200.so" "$OBJ"/fa_nccl.o "$OBJ"/fa_simt.o "$OBJ"/fa_util.o "$OBJ"/fa_capi.o "$OBJ"/fa_fwd_sm100.o "$OBJ"/fa_fwd_pair_sm100.o \
   "$OBJ"/fa_bwd_sm100.o "$OBJ"/fa_bwd_tf32_sm100.o "$OBJ"/fa_gemm_sm100.o "$OBJ"/fa_lm_kernels.o -lcudart -ldl
 
 shim() {  # name convention FW|BW

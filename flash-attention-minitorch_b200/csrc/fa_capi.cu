@@ -524,6 +524,8 @@ void fa_b200_debug_fwd_trace(void* dev_buf) { fa::tc_fwd_set_trace(static_cast<l
 
 void fa_b200_set_host_precision(int precision) { g_host_precision = precision; }
 void fa_b200_set_host_zero_qgrad(int on) { g_host_zero_qgrad = on ? 1 : 0; }
+void fa_b200_set_fwd_pair(int on) { fa::set_fwd_pair(on != 0); }
+int fa_b200_get_fwd_pair(void) { return fa::fwd_pair_enabled() ? 1 : 0; }
 int fa_b200_get_host_precision(void) { return host_precision(); }
 void fa_b200_release_arena(void) {
   std::lock_guard<std::mutex> lk(g_arena_mu);

@@ -496,12 +496,25 @@ cudaError_t launch_fwd(const void* q, const void* k, const void* v, void* o, flo
 }  // namespace
 
 bool tc_fwd_supported(int d) { return d == 64 || d == 128; }
+// d = 128 can run on CTA pairs (fa_fwd_pair_sm100.cu: cta_group::2, P through shared memory).  Parity-green but measured
+// SLOWER than the single-CTA kernel of this file (2.83 against 2.02 ms at config 3), so it is
+// opt-in: FA_B200_FWD_PAIR=1 or fa_b200_set_fwd_pair(1).
+int g_fwd_pair = -1;
+bool fwd_pair_enabled() {
+  if (g_fwd_pair < 0) {
+    const char* e = getenv("FA_B200_FWD_PAIR");
+    g_fwd_pair = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_fwd_pair == 1;
+}
+void set_fwd_pair(bool on) { g_fwd_pair = on ? 1 : 0; }
 bool tc_fwd_tf32_supported(int d) { return d == 32 || d == 64; }
 
 cudaError_t tc_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, bool o_is_f32,
                    float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st,
                    Dropout drop) {
   if (BH > 65535) return cudaErrorInvalidValue;
+  if (d == 128 && fwd_pair_enabled()) return tc_fwd_pair(q, k, v, o, o_is_f32, lse, m_out, l_out, BH, T, causal, st, drop);
   if (d == 128) {
     return o_is_f32 ? launch_fwd<128, float, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, drop, st)
                     : launch_fwd<128, __nv_bfloat16, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, drop, st);

@@ -30,6 +30,12 @@ cudaError_t tc_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
                    float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st,
                    Dropout drop = kNoDropout);
 
+// the same at d = 128 on CTA pairs (tcgen05.mma.cta_group::2, P through shared memory): fa_fwd_pair_sm100.cu
+bool fwd_pair_enabled();
+void set_fwd_pair(bool on);
+cudaError_t tc_fwd_pair(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, bool o_is_f32, float* lse,
+                        float* m_out, float* l_out, int BH, int T, bool causal, cudaStream_t st, Dropout drop = kNoDropout);
+
 // fp32 storage read directly by TMA, kind::tf32 MMAs, fp32 output; d in {32, 64}
 bool tc_fwd_tf32_supported(int d);
 cudaError_t tc_fwd_tf32(const float* q, const float* k, const float* v, float* o, float* lse, float* m_out,

@@ -118,6 +118,10 @@ def load_library() -> ctypes.CDLL:
     lib.fa_b200_set_host_precision.argtypes = [ci]
     lib.fa_b200_set_host_precision.restype = None
     lib.fa_b200_get_host_precision.restype = ci
+    if hasattr(lib, "fa_b200_set_fwd_pair"):
+        lib.fa_b200_set_fwd_pair.argtypes = [ci]
+        lib.fa_b200_set_fwd_pair.restype = None
+        lib.fa_b200_get_fwd_pair.restype = ci
     if hasattr(lib, "fa_b200_set_host_zero_qgrad"):
         lib.fa_b200_set_host_zero_qgrad.argtypes = [ci]
         lib.fa_b200_set_host_zero_qgrad.restype = None

@@ -128,6 +128,11 @@ int fa_b200_get_host_precision(void);
  * (minitorch/cuda_kernel_ops.py:609-611) -- and skips its upload (11 % of the H2D bytes); q_grad is then overwritten.
  * Default 0 (the reference kernels accumulate, src/flash_attn2_bw.cu:228); environment: FA_B200_HOST_ZERO_QGRAD=1. */
 void fa_b200_set_host_zero_qgrad(int on);
+/* on = 1: the bf16 forward at d = 128 runs the CTA-pair kernel (tcgen05.mma.cta_group::2, each CTA stages half of every
+ * K/V tile, P through shared memory) instead of the single-CTA kernel.  Same results (parity-tested); measured slower on
+ * B200, hence off by default (environment: FA_B200_FWD_PAIR=1).  Kept as a tuning knob and as the record of that design. */
+void fa_b200_set_fwd_pair(int on);
+int fa_b200_get_fwd_pair(void);
 /* Release the device arena held by the host-pointer API. */
 void fa_b200_release_arena(void);
 

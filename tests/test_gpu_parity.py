@@ -174,6 +174,46 @@ def test_device_bf16_forward_backward_vs_oracle(cuda_device, BH, T, d, causal):
         assert rel_inf(got.float().cpu().numpy(), ref) <= BF16_REL, name
 
 
+@pytest.fixture
+def pair_forward():
+    """Switch the d = 128 bf16 forward to the CTA-pair kernel (fa_fwd_pair_sm100.cu) for one test."""
+    lib = _lib.load_library()
+    prev = lib.fa_b200_get_fwd_pair()
+    lib.fa_b200_set_fwd_pair(1)
+    yield
+    lib.fa_b200_set_fwd_pair(prev)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("BH,T", [(3, 128), (2, 1), (2, 129), (2, 512), (1, 513), (2, 1000), (1, 2048), (1, 2125)])
+def test_pair_forward_kernel_vs_oracle(cuda_device, pair_forward, BH, T, causal):
+    """The cta_group::2 forward (opt-in: measured slower than the single-CTA kernel, DESIGN.md 3.1a) computes the same O, L
+    and FA-1 statistics: one cluster = 512 query rows, T below / across / far beyond one cluster, ragged tails, the step
+    that only the second CTA of a pair needs (rank 0 rides along with P = 0)."""
+    q, k, v, g = _bf16_problem(BH, T, 128, seed=300 + T)
+    o_r, p, m_r, l_r, L_r = ao.attention_forward(q, k, v, causal, np.float64)
+    o, lse, m, l = device.flash_attn_fwd(*(_to_dev(x, cuda_device) for x in (q, k, v)), causal, want_lm=True)
+    assert rel_inf(o.float().cpu().numpy(), o_r) <= BF16_REL
+    assert np.abs(lse.cpu().numpy() - L_r).max() <= 2e-3
+    import torch
+    assert np.abs((m + torch.log(l)).cpu().numpy() - L_r).max() <= 2e-3
+
+
+def test_pair_forward_kernel_lazy_rescale_and_dropout(cuda_device, pair_forward):
+    q, k, v, g = _bf16_problem(2, 1024, 128, seed=77, scale=6.0)
+    for causal in (False, True):
+        o_r, p, m_r, l_r, L_r = ao.attention_forward(q, k, v, causal, np.float64)
+        o, lse = device.flash_attn_fwd(*(_to_dev(x, cuda_device) for x in (q, k, v)), causal)
+        assert rel_inf(o.float().cpu().numpy(), o_r) <= BF16_REL
+        assert np.abs(lse.cpu().numpy() - L_r).max() <= 1e-2
+    pd, seed, BH, T = 0.1, 4242, 2, 640
+    q, k, v, g = _bf16_problem(BH, T, 128, seed=31)
+    keep = device.dropout_mask(BH, T, pd, seed, device=cuda_device).cpu().numpy()
+    _, _, _, o_r, L_r = ao.attention_dropout_backward(q, k, v, g, True, keep, ao.dropout_keep_scale(pd))
+    o, lse = device.flash_attn_fwd(*(_to_dev(x, cuda_device) for x in (q, k, v)), True, p_drop=pd, seed=seed)
+    assert rel_inf(o.float().cpu().numpy(), o_r) <= BF16_REL and np.abs(lse.cpu().numpy() - L_r).max() <= 2e-3
+
+
 def test_device_bf16_large_scores_exercise_lazy_rescale(cuda_device):
     """|s| up to ~40: the running max moves by far more than the 2^8 slack, so O must be rescaled in TMEM."""
     q, k, v, g = _bf16_problem(2, 1024, 128, seed=77, scale=6.0)

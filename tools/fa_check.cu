@@ -495,7 +495,7 @@ static int trace_fwd(int BH, int T, int d, int causal) {
   printf("  j | T0: S_rdy  loaded  maxed  P_done | T1: S_rdy  loaded  maxed  P_done | MMA: P0_seen iss0  P1_seen   iss1\n");
   for (int j = 0; j < 16; ++j) {
     printf("%3d |", j);
-    for (int e = 0; e < 12; ++e) {
+    for (int e = 0; e < 14; ++e) {
       const long long v = hh[j * 16 + e];
       printf(" %7lld", v ? v - t0 : -1);
       if (e == 3 || e == 7) printf(" |");
