@@ -325,7 +325,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // dropout: one 32-bit hash per 2 x 2 block of (query, key); this thread (one key row) uses the byte of its key
     // parity in the low half (even query) and in the high half (odd query) -- the same bits the forward drew
     const uint32_t kj = uint32_t(j * kTile + r);
-    const uint32_t drop_colkey = drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh) ^ ((kj >> 1) * kDropColMul);
+    const uint32_t drop_head = drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh), drop_colterm = (kj >> 1) * kDropColMul;
     const uint32_t drop_b0 = kj & 1;  // byte b0: even query of the block, byte b0 + 2: odd query
     const uint32_t drop_sel2 = drop_sel_pair(drop_b0, drop_b0 + 2);
     const uint32_t drop_sh = 7 + 8 * drop_b0;
@@ -389,7 +389,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 #pragma unroll
         for (int c = 0; c < 64; c += 4) {
           // the two lanes of a key pair need the same block words: each hashes one, a shuffle gives the other
-          const uint32_t mine = drop_keep_word(drop_mix(drop_colkey ^ ((i2 + (c >> 1) + (lane & 1)) * kDropRowMul)), drop_thr);
+          const uint32_t mine = drop_keep_word(drop_mix(drop_row_key(drop_head, i2 + (c >> 1) + (lane & 1)) ^ drop_colterm), drop_thr);
           const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
           const uint32_t w0 = (lane & 1) ? theirs : mine, w1 = (lane & 1) ? mine : theirs;  // queries c,c+1 | c+2,c+3
           pd[c >> 1] = pk[c >> 1] & drop_prmt(w0, drop_sel2);

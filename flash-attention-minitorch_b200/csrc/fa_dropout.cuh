@@ -8,7 +8,10 @@
 // The mask is a pure function of (seed, head, query row i, key column j), so the forward (thread = query row)
 // and the transposed backward (thread = key row) regenerate identical bits without storing anything:
 //   head_key  = mix(seed_lo ^ mix(seed_hi + 0x9E3779B9 * (head + 1)))
-//   bits      = mix(head_key ^ (i >> 1) * 0x9E3779B1 ^ (j >> 1) * 0x85EBCA77)         one 32-bit word per 2 x 2 block
+//   row_key   = mix(head_key ^ (i >> 1) * 0x9E3779B1)                                 (two rounds: the row term is mixed
+//   bits      = mix(row_key ^ (j >> 1) * 0x85EBCA77)     one 32-bit word per 2 x 2     before the column term comes in, so
+//                                                         block                         the hash input is not an XOR of two
+//                                                                                       linear terms)
 //   keep(i,j) = (byte[(i & 1) * 2 + (j & 1)] of bits) & 0x7f  >=  thr,    thr = round(128 p)   (p_eff = thr / 128)
 // mix() is the 32-bit multiply-xorshift finaliser "lowbias32" (a bijection with full avalanche), i.e. a keyed
 // counter-mode generator.  Seven-bit uniforms make the four comparisons of a word one add:
@@ -47,8 +50,10 @@ FA_HD uint32_t drop_mix(uint32_t x) {
 FA_HD uint32_t drop_head_key(uint32_t seed_lo, uint32_t seed_hi, uint32_t head) {
   return drop_mix(seed_lo ^ drop_mix(seed_hi + 0x9E3779B9u * (head + 1u)));
 }
+// key of the row pair i >> 1 (the forward computes it once per thread, the transposed backward once per hashed word)
+FA_HD uint32_t drop_row_key(uint32_t head_key, uint32_t i_pair) { return drop_mix(head_key ^ (i_pair * kDropRowMul)); }
 FA_HD uint32_t drop_block_bits(uint32_t head_key, uint32_t i, uint32_t j) {
-  return drop_mix(head_key ^ ((i >> 1) * kDropRowMul) ^ ((j >> 1) * kDropColMul));
+  return drop_mix(drop_row_key(head_key, i >> 1) ^ ((j >> 1) * kDropColMul));
 }
 // top bit of byte e (e = (i & 1) * 2 + (j & 1)) of the result = keep of that element of the 2 x 2 block
 FA_HD uint32_t drop_keep_word(uint32_t bits, uint32_t thr) { return (bits & 0x7f7f7f7fu) + (0x80u - thr) * 0x01010101u; }

@@ -311,7 +311,7 @@ fa_fwd_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint32_t s_free_leader = mapa_shared(smem_u32(&bars.s_free[t]), 0);
     const uint32_t p_full_leader = mapa_shared(smem_u32(&bars.p_full[t]), 0);
     float m_ref = -INFINITY, m_true = -INFINITY, l = 0.f;
-    const uint32_t drop_rowkey = drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh) ^ ((uint32_t(row_g) >> 1) * kDropRowMul);
+    const uint32_t drop_rowkey = drop_row_key(drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh), uint32_t(row_g) >> 1);
     const uint32_t drop_thr = p.drop.thr;
     const uint32_t drop_b0 = (row_g & 1) * 2;
     const uint32_t drop_sel2 = drop_sel_pair(drop_b0, drop_b0 + 1);

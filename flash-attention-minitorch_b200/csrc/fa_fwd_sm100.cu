@@ -284,7 +284,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     float m_true = -INFINITY;  // true running row max (only needed for the FA-1 statistics)
     float l = 0.f;
     // dropout: one 32-bit hash per 2 x 2 block of (row, key); this thread uses the two bytes of its row parity
-    const uint32_t drop_rowkey = drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh) ^ ((uint32_t(row_g) >> 1) * kDropRowMul);
+    const uint32_t drop_rowkey = drop_row_key(drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh), uint32_t(row_g) >> 1);
     const uint32_t drop_thr = p.drop.thr;
     const uint32_t drop_b0 = (row_g & 1) * 2;  // bytes b0, b0 + 1 of a block word belong to this row
     const uint32_t drop_sel2 = drop_sel_pair(drop_b0, drop_b0 + 1), drop_selA = drop_sel_word(drop_b0),

@@ -113,7 +113,8 @@ def dropout_keep_mask(seed: int, heads, T: int, p: float) -> np.ndarray:
         i = np.arange(T, dtype=np.uint32)
         rterm = (i >> np.uint32(1)) * np.uint32(0x9E3779B1)
         cterm = (i >> np.uint32(1)) * np.uint32(0x85EBCA77)
-        bits = _mix32(hkey[:, None, None] ^ rterm[None, :, None] ^ cterm[None, None, :])
+        rkey = _mix32(hkey[:, None] ^ rterm[None, :])  # two rounds: the row term is mixed before the column term comes in
+        bits = _mix32(rkey[:, :, None] ^ cterm[None, None, :])
         sh = np.uint32(8) * ((i & np.uint32(1))[:, None] * np.uint32(2) + (i & np.uint32(1))[None, :])
         byte = (bits >> sh[None]) & np.uint32(0x7F)
     return byte >= np.uint32(dropout_threshold(p))
