@@ -520,6 +520,8 @@ int fa_b200_adam_step(float* p, const float* g, float* m, float* v, size_t n, fl
 
 // developer hook (not declared in fa_b200.h): clock64 timeline of one backward CTA, see tools/fa_check.cu
 void fa_b200_debug_bwd_trace(void* dev_buf) { fa::tc_bwd_set_trace(static_cast<long long*>(dev_buf)); }
+void fa_b200_debug_bwd_trace_start(int t0) { fa::tc_bwd_set_trace_start(t0); }
+void fa_b200_debug_bwd_persistent(int on) { fa::tc_bwd_set_persistent(on); }  // A/B switch, default on
 void fa_b200_debug_fwd_trace(void* dev_buf) { fa::tc_fwd_set_trace(static_cast<long long*>(dev_buf)); }
 
 void fa_b200_set_host_precision(int precision) { g_host_precision = precision; }

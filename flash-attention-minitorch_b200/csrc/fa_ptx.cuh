@@ -155,6 +155,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, uin
         "r"(c2), "l"(hint)
       : "memory");
 }
+// L2 prefetch of a tile (no shared-memory destination, no completion): warms the L2 for a tile that is loaded later
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // 1-D bulk copy global -> shared (size multiple of 16 B, both addresses 16-B aligned)
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -33,7 +33,7 @@ inline PFN_tmapEncodeTiled get_tmap_encode() {
 // Row-major [d2][d1][d0] tensor (d0 contiguous) of `esize`-byte elements; box = [1][box1][box0],
 // out-of-bounds elements read as zero / are not written.  swizzle_mode: 0 none, 1 = 128 B (16-B
 // chunks, box0 * esize must be 128), 2 = 128 B with 32-B atomicity (required by UMMA for MN-major
-// 32-bit operands).  Returns 0 on success.
+// 32-bit operands), 3 = 64 B (box0 * esize must be 64).  Returns 0 on success.
 inline int make_tmap_3d(CUtensorMap* map, const void* base, int esize, uint64_t d0, uint64_t d1, uint64_t d2,
                         uint32_t box0, uint32_t box1, int swizzle_mode = 1) {
   PFN_tmapEncodeTiled enc = get_tmap_encode();
@@ -46,6 +46,7 @@ inline int make_tmap_3d(CUtensorMap* map, const void* base, int esize, uint64_t 
   CUresult r = enc(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle_mode == 1   ? CU_TENSOR_MAP_SWIZZLE_128B
                    : swizzle_mode == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                   : swizzle_mode == 3 ? CU_TENSOR_MAP_SWIZZLE_64B
                                        : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -507,7 +507,8 @@ static int trace_fwd(int BH, int T, int d, int causal) {
 
 extern "C" void fa_b200_debug_bwd_trace(void* dev_buf);
 
-static int trace_bwd(int BH, int T, int d, int causal) {
+extern "C" void fa_b200_debug_bwd_trace_start(int t0);
+static int trace_bwd(int BH, int T, int d, int causal, int t_start = 0) {
   const size_t n = (size_t)BH * T * d, rows = (size_t)BH * T;
   Dev dev;
   __nv_bfloat16* t[8];
@@ -526,6 +527,7 @@ static int trace_bwd(int BH, int T, int d, int causal) {
   CK(cudaDeviceSynchronize());
   CK(cudaMemset(tr, 0, 512 * 8));
   fa_b200_debug_bwd_trace(tr);
+  fa_b200_debug_bwd_trace_start(t_start);
   FA(fa_b200_bwd(t[0], t[1], t[2], t[3], t[4], lse, t[5], t[6], t[7], FA_DTYPE_BF16, FA_PREC_BF16_TC, BH, T, d, causal, 0, ws, wb, nullptr));
   CK(cudaDeviceSynchronize());
   fa_b200_debug_bwd_trace(nullptr);
@@ -536,7 +538,7 @@ static int trace_bwd(int BH, int T, int d, int causal) {
   // dQ drained & dO landed, dP issued, P ready, dV issued, S(i+2) issued}
   const long long* hh = hst.data();
   const long long t0 = hh[0];
-  printf("bwd timeline of CTA(0,0), cycles relative to first S ready\n");
+  printf("bwd timeline of CTA 0, tile pairs %d.. (running count), cycles relative to the first S ready\n", t_start);
   printf(" il | CW: S_rdy  P_done  dP_rdy dS_w0   dS_w7 | DW: dQ_rdy drained  staged | MMA: dS_rdy  iss_dK dO_seen  iss_dP  P_seen  iss_dV   iss_S\n");
   for (int il = 0; il < 16; ++il) {
     printf("%3d |", il);
@@ -548,12 +550,11 @@ static int trace_bwd(int BH, int T, int d, int causal) {
     printf("\n");
   }
   // second table: inside the compute warp 0 (slots 256 + il * 16 + e)
-  printf(" il | CW0: S_ld'd   exp'd drained     -    P_st'd | dP_ld'd ds_empty  dS_st'd | loads (relative to S_rdy of the same il): dO_issue  Q_issue  dO_landed  Q_landed\n");
+  printf(" il | CW0: S_ld'd   exp'd drained     -    P_st'd | dP_ld'd ds_empty  dS_st'd | TMA lane: K Q dO V issued (8-11; K, V at item starts only) | MMA warp at an item start: head reached, K seen, Q seen, tail issued (12-15)\n");
   for (int il = 0; il < 16; ++il) {
     printf("%3d |", il);
     const long long base = hh[il * 16 + 0];
-    for (int e = 0; e < 15; ++e) {
-      if (e >= 8 && e <= 10) continue;
+    for (int e = 0; e < 16; ++e) {
       const long long v = hh[256 + il * 16 + e];
       printf(" %7lld", v ? v - base : -1);
       if (e == 4 || e == 7) printf(" |");
@@ -615,7 +616,7 @@ int main(int argc, char** argv) {
                      argc > 5 ? atoi(argv[5]) : 1);
   } else if (mode == "trace") {
     return trace_bwd(argc > 2 ? atoi(argv[2]) : 512, argc > 3 ? atoi(argv[3]) : 4096, argc > 4 ? atoi(argv[4]) : 128,
-                     argc > 5 ? atoi(argv[5]) : 1);
+                     argc > 5 ? atoi(argv[5]) : 1, argc > 6 ? atoi(argv[6]) : 0);
   } else if (mode == "time") {
     int BH = argc > 2 ? atoi(argv[2]) : 512, T = argc > 3 ? atoi(argv[3]) : 4096, d = argc > 4 ? atoi(argv[4]) : 128;
     int causal = argc > 5 ? atoi(argv[5]) : 1, iters = argc > 6 ? atoi(argv[6]) : 10;
