@@ -838,6 +838,7 @@ int tc_bwd_num_launches(bool grads_f32) {
 void tc_bwd_set_trace(long long* buf) { g_bwd_trace = buf; }
 void tc_bwd_set_trace_start(int t0) { g_bwd_trace_t0 = t0; }
 void tc_bwd_set_persistent(int on) { g_bwd_persistent = on ? 1 : 0; }
+int tc_bwd_get_persistent() { return bwd_persistent() ? 1 : 0; }
 
 size_t tc_bwd_workspace_bytes(int BH, int T, int d) {
   // work-item counter + lse_pad + delta_pad + fp32 dQ accumulator (the latter only used for bf16 gradients)

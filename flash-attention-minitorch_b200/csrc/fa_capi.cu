@@ -521,13 +521,14 @@ int fa_b200_adam_step(float* p, const float* g, float* m, float* v, size_t n, fl
 // developer hook (not declared in fa_b200.h): clock64 timeline of one backward CTA, see tools/fa_check.cu
 void fa_b200_debug_bwd_trace(void* dev_buf) { fa::tc_bwd_set_trace(static_cast<long long*>(dev_buf)); }
 void fa_b200_debug_bwd_trace_start(int t0) { fa::tc_bwd_set_trace_start(t0); }
-void fa_b200_debug_bwd_persistent(int on) { fa::tc_bwd_set_persistent(on); }  // A/B switch, default on
 void fa_b200_debug_fwd_trace(void* dev_buf) { fa::tc_fwd_set_trace(static_cast<long long*>(dev_buf)); }
 
 void fa_b200_set_host_precision(int precision) { g_host_precision = precision; }
 void fa_b200_set_host_zero_qgrad(int on) { g_host_zero_qgrad = on ? 1 : 0; }
 void fa_b200_set_fwd_pair(int on) { fa::set_fwd_pair(on != 0); }
 int fa_b200_get_fwd_pair(void) { return fa::fwd_pair_enabled() ? 1 : 0; }
+void fa_b200_set_bwd_persistent(int on) { fa::tc_bwd_set_persistent(on); }
+int fa_b200_get_bwd_persistent(void) { return fa::tc_bwd_get_persistent(); }
 int fa_b200_get_host_precision(void) { return host_precision(); }
 void fa_b200_release_arena(void) {
   std::lock_guard<std::mutex> lk(g_arena_mu);

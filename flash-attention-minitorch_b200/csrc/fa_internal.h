@@ -47,6 +47,7 @@ void tc_fwd_set_trace(long long* dev_buf);  // same for the forward (CTA (0,0): 
 void tc_bwd_set_trace(long long* dev_buf);  // developer timeline buffer (256 int64), nullptr = off
 void tc_bwd_set_trace_start(int t0);        // first tile pair (running count of CTA 0) the timeline records
 void tc_bwd_set_persistent(int on);         // A/B switch: 0 = one CTA per work item (default: persistent, FA_B200_BWD_PERSISTENT)
+int tc_bwd_get_persistent();
 size_t tc_bwd_workspace_bytes(int BH, int T, int d);
 // dq/dk/dv are bf16 or fp32 (grads_f32).  workspace: tc_bwd_workspace_bytes() bytes of device memory.
 cudaError_t tc_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* o,

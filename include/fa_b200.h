@@ -133,6 +133,12 @@ void fa_b200_set_host_zero_qgrad(int on);
  * B200, hence off by default (environment: FA_B200_FWD_PAIR=1).  Kept as a tuning knob and as the record of that design. */
 void fa_b200_set_fwd_pair(int on);
 int fa_b200_get_fwd_pair(void);
+/* The bf16 tensor-core backward (d = 64, 128) is a PERSISTENT kernel: one CTA per SM draws (head, K/V tile) work items from
+ * a counter and keeps its TMA / MMA / softmax-gradient pipelines running across items.  on = 0 launches one CTA per work item
+ * instead (the round-1 schedule; same arithmetic, dK / dV bit-identical, dQ equal up to the order of its fp32 reduce-adds);
+ * measured 4-6 % slower at config 3.  Default 1 (environment: FA_B200_BWD_PERSISTENT=0).  A tuning / test knob. */
+void fa_b200_set_bwd_persistent(int on);
+int fa_b200_get_bwd_persistent(void);
 /* Release the device arena held by the host-pointer API. */
 void fa_b200_release_arena(void);
 

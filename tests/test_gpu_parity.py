@@ -214,6 +214,37 @@ def test_pair_forward_kernel_lazy_rescale_and_dropout(cuda_device, pair_forward)
     assert rel_inf(o.float().cpu().numpy(), o_r) <= BF16_REL and np.abs(lse.cpu().numpy() - L_r).max() <= 2e-3
 
 
+@pytest.mark.parametrize("BH,T,d,causal,p_drop", [(40, 1024, 128, True, 0.0), (40, 1024, 128, False, 0.0), (5, 2125, 128, True, 0.0),
+                                                 (300, 128, 128, True, 0.0), (37, 700, 64, True, 0.0), (21, 1100, 128, True, 0.1),
+                                                 (3, 4224, 128, True, 0.0)])
+def test_persistent_backward_equals_one_cta_per_work_item(cuda_device, BH, T, d, causal, p_drop):
+    """The persistent backward (148 CTAs draw (head, K/V tile) items from a counter; K/V buffers swap roles from item to item,
+    the first S of the next item is issued ahead of the last dK / dQ of the current one) against the same kernel launched
+    with one CTA per item: dK, dV bit-identical (no atomics on their path, the same MMA sequence per item), dQ equal up
+    to the order of its fp32 reduce-adds; two persistent runs give bit-identical dK, dV.  Shapes: many more items than
+    SMs, one-pair items (T = 128), ragged T, d = 64 (two dO stages), dropout, one head longer than a wave."""
+    import torch
+    lib = _lib.load_library()
+    q, k, v, g = _bf16_problem(BH, T, d, seed=900 + BH + T)
+    tq, tk, tv, tg = (_to_dev(x, cuda_device) for x in (q, k, v, g))
+    kw = dict(p_drop=p_drop, seed=99) if p_drop else {}
+    o, lse = device.flash_attn_fwd(tq, tk, tv, causal, **kw)
+    prev = lib.fa_b200_get_bwd_persistent()
+    try:
+        lib.fa_b200_set_bwd_persistent(0)
+        dq0, dk0, dv0 = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, causal, **kw)
+        lib.fa_b200_set_bwd_persistent(1)
+        dq1, dk1, dv1 = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, causal, **kw)
+        dq2, dk2, dv2 = device.flash_attn_bwd(tq, tk, tv, o, tg, lse, causal, **kw)
+    finally:
+        lib.fa_b200_set_bwd_persistent(prev)
+    assert torch.equal(dk0, dk1) and torch.equal(dv0, dv1)
+    assert torch.equal(dk1, dk2) and torch.equal(dv1, dv2)
+    ref = dq0.float()
+    assert float((dq1.float() - ref).abs().max()) <= 8e-3 * float(ref.abs().max())  # one bf16 ulp of the largest element
+    assert bool(torch.isfinite(dq1.float()).all())
+
+
 def test_device_bf16_large_scores_exercise_lazy_rescale(cuda_device):
     """|s| up to ~40: the running max moves by far more than the 2^8 slack, so O must be rescaled in TMEM."""
     q, k, v, g = _bf16_problem(2, 1024, 128, seed=77, scale=6.0)
