@@ -527,6 +527,8 @@ void fa_b200_set_host_precision(int precision) { g_host_precision = precision; }
 void fa_b200_set_host_zero_qgrad(int on) { g_host_zero_qgrad = on ? 1 : 0; }
 void fa_b200_set_fwd_pair(int on) { fa::set_fwd_pair(on != 0); }
 int fa_b200_get_fwd_pair(void) { return fa::fwd_pair_enabled() ? 1 : 0; }
+void fa_b200_set_fwd_persistent(int on) { fa::tc_fwd_set_persistent(on); }
+int fa_b200_get_fwd_persistent(void) { return fa::tc_fwd_get_persistent(); }
 void fa_b200_set_bwd_persistent(int on) { fa::tc_bwd_set_persistent(on); }
 int fa_b200_get_bwd_persistent(void) { return fa::tc_bwd_get_persistent(); }
 int fa_b200_get_host_precision(void) { return host_precision(); }

@@ -23,6 +23,10 @@
 #include <stdlib.h>
 #include <math.h>
 
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+
 #include "fa_internal.h"
 #include "fa_ptx.cuh"
 #include "fa_tma_host.h"
@@ -32,7 +36,49 @@ namespace fa {
 long long* g_fwd_trace = nullptr;  // developer timeline buffer (tc_fwd_set_trace)
 void tc_fwd_set_trace(long long* buf) { g_fwd_trace = buf; }
 
+// Work-item counters of the persistent forward: {next item, finished CTAs} per slot.  The kernel leaves its slot zeroed
+// (the last CTA resets it), so a launch needs no memset; consecutive launches rotate through the slots so that launches
+// in flight on different streams never share one (up to kFwdSchedSlots concurrent launches per device).
+constexpr int kFwdSchedSlots = 256;
+__device__ int g_fwd_sched[kFwdSchedSlots][2];
+int g_fwd_persistent = -1;  // -1: FA_B200_FWD_PERSISTENT (read once), default on
+bool fwd_persistent() {
+  if (g_fwd_persistent < 0) {
+    const char* e = getenv("FA_B200_FWD_PERSISTENT");
+    g_fwd_persistent = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_fwd_persistent != 0;
+}
+void tc_fwd_set_persistent(int on) { g_fwd_persistent = on ? 1 : 0; }
+int tc_fwd_get_persistent() { return fwd_persistent() ? 1 : 0; }
+
 namespace {
+
+int* fwd_sched_slot() {
+  static std::atomic<unsigned> next{0};
+  static std::mutex mu;
+  static int* base[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!base[dev]) {
+      void* ptr = nullptr;
+      if (cudaGetSymbolAddress(&ptr, g_fwd_sched) != cudaSuccess) return nullptr;
+      base[dev] = static_cast<int*>(ptr);
+    }
+  }
+  return base[dev] + 2 * (next.fetch_add(1) % kFwdSchedSlots);
+}
+int fwd_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
 
 constexpr int kBlockM = 128;  // rows per Q tile (= TMEM lanes)
 constexpr int kBlockN = 128;  // keys per K/V tile
@@ -57,6 +103,12 @@ constexpr int kFwdThreads = 384;  // warps 0-7 softmax, 8 TMA, 9 MMA, 10-11 idle
 
 struct FwdParams {
   int T, BH, causal;
+  int nblk;         // 256-row query blocks per head
+  int total_items;  // BH * nblk work items
+  int persistent;   // 1: CTAs draw items from sched[0] until it runs dry (sched[1] counts finished CTAs: the last one
+                    // resets both words, so the slot is zero again for the next launch); 0: CTA b works on item b only
+  int* sched;
+  int wide_stores;  // o is 32-byte aligned: 256-bit stores in the epilogue
   float tau;         // 1/sqrt(d)
   float scale_log2;  // tau * log2(e)
   void* o;
@@ -85,29 +137,45 @@ struct FwdCfg {
 };
 
 struct FwdBarriers {
-  uint64_t q_full;
+  uint64_t q_full, q_free;                  // per work item
+  uint64_t sched_full[2], sched_empty[2];   // work-item ring
+  int sched_item[2];
   uint64_t k_full[4], k_empty[4], v_full[4], v_empty[4];
   uint64_t s_full[2], p_full[2][FA_FWD_PSIG], o_full[2];
 };
 
+// 32 consecutive output columns of one row -> global memory.  A thread owns a row, so a warp's store instruction touches
+// 32 different lines; the 256-bit stores of sm_100 (STG.256, `wide`: the caller's pointer is 32-byte aligned) halve the
+// number of instructions and tag lookups.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 template <typename OutT>
-__device__ __forceinline__ void store_row_chunk32(OutT* dst, const float* x);
+__device__ __forceinline__ void store_row_chunk32(OutT* dst, const float* x, bool wide);
 
 template <>
-__device__ __forceinline__ void store_row_chunk32<float>(float* dst, const float* x) {
+__device__ __forceinline__ void store_row_chunk32<float>(float* dst, const float* x, bool wide) {
+  if (wide) {
 #pragma unroll
-  for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+    for (int i = 0; i < 32; i += 8) st_global_v8(dst + i, reinterpret_cast<const uint32_t*>(x) + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+  }
 }
 template <>
-__device__ __forceinline__ void store_row_chunk32<__nv_bfloat16>(__nv_bfloat16* dst, const float* x) {
+__device__ __forceinline__ void store_row_chunk32<__nv_bfloat16>(__nv_bfloat16* dst, const float* x, bool wide) {
+  uint32_t v[16];
 #pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    uint4 v;
-    v.x = pack_bf16x2(x[i], x[i + 1]);
-    v.y = pack_bf16x2(x[i + 2], x[i + 3]);
-    v.z = pack_bf16x2(x[i + 4], x[i + 5]);
-    v.w = pack_bf16x2(x[i + 6], x[i + 7]);
-    *reinterpret_cast<uint4*>(dst + i) = v;
+  for (int i = 0; i < 16; ++i) v[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+  if (wide) {
+    st_global_v8(dst, v);
+    st_global_v8(dst + 16, v + 8);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) *reinterpret_cast<uint4*>(dst + 2 * i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
   }
 }
 
@@ -128,16 +196,37 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int T = p.T;
-  const int bh = blockIdx.y;
-  const int blk = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;  // heavy causal blocks first
   const int nkv = (T + kBlockN - 1) / kBlockN;
-  const int n0 = p.causal ? min(2 * blk + 1, nkv) : nkv;
-  const int n1 = p.causal ? min(2 * blk + 2, nkv) : nkv;
-  long long* const tr = (blockIdx.x == 0 && blockIdx.y == 0) ? p.trace : nullptr;
-#define FA_TRF(j_, e_) do { if (tr && (j_) < 16 && lane == 0) tr[(j_) * 16 + (e_)] = clock64(); } while (0)
+  const int nblk = p.nblk;
+  long long* const tr = blockIdx.x == 0 ? p.trace : nullptr;
+#define FA_TRF(j_, e_) do { if (tr && m == 0 && (j_) < 16 && lane == 0) tr[(j_) * 16 + (e_)] = clock64(); } while (0)
+
+  // The kernel is PERSISTENT: one CTA per SM draws work items (one 256-row query block of one head, heaviest causal blocks
+  // of a head first) from a global counter.  The K/V ring, the S / P / O hand-offs and their mbarrier parities run on
+  // RUNNING counters, so nothing drains between items: Q of the next item is loaded as soon as the last QK of this one has
+  // been issued (one K/V step before the item ends), its first scores are in TMEM before the softmax warps have stored O.
+  auto decode = [&](int item, int& bh, int& blk, int& n0, int& n1) {
+    bh = item / nblk;
+    const int x = item - bh * nblk;
+    blk = p.causal ? nblk - 1 - x : x;
+    n0 = p.causal ? min(2 * blk + 1, nkv) : nkv;
+    n1 = p.causal ? min(2 * blk + 2, nkv) : nkv;
+  };
+  auto next_item = [&](int m) {
+    mbar_wait(&bars.sched_full[m & 1], (m >> 1) & 1);
+    const int item = *reinterpret_cast<volatile int*>(&bars.sched_item[m & 1]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars.sched_empty[m & 1]);
+    return item;
+  };
 
   if (threadIdx.x == 0) {
     mbar_init(&bars.q_full, 1);
+    mbar_init(&bars.q_free, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.sched_full[i], 1);
+      mbar_init(&bars.sched_empty[i], 9);  // 8 softmax warps + the MMA warp
+    }
     for (int i = 0; i < S; ++i) {
       mbar_init(&bars.k_full[i], 1);
       mbar_init(&bars.k_empty[i], 1);
@@ -165,29 +254,51 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // and it must sit inside the role branch for ptxas to apply the budget to the right code.
     reg_dealloc<80>();
   if (warp == 8) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ scheduler + TMA producer
     if (lane == 0) {
       tma_prefetch_desc(&map_q);
       tma_prefetch_desc(&map_k);
       tma_prefetch_desc(&map_v);
-      mbar_arrive_expect_tx(&bars.q_full, 2 * Cfg::kTileBytes);
-      for (int t = 0; t < 2; ++t)
-        for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_3d(sQ + t * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_q, &bars.q_full, b * Cfg::kAtom,
-                      (2 * blk + t) * kBlockM, bh, kEvictFirst);
-      for (int j = 0; j < n1; ++j) {
-        const int st = j % S;
-        const uint32_t ph = (j / S) & 1;
-        mbar_wait(&bars.k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&bars.k_full[st], Cfg::kTileBytes);
-        for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_3d(sK + st * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_k, &bars.k_full[st], b * Cfg::kAtom, j * kBlockN,
-                      bh, kEvictLast);
-        mbar_wait(&bars.v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&bars.v_full[st], Cfg::kTileBytes);
-        for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_3d(sV + st * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_v, &bars.v_full[st], b * Cfg::kAtom, j * kBlockN,
-                      bh, kEvictLast);
+      int item = p.persistent ? atomicAdd(&p.sched[0], 1) : (int)blockIdx.x;
+      uint32_t jt = 0;  // running K/V step count: ring stage and parity
+      for (int m = 0;; ++m) {
+        mbar_wait(&bars.sched_empty[m & 1], ((m >> 1) & 1) ^ 1);  // every consumer has read item m - 2
+        bars.sched_item[m & 1] = item;
+        mbar_arrive(&bars.sched_full[m & 1]);
+        if (item >= p.total_items) break;
+        const int next = p.persistent ? atomicAdd(&p.sched[0], 1) : p.total_items;
+        int bh, blk, n0, n1;
+        decode(item, bh, blk, n0, n1);
+        if (m > 0) mbar_wait(&bars.q_free, (m - 1) & 1);  // the last QK of the previous item has read Q
+        mbar_arrive_expect_tx(&bars.q_full, 2 * Cfg::kTileBytes);
+        for (int t = 0; t < 2; ++t)
+          for (int b = 0; b < Cfg::kBoxes; ++b)
+            tma_load_3d(sQ + t * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_q, &bars.q_full, b * Cfg::kAtom,
+                        (2 * blk + t) * kBlockM, bh, kEvictFirst);
+        for (int j = 0; j < n1; ++j, ++jt) {
+          const int st = jt % S;
+          const uint32_t ph = (jt / S) & 1;
+          mbar_wait(&bars.k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&bars.k_full[st], Cfg::kTileBytes);
+          for (int b = 0; b < Cfg::kBoxes; ++b)
+            tma_load_3d(sK + st * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_k, &bars.k_full[st], b * Cfg::kAtom, j * kBlockN,
+                        bh, kEvictLast);
+          mbar_wait(&bars.v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&bars.v_full[st], Cfg::kTileBytes);
+          for (int b = 0; b < Cfg::kBoxes; ++b)
+            tma_load_3d(sV + st * Cfg::kTileBytes + b * Cfg::kBoxBytes, &map_v, &bars.v_full[st], b * Cfg::kAtom, j * kBlockN,
+                        bh, kEvictLast);
+        }
+        item = next;
+      }
+      if (p.persistent) {
+        // every CTA draws exactly one item >= total; the last CTA to get here leaves the slot zeroed for the next launch
+        __threadfence();
+        if (atomicAdd(&p.sched[1], 1) == (int)gridDim.x - 1) {
+          p.sched[0] = 0;
+          p.sched[1] = 0;
+          __threadfence();
+        }
       }
     }
   } else if (warp == 9) {
@@ -208,7 +319,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           umma_ss_w<kTF32>(tmem + t * 128, desc_advance(q0, off), desc_advance(k0, off), idesc_qk, kk > 0);
         }
       };
-      auto issue_pv = [&](int t, int st, bool acc, int j) {
+      auto issue_pv = [&](int t, int st, bool acc, uint32_t par) {
         const uint32_t va = sVa + st * Cfg::kTileBytes;
         // bf16: 16 key rows (2 KB) per k-step, 64-column atoms one box apart, 128B swizzle.
         // tf32: P is one tf32 per TMEM column, 8 columns per k-step; V: 8 key rows (1 KB) per k-step, 4-row groups
@@ -217,7 +328,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         constexpr int kPerPiece = Cfg::kKStepsPV / FA_FWD_PSIG;
 #pragma unroll
         for (int h = 0; h < FA_FWD_PSIG; ++h) {
-          mbar_wait_w(&bars.p_full[t][h], j & 1);  // piece h of P_t is in TMEM
+          mbar_wait_w(&bars.p_full[t][h], par);  // piece h of P_t is in TMEM
           tc_fence_after();
 #pragma unroll
           for (int k2 = 0; k2 < kPerPiece; ++k2) {
@@ -227,44 +338,57 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           }
         }
       };
-      mbar_wait_w(&bars.q_full, 0);
-      mbar_wait_w(&bars.k_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      umma_commit_w(&bars.s_full[0]);
-      issue_qk(1, 0);
-      umma_commit_w(&bars.s_full[1]);
-      umma_commit_w(&bars.k_empty[0]);
-      for (int j = 0; j < n1; ++j) {
-        const int st = j % S;
-        const uint32_t ph = (j / S) & 1;
-        const int jn = j + 1, stn = jn % S;
-        const uint32_t phn = (jn / S) & 1;
-        mbar_wait_w(&bars.v_full[st], ph);
-        if (j < n0) {
-          FA_TRF(j, 8);
-          issue_pv(0, st, j > 0, j);
-          umma_commit_w(&bars.o_full[0]);
+      uint32_t jt = 0;          // running K/V step count (ring stage / parity)
+      uint32_t c0 = 0, c1 = 0;  // running step counts of the two Q tiles (parities of their P / O hand-offs)
+      for (int m = 0;; ++m) {
+        // the max-reduction makes the item (and the loop bounds derived from it) provably warp-uniform for ptxas
+        const int item = __reduce_max_sync(0xffffffffu, next_item(m));
+        if (item >= p.total_items) break;
+        int bh, blk, n0, n1;
+        decode(item, bh, blk, n0, n1);
+        mbar_wait_w(&bars.q_full, m & 1);
+        mbar_wait_w(&bars.k_full[jt % S], (jt / S) & 1);
+        tc_fence_after();
+        issue_qk(0, jt % S);
+        umma_commit_w(&bars.s_full[0]);
+        issue_qk(1, jt % S);
+        umma_commit_w(&bars.s_full[1]);
+        umma_commit_w(&bars.k_empty[jt % S]);
+        if (n1 == 1) umma_commit_w(&bars.q_free);
+        for (int j = 0; j < n1; ++j, ++jt) {
+          const int st = jt % S;
+          const uint32_t ph = (jt / S) & 1;
+          const int jn = j + 1, stn = (jt + 1) % S;
+          const uint32_t phn = ((jt + 1) / S) & 1;
+          mbar_wait_w(&bars.v_full[st], ph);
+          if (j < n0) {
+            FA_TRF(j, 8);
+            issue_pv(0, st, j > 0, c0 & 1);
+            umma_commit_w(&bars.o_full[0]);
+            ++c0;
+          }
+          if (jn < n0) {
+            mbar_wait_w(&bars.k_full[stn], phn);
+            tc_fence_after();
+            issue_qk(0, stn);
+            umma_commit_w(&bars.s_full[0]);
+          }
+          FA_TRF(j, 9);
+          FA_TRF(j, 10);
+          issue_pv(1, st, j > 0, c1 & 1);
+          umma_commit_w(&bars.o_full[1]);
+          umma_commit_w(&bars.v_empty[st]);
+          ++c1;
+          if (jn < n1) {
+            mbar_wait_w(&bars.k_full[stn], phn);
+            tc_fence_after();
+            issue_qk(1, stn);
+            umma_commit_w(&bars.s_full[1]);
+            umma_commit_w(&bars.k_empty[stn]);
+            if (jn == n1 - 1) umma_commit_w(&bars.q_free);  // the last QK of the item: Q of the next one may land
+          }
+          FA_TRF(j, 11);
         }
-        if (jn < n0) {
-          mbar_wait_w(&bars.k_full[stn], phn);
-          tc_fence_after();
-          issue_qk(0, stn);
-          umma_commit_w(&bars.s_full[0]);
-        }
-        FA_TRF(j, 9);
-        FA_TRF(j, 10);
-        issue_pv(1, st, j > 0, j);
-        umma_commit_w(&bars.o_full[1]);
-        umma_commit_w(&bars.v_empty[st]);
-        if (jn < n1) {
-          mbar_wait_w(&bars.k_full[stn], phn);
-          tc_fence_after();
-          issue_qk(1, stn);
-          umma_commit_w(&bars.s_full[1]);
-          umma_commit_w(&bars.k_empty[stn]);
-        }
-        FA_TRF(j, 11);
       }
     }
   }
@@ -276,180 +400,190 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     const uint32_t tS = tmem + t * 128 + lane_base;
     const uint32_t tO = tmem + 256 + t * 128 + lane_base;
-    const int qt = 2 * blk + t;
-    const int nt = t == 0 ? n0 : n1;
-    const int row_g = qt * kBlockM + r;
     const float c2 = p.scale_log2;
-    float m_ref = -INFINITY;   // reference max (raw S units) used in the exponent
-    float m_true = -INFINITY;  // true running row max (only needed for the FA-1 statistics)
-    float l = 0.f;
-    // dropout: one 32-bit hash per 2 x 2 block of (row, key); this thread uses the two bytes of its row parity
-    const uint32_t drop_rowkey = drop_row_key(drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh), uint32_t(row_g) >> 1);
     const uint32_t drop_thr = p.drop.thr;
-    const uint32_t drop_b0 = (row_g & 1) * 2;  // bytes b0, b0 + 1 of a block word belong to this row
-    const uint32_t drop_sel2 = drop_sel_pair(drop_b0, drop_b0 + 1), drop_selA = drop_sel_word(drop_b0),
-                   drop_selB = drop_sel_word(drop_b0 + 1);
+    uint32_t cs = 0;  // running step count of this Q tile
+    for (int m = 0;; ++m) {
+      const int item = next_item(m);
+      if (item >= p.total_items) break;
+      int bh, blk, n0, n1;
+      decode(item, bh, blk, n0, n1);
+      const int qt = 2 * blk + t;
+      const int nt = t == 0 ? n0 : n1;
+      const int row_g = qt * kBlockM + r;
+      float m_ref = -INFINITY;   // reference max (raw S units) used in the exponent
+      float m_true = -INFINITY;  // true running row max (only needed for the FA-1 statistics)
+      float l = 0.f;
+      // dropout: one 32-bit hash per 2 x 2 block of (row, key); this thread uses the two bytes of its row parity
+      const uint32_t drop_rowkey = drop_row_key(drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh), uint32_t(row_g) >> 1);
+      const uint32_t drop_b0 = (row_g & 1) * 2;  // bytes b0, b0 + 1 of a block word belong to this row
+      const uint32_t drop_sel2 = drop_sel_pair(drop_b0, drop_b0 + 1), drop_selA = drop_sel_word(drop_b0),
+                     drop_selB = drop_sel_word(drop_b0 + 1);
 
-    for (int j = 0; j < nt; ++j) {
-      mbar_wait(&bars.s_full[t], j & 1);
-      tc_fence_after();
-      if ((warp & 3) == 0) FA_TRF(j, 4 * t + 0);
-      float s[128];
-      {
-        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
-        tmem_ld_x32(tS + 0, sr + 0);
-        tmem_ld_x32(tS + 32, sr + 32);
-        tmem_ld_x32(tS + 64, sr + 64);
-        tmem_ld_x32(tS + 96, sr + 96);
-        tmem_wait_ld();
-      }
-      if ((warp & 3) == 0) FA_TRF(j, 4 * t + 1);
-      const bool diag = p.causal && (j == qt);
-      const bool tail = (j == nkv - 1) && (T - j * kBlockN < kBlockN);
-      if (diag || tail) {
-        int limit = 127;
-        if (diag) limit = r;
-        if (tail) limit = min(limit, T - 1 - j * kBlockN);
-#pragma unroll
-        for (int c = 0; c < 128; ++c)
-          if (c > limit) s[c] = -INFINITY;
-      }
-      // one chunk = 32 score columns: exponentials against the reference -nm / c2, row-sum partials, packed P words
-      constexpr int kPk = kTF32 ? 32 : 16;
-      const float2 c2v = make_float2(c2, c2);
-      auto exp_chunk = [&](const int q4, const float nm_, uint32_t* pk, float2& la, float2& lb) {
-        const float2 nmv = make_float2(nm_, nm_);
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const int cc = q4 * 32 + c;
-          const float2 x0 = ffma2(make_float2(s[cc], s[cc + 1]), c2v, nmv);
-          const float2 x1 = ffma2(make_float2(s[cc + 2], s[cc + 3]), c2v, nmv);
-          float2 p0 = make_float2(ex2_mixed(x0.x, cc), ex2_mixed(x0.y, cc + 1));
-          float2 p1;
-          if (FA_EX2_POLY2_PERIOD > 0 && ((cc >> 2) % (FA_EX2_POLY2_PERIOD > 0 ? FA_EX2_POLY2_PERIOD : 1)) == 0) p1 = ex2_poly2(x1);
-          else p1 = make_float2(ex2_mixed(x1.x, cc + 2), ex2_mixed(x1.y, cc + 3));
-          if constexpr (kTF32) {  // round P to tf32 once, so that the row sum and the PV product see the same values
-            p0 = make_float2(round_tf32(p0.x), round_tf32(p0.y));
-            p1 = make_float2(round_tf32(p1.x), round_tf32(p1.y));
-          }
-          la = fadd2(la, p0);
-          lb = fadd2(lb, p1);
-          if constexpr (kTF32) {
-            pk[c] = __float_as_uint(p0.x);
-            pk[c + 1] = __float_as_uint(p0.y);
-            pk[c + 2] = __float_as_uint(p1.x);
-            pk[c + 3] = __float_as_uint(p1.y);
-          } else {
-            pk[c >> 1] = pack_bf16x2(p0.x, p0.y);
-            pk[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
-          }
-          if constexpr (kDrop) {  // la / lb are the undropped row sum; only P fed to the PV product is thinned
-            // the two lanes of a row pair need the same two block words: each hashes one, a shuffle gives the other
-            const uint32_t j2 = (uint32_t(j * kBlockN + cc) >> 1) + (lane & 1);
-            const uint32_t mine = drop_keep_word(drop_mix(drop_rowkey ^ (j2 * kDropColMul)), drop_thr);
-            const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
-            const uint32_t w0 = (lane & 1) ? theirs : mine, w1 = (lane & 1) ? mine : theirs;  // columns cc,cc+1 | cc+2,cc+3
+      for (int j = 0; j < nt; ++j, ++cs) {
+        mbar_wait(&bars.s_full[t], cs & 1);
+        tc_fence_after();
+        if ((warp & 3) == 0) FA_TRF(j, 4 * t + 0);
+        float s[128];
+        {
+          uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+          tmem_ld_x32(tS + 0, sr + 0);
+          tmem_ld_x32(tS + 32, sr + 32);
+          tmem_ld_x32(tS + 64, sr + 64);
+          tmem_ld_x32(tS + 96, sr + 96);
+          tmem_wait_ld();
+        }
+        if ((warp & 3) == 0) FA_TRF(j, 4 * t + 1);
+        const bool diag = p.causal && (j == qt);
+        const bool tail = (j == nkv - 1) && (T - j * kBlockN < kBlockN);
+        if (diag || tail) {
+          int limit = 127;
+          if (diag) limit = r;
+          if (tail) limit = min(limit, T - 1 - j * kBlockN);
+  #pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (c > limit) s[c] = -INFINITY;
+        }
+        // one chunk = 32 score columns: exponentials against the reference -nm / c2, row-sum partials, packed P words
+        constexpr int kPk = kTF32 ? 32 : 16;
+        const float2 c2v = make_float2(c2, c2);
+        auto exp_chunk = [&](const int q4, const float nm_, uint32_t* pk, float2& la, float2& lb) {
+          const float2 nmv = make_float2(nm_, nm_);
+  #pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const int cc = q4 * 32 + c;
+            const float2 x0 = ffma2(make_float2(s[cc], s[cc + 1]), c2v, nmv);
+            const float2 x1 = ffma2(make_float2(s[cc + 2], s[cc + 3]), c2v, nmv);
+            float2 p0 = make_float2(ex2_mixed(x0.x, cc), ex2_mixed(x0.y, cc + 1));
+            float2 p1;
+            if (FA_EX2_POLY2_PERIOD > 0 && ((cc >> 2) % (FA_EX2_POLY2_PERIOD > 0 ? FA_EX2_POLY2_PERIOD : 1)) == 0) p1 = ex2_poly2(x1);
+            else p1 = make_float2(ex2_mixed(x1.x, cc + 2), ex2_mixed(x1.y, cc + 3));
+            if constexpr (kTF32) {  // round P to tf32 once, so that the row sum and the PV product see the same values
+              p0 = make_float2(round_tf32(p0.x), round_tf32(p0.y));
+              p1 = make_float2(round_tf32(p1.x), round_tf32(p1.y));
+            }
+            la = fadd2(la, p0);
+            lb = fadd2(lb, p1);
             if constexpr (kTF32) {
-              pk[c] &= drop_prmt(w0, drop_selA);
-              pk[c + 1] &= drop_prmt(w0, drop_selB);
-              pk[c + 2] &= drop_prmt(w1, drop_selA);
-              pk[c + 3] &= drop_prmt(w1, drop_selB);
+              pk[c] = __float_as_uint(p0.x);
+              pk[c + 1] = __float_as_uint(p0.y);
+              pk[c + 2] = __float_as_uint(p1.x);
+              pk[c + 3] = __float_as_uint(p1.y);
             } else {
-              pk[c >> 1] &= drop_prmt(w0, drop_sel2);
-              pk[(c >> 1) + 1] &= drop_prmt(w1, drop_sel2);
+              pk[c >> 1] = pack_bf16x2(p0.x, p0.y);
+              pk[(c >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+            }
+            if constexpr (kDrop) {  // la / lb are the undropped row sum; only P fed to the PV product is thinned
+              // the two lanes of a row pair need the same two block words: each hashes one, a shuffle gives the other
+              const uint32_t j2 = (uint32_t(j * kBlockN + cc) >> 1) + (lane & 1);
+              const uint32_t mine = drop_keep_word(drop_mix(drop_rowkey ^ (j2 * kDropColMul)), drop_thr);
+              const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
+              const uint32_t w0 = (lane & 1) ? theirs : mine, w1 = (lane & 1) ? mine : theirs;  // columns cc,cc+1 | cc+2,cc+3
+              if constexpr (kTF32) {
+                pk[c] &= drop_prmt(w0, drop_selA);
+                pk[c + 1] &= drop_prmt(w0, drop_selB);
+                pk[c + 2] &= drop_prmt(w1, drop_selA);
+                pk[c + 3] &= drop_prmt(w1, drop_selB);
+              } else {
+                pk[c >> 1] &= drop_prmt(w0, drop_sel2);
+                pk[(c >> 1) + 1] &= drop_prmt(w1, drop_sel2);
+              }
             }
           }
-        }
-      };
-      auto store_chunk = [&](const int q4, const uint32_t* pk) {
-        if constexpr (kTF32) tmem_st_x32(tS + q4 * 32, pk);   // tf32: P fills all 128 columns of S
-        else tmem_st_x16(tS + q4 * 16, pk);                    // bf16: two probabilities per column
-      };
-      auto signal_p = [&](const int h) {  // piece h of P_t is complete in TMEM
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.p_full[t][h]);
-      };
+        };
+        auto store_chunk = [&](const int q4, const uint32_t* pk) {
+          if constexpr (kTF32) tmem_st_x32(tS + q4 * 32, pk);   // tf32: P fills all 128 columns of S
+          else tmem_st_x16(tS + q4 * 16, pk);                    // bf16: two probabilities per column
+        };
+        auto signal_p = [&](const int h) {  // piece h of P_t is complete in TMEM
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.p_full[t][h]);
+        };
 
-      // Chunk 0 goes first, against the reference max of the previous step (speculation: independent of the max tree
-      // below, so ptxas interleaves the two).  j == 0 has no reference yet (m_ref = -inf gives inf / NaN here): it always
-      // takes the recompute branch, like any step whose row max outgrows the reference by more than 2^8.
-      uint32_t pk0[kPk];
-      float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
-      float nm = -m_ref * c2;
-      if (FA_FWD_SPEC) exp_chunk(0, nm, pk0, la, lb);
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
-#pragma unroll
-      for (int c = 4; c < 128; c += 4) {
-        mx0 = fmaxf(mx0, s[c]);
-        mx1 = fmaxf(mx1, s[c + 1]);
-        mx2 = fmaxf(mx2, s[c + 2]);
-        mx3 = fmaxf(mx3, s[c + 3]);
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      m_true = fmaxf(m_true, mx);
-      const bool need = (j == 0) || (mx - m_ref) * c2 > 8.f;
-      if (__any_sync(0xffffffffu, need)) {
-        const float m_new = fmaxf(m_ref, mx);
-        if (j > 0) {
-          // O_t must be quiescent: PV(t, j-1) retired, PV(t, j) not yet issued (it waits for our P).
-          mbar_wait(&bars.o_full[t], (j - 1) & 1);
-          tc_fence_after();
-          const float f = ex2_approx((m_ref - m_new) * c2);
-          l *= f;
-#pragma unroll
-          for (int c0 = 0; c0 < D; c0 += 32) {
-            uint32_t orr[32];
-            tmem_ld_x32(tO + c0, orr);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
-            tmem_st_x32(tO + c0, orr);
-          }
-        }
-        m_ref = m_new;
-        nm = -m_ref * c2;
-        la = make_float2(0.f, 0.f);
-        lb = make_float2(0.f, 0.f);
+        // Chunk 0 goes first, against the reference max of the previous step (speculation: independent of the max tree
+        // below, so ptxas interleaves the two).  j == 0 has no reference yet (m_ref = -inf gives inf / NaN here): it always
+        // takes the recompute branch, like any step whose row max outgrows the reference by more than 2^8.
+        uint32_t pk0[kPk];
+        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+        float nm = -m_ref * c2;
         if (FA_FWD_SPEC) exp_chunk(0, nm, pk0, la, lb);
+        float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+  #pragma unroll
+        for (int c = 4; c < 128; c += 4) {
+          mx0 = fmaxf(mx0, s[c]);
+          mx1 = fmaxf(mx1, s[c + 1]);
+          mx2 = fmaxf(mx2, s[c + 2]);
+          mx3 = fmaxf(mx3, s[c + 3]);
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        m_true = fmaxf(m_true, mx);
+        const bool need = (j == 0) || (mx - m_ref) * c2 > 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = fmaxf(m_ref, mx);
+          if (j > 0) {
+            // O_t must be quiescent: PV(t, j-1) retired, PV(t, j) not yet issued (it waits for our P).
+            mbar_wait(&bars.o_full[t], (cs - 1) & 1);
+            tc_fence_after();
+            const float f = ex2_approx((m_ref - m_new) * c2);
+            l *= f;
+  #pragma unroll
+            for (int c0 = 0; c0 < D; c0 += 32) {
+              uint32_t orr[32];
+              tmem_ld_x32(tO + c0, orr);
+              tmem_wait_ld();
+  #pragma unroll
+              for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
+              tmem_st_x32(tO + c0, orr);
+            }
+          }
+          m_ref = m_new;
+          nm = -m_ref * c2;
+          la = make_float2(0.f, 0.f);
+          lb = make_float2(0.f, 0.f);
+          if (FA_FWD_SPEC) exp_chunk(0, nm, pk0, la, lb);
+        }
+        if (!FA_FWD_SPEC) exp_chunk(0, nm, pk0, la, lb);
+        if ((warp & 3) == 0) FA_TRF(j, 4 * t + 2);
+        store_chunk(0, pk0);
+  #pragma unroll
+        for (int q4 = 1; q4 < 4; ++q4) {
+          uint32_t pk[kPk];
+          exp_chunk(q4, nm, pk, la, lb);
+          store_chunk(q4, pk);
+          if (FA_FWD_PSIG == 2 && q4 == 1) signal_p(0);
+        }
+        signal_p(FA_FWD_PSIG - 1);
+        l += (la.x + la.y) + (lb.x + lb.y);
+        if ((warp & 3) == 0) FA_TRF(j, 4 * t + 3);
       }
-      if (!FA_FWD_SPEC) exp_chunk(0, nm, pk0, la, lb);
-      if ((warp & 3) == 0) FA_TRF(j, 4 * t + 2);
-      store_chunk(0, pk0);
-#pragma unroll
-      for (int q4 = 1; q4 < 4; ++q4) {
-        uint32_t pk[kPk];
-        exp_chunk(q4, nm, pk, la, lb);
-        store_chunk(q4, pk);
-        if (FA_FWD_PSIG == 2 && q4 == 1) signal_p(0);
-      }
-      signal_p(FA_FWD_PSIG - 1);
-      l += (la.x + la.y) + (lb.x + lb.y);
-      if ((warp & 3) == 0) FA_TRF(j, 4 * t + 3);
-    }
 
-    // epilogue: O_t / l -> global, statistics
-    mbar_wait(&bars.o_full[t], (nt - 1) & 1);
-    tc_fence_after();
-    const float inv_l = (kDrop ? p.drop.keep_scale : 1.f) / l;
-    const bool row_ok = row_g < T;
-    OutT* orow = reinterpret_cast<OutT*>(p.o) + ((size_t)bh * T + (row_ok ? row_g : 0)) * D;
+
+      // epilogue of the item: O_t / l -> global, statistics.  (The MMA warp already has the first scores of the next item
+      // in S_t; it restarts O_t only after the next P hand-off of this group, i.e. after this code.)
+      mbar_wait(&bars.o_full[t], (cs - 1) & 1);
+      tc_fence_after();
+      const float inv_l = (kDrop ? p.drop.keep_scale : 1.f) / l;
+      const bool row_ok = row_g < T;
+      OutT* orow = reinterpret_cast<OutT*>(p.o) + ((size_t)bh * T + (row_ok ? row_g : 0)) * D;
 #pragma unroll
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      uint32_t orr[32];
-      tmem_ld_x32(tO + c0, orr);
-      tmem_wait_ld();
-      float x[32];
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t orr[32];
+        tmem_ld_x32(tO + c0, orr);
+        tmem_wait_ld();
+        float x[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(orr[i]) * inv_l;
-      if (row_ok) store_row_chunk32<OutT>(orow + c0, x);
-    }
-    if (row_ok) {
-      const size_t idx = (size_t)bh * T + row_g;
-      if (p.lse) p.lse[idx] = m_ref * p.tau + logf(l);
-      if (p.m_out) p.m_out[idx] = m_true * p.tau;
-      if (p.l_out) p.l_out[idx] = l * expf((m_ref - m_true) * p.tau);
+        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(orr[i]) * inv_l;
+        if (row_ok) store_row_chunk32<OutT>(orow + c0, x, p.wide_stores != 0);
+      }
+      tc_fence_before();  // orders the TMEM reads above before the next p_full arrival
+      if (row_ok) {
+        const size_t idx = (size_t)bh * T + row_g;
+        if (p.lse) p.lse[idx] = m_ref * p.tau + logf(l);
+        if (p.m_out) p.m_out[idx] = m_true * p.tau;
+        if (p.l_out) p.l_out[idx] = l * expf((m_ref - m_true) * p.tau);
+      }
     }
   }
 
@@ -472,6 +606,15 @@ cudaError_t launch_fwd_impl(const void* q, const void* k, const void* v, void* o
   FwdParams p;
   p.T = T;
   p.BH = BH;
+  p.nblk = (T + 2 * kBlockM - 1) / (2 * kBlockM);
+  p.total_items = BH * p.nblk;
+  p.persistent = fwd_persistent() ? 1 : 0;
+  p.sched = nullptr;
+  if (p.persistent) {
+    p.sched = fwd_sched_slot();
+    if (!p.sched) return cudaErrorInvalidValue;
+  }
+  p.wide_stores = (reinterpret_cast<uintptr_t>(o) & 31) == 0 ? 1 : 0;
   p.causal = causal ? 1 : 0;
   p.tau = sqrtf(1.0f / (float)D);
   p.scale_log2 = p.tau * 1.4426950408889634f;
@@ -481,7 +624,8 @@ cudaError_t launch_fwd_impl(const void* q, const void* k, const void* v, void* o
   p.l_out = l_out;
   p.drop = drop;
   p.trace = g_fwd_trace;
-  dim3 grid((T + 2 * kBlockM - 1) / (2 * kBlockM), BH);
+  // persistent: one CTA per SM (1 CTA fits: ~200 KB of shared memory, all 512 TMEM columns), items drawn dynamically
+  const unsigned grid = p.persistent ? (unsigned)std::min(p.total_items, fwd_num_sms()) : (unsigned)p.total_items;
   fa_fwd_kernel<D, OutT, kTF32, kDrop><<<grid, kFwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, p);
   return cudaGetLastError();
 }
@@ -513,7 +657,6 @@ bool tc_fwd_tf32_supported(int d) { return d == 32 || d == 64; }
 cudaError_t tc_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, bool o_is_f32,
                    float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st,
                    Dropout drop) {
-  if (BH > 65535) return cudaErrorInvalidValue;
   if (d == 128 && fwd_pair_enabled()) return tc_fwd_pair(q, k, v, o, o_is_f32, lse, m_out, l_out, BH, T, causal, st, drop);
   if (d == 128) {
     return o_is_f32 ? launch_fwd<128, float, false>(q, k, v, o, lse, m_out, l_out, BH, T, causal, drop, st)

@@ -26,6 +26,8 @@ cudaError_t simt_bwd(const float* q, const float* k, const float* v, const float
 // lse = natural-log logsumexp of tau*QK^T per row (the FA-2 "L"); m_out/l_out (optional) give the
 // FA-1 pair (row max of tau*S, sum exp(tau*S - m)).
 bool tc_fwd_supported(int d);
+void tc_fwd_set_persistent(int on);  // A/B switch: 0 = one CTA per 256-row block (default: persistent, FA_B200_FWD_PERSISTENT)
+int tc_fwd_get_persistent();
 cudaError_t tc_fwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, void* o, bool o_is_f32,
                    float* lse, float* m_out, float* l_out, int BH, int T, int d, bool causal, cudaStream_t st,
                    Dropout drop = kNoDropout);

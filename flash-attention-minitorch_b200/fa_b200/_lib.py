@@ -122,6 +122,11 @@ def load_library() -> ctypes.CDLL:
         lib.fa_b200_set_fwd_pair.argtypes = [ci]
         lib.fa_b200_set_fwd_pair.restype = None
         lib.fa_b200_get_fwd_pair.restype = ci
+    if hasattr(lib, "fa_b200_set_fwd_persistent"):
+        lib.fa_b200_set_fwd_persistent.argtypes = [ci]
+        lib.fa_b200_set_fwd_persistent.restype = None
+        lib.fa_b200_get_fwd_persistent.argtypes = []
+        lib.fa_b200_get_fwd_persistent.restype = ci
     if hasattr(lib, "fa_b200_set_bwd_persistent"):
         lib.fa_b200_set_bwd_persistent.argtypes = [ci]
         lib.fa_b200_set_bwd_persistent.restype = None

@@ -139,6 +139,11 @@ int fa_b200_get_fwd_pair(void);
  * measured 4-6 % slower at config 3.  Default 1 (environment: FA_B200_BWD_PERSISTENT=0).  A tuning / test knob. */
 void fa_b200_set_bwd_persistent(int on);
 int fa_b200_get_bwd_persistent(void);
+/* The same for the tensor-core forward (bf16 d = 64, 128; tf32 d = 32, 64): persistent by default, work item = one 256-row
+ * query block of one head, the work-item counter lives in a library-owned slot that the kernel leaves zeroed.  on = 0
+ * launches one CTA per block (bit-identical results: no cross-CTA arithmetic).  Environment: FA_B200_FWD_PERSISTENT=0. */
+void fa_b200_set_fwd_persistent(int on);
+int fa_b200_get_fwd_persistent(void);
 /* Release the device arena held by the host-pointer API. */
 void fa_b200_release_arena(void);
 

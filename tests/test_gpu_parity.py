@@ -214,6 +214,35 @@ def test_pair_forward_kernel_lazy_rescale_and_dropout(cuda_device, pair_forward)
     assert rel_inf(o.float().cpu().numpy(), o_r) <= BF16_REL and np.abs(lse.cpu().numpy() - L_r).max() <= 2e-3
 
 
+@pytest.mark.parametrize("BH,T,d,causal,p_drop,bf16", [(40, 1024, 128, True, 0.0, True), (40, 1024, 128, False, 0.0, True),
+                                                      (5, 2125, 128, True, 0.0, True), (400, 200, 128, True, 0.0, True),
+                                                      (37, 700, 64, True, 0.0, True), (21, 1100, 128, True, 0.1, True),
+                                                      (3, 4224, 128, True, 0.0, True), (30, 1000, 64, False, 0.0, False),
+                                                      (50, 600, 32, True, 0.0, False)])
+def test_persistent_forward_equals_one_cta_per_block(cuda_device, BH, T, d, causal, p_drop, bf16):
+    """The persistent forward (one CTA per SM draws 256-row query blocks from a library-owned counter that the kernel leaves
+    zeroed; K/V ring, S / P / O hand-offs run on across items) against the same kernel launched with one CTA per block:
+    O, L and the FA-1 statistics bit-identical (no cross-CTA arithmetic), twice in a row (the counter slot was reset).
+    bf16 and tf32 (fp32 storage) kernels; many more items than SMs, one-step items, ragged T, dropout."""
+    import torch
+    lib = _lib.load_library()
+    q, k, v, g = _bf16_problem(BH, T, d, seed=700 + BH + T)
+    tq, tk, tv = (_to_dev(x, cuda_device, bf16=bf16) for x in (q, k, v))
+    kw = dict(p_drop=p_drop, seed=99) if p_drop else {}
+    prec = dict() if bf16 else dict(precision=_lib.FA_PREC_TF32_TC)
+    prev = lib.fa_b200_get_fwd_persistent()
+    try:
+        lib.fa_b200_set_fwd_persistent(0)
+        ref = device.flash_attn_fwd(tq, tk, tv, causal, want_lm=not p_drop, **kw, **prec)
+        lib.fa_b200_set_fwd_persistent(1)
+        for _ in range(2):
+            got = device.flash_attn_fwd(tq, tk, tv, causal, want_lm=not p_drop, **kw, **prec)
+            for a, b in zip(got, ref):
+                assert torch.equal(a, b)
+    finally:
+        lib.fa_b200_set_fwd_persistent(prev)
+
+
 @pytest.mark.parametrize("BH,T,d,causal,p_drop", [(40, 1024, 128, True, 0.0), (40, 1024, 128, False, 0.0), (5, 2125, 128, True, 0.0),
                                                  (300, 128, 128, True, 0.0), (37, 700, 64, True, 0.0), (21, 1100, 128, True, 0.1),
                                                  (3, 4224, 128, True, 0.0)])
