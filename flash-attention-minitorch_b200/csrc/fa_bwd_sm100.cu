@@ -49,7 +49,9 @@ namespace fa {
 namespace {
 
 constexpr int kTile = 128;
-constexpr int kMmaUnroll = FA_BWD_MMA_UNROLL;
+#ifndef FA_BWD_MMA_UNROLL_DROP
+#define FA_BWD_MMA_UNROLL_DROP 1  // the dropout variant (hash-heavy compute warps share the issue slots), config 4: 1: 30.4-31.0 ms, 2: 30.7-31.2, 4: 36.5, 8: 35.0
+#endif
 long long* g_bwd_trace = nullptr;  // developer timeline buffer (tc_bwd_set_trace)
 int g_bwd_trace_t0 = 0;            // first tile pair of CTA 0 that the timeline records
 int g_bwd_persistent = -1;         // -1: FA_B200_BWD_PERSISTENT (read once), default on
@@ -324,6 +326,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // so the boundary runs the same (instruction-cache-hot) code as the steady state -- a separate head / tail path was
     // measured at ~4400 cycles for its 24 MMAs (cold code: the kernel is 90 KB, the SM's instruction cache 32 KB).  The k-steps
     // are rolled loops for the same reason: the issue code of a step is ~1 KB instead of ~10 KB.
+    constexpr int kMmaUnroll = kDrop ? FA_BWD_MMA_UNROLL_DROP : D == 64 ? 8 : FA_BWD_MMA_UNROLL;  // d = 64: 4.15 (8) against 4.29 ms (4)
     constexpr uint32_t idesc_sT = make_idesc(kFmtBF16, 128, 128, 0, 0);  // K-major x K-major
     constexpr uint32_t idesc_acc = make_idesc(kFmtBF16, 128, D, 0, 1);   // (TMEM | K-major) x MN-major
     constexpr uint32_t idesc_dq = make_idesc(kFmtBF16, 128, D, 1, 1);    // MN-major x MN-major
