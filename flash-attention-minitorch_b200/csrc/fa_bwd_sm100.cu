@@ -119,7 +119,8 @@ struct BwdCfg {
   static constexpr int kOffDS = kOffDO + kDoStages * kTileBytes;  // dS^T: 128 x 128 bf16 = two boxes
   static constexpr int kOffStage = kOffDS + 2 * kBoxBytes;        // dQ staging: 2 slabs
   static constexpr int kOffStats = kOffStage + 2 * kStageBytes;   // [2 stages][L, delta][128] fp32
-  static constexpr int kOffBars = kOffStats + 2 * 2 * 128 * 4;
+  static constexpr int kOffRowKeys = kOffStats + 2 * 2 * 128 * 4;  // dropout: [2 stages][64 query pairs] row keys of the mask hash
+  static constexpr int kOffBars = kOffRowKeys + 2 * 64 * 4;
   static constexpr int kSmemBytes = kOffBars + 320;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
   // TMEM columns: R0 = S(i) then dP(i); R1 = dQ(i-1) then P(i)
@@ -192,6 +193,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   uint8_t* sDS = smem + Cfg::kOffDS;
   uint8_t* sStage = smem + Cfg::kOffStage;
   float* sStats = reinterpret_cast<float*>(smem + Cfg::kOffStats);
+  uint32_t* sRowKeys = reinterpret_cast<uint32_t*>(smem + Cfg::kOffRowKeys);
   BwdBarriers& bars = *reinterpret_cast<BwdBarriers*>(smem + Cfg::kOffBars);
 
   const int warp = threadIdx.x >> 5;
@@ -479,6 +481,14 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const int i = i0 + il;
         const float* sL = sStats + (t & 1) * 256 + g * 64;  // -L log2(e) of the 64 query columns (-inf on padding rows)
         const float* sD = sL + 128;                         // -tau * delta
+        if constexpr (kDrop) {
+          // The first round of the mask hash (row key of a query pair) does not depend on the key row: the 64 keys of this
+          // Q tile are hashed once per CTA -- one each by the first 64 compute threads -- instead of once per thread and
+          // word (half of the hash instructions of this loop).  Two buffers: after the barrier a warp is at most one tile
+          // pair ahead of the slowest one.
+          if (threadIdx.x < 64) sRowKeys[(t & 1) * 64 + threadIdx.x] = drop_row_key(drop_head, (uint32_t(i * kTile) >> 1) + threadIdx.x);
+          named_bar_sync(2, 256);
+        }
         // ---- P^T = exp2(c * S^T - L)
         mbar_wait(&bars.q_full[t & 1], (t >> 1) & 1);  // L / delta of this Q tile have landed
         mbar_wait(&bars.s_full, t & 1);
@@ -529,11 +539,11 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         FA_TR2(t, 2);
         if constexpr (kDrop) {  // P^T o keep feeds dV; pk[] itself stays undropped for dS
           uint32_t pd[32];
-          const uint32_t i2 = uint32_t(i * kTile + g * 64) >> 1;
+          const uint32_t* rk = sRowKeys + (t & 1) * 64 + g * 32 + (lane & 1);
 #pragma unroll
           for (int c = 0; c < 64; c += 4) {
             // the two lanes of a key pair need the same block words: each hashes one, a shuffle gives the other
-            const uint32_t mine = drop_keep_word(drop_mix(drop_row_key(drop_head, i2 + (c >> 1) + (lane & 1)) ^ drop_colterm), drop_thr);
+            const uint32_t mine = drop_keep_word(drop_mix(rk[c >> 1] ^ drop_colterm), drop_thr);
             const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
             const uint32_t w0 = (lane & 1) ? theirs : mine, w1 = (lane & 1) ? mine : theirs;  // queries c,c+1 | c+2,c+3
             pd[c >> 1] = pk[c >> 1] & drop_prmt(w0, drop_sel2);
