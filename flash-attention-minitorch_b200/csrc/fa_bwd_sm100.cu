@@ -3,8 +3,9 @@
 // Replaces the reference kernels src/flash_attn2_bw.cu:21-263 (FA-2 backward: P = exp(S - L), atomicAdd
 // into dQ) and src/flash_attn_bw.cu:21-261 (FA-1 backward; its (l, m) pair is folded into L up front).
 //
-// One CTA owns one 128-row K/V tile j of one (batch, head) and streams the Q/dO tiles i that attend
-// to it (i >= j when causal).  All five contractions of a tile pair run on the tensor pipe, with the
+// A work item is one 128-row K/V tile j of one (batch, head): the CTA streams the Q/dO tiles i that attend to it
+// (i >= j when causal).  The kernel is persistent -- one CTA per SM draws items from a counter and keeps its pipelines
+// running across them, see the comment above fa_bwd_kernel.  All five contractions of a tile pair run on the tensor pipe, with the
 // score matrices held TRANSPOSED (lanes = key rows) so that P^T is directly the TMEM A operand of dV:
 //     S^T  = K_j  Q_i^T          (smem x smem  -> TMEM)        P^T = exp2(c S^T - L_i)        [registers]
 //     dP^T = V_j  dO_i^T         (smem x smem  -> TMEM)        dS^T = tau P^T o (dP^T - D_i)   [registers]
@@ -16,15 +17,15 @@
 // MN-major A of dQ; K_j is the K-major A of S^T and the MN-major B of dQ.  Nothing is transposed in memory.
 //
 // Warp roles (512 threads): warps 0-7 compute (thread = one key row x 64 query columns), warps 8-11 drain
-// dQ (TMEM -> swizzled smem -> cp.reduce.async.bulk), warp 12 TMA producer, warp 13 MMA issuer.
+// dQ (TMEM -> swizzled smem -> cp.reduce.async.bulk), warp 12 scheduler + TMA producer, warp 13 MMA issuer.
 // TMEM (512 columns at d = 128): R0 | R1 | dV | dK.  The two 128-column regions R0 / R1 are time-shared by FOUR tenants so
 // that no product ever waits for the drain of another (round 1 kept dQ in the dP columns, which put the chain
 // dS(i) -> dQ(i) -> drain -> dP(i+1) -> dS(i+1) on the critical path, ~4100 cycles per tile pair):
 //     R0:  S(i)  -> [compute warps pull it into registers at the start of the P phase] -> dP(i) -> [pulled into registers
 //          at the start of the dS phase] -> S(i+1)
 //     R1:  dQ(i-1) -> [drain warps pull it out] -> P(i) (bf16, stored at the END of the P phase) -> [dV(i) reads it] -> dQ(i)
-// MMA issue order per step  dQ(i-1) dP(i) dK(i-1) dV(i) S(i+1):  every wait of the issuing warp is for an event that lies
-// early in the compute warps' phase structure, so the tensor pipe runs ahead of them.
+// MMA issue order per step  dK(i-1) dQ(i-1) dP(i) dV(i) S(i+1)  (S(i+1) may be S(0) of the next work item):  every wait of
+// the issuing warp is for an event that lies early in the compute warps' phase structure, so the tensor pipe runs ahead.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -40,6 +41,9 @@
 #ifndef FA_BWD_PREFETCH_KV
 #define FA_BWD_PREFETCH_KV 1  // L2 prefetch of the next item's K / V tiles
 #endif
+#ifndef FA_BWD_MMA_UNROLL_DROP
+#define FA_BWD_MMA_UNROLL_DROP 1  // the dropout variant (hash-heavy compute warps share the issue slots), config 4: 1: 30.4-31.0 ms, 2: 30.7-31.2, 4: 36.5, 8: 35.0
+#endif
 #ifndef FA_BWD_MMA_UNROLL
 #define FA_BWD_MMA_UNROLL 4  // k-step loops of the MMA issuer: 1 = rolled (7.1 ms: issue-bound), 2: 6.7, 4: 6.45-6.65, 8 = fully unrolled: 6.7-6.85
 #endif
@@ -49,9 +53,6 @@ namespace fa {
 namespace {
 
 constexpr int kTile = 128;
-#ifndef FA_BWD_MMA_UNROLL_DROP
-#define FA_BWD_MMA_UNROLL_DROP 1  // the dropout variant (hash-heavy compute warps share the issue slots), config 4: 1: 30.4-31.0 ms, 2: 30.7-31.2, 4: 36.5, 8: 35.0
-#endif
 long long* g_bwd_trace = nullptr;  // developer timeline buffer (tc_bwd_set_trace)
 int g_bwd_trace_t0 = 0;            // first tile pair of CTA 0 that the timeline records
 int g_bwd_persistent = -1;         // -1: FA_B200_BWD_PERSISTENT (read once), default on
