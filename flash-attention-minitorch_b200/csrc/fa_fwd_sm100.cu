@@ -3,11 +3,13 @@
 // Replaces the reference kernels src/flash_attn2_fw.cu:23-297 (FA-2 forward) and
 // src/flash_attn_fw.cu:22-287 (FA-1 forward; same O, different saved statistics).
 //
-// One CTA owns 256 consecutive query rows of one (batch, head): two 128-row Q tiles that share
-// every K/V tile streamed through shared memory.  Warp roles:
+// A work item is 256 consecutive query rows of one (batch, head): two 128-row Q tiles that share
+// every K/V tile streamed through shared memory.  The kernel is persistent: one CTA per SM draws items from a
+// counter and keeps its K/V ring and its S / P / O hand-offs running across them (see the comment in the kernel).
+// Warp roles:
 //   warps 0-3   softmax group for Q tile 0   (thread r owns row r: TMEM lane r)
 //   warps 4-7   softmax group for Q tile 1
-//   warp  8     TMA producer (one lane): Q once, then the K/V ring
+//   warp  8     scheduler + TMA producer (one lane): per item Q, then the K/V ring
 //   warp  9     MMA issuer   (one lane): S_t = Q_t K_j^T and O_t += P_t V_j
 // (registers are moved from warps 8-11 to the softmax warps with setmaxnreg: 208 vs 80 per thread)
 // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [384,384+D).  P_t (bf16) overwrites the
