@@ -53,6 +53,7 @@ namespace fa {
 namespace {
 
 constexpr int kTile = 128;
+constexpr int kHeadGroup = 8;  // heads whose work items are interleaved longest-first (see `decode` in the kernel)
 long long* g_bwd_trace = nullptr;  // developer timeline buffer (tc_bwd_set_trace)
 int g_bwd_trace_t0 = 0;            // first tile pair of CTA 0 that the timeline records
 int g_bwd_persistent = -1;         // -1: FA_B200_BWD_PERSISTENT (read once), default on
@@ -78,6 +79,7 @@ constexpr int kBoxBytes = 128 * 128;  // 128 rows x 128 B
 
 struct BwdParams {
   int T, Tpad, causal;
+  int BH;
   int nkv;          // K/V tiles per head (= Tpad / 128)
   int total_items;  // BH * nkv work items (one item = one K/V tile of one head)
   int wide_stores;  // dk / dv are 32-byte aligned: 256-bit stores in the epilogue
@@ -134,7 +136,7 @@ struct BwdBarriers {
   uint64_t s_full, s_loaded, p_full, dp_full, dp_loaded, ds_full, ds_empty, dq_full, dq_drained;  // per tile pair
   uint64_t dv_full, dk_full;                               // per work item
   uint64_t sched_full[2], sched_empty[2];                  // work-item ring
-  int sched_item[2];
+  int sched_item[2];  // (head << 16) | K/V tile, -1 = no more work
   uint32_t tmem_slot;
 };
 static_assert(sizeof(BwdBarriers) <= 320, "barrier block");
@@ -251,6 +253,24 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     return item;
   };
 
+  // Item order: heads in groups of kHeadGroup; inside a group all K/V tiles j = 0 (the longest items when causal) of the
+  // group's heads come first, then all j = 1, ... -- the counter hands the longest items out first ACROSS heads, so the
+  // last items a CTA can draw are the shortest ones (simulated schedule efficiency at 64 heads, the strong-scaling share
+  // of one of 8 GPUs: 0.93 head by head, 0.99 in groups), while a group's tensors (8 heads x 8 MB) stay inside the L2.
+  // The scheduler lane decodes an item number once and publishes (head << 16) | j (-1 = no more work) through the ring.
+  auto encode = [&](int item) {
+    if (item >= p.total_items) return -1;
+    const int per_group = kHeadGroup * nq;
+    const int grp = item / per_group, r = item - grp * per_group;
+    const int gs = min(kHeadGroup, p.BH - grp * kHeadGroup);
+    const int j = r / gs;
+    return ((grp * kHeadGroup + (r - j * gs)) << 16) | j;
+  };
+  auto decode = [&](int code, int& bh, int& j) {
+    bh = code >> 16;
+    j = code & 0xffff;
+  };
+
   if (warp >= 12) {
     reg_dealloc<Cfg::kRegMisc>();
   }
@@ -265,22 +285,25 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       uint32_t t = 0;
       for (int m = 0;; ++m) {
         mbar_wait(&bars.sched_empty[m & 1], ((m >> 1) & 1) ^ 1);  // every consumer has read item m - 2
-        bars.sched_item[m & 1] = item;
+        const int code = encode(item);
+        bars.sched_item[m & 1] = code;
         mbar_arrive(&bars.sched_full[m & 1]);
-        if (item >= p.total_items) break;
+        if (code < 0) break;
         const int next = p.persistent ? atomicAdd(p.sched_counter, 1) : p.total_items;  // its latency hides under the loads
 #if FA_BWD_PREFETCH_KV
         if (next < p.total_items) {
           // K / V of the next item come from HBM (no other CTA reads them): pull them into the L2 an item ahead, so that the
           // loads at the item boundary -- which sit on the critical path -- are L2 hits
-          const int nbh = next / nq, nj = next - nbh * nq;
+          int nbh, nj;
+          decode(encode(next), nbh, nj);
           for (int b = 0; b < Cfg::kBoxes; ++b) {
             tma_prefetch_l2_3d(&map_k, b * 64, nj * kTile, nbh);
             tma_prefetch_l2_3d(&map_v, b * 64, nj * kTile, nbh);
           }
         }
 #endif
-        const int bh = item / nq, j = item - bh * nq;
+        int bh, j;
+        decode(code, bh, j);
         const int i0 = p.causal ? j : 0, n = nq - i0;
         uint8_t* bufK = sKV + (m & 1) * Cfg::kTileBytes;
         uint8_t* bufV = sKV + ((m & 1) ^ 1) * Cfg::kTileBytes;
@@ -371,8 +394,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
     int m = 0;
     int item = fetch(0);
-    if (item < p.total_items) {
-      int n = nq - (p.causal ? item % nq : 0);  // tile pairs of the current item
+    if (item >= 0) {
+      int n = nq - (p.causal ? (item & 0xffff) : 0);  // tile pairs of the current item
       int il = 0;                               // position of pair t inside its item
       uint32_t aK = aKV, aV = aKV + Cfg::kTileBytes;
       uint32_t prev_aK = 0;
@@ -429,10 +452,10 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         if (last) {
           ++m;
           item = fetch(m);
-          if (item >= p.total_items) {
+          if (item < 0) {
             done = true;
           } else {
-            n = nq - (p.causal ? item % nq : 0);
+            n = nq - (p.causal ? (item & 0xffff) : 0);
             il = 0;
             aK = aKV + (m & 1) * Cfg::kTileBytes;
             aV = aKV + ((m & 1) ^ 1) * Cfg::kTileBytes;
@@ -468,8 +491,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     uint32_t t = 0;
     for (int m = 0;; ++m) {
       const int item = next_item(m);
-      if (item >= p.total_items) break;
-      const int bh = item / nq, j = item - bh * nq;
+      if (item < 0) break;
+      int bh, j;
+      decode(item, bh, j);
       const int i0 = p.causal ? j : 0, n = nq - i0;
       // dropout: one 32-bit hash per 2 x 2 block of (query, key); this thread (one key row) uses the byte of its key
       // parity in the low half (even query) and in the high half (odd query) -- the same bits the forward drew
@@ -648,8 +672,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     uint32_t t = 0;
     for (int m = 0;; ++m) {
       const int item = next_item(m);
-      if (item >= p.total_items) break;
-      const int bh = item / nq, j = item - bh * nq;
+      if (item < 0) break;
+      int bh, j;
+      decode(item, bh, j);
       const int i0 = p.causal ? j : 0, n = nq - i0;
       for (int il = 0; il < n; ++il, ++t) {
         const int i = i0 + il;
@@ -822,6 +847,7 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   p.trace = g_bwd_trace;
   p.trace_t0 = g_bwd_trace_t0;
   p.dq_debug = 0;
+  p.BH = BH;
   p.nkv = (int)(Tpad / kTile);
   p.total_items = BH * p.nkv;
   p.persistent = bwd_persistent() ? 1 : 0;
@@ -863,7 +889,8 @@ cudaError_t tc_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
                    const __nv_bfloat16* dO, const float* lse, void* dq, void* dk, void* dv, bool grads_f32,
                    bool accumulate_dq, void* workspace, int BH, int T, int d, bool causal, cudaStream_t st,
                    Dropout drop) {
-  if (!workspace || (long long)BH * (long long)((T + kTile - 1) / kTile) > 0x7fffff00ll) return cudaErrorInvalidValue;
+  // the work-item ring packs (head << 16) | K/V tile
+  if (!workspace || BH >= 32768 || (T + kTile - 1) / kTile >= 65536) return cudaErrorInvalidValue;
   if (d == 128) {
     return grads_f32 ? launch_bwd<128, float>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, drop, st)
                      : launch_bwd<128, __nv_bfloat16>(q, k, v, o, dO, lse, dq, dk, dv, accumulate_dq, workspace, BH, T, causal, drop, st);

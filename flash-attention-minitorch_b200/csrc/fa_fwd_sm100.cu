@@ -82,6 +82,7 @@ int fwd_num_sms() {
   return n;
 }
 
+constexpr int kHeadGroup = 16;  // heads whose work items are interleaved longest-first (see `decode` in the kernel)
 constexpr int kBlockM = 128;  // rows per Q tile (= TMEM lanes)
 constexpr int kBlockN = 128;  // keys per K/V tile
 constexpr int kFwdThreads = 384;  // warps 0-7 softmax, 8 TMA, 9 MMA, 10-11 idle (complete the 4-warp group for setmaxnreg)
@@ -111,6 +112,7 @@ struct FwdParams {
                     // resets both words, so the slot is zero again for the next launch); 0: CTA b works on item b only
   int* sched;
   int wide_stores;  // o is 32-byte aligned: 256-bit stores in the epilogue
+  int head_group;   // heads whose work items are interleaved longest-first (1 = head by head), see `decode`
   float tau;         // 1/sqrt(d)
   float scale_log2;  // tau * log2(e)
   void* o;
@@ -141,7 +143,7 @@ struct FwdCfg {
 struct FwdBarriers {
   uint64_t q_full, q_free;                  // per work item
   uint64_t sched_full[2], sched_empty[2];   // work-item ring
-  int sched_item[2];
+  int sched_item[2];  // (head << 16) | query block of the item, -1 = no more work (decoded once, by the scheduler lane)
   uint64_t k_full[4], k_empty[4], v_full[4], v_empty[4];
   uint64_t s_full[2], p_full[2][FA_FWD_PSIG], o_full[2];
 };
@@ -207,10 +209,25 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   // of a head first) from a global counter.  The K/V ring, the S / P / O hand-offs and their mbarrier parities run on
   // RUNNING counters, so nothing drains between items: Q of the next item is loaded as soon as the last QK of this one has
   // been issued (one K/V step before the item ends), its first scores are in TMEM before the softmax warps have stored O.
-  auto decode = [&](int item, int& bh, int& blk, int& n0, int& n1) {
-    bh = item / nblk;
-    const int x = item - bh * nblk;
-    blk = p.causal ? nblk - 1 - x : x;
+  // Item order: heads in groups of kHeadGroup; inside a group the last (longest, when causal) query blocks of all the
+  // group's heads come first, then the next-to-last ones, ... -- the counter hands the longest items out first ACROSS
+  // heads, so the last items a CTA can draw are the shortest (simulated schedule efficiency at 64 heads, the
+  // strong-scaling share of one of 8 GPUs: 0.86 head by head, 0.98 in groups of 16) while the group's Q / K / V / O
+  // (16 heads x 4 MB) stay inside the L2.  Measured (fa_check time, T = 4096, d = 128, causal): 64 heads 0.248 against
+  // 0.268 ms head by head; 512 heads (55 items per CTA: the tail is 2 % either way) 1.87 against 1.85 ms -- the group
+  // order costs a little L2 locality -- so the launcher groups only when a CTA draws fewer than 32 items.
+  auto encode = [&](int item) {  // scheduler lane only: item number -> (head << 16) | block
+    if (item >= p.total_items) return -1;
+    const int per_group = p.head_group * nblk;
+    const int grp = item / per_group, r = item - grp * per_group;
+    const int gs = min(p.head_group, p.BH - grp * p.head_group);
+    const int x = r / gs;
+    const int bh = grp * p.head_group + (r - x * gs);
+    return (bh << 16) | (p.causal ? nblk - 1 - x : x);
+  };
+  auto decode = [&](int code, int& bh, int& blk, int& n0, int& n1) {
+    bh = code >> 16;
+    blk = code & 0xffff;
     n0 = p.causal ? min(2 * blk + 1, nkv) : nkv;
     n1 = p.causal ? min(2 * blk + 2, nkv) : nkv;
   };
@@ -265,12 +282,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       uint32_t jt = 0;  // running K/V step count: ring stage and parity
       for (int m = 0;; ++m) {
         mbar_wait(&bars.sched_empty[m & 1], ((m >> 1) & 1) ^ 1);  // every consumer has read item m - 2
-        bars.sched_item[m & 1] = item;
+        const int code = encode(item);
+        bars.sched_item[m & 1] = code;
         mbar_arrive(&bars.sched_full[m & 1]);
-        if (item >= p.total_items) break;
+        if (code < 0) break;
         const int next = p.persistent ? atomicAdd(&p.sched[0], 1) : p.total_items;
         int bh, blk, n0, n1;
-        decode(item, bh, blk, n0, n1);
+        decode(code, bh, blk, n0, n1);
         if (m > 0) mbar_wait(&bars.q_free, (m - 1) & 1);  // the last QK of the previous item has read Q
         mbar_arrive_expect_tx(&bars.q_full, 2 * Cfg::kTileBytes);
         for (int t = 0; t < 2; ++t)
@@ -345,7 +363,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       for (int m = 0;; ++m) {
         // the max-reduction makes the item (and the loop bounds derived from it) provably warp-uniform for ptxas
         const int item = __reduce_max_sync(0xffffffffu, next_item(m));
-        if (item >= p.total_items) break;
+        if (item < 0) break;
         int bh, blk, n0, n1;
         decode(item, bh, blk, n0, n1);
         mbar_wait_w(&bars.q_full, m & 1);
@@ -407,7 +425,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     uint32_t cs = 0;  // running step count of this Q tile
     for (int m = 0;; ++m) {
       const int item = next_item(m);
-      if (item >= p.total_items) break;
+      if (item < 0) break;
       int bh, blk, n0, n1;
       decode(item, bh, blk, n0, n1);
       const int qt = 2 * blk + t;
@@ -610,6 +628,7 @@ cudaError_t launch_fwd_impl(const void* q, const void* k, const void* v, void* o
   p.BH = BH;
   p.nblk = (T + 2 * kBlockM - 1) / (2 * kBlockM);
   p.total_items = BH * p.nblk;
+  if (BH >= 32768 || p.nblk >= 65536) return cudaErrorInvalidValue;  // the work-item ring packs (head << 16) | block
   p.persistent = fwd_persistent() ? 1 : 0;
   p.sched = nullptr;
   if (p.persistent) {
@@ -628,6 +647,7 @@ cudaError_t launch_fwd_impl(const void* q, const void* k, const void* v, void* o
   p.trace = g_fwd_trace;
   // persistent: one CTA per SM (1 CTA fits: ~200 KB of shared memory, all 512 TMEM columns), items drawn dynamically
   const unsigned grid = p.persistent ? (unsigned)std::min(p.total_items, fwd_num_sms()) : (unsigned)p.total_items;
+  p.head_group = (p.persistent && p.total_items < 32 * (int)grid) ? kHeadGroup : 1;
   fa_fwd_kernel<D, OutT, kTF32, kDrop><<<grid, kFwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, p);
   return cudaGetLastError();
 }
