@@ -53,7 +53,10 @@ namespace fa {
 namespace {
 
 constexpr int kTile = 128;
-constexpr int kHeadGroup = 8;  // heads whose work items are interleaved longest-first (see `decode` in the kernel)
+#ifndef FA_BWD_HEAD_GROUP
+#define FA_BWD_HEAD_GROUP 16  // same-box A/B at 64 | 128 | 512 heads (T = 4096): 8: 0.758 | 1.49 | 6.61 ms, 16: 0.738 | 1.475 | 6.60, 32: 0.750 | 1.505 | 6.70-6.95 (a group no longer fits the L2)
+#endif
+constexpr int kHeadGroup = FA_BWD_HEAD_GROUP;  // heads whose work items are interleaved longest-first (see `decode` in the kernel)
 long long* g_bwd_trace = nullptr;  // developer timeline buffer (tc_bwd_set_trace)
 int g_bwd_trace_t0 = 0;            // first tile pair of CTA 0 that the timeline records
 int g_bwd_persistent = -1;         // -1: FA_B200_BWD_PERSISTENT (read once), default on
@@ -256,7 +259,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   // Item order: heads in groups of kHeadGroup; inside a group all K/V tiles j = 0 (the longest items when causal) of the
   // group's heads come first, then all j = 1, ... -- the counter hands the longest items out first ACROSS heads, so the
   // last items a CTA can draw are the shortest ones (simulated schedule efficiency at 64 heads, the strong-scaling share
-  // of one of 8 GPUs: 0.93 head by head, 0.99 in groups), while a group's tensors (8 heads x 8 MB) stay inside the L2.
+  // of one of 8 GPUs: 0.93 head by head, 0.99 in groups), while a group's tensors (16 heads x 8 MB) stay inside the L2.
   // The scheduler lane decodes an item number once and publishes (head << 16) | j (-1 = no more work) through the ring.
   auto encode = [&](int item) {
     if (item >= p.total_items) return -1;

@@ -82,7 +82,10 @@ int fwd_num_sms() {
   return n;
 }
 
-constexpr int kHeadGroup = 16;  // heads whose work items are interleaved longest-first (see `decode` in the kernel)
+#ifndef FA_FWD_HEAD_GROUP
+#define FA_FWD_HEAD_GROUP 32  // same-box A/B at 64 | 128 heads: 16: 0.243 | 0.468 ms, 32: 0.237 | 0.467, 64: 0.243 | 0.485
+#endif
+constexpr int kHeadGroup = FA_FWD_HEAD_GROUP;  // heads whose work items are interleaved longest-first (see `decode` in the kernel)
 constexpr int kBlockM = 128;  // rows per Q tile (= TMEM lanes)
 constexpr int kBlockN = 128;  // keys per K/V tile
 constexpr int kFwdThreads = 384;  // warps 0-7 softmax, 8 TMA, 9 MMA, 10-11 idle (complete the 4-warp group for setmaxnreg)
@@ -212,9 +215,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   // Item order: heads in groups of kHeadGroup; inside a group the last (longest, when causal) query blocks of all the
   // group's heads come first, then the next-to-last ones, ... -- the counter hands the longest items out first ACROSS
   // heads, so the last items a CTA can draw are the shortest (simulated schedule efficiency at 64 heads, the
-  // strong-scaling share of one of 8 GPUs: 0.86 head by head, 0.98 in groups of 16) while the group's Q / K / V / O
-  // (16 heads x 4 MB) stay inside the L2.  Measured (fa_check time, T = 4096, d = 128, causal): 64 heads 0.248 against
-  // 0.268 ms head by head; 512 heads (55 items per CTA: the tail is 2 % either way) 1.87 against 1.85 ms -- the group
+  // strong-scaling share of one of 8 GPUs: 0.86 head by head, 0.98 in groups) while the group's Q / K / V / O
+  // (32 heads x 4 MB) stay inside the L2.  Measured (fa_check time, T = 4096, d = 128, causal): 64 heads 0.237 against
+  // 0.270 ms head by head; 512 heads (55 items per CTA: the tail is 2 % either way) 1.87 against 1.85 ms -- the group
   // order costs a little L2 locality -- so the launcher groups only when a CTA draws fewer than 32 items.
   auto encode = [&](int item) {  // scheduler lane only: item number -> (head << 16) | block
     if (item >= p.total_items) return -1;
