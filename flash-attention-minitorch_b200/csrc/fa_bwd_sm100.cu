@@ -83,6 +83,7 @@ constexpr int kBoxBytes = 128 * 128;  // 128 rows x 128 B
 struct BwdParams {
   int T, Tpad, causal;
   int BH;
+  int head_group;   // heads whose work items are interleaved longest-first (see `encode` in the kernel)
   int nkv;          // K/V tiles per head (= Tpad / 128)
   int total_items;  // BH * nkv work items (one item = one K/V tile of one head)
   int wide_stores;  // dk / dv are 32-byte aligned: 256-bit stores in the epilogue
@@ -256,18 +257,18 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     return item;
   };
 
-  // Item order: heads in groups of kHeadGroup; inside a group all K/V tiles j = 0 (the longest items when causal) of the
+  // Item order: heads in groups of p.head_group (<= kHeadGroup, sized to the L2 by the launcher); inside a group all K/V tiles j = 0 (the longest items when causal) of the
   // group's heads come first, then all j = 1, ... -- the counter hands the longest items out first ACROSS heads, so the
   // last items a CTA can draw are the shortest ones (simulated schedule efficiency at 64 heads, the strong-scaling share
   // of one of 8 GPUs: 0.93 head by head, 0.99 in groups), while a group's tensors (16 heads x 8 MB) stay inside the L2.
   // The scheduler lane decodes an item number once and publishes (head << 16) | j (-1 = no more work) through the ring.
   auto encode = [&](int item) {
     if (item >= p.total_items) return -1;
-    const int per_group = kHeadGroup * nq;
+    const int per_group = p.head_group * nq;
     const int grp = item / per_group, r = item - grp * per_group;
-    const int gs = min(kHeadGroup, p.BH - grp * kHeadGroup);
+    const int gs = min(p.head_group, p.BH - grp * p.head_group);
     const int j = r / gs;
-    return ((grp * kHeadGroup + (r - j * gs)) << 16) | j;
+    return ((grp * p.head_group + (r - j * gs)) << 16) | j;
   };
   auto decode = [&](int code, int& bh, int& j) {
     bh = code >> 16;
@@ -851,6 +852,12 @@ cudaError_t launch_bwd(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   p.trace_t0 = g_bwd_trace_t0;
   p.dq_debug = 0;
   p.BH = BH;
+  {
+    // a group's tensors (Q, K, V, dO, dK, dV in bf16 + the fp32 dQ accumulator: 16 bytes per element) should fit the L2
+    // about twice over: 16 heads at T = 4096, d = 128 (same-box sweep above), 4 at T = 16384 (16: -1.7 % at config 4)
+    const size_t per_head = (size_t)T * D * 16;
+    p.head_group = (int)std::max<size_t>(1, std::min<size_t>(kHeadGroup, ((size_t)128 << 20) / per_head));
+  }
   p.nkv = (int)(Tpad / kTile);
   p.total_items = BH * p.nkv;
   p.persistent = bwd_persistent() ? 1 : 0;

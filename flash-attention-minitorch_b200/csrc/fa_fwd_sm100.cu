@@ -650,7 +650,10 @@ cudaError_t launch_fwd_impl(const void* q, const void* k, const void* v, void* o
   p.trace = g_fwd_trace;
   // persistent: one CTA per SM (1 CTA fits: ~200 KB of shared memory, all 512 TMEM columns), items drawn dynamically
   const unsigned grid = p.persistent ? (unsigned)std::min(p.total_items, fwd_num_sms()) : (unsigned)p.total_items;
-  p.head_group = (p.persistent && p.total_items < 32 * (int)grid) ? kHeadGroup : 1;
+  // grouped order only where the tail matters (a CTA draws < 32 items); a group's Q / K / V / O should fit the L2
+  const size_t per_head = (size_t)T * D * Cfg::kElem * 4;
+  p.head_group = (p.persistent && p.total_items < 32 * (int)grid)
+                     ? (int)std::max<size_t>(1, std::min<size_t>(kHeadGroup, ((size_t)128 << 20) / per_head)) : 1;
   fa_fwd_kernel<D, OutT, kTF32, kDrop><<<grid, kFwdThreads, Cfg::kSmemBytes, st>>>(mq, mk, mv, p);
   return cudaGetLastError();
 }
