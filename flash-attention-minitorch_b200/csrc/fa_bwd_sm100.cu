@@ -505,7 +505,6 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const uint32_t drop_head = drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh), drop_colterm = (kj >> 1) * kDropColMul;
       const uint32_t drop_b0 = kj & 1;  // byte b0: even query of the block, byte b0 + 2: odd query
       const uint32_t drop_sel2 = drop_sel_pair(drop_b0, drop_b0 + 2);
-      const uint32_t drop_sh = 7 + 8 * drop_b0;
       for (int il = 0; il < n; ++il, ++t) {
         const int i = i0 + il;
         const float* sL = sStats + (t & 1) * 256 + g * 64;  // -L log2(e) of the 64 query columns (-inf on padding rows)
@@ -556,13 +555,6 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 #pragma unroll
           for (int c = 0; c < 64; c += 2) pk[c >> 1] = pack_bf16x2(pr[c], pr[c + 1]);
         }
-        // keep bits of this key row: query pair pi = c >> 1 of each 32-column half sits at bit (15 - pi % 16) for the
-        // even query and bit (31 - pi % 16) for the odd one (shift-in order), halves 0 / 1 in keep_a / keep_b
-        uint32_t keep_a = 0u, keep_b = 0u;
-        auto kept = [&](int c) {
-          const int pos = 15 - ((c >> 1) & 15) + 16 * (c & 1);
-          return (((c < 32 ? keep_a : keep_b) >> pos) & 1u) != 0u;
-        };
         // R1 still holds dQ(t-1) until the drain warps have pulled it out
         if (t > 0) mbar_wait(&bars.dq_drained, (t - 1) & 1);
         FA_TR2(t, 2);
@@ -577,9 +569,6 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             const uint32_t w0 = (lane & 1) ? theirs : mine, w1 = (lane & 1) ? mine : theirs;  // queries c,c+1 | c+2,c+3
             pd[c >> 1] = pk[c >> 1] & drop_prmt(w0, drop_sel2);
             pd[(c >> 1) + 1] = pk[(c >> 1) + 1] & drop_prmt(w1, drop_sel2);
-            uint32_t& acc = c < 32 ? keep_a : keep_b;
-            acc = (acc << 1) | ((w0 >> drop_sh) & 0x00010001u);
-            acc = (acc << 1) | ((w1 >> drop_sh) & 0x00010001u);
           }
           tmem_st_x32(tR1, pd);
         } else {
@@ -607,23 +596,39 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         if (t > 0) mbar_wait(&bars.ds_empty, (t - 1) & 1);  // dK(t-1) / dQ(t-1) have finished reading dS
         FA_TR2(t, 6);
         const float2 tau2 = make_float2(p.tau, p.tau);
+        const float2 tk2 = make_float2(tau_keep, tau_keep);
+        auto unpack = [](uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); };
+        uint32_t pdr[16];  // dropout: 16 packed columns (32 queries) of the dropped P, re-read from R1
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {  // 16-byte chunk of this thread's 128-byte dS^T row: 8 query columns
           uint32_t out[4];
+          // dropout: dS = tau Z (P o keep) o dP - P o tau delta.  The dropped P is what this thread stored into R1 for the dV
+          // product -- it stays there until dQ(t) is issued, i.e. past this phase -- so it is read back (16 packed columns
+          // at a time) instead of carrying 64 keep bits per thread through the P phase and turning them into per-element
+          // selects here (-320 of ~1100 instructions per thread and tile pair)
+          if constexpr (kDrop) {
+            if ((ch & 3) == 0) {
+              tmem_ld_x16(tR1 + (ch >> 2) * 16, pdr);
+              tmem_wait_ld();
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 8; e += 4) {
             const float4 D4 = *reinterpret_cast<const float4*>(sD + ch * 8 + e);
             const int c = ch * 8 + e;
-            float2 m0 = tau2, m1 = tau2;
-            if constexpr (kDrop) {
-              m0 = make_float2(kept(c + 0) ? tau_keep : 0.f, kept(c + 1) ? tau_keep : 0.f);
-              m1 = make_float2(kept(c + 2) ? tau_keep : 0.f, kept(c + 3) ? tau_keep : 0.f);
-            }
-            const float2 t0 = ffma2(make_float2(dp[c + 0], dp[c + 1]), m0, make_float2(D4.x, D4.y));
-            const float2 t1 = ffma2(make_float2(dp[c + 2], dp[c + 3]), m1, make_float2(D4.z, D4.w));
             const uint32_t w0 = pk[c >> 1], w1 = pk[(c >> 1) + 1];
-            const float2 a = fmul2(make_float2(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u)), t0);
-            const float2 b = fmul2(make_float2(__uint_as_float(w1 << 16), __uint_as_float(w1 & 0xffff0000u)), t1);
+            float2 a, b;
+            if constexpr (kDrop) {
+              const uint32_t d0 = pdr[(c >> 1) & 15], d1 = pdr[((c >> 1) + 1) & 15];
+              const float2 u0 = fmul2(unpack(w0), make_float2(D4.x, D4.y)), u1 = fmul2(unpack(w1), make_float2(D4.z, D4.w));
+              a = ffma2(fmul2(unpack(d0), make_float2(dp[c + 0], dp[c + 1])), tk2, u0);
+              b = ffma2(fmul2(unpack(d1), make_float2(dp[c + 2], dp[c + 3])), tk2, u1);
+            } else {
+              const float2 t0 = ffma2(make_float2(dp[c + 0], dp[c + 1]), tau2, make_float2(D4.x, D4.y));
+              const float2 t1 = ffma2(make_float2(dp[c + 2], dp[c + 3]), tau2, make_float2(D4.z, D4.w));
+              a = fmul2(unpack(w0), t0);
+              b = fmul2(unpack(w1), t1);
+            }
             out[(e >> 1) + 0] = pack_bf16x2(a.x, a.y);
             out[(e >> 1) + 1] = pack_bf16x2(b.x, b.y);
           }
