@@ -106,10 +106,10 @@ struct BwdCfg {
   static constexpr int kBoxes = D / 64;
   static constexpr int kTileBytes = kBoxes * kBoxBytes;
   // setmaxnreg split of the 128 registers per thread the CTA is launched with (x 32 lanes: 8 compute, 4 drain, 4 other
-  // warps).  Without dropout the drain warps take a whole dQ tile (D registers) out of TMEM at once; the dropout variant
-  // needs ~24 more registers in the compute warps (mask words), so its drain works in two halves.
+  // warps).  The drain warps take a whole dQ tile (D registers) out of TMEM at once.  The dropout variant runs on the same
+  // split since its dS phase re-reads the dropped P from TMEM instead of carrying mask words (it used 160 / 104 / 88 and
+  // a two-part drain before: config 4 backward 28.1 -> 27.0 ms).
   static constexpr int kRegCompute = 136, kRegDrain = 152, kRegMisc = 88;       // 8*136 + 4*152 + 4*88 = 16*128
-  static constexpr int kRegComputeDrop = 160, kRegDrainDrop = 104;              // 8*160 + 4*104 + 4*88 <= 16*128
   static constexpr int kQStages = 2;
   // One dO stage at d = 128 (all that fits): the load of dO(t+1) can only start when dV(t) has finished, and under the
   // reduce-add stream a tile load takes ~2000-2400 cycles WHATEVER its size (measured with 16 KB half tiles in a ring of
@@ -482,7 +482,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ compute warps
-    reg_alloc<kDrop ? Cfg::kRegComputeDrop : Cfg::kRegCompute>();
+    reg_alloc<Cfg::kRegCompute>();
     const int g = warp >> 2;                 // which half of the 128 query columns
     const int r = (warp & 3) * 32 + lane;    // key row within the tile == TMEM lane
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
@@ -671,8 +671,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else if (warp < 12) {
     // ------------------------------------------------------------------ dQ drain warps
-    if constexpr (kDrop) reg_dealloc<Cfg::kRegDrainDrop>();  // below the launch value: a decrease
-    else reg_alloc<Cfg::kRegDrain>();
+    reg_alloc<Cfg::kRegDrain>();
     const int w = warp - 8;
     const int r = w * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t tDQ = tmem + Cfg::kColR1 + (uint32_t(w * 32) << 16);
@@ -692,8 +691,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         if (warp == 8) FA_TR(t, 5);
         // The whole dQ tile leaves TMEM at once (D registers per thread), so that P(t+1) -- which takes these columns --
         // is released after one TMEM read instead of after three staging rounds; the staging / reduce-adds below then
-        // overlap the next tile pair.  (Dropout variant: two halves, the compute warps need the registers.)
-        constexpr int kParts = kDrop ? 2 : 1, kColsPart = D / kParts;
+        // overlap the next tile pair.
+        constexpr int kParts = 1, kColsPart = D / kParts;
 #pragma unroll
         for (int part = 0; part < kParts; ++part) {
           uint32_t rr[kColsPart];
