@@ -504,7 +504,10 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const uint32_t kj = uint32_t(j * kTile + r);
       const uint32_t drop_head = drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh), drop_colterm = (kj >> 1) * kDropColMul;
       const uint32_t drop_b0 = kj & 1;  // byte b0: even query of the block, byte b0 + 2: odd query
-      const uint32_t drop_sel2 = drop_sel_pair(drop_b0, drop_b0 + 2);
+      // mask selectors over the word pair (mine, theirs): queries c, c+1 take the even lane's word, c+2, c+3 the odd lane's
+      const uint32_t drop_o0 = (lane & 1) * 4, drop_o1 = 4 - drop_o0;
+      const uint32_t drop_sel2a = drop_sel_pair(drop_b0 + drop_o0, drop_b0 + 2 + drop_o0),
+                     drop_sel2b = drop_sel_pair(drop_b0 + drop_o1, drop_b0 + 2 + drop_o1);
       for (int il = 0; il < n; ++il, ++t) {
         const int i = i0 + il;
         const float* sL = sStats + (t & 1) * 256 + g * 64;  // -L log2(e) of the 64 query columns (-inf on padding rows)
@@ -566,9 +569,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             // the two lanes of a key pair need the same block words: each hashes one, a shuffle gives the other
             const uint32_t mine = drop_keep_word(drop_mix(rk[c >> 1] ^ drop_colterm), drop_thr);
             const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
-            const uint32_t w0 = (lane & 1) ? theirs : mine, w1 = (lane & 1) ? mine : theirs;  // queries c,c+1 | c+2,c+3
-            pd[c >> 1] = pk[c >> 1] & drop_prmt(w0, drop_sel2);
-            pd[(c >> 1) + 1] = pk[(c >> 1) + 1] & drop_prmt(w1, drop_sel2);
+            pd[c >> 1] = pk[c >> 1] & drop_prmt2(mine, theirs, drop_sel2a);
+            pd[(c >> 1) + 1] = pk[(c >> 1) + 1] & drop_prmt2(mine, theirs, drop_sel2b);
           }
           tmem_st_x32(tR1, pd);
         } else {

@@ -68,6 +68,14 @@ __device__ __forceinline__ uint32_t drop_prmt(uint32_t w, uint32_t selector) {
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0u), "r"(selector));
   return r;
 }
+// The same over a PAIR of words: bytes 0-3 = a, 4-7 = b.  The kernels hash one block word per lane and get the partner
+// lane's word by shuffle; which of the two belongs to which element pair depends on the lane parity, and folding that
+// choice into the selector (byte index + 4) saves the two selects per four elements.
+__device__ __forceinline__ uint32_t drop_prmt2(uint32_t a, uint32_t b, uint32_t selector) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(selector));
+  return r;
+}
 // selector expanding the keep bits of bytes b0 and b1 into the low / high 16 bits of a mask word (packed bf16x2)
 __device__ __forceinline__ uint32_t drop_sel_pair(uint32_t b0, uint32_t b1) {
   return (8u | b0) * 0x11u | ((8u | b1) * 0x11u << 8);

@@ -440,8 +440,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       // dropout: one 32-bit hash per 2 x 2 block of (row, key); this thread uses the two bytes of its row parity
       const uint32_t drop_rowkey = drop_row_key(drop_head_key(p.drop.seed_lo, p.drop.seed_hi, bh), uint32_t(row_g) >> 1);
       const uint32_t drop_b0 = (row_g & 1) * 2;  // bytes b0, b0 + 1 of a block word belong to this row
-      const uint32_t drop_sel2 = drop_sel_pair(drop_b0, drop_b0 + 1), drop_selA = drop_sel_word(drop_b0),
-                     drop_selB = drop_sel_word(drop_b0 + 1);
+      // mask selectors over the word pair (mine, theirs): columns cc, cc+1 take the even lane's word, cc+2, cc+3 the odd lane's
+      const uint32_t drop_o0 = (lane & 1) * 4, drop_o1 = 4 - drop_o0;  // where the word of columns cc,cc+1 / cc+2,cc+3 sits
+      const uint32_t drop_sel2a = drop_sel_pair(drop_b0 + drop_o0, drop_b0 + 1 + drop_o0),
+                     drop_sel2b = drop_sel_pair(drop_b0 + drop_o1, drop_b0 + 1 + drop_o1);
+      const uint32_t drop_selA0 = drop_sel_word(drop_b0 + drop_o0), drop_selB0 = drop_sel_word(drop_b0 + 1 + drop_o0),
+                     drop_selA1 = drop_sel_word(drop_b0 + drop_o1), drop_selB1 = drop_sel_word(drop_b0 + 1 + drop_o1);
 
       for (int j = 0; j < nt; ++j, ++cs) {
         mbar_wait(&bars.s_full[t], cs & 1);
@@ -501,15 +505,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
               const uint32_t j2 = (uint32_t(j * kBlockN + cc) >> 1) + (lane & 1);
               const uint32_t mine = drop_keep_word(drop_mix(drop_rowkey ^ (j2 * kDropColMul)), drop_thr);
               const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
-              const uint32_t w0 = (lane & 1) ? theirs : mine, w1 = (lane & 1) ? mine : theirs;  // columns cc,cc+1 | cc+2,cc+3
               if constexpr (kTF32) {
-                pk[c] &= drop_prmt(w0, drop_selA);
-                pk[c + 1] &= drop_prmt(w0, drop_selB);
-                pk[c + 2] &= drop_prmt(w1, drop_selA);
-                pk[c + 3] &= drop_prmt(w1, drop_selB);
+                pk[c] &= drop_prmt2(mine, theirs, drop_selA0);
+                pk[c + 1] &= drop_prmt2(mine, theirs, drop_selB0);
+                pk[c + 2] &= drop_prmt2(mine, theirs, drop_selA1);
+                pk[c + 3] &= drop_prmt2(mine, theirs, drop_selB1);
               } else {
-                pk[c >> 1] &= drop_prmt(w0, drop_sel2);
-                pk[(c >> 1) + 1] &= drop_prmt(w1, drop_sel2);
+                pk[c >> 1] &= drop_prmt2(mine, theirs, drop_sel2a);
+                pk[(c >> 1) + 1] &= drop_prmt2(mine, theirs, drop_sel2b);
               }
             }
           }
