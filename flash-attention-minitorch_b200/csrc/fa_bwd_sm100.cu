@@ -207,11 +207,22 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int T = p.T;
   const int nq = p.nkv;  // Q tiles per head == K/V tiles per head
+#ifdef FA_B200_TRACE_HOOKS
   long long* const tr = blockIdx.x == 0 ? p.trace : nullptr;
   const int tr0 = p.trace_t0;
+#endif
+// developer timeline (tools/fa_check trace): compiled in only with -DFA_B200_TRACE_HOOKS (tools/build_variant.sh trace
+// -DFA_B200_TRACE_HOOKS).  Each hook is ~8 instructions of predicate arithmetic even when the buffer is null -- about 100
+// of the ~600 instructions a compute thread executes per tile pair, and in the power-capped steady state instructions are time.
+#ifdef FA_B200_TRACE_HOOKS
 #define FA_TR(t_, e_) do { if (tr && (t_) >= tr0 && (t_) < tr0 + 16 && lane == 0) tr[((t_) - tr0) * 16 + (e_)] = clock64(); } while (0)
 #define FA_TR3(t_, e_) do { if (tr && (t_) >= tr0 && (t_) < tr0 + 16 && lane == 0) tr[256 + ((t_) - tr0) * 16 + (e_)] = clock64(); } while (0)
 #define FA_TR2(t_, e_) do { if (tr && (t_) >= tr0 && (t_) < tr0 + 16 && lane == 0 && warp == 0) tr[256 + ((t_) - tr0) * 16 + (e_)] = clock64(); } while (0)
+#else
+#define FA_TR(t_, e_) do { } while (0)
+#define FA_TR3(t_, e_) do { } while (0)
+#define FA_TR2(t_, e_) do { } while (0)
+#endif
 
   if (threadIdx.x == 0) {
     mbar_init(&bars.k_full, 1);
@@ -550,6 +561,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             pr[c + 3] = ex2_approx(x1.y);
           }
           if (diag) {
+            // a real branch: without the (empty) volatile asm the block is if-converted into 64 ISETP + 64 FSEL that
+            // EVERY tile pair executes (~130 of ~800 instructions of the loop) although one pair in 16 needs them
+            asm volatile("" ::: "memory");
 #pragma unroll
             for (int c = 0; c < 64; ++c)
               if (g * 64 + c < r) pr[c] = 0.f;  // key index > query index

@@ -206,7 +206,22 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   const int nkv = (T + kBlockN - 1) / kBlockN;
   const int nblk = p.nblk;
   long long* const tr = blockIdx.x == 0 ? p.trace : nullptr;
-#define FA_TRF(j_, e_) do { if (tr && m == 0 && (j_) < 16 && lane == 0) tr[(j_) * 16 + (e_)] = clock64(); } while (0)
+// developer timeline (tools/fa_check tracefwd).  FA_B200_FWD_TRACE_HOOKS: bit 0 = the sites of the softmax warps, bit 1 =
+// the sites of the MMA warp; a full timeline needs a -DFA_B200_FWD_TRACE_HOOKS=3 build (tools/build_variant.sh).  The
+// shipped value is what measured fastest, four interleaved same-box rounds at config 3 (tools/batches/r02bs.sh):
+//   3 (all sites)  1.891-1.907 ms  |  1 (softmax only)  1.933-1.971  |  0 (none)  1.915-1.926  |  2 (MMA warp only)  1.876-1.884
+// The ~8 predicate instructions of a null hook cost the softmax warps 1 %; in the MMA warp they sit between a barrier
+// wait and the issue of the next MMA batch and the kernel is 2 % FASTER with them -- the issuing warp shares a scheduler
+// with two softmax warps, and what it does between its waits shifts when those get their issue slots.  (The backward is
+// the opposite case: its hooks cost 8 %, see fa_bwd_sm100.cu.)
+#ifndef FA_B200_FWD_TRACE_HOOKS
+#define FA_B200_FWD_TRACE_HOOKS 2
+#endif
+#if FA_B200_FWD_TRACE_HOOKS  // bit 0: sites of the softmax warps (slots 0-7), bit 1: sites of the MMA warp (slots 8-11)
+#define FA_TRF(j_, e_) do { if ((FA_B200_FWD_TRACE_HOOKS & ((e_) >= 8 ? 2 : 1)) && tr && m == 0 && (j_) < 16 && lane == 0) tr[(j_) * 16 + (e_)] = clock64(); } while (0)
+#else
+#define FA_TRF(j_, e_) do { } while (0)
+#endif
 
   // The kernel is PERSISTENT: one CTA per SM draws work items (one 256-row query block of one head, heaviest causal blocks
   // of a head first) from a global counter.  The K/V ring, the S / P / O hand-offs and their mbarrier parities run on

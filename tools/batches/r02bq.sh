@@ -1,0 +1,9 @@
+cd $GRAFT_REPO_ROOT
+P=tools/sustained_probe.sh
+LD_LIBRARY_PATH=build/variants/v2 timeout 300 build/fa_check bwd | tail -n 1
+LD_LIBRARY_PATH=build/variants/v2 timeout 300 build/fa_check drop | tail -n 1
+for r in 1 2 3; do for v in notrace v2; do printf "$v "; LD_LIBRARY_PATH=build/variants/$v build/fa_check time 512 4096 128 1 10 1 | tail -1; done; done
+for r in 1 2; do for v in notrace v2; do printf "$v "; LD_LIBRARY_PATH=build/variants/$v build/fa_check time 512 4096 128 0 5 1 | tail -1; done; done
+for r in 1 2; do for v in base notrace v2; do printf "$v "; LD_LIBRARY_PATH=build/variants/$v build/fa_check time 128 16384 128 1 3 1 0.1 | tail -1; done; done
+sleep 2
+for v in notrace v2; do LD_LIBRARY_PATH=build/variants/$v $P "$v bwd x300" build/fa_check time 512 4096 128 1 300 1; sleep 2; done

@@ -538,6 +538,15 @@ static int trace_bwd(int BH, int T, int d, int causal, int t_start = 0) {
   // dQ drained & dO landed, dP issued, P ready, dV issued, S(i+2) issued}
   const long long* hh = hst.data();
   const long long t0 = hh[0];
+  {
+    bool any = false;
+    for (long long v : hst) any = any || v != 0;
+    if (!any) {
+      printf("no stamps: the backward's timeline hooks are compiled out of the shipped library -- build one with\n"
+             "  tools/build_variant.sh trace -DFA_B200_TRACE_HOOKS   and run   LD_LIBRARY_PATH=build/variants/trace build/fa_check trace ...\n");
+      return 1;
+    }
+  }
   printf("bwd timeline of CTA 0, tile pairs %d.. (running count), cycles relative to the first S ready\n", t_start);
   printf(" il | CW: S_rdy  P_done  dP_rdy dS_w0   dS_w7 | DW: dQ_rdy drained  staged | MMA: dS_rdy  iss_dK dO_seen  iss_dP  P_seen  iss_dV   iss_S\n");
   for (int il = 0; il < 16; ++il) {
