@@ -41,11 +41,16 @@
 #ifndef FA_BWD_PREFETCH_KV
 #define FA_BWD_PREFETCH_KV 1  // L2 prefetch of the next item's K / V tiles
 #endif
+// k-step loops of the MMA issuer.  Round-2 history: while the issue code ran on vector registers (see the REDUX of the TMEM
+// base in the issuer) the unroll factor was worth 10 % (1 = rolled: 7.1 ms = issue-bound, 2: 6.7, 4: 6.45-6.65, 8: 6.7-6.85:
+// instruction cache) and the hash-heavy dropout variant wanted rolled loops (30.4 ms against 36.5 with 4).  On the uniform
+// datapath an MMA costs ~3 issue slots and the factor is worth < 1 %: 1: 5.85-5.89 ms, 2: 5.81-5.87, 4: 5.85-5.86, 8: 5.79-5.82
+// (config 4, dropout: 23.7-24.1 ms for every factor).
 #ifndef FA_BWD_MMA_UNROLL_DROP
-#define FA_BWD_MMA_UNROLL_DROP 1  // the dropout variant (hash-heavy compute warps share the issue slots), config 4: 1: 30.4-31.0 ms, 2: 30.7-31.2, 4: 36.5, 8: 35.0
+#define FA_BWD_MMA_UNROLL_DROP 8
 #endif
 #ifndef FA_BWD_MMA_UNROLL
-#define FA_BWD_MMA_UNROLL 4  // k-step loops of the MMA issuer: 1 = rolled (7.1 ms: issue-bound), 2: 6.7, 4: 6.45-6.65, 8 = fully unrolled: 6.7-6.85
+#define FA_BWD_MMA_UNROLL 8
 #endif
 
 namespace fa {
@@ -362,12 +367,16 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else if (warp == 13) {
     // ------------------------------------------------------------------ MMA issuer: the whole warp runs the issue code
+    // REDUX inside this branch: a shared-memory load is not provably warp-uniform for ptxas, and with ONE non-uniform operand
+    // (every MMA takes tmem + const) it builds ALL operands of the issue loops in vector registers and wraps each UTCHMMA
+    // into ELECT + four R2UR.BROADCAST (~16 instructions per MMA instead of ~3 on the uniform datapath)
+    const uint32_t tmem = __reduce_max_sync(0xffffffffu, bars.tmem_slot);
     // (uniform-register descriptors, see fa_ptx.cuh `_w` forms); one elected lane issues each MMA / commit.
     // ONE flat loop over the tile pairs of all items: an item boundary only changes descriptors and which commits fire,
     // so the boundary runs the same (instruction-cache-hot) code as the steady state -- a separate head / tail path was
     // measured at ~4400 cycles for its 24 MMAs (cold code: the kernel is 90 KB, the SM's instruction cache 32 KB).  The k-steps
     // are rolled loops for the same reason: the issue code of a step is ~1 KB instead of ~10 KB.
-    constexpr int kMmaUnroll = kDrop ? FA_BWD_MMA_UNROLL_DROP : D == 64 ? 8 : FA_BWD_MMA_UNROLL;  // d = 64: 4.15 (8) against 4.29 ms (4)
+    constexpr int kMmaUnroll = kDrop ? FA_BWD_MMA_UNROLL_DROP : FA_BWD_MMA_UNROLL;
     constexpr uint32_t idesc_sT = make_idesc(kFmtBF16, 128, 128, 0, 0);  // K-major x K-major
     constexpr uint32_t idesc_acc = make_idesc(kFmtBF16, 128, D, 0, 1);   // (TMEM | K-major) x MN-major
     constexpr uint32_t idesc_dq = make_idesc(kFmtBF16, 128, D, 1, 1);    // MN-major x MN-major

@@ -187,6 +187,10 @@ fa_bwd_tf32_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
   } else if (warp == 13) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, `_w` forms)
+    // REDUX inside this branch: a shared-memory load is not provably warp-uniform for ptxas, and with ONE non-uniform operand
+    // (every MMA takes tmem + const) it builds ALL operands of the issue loops in vector registers and wraps each UTCHMMA
+    // into ELECT + four R2UR.BROADCAST (~16 instructions per MMA instead of ~3 on the uniform datapath)
+    const uint32_t tmem = __reduce_max_sync(0xffffffffu, *tmem_slot);
     constexpr uint32_t idesc_sT = make_idesc(kFmtTF32, 128, kTQ, 0, 0);  // K-major x K-major
     constexpr uint32_t idesc_acc = make_idesc(kFmtTF32, 128, kD, 0, 1);  // TMEM x MN-major
     constexpr uint32_t idesc_dq = make_idesc(kFmtTF32, kTQ, kD, 1, 1);   // MN-major x MN-major, M = kTQ queries

@@ -172,6 +172,8 @@ fa_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (warp == 5) {
     // the whole warp runs the issue code (warp-uniform descriptors, one elected lane issues: `_w` forms of fa_ptx.cuh)
     {
+      // REDUX: makes the TMEM base provably warp-uniform for ptxas (see the MMA issuer of fa_bwd_sm100.cu)
+      const uint32_t tmem = __reduce_max_sync(0xffffffffu, tmem_slot);
       constexpr uint32_t idesc = make_idesc(kFmtTF32, kBM, kBN, kAMn ? 1 : 0, kBMn ? 1 : 0);
       const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
       for (int kb = 0; kb < nk; ++kb) {
