@@ -701,7 +701,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const int r = w * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t tDQ = tmem + Cfg::kColR1 + (uint32_t(w * 32) << 16);
     const bool leader = (warp == 8 && lane == 0);
-    uint32_t chunk_no = 0;
+    // staging addresses of this thread's eight 16-byte chunks (128-B swizzle): computed once -- per store they cost three ALU
+    // instructions, 100 of the ~340 a drain thread executes per tile pair.  A pair fills an even number of slabs (D / 32), so the
+    // slab a chunk goes to is a compile-time constant and folds into the store's immediate offset.
+    static_assert((D / 32) % 2 == 0, "slab parity per pair");
+    uint32_t st_addr[8];
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) st_addr[ch] = smem_u32(sStage) + r * 128 + ((ch ^ (r & 7)) << 4);
     uint32_t t = 0;
     for (int m = 0;; ++m) {
       const int item = next_item(m);
@@ -731,19 +737,23 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             if (warp == 8) FA_TR(t, 6);
           }
 #pragma unroll
-          for (int c = 0; c < kColsPart / 32; ++c, ++chunk_no) {
-            uint8_t* buf = sStage + (chunk_no & 1) * Cfg::kStageBytes;
-            if (leader && chunk_no >= 2) tma_store_wait_read<1>();  // staging buffer no longer being read
+          for (int c = 0; c < kColsPart / 32; ++c) {
+            uint8_t* buf = sStage + (c & 1) * Cfg::kStageBytes;
+            if (leader && (t > 0 || c >= 2)) tma_store_wait_read<1>();  // staging buffer no longer being read
             named_bar_sync(1, 128);
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch)
-              *reinterpret_cast<uint4*>(buf + r * 128 + ((ch ^ (r & 7)) << 4)) =
-                  make_uint4(rr[c * 32 + ch * 4], rr[c * 32 + ch * 4 + 1], rr[c * 32 + ch * 4 + 2], rr[c * 32 + ch * 4 + 3]);
+              st_shared_v4(st_addr[ch] + (c & 1) * Cfg::kStageBytes, rr[c * 32 + ch * 4], rr[c * 32 + ch * 4 + 1], rr[c * 32 + ch * 4 + 2],
+                           rr[c * 32 + ch * 4 + 3]);
             fence_proxy_async_smem();
             named_bar_sync(1, 128);
             if (leader) {
+#ifdef FA_B200_DEBUG_HOOKS  // timing experiments (wrong results): skip the reduce-adds / plain stores instead
               if (p.dq_debug == 0) tma_reduce_add_3d(&map_dq, buf, part * kColsPart + c * 32, i * kTile, bh);
               else if (p.dq_debug == 2) tma_store_3d(&map_dq, buf, part * kColsPart + c * 32, i * kTile, bh);
+#else
+              tma_reduce_add_3d(&map_dq, buf, part * kColsPart + c * 32, i * kTile, bh);
+#endif
               tma_store_commit();
             }
           }

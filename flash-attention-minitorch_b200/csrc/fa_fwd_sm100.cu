@@ -341,6 +341,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer: the whole warp runs the issue code
+    // tf32 variants: TMEM base and running counters made provably warp-uniform (REDUX), which puts the issue loops on the
+    // uniform datapath (fa_bwd_sm100.cu): config 2 0.273 -> 0.272 ms, the MT attention shape (BH = 88, T = 512,
+    // d = 32) 0.023 -> 0.022 ms.  The bf16 variants measured 1 % SLOWER that way (1.83-1.84 -> 1.85 ms) and keep the old code.
+    const uint32_t tmem_loaded = tmem;
+    const uint32_t tmem = kTF32 ? __reduce_max_sync(0xffffffffu, tmem_base_smem) : tmem_loaded;
     // (warp-uniform descriptors, one elected lane issues each MMA / commit: the `_w` forms of fa_ptx.cuh)
     {
       constexpr uint32_t kFmt = kTF32 ? kFmtTF32 : kFmtBF16;
@@ -384,6 +389,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         if (item < 0) break;
         int bh, blk, n0, n1;
         decode(item, bh, blk, n0, n1);
+        if constexpr (kTF32) {  // loop-carried across items, where ptxas loses their uniformity
+          jt = __reduce_max_sync(0xffffffffu, jt);
+          c0 = __reduce_max_sync(0xffffffffu, c0);
+          c1 = __reduce_max_sync(0xffffffffu, c1);
+        }
         mbar_wait_w(&bars.q_full, m & 1);
         mbar_wait_w(&bars.k_full[jt % S], (jt / S) & 1);
         tc_fence_after();
