@@ -206,19 +206,22 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   const int nkv = (T + kBlockN - 1) / kBlockN;
   const int nblk = p.nblk;
   long long* const tr = blockIdx.x == 0 ? p.trace : nullptr;
-// developer timeline (tools/fa_check tracefwd).  FA_B200_FWD_TRACE_HOOKS: bit 0 = the sites of the softmax warps, bit 1 =
-// the sites of the MMA warp; a full timeline needs a -DFA_B200_FWD_TRACE_HOOKS=3 build (tools/build_variant.sh).  The
-// shipped value is what measured fastest, four interleaved same-box rounds at config 3 (tools/batches/r02bs.sh):
-//   3 (all sites)  1.891-1.907 ms  |  1 (softmax only)  1.933-1.971  |  0 (none)  1.915-1.926  |  2 (MMA warp only)  1.876-1.884
-// The ~8 predicate instructions of a null hook cost the softmax warps 1 %; in the MMA warp they sit between a barrier
-// wait and the issue of the next MMA batch and the kernel is 2 % FASTER with them -- the issuing warp shares a scheduler
-// with two softmax warps, and what it does between its waits shifts when those get their issue slots.  (The backward is
-// the opposite case: its hooks cost 8 %, see fa_bwd_sm100.cu.)
+// developer timeline (tools/fa_check tracefwd).  FA_B200_FWD_TRACE_HOOKS: bit 0 = the sites of the softmax warps, bits 1-3 =
+// the sites of the MMA warp (slot 8: before PV of tile 0 | slots 9, 10: before PV of tile 1 | slot 11: end of the K/V step); a
+// full timeline needs a -DFA_B200_FWD_TRACE_HOOKS=15 build (tools/build_variant.sh).  The shipped value is what measured
+// fastest at config 3, interleaved same-box rounds (tools/batches/r02bs.sh, r02cd.sh):
+//   all sites 1.891-1.907 ms | softmax sites only 1.933-1.971 | none 1.915-1.926 | MMA-warp sites only 1.876-1.884      (box A)
+//   none 1.857-1.869 | slot 8 only 1.854-1.864 | 9, 10 only 1.850-1.885 | 11 only 1.857-1.872 | 8 + 9, 10: 1.816-1.819 |
+//   8 + 11: 1.827-1.838 | 9, 10 + 11: 1.852-1.873 | all three 1.820-1.827                                                   (box B)
+// The ~8 predicate instructions of a null hook cost the softmax warps 1 %; in the MMA warp, ahead of BOTH PV issues, they make the
+// kernel 2 % FASTER.  The generated issue code is the same apart from the hooks (same UTCHMMA / R2UR / ELECT / branch counts),
+// so it is their delay that acts; a suspend-time hint on the issuer's barrier waits (fewer polls instead of later ones) is
+// 1 % slower, uniform-datapath issue (fewer instructions per MMA) 1 % slower too.  Unexplained; recorded in DESIGN.md 3.2e.
 #ifndef FA_B200_FWD_TRACE_HOOKS
-#define FA_B200_FWD_TRACE_HOOKS 2
+#define FA_B200_FWD_TRACE_HOOKS 6
 #endif
-#if FA_B200_FWD_TRACE_HOOKS  // bit 0: sites of the softmax warps (slots 0-7), bit 1: sites of the MMA warp (slots 8-11)
-#define FA_TRF(j_, e_) do { if ((FA_B200_FWD_TRACE_HOOKS & ((e_) >= 8 ? 2 : 1)) && tr && m == 0 && (j_) < 16 && lane == 0) tr[(j_) * 16 + (e_)] = clock64(); } while (0)
+#if FA_B200_FWD_TRACE_HOOKS  // bit 0: sites of the softmax warps (slots 0-7), bits 1-3: sites of the MMA warp (slot 8 | 9, 10 | 11)
+#define FA_TRF(j_, e_) do { if ((FA_B200_FWD_TRACE_HOOKS & ((e_) == 8 ? 2 : (e_) == 9 || (e_) == 10 ? 4 : (e_) == 11 ? 8 : 1)) && tr && m == 0 && (j_) < 16 && lane == 0) tr[(j_) * 16 + (e_)] = clock64(); } while (0)
 #else
 #define FA_TRF(j_, e_) do { } while (0)
 #endif
