@@ -39,7 +39,11 @@
 
 // A/B switches for same-box experiments (tools/build_variant.sh + tools/ab.sh).
 #ifndef FA_BWD_PREFETCH_KV
-#define FA_BWD_PREFETCH_KV 1  // L2 prefetch of the next item's K / V tiles
+// L2 prefetch of the next item's K / V tiles (cp.async.bulk.prefetch.tensor an item ahead).  Worth 1 % when it was added (the K / V
+// loads at an item boundary are HBM-cold); re-measured after the codegen fixes of the last session it COSTS 1 % everywhere
+// (config 3: 5.53-5.56 against 5.57-5.62 ms, 5.953 against 6.024 ms power-capped; 64 heads 0.689 against 0.697 ms; config 4
+// 23.78 against 23.87-24.1 ms): the extra TMA operations and L2 traffic are energy, and the step is power-capped.  Off.
+#define FA_BWD_PREFETCH_KV 0
 #endif
 // k-step loops of the MMA issuer.  Round-2 history: while the issue code ran on vector registers (see the REDUX of the TMEM
 // base in the issuer) the unroll factor was worth 10 % (1 = rolled: 7.1 ms = issue-bound, 2: 6.7, 4: 6.45-6.65, 8: 6.7-6.85:
