@@ -106,6 +106,7 @@ constexpr int kFwdThreads = 384;  // warps 0-7 softmax, 8 TMA, 9 MMA, 10-11 idle
 #ifndef FA_FWD_PSIG
 #define FA_FWD_PSIG 2
 #endif
+static_assert(FA_FWD_PSIG == 1 || FA_FWD_PSIG == 2, "the softmax warps signal P whole or in two halves (4 pieces: no gain in round 1, code removed)");
 
 struct FwdParams {
   int T, BH, causal;
