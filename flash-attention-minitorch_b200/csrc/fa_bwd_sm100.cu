@@ -378,8 +378,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // (uniform-register descriptors, see fa_ptx.cuh `_w` forms); one elected lane issues each MMA / commit.
     // ONE flat loop over the tile pairs of all items: an item boundary only changes descriptors and which commits fire,
     // so the boundary runs the same (instruction-cache-hot) code as the steady state -- a separate head / tail path was
-    // measured at ~4400 cycles for its 24 MMAs (cold code: the kernel is 90 KB, the SM's instruction cache 32 KB).  The k-steps
-    // are rolled loops for the same reason: the issue code of a step is ~1 KB instead of ~10 KB.
+    // measured at ~4400 cycles for its 24 MMAs (cold code: the SM's instruction cache is 32 KB).  The k-step loops are fully
+    // unrolled: on the uniform datapath a k-step is ~3 instructions (see FA_BWD_MMA_UNROLL above).
     constexpr int kMmaUnroll = kDrop ? FA_BWD_MMA_UNROLL_DROP : FA_BWD_MMA_UNROLL;
     constexpr uint32_t idesc_sT = make_idesc(kFmtBF16, 128, 128, 0, 0);  // K-major x K-major
     constexpr uint32_t idesc_acc = make_idesc(kFmtBF16, 128, D, 0, 1);   // (TMEM | K-major) x MN-major
