@@ -491,6 +491,11 @@ static int trace_fwd(int BH, int T, int d, int causal) {
   std::vector<long long> hh(512);
   CK(cudaMemcpy(hh.data(), tr, 512 * 8, cudaMemcpyDeviceToHost));
   const long long t0 = hh[0];
+  if (t0 == 0) {
+    printf("no softmax-warp stamps: the shipped library keeps only the forward's MMA-warp hook sites -- build a full one with\n"
+           "  tools/build_variant.sh tracefwd -DFA_B200_FWD_TRACE_HOOKS=15   and run   LD_LIBRARY_PATH=build/variants/tracefwd build/fa_check tracefwd ...\n");
+    return 1;
+  }
   printf("fwd timeline of CTA(0,0), cycles relative to the first S0 ready\n");
   printf("  j | T0: S_rdy  loaded  maxed  P_done | T1: S_rdy  loaded  maxed  P_done | MMA: P0_seen iss0  P1_seen   iss1\n");
   for (int j = 0; j < 16; ++j) {
